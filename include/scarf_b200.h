@@ -1,0 +1,131 @@
+/* scarf_b200 -- C-ABI of the B200-native make_graph hot path.
+ *
+ * The reference (parashardhapola/scarf 0.32.3) has no FFI: its seam is Python
+ * (GraphDataStore.make_graph, scarf/datastore/graph_datastore.py:513).  Each entry point below
+ * replaces the arithmetic of one reference call site (cited per function, paths relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes stub a Scarf maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless marked "host";
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no hidden
+ *     allocation, no global mutable state; scratch is passed in (see *_workspace_bytes);
+ *   - return value: 0 = ok, >0 = argument error, <0 = -(cudaError_t); text via scf_last_error()
+ *     (thread local);
+ *   - "fx" arrays are int64 fixed-point accumulators (value * 2^shift): integer adds are
+ *     associative, so results are bit-identical for any launch geometry and any number of GPUs
+ *     (an int64 sum all-reduce between ranks keeps that property).
+ */
+#ifndef SCARF_B200_H
+#define SCARF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCF_VERSION 100
+#define SCF_COLSTAT_SHIFT 34 /* sum x, sum x^2 : x <= log1p(sf) */
+#define SCF_GRAM_SHIFT 36    /* |sum z_j z_k| <= n_rows (unit-variance columns) */
+
+int32_t scf_version(void);
+const char* scf_last_error(void);
+
+/* ---- K0a: per-row sum and count of stored values over a column subset -----------------------
+ * Replaces  nCounts / nFeatures  (scarf/datastore/base_datastore.py:345-366) when col_map==NULL
+ * and the renormalisation scalar  counts.sum(axis=1)  of RNAassay.normed (scarf/assay.py:814-823)
+ * when col_map selects the HVG columns (col_map[g] < 0 = not selected).
+ * row_ids (nullable): CSR rows to process, output row r <-> CSR row row_ids[r]. */
+int32_t scf_csr_row_sums(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
+                         const int64_t* row_ids, int64_t n_sel, const int32_t* col_map,
+                         double* out_sum, int32_t* out_nnz, void* stream);
+
+/* ---- K0b: per-gene nnz / sum / sum of squares of v = sf*c/row_div[r] -------------------------
+ * Replaces the three dask passes of RNAassay.set_feature_stats (scarf/assay.py:848-858) over
+ * norm_lib_size (scarf/assay.py:41-51): row_div[r] = nCounts of output row r.  row_div==NULL ->
+ * v = c (gives per-feature nCells, scarf/assay.py:201-225).  Outputs are ACCUMULATED (caller
+ * zeroes); gene_sum / gene_sumsq may be NULL. */
+int32_t scf_csr_gene_stats(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
+                           const int64_t* row_ids, int64_t n_sel, int32_t n_genes,
+                           const double* row_div, double sf, unsigned long long* gene_nnz,
+                           double* gene_sum, double* gene_sumsq, void* stream);
+
+/* ---- K1a: column sums of the normalised HVG matrix -------------------------------------------
+ * x = log1p(sf*c/row_sum[r]) (log_transform) or sf*c/row_sum[r]   (scarf/assay.py:54-64,826)
+ * accumulates sum x and sum x^2 per selected column as int64 fixed point (<< SCF_COLSTAT_SHIFT):
+ * the mu / sigma block of make_graph (scarf/datastore/graph_datastore.py:767-796). */
+int32_t scf_csr_hvg_colstats(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
+                             const int64_t* row_ids, int64_t n_sel, const int32_t* col_map,
+                             const double* row_sum, double sf, int32_t log_transform,
+                             int64_t* sum_fx, int64_t* sumsq_fx, void* stream);
+
+/* ---- K1b: fused lib-size normalise -> log1p -> HVG gather -> z-scale --------------------------
+ * Z[r, col_map[g]] = (x - mu)/sigma   (AnnStream.transform_z, scarf/ann.py:191-192; the dense
+ * row also gets (0 - mu)/sigma where the cell has no count).  Z is float32 row-major with row
+ * stride ldz >= n_cols; columns [n_cols, ldz) are written as 0.  mu==NULL -> 0, sigma==NULL -> 1
+ * (plain normalised values, used by the parity tests of the normalisation itself).
+ * missing_fill (nullable, float64[n_cols]): value of x for columns that do not exist in this
+ * matrix at all (align_features fills them with 1.0, scarf/mapping_utils.py:208-211); a column
+ * with missing_fill[j] == missing_fill[j] (not NaN) ignores the CSR and uses that x. */
+int32_t scf_csr_norm_scale(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
+                           const int64_t* row_ids, int64_t n_sel, const int32_t* col_map,
+                           int32_t n_cols, const double* row_sum, double sf, int32_t log_transform,
+                           const double* mu, const double* sigma, const double* missing_fill,
+                           float* z, int64_t ldz, void* stream);
+
+/* ---- K2: Gram accumulation  G += Z^T Z  (upper-left n_cols x n_cols, full square written) -----
+ * Replaces the per-block SVD updates of sklearn IncrementalPCA.partial_fit driven by
+ * AnnStream._fit_pca (scarf/ann.py:207-256) by the exact covariance route.
+ * Rows are consumed in fixed slabs of SCF_GRAM_SLAB rows (float32 partials inside a slab, int64
+ * fixed point << SCF_GRAM_SHIFT across slabs).  n_rows must be a multiple of SCF_GRAM_SLAB or the
+ * tail rows of the last slab must be readable zeros (callers pad Z).  ldg = row stride of g_fx.
+ * mode: 0 = FP32 SIMT, 1 = TF32 tcgen05, 3 = 3xTF32 tcgen05. */
+#define SCF_GRAM_SLAB 2048
+int32_t scf_gram_accumulate(const float* z, int64_t ldz, int64_t n_rows, int32_t n_cols,
+                            int64_t* g_fx, int64_t ldg, int32_t mode, void* stream);
+
+/* ---- K4: projection  Y[:, :dims] = Z @ V ;  Y[:, dims:ldy] = 0 ----------------------------------
+ * AnnStream.reducer (scarf/ann.py:138): V = loadings (n_cols x dims, float32 row-major, stride ldv) */
+int32_t scf_project(const float* z, int64_t ldz, int64_t n_rows, int32_t n_cols, const float* v,
+                    int64_t ldv, int32_t dims, float* y, int64_t ldy, void* stream);
+
+/* ---- K5: exact k nearest neighbours, squared L2 --------------------------------------------------
+ * Replaces hnswlib Index(space='l2').knn_query + fix_knn_query (scarf/ann.py:14-52,194-205):
+ *   d(a,b) = (float) sum_t ((double)a_t - (double)b_t)^2   (t ascending), order by (d, index),
+ *   query i is reference i + self_offset and is excluded when self_offset >= 0 (-1: keep all).
+ * q: nq x ld float32, ref: nref x ld float32 (row stride ld >= dim).  out_idx int64 [nq,k],
+ * out_dist float32 [nq,k].  method: 0 = FP64 SIMT brute force, 1 = tcgen05 TF32 candidates +
+ * exact FP64 re-rank with a proven guard band (rows that fail the guard are recomputed by
+ * method 0 inside the same call).  workspace: scf_knn_workspace_bytes(nq, nref, dim, k, method). */
+int64_t scf_knn_workspace_bytes(int64_t nq, int64_t nref, int32_t dim, int32_t k, int32_t method);
+int32_t scf_knn_l2(const float* q, int64_t nq, const float* ref, int64_t nref, int32_t dim,
+                   int64_t ld, int32_t k, int64_t self_offset, int64_t* out_idx, float* out_dist,
+                   int32_t method, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- K6: smooth_knn_dist + compute_membership_strengths + COO assembly ---------------------------
+ * umap-learn functions called per chunk by smoothen_dists (scarf/knn_utils.py:89-159).
+ * dist float32 [n,k] ascending; idx int64 [n,k] GLOBAL ids.  Row r belongs to chunk
+ * (row_offset + r) / chunk_size; its chunk-local id (used by the "neighbour == i" rule, SURVEY
+ * fact 6) is (row_offset + r) % chunk_size.  chunk_mean float32 [n_chunks_total] = mean distance
+ * of each chunk, indexed by the GLOBAL chunk id: scf_chunk_sums gives this shard's float64 sum
+ * per chunk (written only for the chunks the shard touches; sum all-reduce completes a chunk that
+ * straddles shards), the caller divides by rows_in_chunk * k and rounds to float32.
+ * Outputs: sigma,rho float32 [n]; edges int64 [n*k,2] (row_offset + r, idx); weights float32 [n*k];
+ * chunk_min float32 [n_chunks_total] = min non-zero weight per chunk (caller presets +inf),
+ * chunk_has_zero int32 [n_chunks_total] = 1 where the chunk produced a zero weight (caller presets 0):
+ * the floor of scarf/knn_utils.py:121,147-158 is min(1, min over chunks with a zero of chunk_min). */
+int32_t scf_chunk_sums(const float* dist, int64_t n, int32_t k, int64_t row_offset,
+                       int64_t chunk_size, double* chunk_sum, void* stream);
+int32_t scf_smooth_knn(const float* dist, int64_t n, int32_t k, float local_connectivity,
+                       float bandwidth, int64_t row_offset, int64_t chunk_size,
+                       const float* chunk_mean, float* sigma, float* rho, void* stream);
+int32_t scf_membership_coo(const int64_t* idx, const float* dist, const float* sigma,
+                           const float* rho, int64_t n, int32_t k, int64_t row_offset,
+                           int64_t chunk_size, int64_t* edges, float* weights, float* chunk_min,
+                           int32_t* chunk_has_zero, void* stream);
+/* zero weights := floor (scarf/knn_utils.py:154-158); floor is a host value */
+int32_t scf_fill_zero_weights(float* weights, int64_t n, float floor_value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

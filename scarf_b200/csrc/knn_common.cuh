@@ -1,0 +1,13 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// method 0 (knn_exact.cu); q_ids (nullable) = subset of query rows to (re)compute in place
+int32_t knn_exact_launch(const float* q, const int64_t* q_ids, int64_t nq, const float* ref, int64_t nref, int dim,
+                         int64_t ld, int k, int64_t self_offset, int64_t* out_idx, float* out_dist,
+                         cudaStream_t stream);
+// method 1 (knn_tc.cu)
+int64_t knn_tc_workspace_bytes(int64_t nq, int64_t nref, int dim, int k);
+int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref, int dim, int64_t ld, int k,
+                      int64_t self_offset, int64_t* out_idx, float* out_dist, void* workspace,
+                      int64_t workspace_bytes, cudaStream_t stream);

@@ -1,0 +1,134 @@
+// K5, method 0: brute-force kNN with the oracle's arithmetic in FP64 (oracle/oracle_c.c defines it):
+//   d(a,b) = (float) sum_t ((double)a_t - (double)b_t)^2, t ascending, separate mul and add (no FMA),
+//   neighbours ordered by (d, index).
+// It is the exactness anchor of the library: the tcgen05 path (knn_tc.cu) re-ranks its candidates with
+// the same arithmetic and sends every query whose guard band cannot be proven through this kernel.
+#include <float.h>
+#include "common.cuh"
+#include "knn_common.cuh"
+
+namespace {
+
+constexpr int TQ = 64, TR = 64, DK = 32;
+
+// dynamic smem layout: Qs[dim_pad][TQ] | Rs[DK][TR+1] | Ds[TQ][TR+1] | Ld[TQ][k] | Li[TQ][k]
+__global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict__ q, const int64_t* __restrict__ q_ids,
+                                                        int64_t nq, const float* __restrict__ ref, int64_t nref,
+                                                        int dim, int64_t ld, int k, int64_t self_offset,
+                                                        int64_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int dim_pad = (dim + DK - 1) / DK * DK;
+  float* Qs = reinterpret_cast<float*>(smem_raw);
+  float* Rs = Qs + (size_t)dim_pad * TQ;
+  float* Ds = Rs + DK * (TR + 1);
+  float* Ld = Ds + TQ * (TR + 1);
+  int* Li = reinterpret_cast<int*>(Ld + (size_t)TQ * k);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t q0 = (int64_t)blockIdx.x * TQ;
+  // query tile, transposed, zero padded
+  for (int e = tid; e < dim_pad * TQ; e += 256) {
+    const int t = e % dim_pad, qq = e / dim_pad;
+    float v = 0.f;
+    if (q0 + qq < nq && t < dim) {
+      const int64_t qi = q_ids ? q_ids[q0 + qq] : q0 + qq;
+      v = q[qi * ld + t];
+    }
+    Qs[t * TQ + qq] = v;
+  }
+  int cnt = 0;  // threads 0..TQ-1: entries in this query's list
+  int64_t self = -1;
+  if (tid < TQ && q0 + tid < nq && self_offset >= 0) self = (q_ids ? q_ids[q0 + tid] : q0 + tid) + self_offset;
+  __syncthreads();
+  for (int64_t r0 = 0; r0 < nref; r0 += TR) {
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int t0 = 0; t0 < dim_pad; t0 += DK) {
+      // ref chunk: TR rows x DK dims, coalesced along t
+      for (int e = tid; e < TR * DK; e += 256) {
+        const int t = e % DK, rr = e / DK;
+        float v = 0.f;
+        if (r0 + rr < nref && t0 + t < dim) v = __ldg(ref + (r0 + rr) * ld + t0 + t);
+        Rs[t * (TR + 1) + rr] = v;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int t = 0; t < DK; ++t) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = (double)Qs[(t0 + t) * TQ + ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = (double)Rs[t * (TR + 1) + tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double df = __dsub_rn(a[i], b[j]);
+            acc[i][j] = __dadd_rn(acc[i][j], __dmul_rn(df, df));
+          }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ds[(ty * 4 + i) * (TR + 1) + tx * 4 + j] = (float)acc[i][j];
+    __syncthreads();
+    if (tid < TQ && q0 + tid < nq) {
+      float* ld_ = Ld + (size_t)tid * k;
+      int* li_ = Li + (size_t)tid * k;
+      const int lim = (int)min((int64_t)TR, nref - r0);
+      for (int rr = 0; rr < lim; ++rr) {
+        const int64_t j = r0 + rr;
+        if (j == self) continue;
+        const float d = Ds[tid * (TR + 1) + rr];
+        if (cnt == k && !(d < ld_[k - 1])) continue;  // equal d with a larger index never wins
+        int p = cnt < k ? cnt : k - 1;
+        while (p > 0 && d < ld_[p - 1]) {
+          ld_[p] = ld_[p - 1];
+          li_[p] = li_[p - 1];
+          --p;
+        }
+        ld_[p] = d;
+        li_[p] = (int)j;
+        if (cnt < k) ++cnt;
+      }
+    }
+    // the next tile's first __syncthreads (after loading Rs) orders these reads of Ds before its rewrite
+  }
+  if (tid < TQ && q0 + tid < nq) {
+    const int64_t qi = q_ids ? q_ids[q0 + tid] : q0 + tid;
+    for (int p = 0; p < k; ++p) {
+      out_idx[qi * k + p] = p < cnt ? (int64_t)Li[(size_t)tid * k + p] : -1;
+      out_dist[qi * k + p] = p < cnt ? Ld[(size_t)tid * k + p] : FLT_MAX;
+    }
+  }
+}
+
+}  // namespace
+
+size_t knn_exact_smem(int dim, int k) {
+  const int dim_pad = (dim + DK - 1) / DK * DK;
+  return sizeof(float) * ((size_t)dim_pad * TQ + DK * (TR + 1) + TQ * (TR + 1)) + (size_t)TQ * k * 8;
+}
+
+int32_t knn_exact_launch(const float* q, const int64_t* q_ids, int64_t nq, const float* ref, int64_t nref, int dim,
+                         int64_t ld, int k, int64_t self_offset, int64_t* out_idx, float* out_dist,
+                         cudaStream_t stream) {
+  if (nq == 0) return 0;
+  const size_t smem = knn_exact_smem(dim, k);
+  if (smem > 227 * 1024) {
+    scf_set_error("scf_knn_l2: dim/k too large for the exact kernel (%zu B of shared memory)", smem);
+    return 1;
+  }
+  cudaError_t e = cudaFuncSetAttribute(knn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
+    return -(int32_t)e;
+  }
+  knn_exact_kernel<<<(unsigned)((nq + TQ - 1) / TQ), 256, smem, stream>>>(q, q_ids, nq, ref, nref, dim, ld, k,
+                                                                         self_offset, out_idx, out_dist);
+  return scf_check_launch("scf_knn_l2(exact)");
+}

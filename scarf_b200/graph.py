@@ -1,0 +1,247 @@
+"""The make_graph hot path on device-resident CSR shards.
+
+``mark_hvgs_csr`` and ``make_graph_csr`` are the numeric cores that the Scarf-compatible
+``DataStore`` (scarf_b200/datastore.py) calls; they take and return torch tensors so that the
+benchmark can time them with the inputs already in HBM.  Reference call stack: SURVEY.md 3.1-3.3.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import hvg as hvg_host
+from . import lib, ops
+from .dist import Comm
+from .ops import CsrDevice, round_up
+
+SF = 1000.0  # RNAassay.sf (scarf/assay.py:776)
+
+
+# =============================================================================================
+# statistics that the reference computes when a DataStore is first opened / in mark_hvgs
+# =============================================================================================
+def cell_totals(csr: CsrDevice):
+    """nCounts (float64) and nFeatures (int32) of every stored cell (scarf/datastore/base_datastore.py:345-366)."""
+    return ops.csr_row_sums(csr)
+
+
+def gene_ncells(csr: CsrDevice, comm: Comm | None = None):
+    """Per-feature nCells over ALL stored cells (scarf/assay.py:201-225)."""
+    nnz, _, _ = ops.csr_gene_stats(csr, None, None, with_moments=False)
+    if comm is not None:
+        comm.allreduce_sum_(nnz)
+    return nnz
+
+
+def hvg_gene_stats(csr: CsrDevice, cell_idx, n_counts, n_cells_total: int, comm: Comm | None = None):
+    """RNAassay.set_feature_stats (scarf/assay.py:830-897): per-gene normed_n / normed_tot / sigmas /
+    avg / nz_mean of ``sf*c/nCounts`` over the ``cell_idx`` rows.  Returns float64 numpy vectors over all genes."""
+    row_div = n_counts[cell_idx] if cell_idx is not None else n_counts
+    nnz, sm, sq = ops.csr_gene_stats(csr, cell_idx, row_div.contiguous(), SF)
+    m = torch.tensor([csr.n_rows if cell_idx is None else cell_idx.numel()], dtype=torch.int64, device=csr.device)
+    if comm is not None:
+        comm.allreduce_sum_(nnz), comm.allreduce_sum_(sm), comm.allreduce_sum_(sq), comm.allreduce_sum_(m)
+    m = float(m.item())
+    n = nnz.to(torch.float64)
+    mean = sm / m
+    var = torch.clamp(sq / m - mean * mean, min=0.0)  # population variance (dask var, ddof 0)
+    nz_mean = torch.where(n > 0, sm / torch.clamp(n, min=1.0), torch.zeros_like(sm))
+    out = {"normed_n": n, "normed_tot": sm, "sigmas": var, "avg": sm / float(n_cells_total), "nz_mean": nz_mean}
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def mark_hvgs_csr(csr: CsrDevice, cell_idx, feat_I, n_counts, n_cells_total, gene_names=None, top_n=500,
+                  min_cells=None, max_cells=np.inf, min_mean=-np.inf, max_mean=np.inf, n_bins=200, lowess_frac=0.1,
+                  blacklist=hvg_host.DEFAULT_BLACKLIST, comm: Comm | None = None, return_stats=False):
+    """DataStore.mark_hvgs (scarf/datastore/datastore.py:223-314) -> bool mask over all genes (numpy)."""
+    if min_cells is None:
+        min_cells = int(0.01 * n_cells_total)  # datastore.py:291
+    st = hvg_gene_stats(csr, cell_idx, n_counts, n_cells_total, comm)
+    feat_I = np.asarray(feat_I, dtype=bool)
+    nan = np.full(csr.n_cols, np.nan)
+    c_var = nan.copy()
+    c_var[feat_I] = hvg_host.remove_trend(st["avg"][feat_I], st["sigmas"][feat_I], n_bins, lowess_frac)
+    normed_n = np.where(feat_I, st["normed_n"], np.nan)
+    nz_mean = np.where(feat_I, st["nz_mean"], np.nan)
+    mask = hvg_host.choose_hvgs(normed_n, nz_mean, c_var, feat_I, gene_names, top_n, min_cells, max_cells,
+                                min_mean, max_mean, blacklist=blacklist)
+    if return_stats:
+        st["c_var"] = c_var
+        return mask, st
+    return mask
+
+
+# =============================================================================================
+# make_graph
+# =============================================================================================
+@dataclass
+class GraphResult:
+    """Device tensors produced by :func:`make_graph_csr` for this rank's rows."""
+    n_cells: int            # selected cells over all ranks
+    row_offset: int         # global (selected-row) id of this rank's first row
+    feat_idx: np.ndarray    # ascending gene ids of the features used
+    mu: torch.Tensor        # float64 [H]
+    sigma: torch.Tensor     # float64 [H]
+    loadings: torch.Tensor  # float64 [H, dims]
+    eigenvalues: torch.Tensor
+    embedding: torch.Tensor  # float32 [n_local, ldy] (pad columns zero) -- what hnswlib would have indexed
+    dims: int
+    k: int
+    indices: torch.Tensor    # int64 [n_local, k]
+    distances: torch.Tensor  # float32 [n_local, k] squared L2
+    edges: torch.Tensor      # int64 [n_local*k, 2]
+    weights: torch.Tensor    # float32 [n_local*k]
+
+
+def clean_array(x, fill_val=0.0):
+    """scarf/utils.py:143-153."""
+    x = torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)
+    return torch.where(x == 0, torch.full_like(x, fill_val), x)
+
+
+def clamp_dims(dims, n_cells, batch_size):
+    """scarf/ann.py:173-185."""
+    if dims > n_cells:
+        dims = n_cells
+    if dims >= batch_size:
+        dims = batch_size - 1
+    return dims
+
+
+def sign_rule(vt):
+    """sklearn svd_flip(u_based_decision=False): the largest-|.| entry of every component is positive."""
+    j = vt.abs().argmax(dim=1, keepdim=True)
+    s = torch.sign(torch.gather(vt, 1, j))
+    s[s == 0] = 1
+    return vt * s
+
+
+def eig_topk(cov, dims):
+    """K3: top-``dims`` eigenpairs of the symmetric float64 matrix ``cov`` (replicated on every rank)."""
+    w, v = torch.linalg.eigh(cov)
+    w = torch.flip(w[-dims:], dims=[0])
+    vt = sign_rule(torch.flip(v[:, -dims:], dims=[1]).T.contiguous())
+    return w, vt.T.contiguous()
+
+
+def normalise_stats(csr, cell_idx, col_map, n_feat, comm, log_transform=True, renormalize_subset=True,
+                    n_counts=None):
+    """Row scalars + mu / sigma of the normalised feature matrix (graph_datastore.py:767-796)."""
+    if renormalize_subset:
+        row_sum, _ = ops.csr_row_sums(csr, cell_idx, col_map)  # scarf/assay.py:814-823
+    else:
+        row_sum = (n_counts[cell_idx] if cell_idx is not None else n_counts).contiguous()
+    sx, sxx = ops.csr_hvg_colstats(csr, cell_idx, col_map, n_feat, row_sum, SF, log_transform)
+    n_local = csr.n_rows if cell_idx is None else int(cell_idx.numel())
+    cnt = torch.tensor([n_local], dtype=torch.int64, device=csr.device)
+    comm.allreduce_sum_(sx), comm.allreduce_sum_(sxx), comm.allreduce_sum_(cnt)
+    n = float(cnt.item())
+    scale = 2.0 ** -lib.COLSTAT_SHIFT
+    mean = sx.to(torch.float64) * scale / n
+    var = torch.clamp(sxx.to(torch.float64) * scale / n - mean * mean, min=0.0)
+    mu = clean_array(mean)
+    sigma = clean_array(torch.sqrt(var), 1.0)
+    return row_sum, mu, sigma, int(n)
+
+
+def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, bw=1.5, batch_size=1000,
+                   log_transform=True, renormalize_subset=True, n_counts=None, comm: Comm | None = None,
+                   gram_mode=0, knn_method=0, loadings=None, mu=None, sigma=None, timers=None) -> GraphResult:
+    """normalise -> mu/sigma -> Z -> Gram -> eig -> project -> exact kNN -> edge weights for this rank's rows.
+
+    ``timers``: optional list; (stage name, torch.cuda.Event) pairs are appended at every stage boundary.
+    ``cell_idx``: int64 device tensor of the local CSR rows to use (None = all).  ``feat_mask``: bool over all
+    genes (numpy), e.g. from :func:`mark_hvgs_csr`.  With ``comm.world > 1`` every rank passes its own shard and
+    receives its own rows of the global graph; neighbour ids are global selected-row ids.
+    """
+    comm = comm or Comm()
+    dev = csr.device
+
+    def mark(name):  # CUDA events on the launching stream; read by the caller after its own synchronize
+        if timers is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            timers.append((name, e))
+
+    mark("start")
+    feat_idx = np.where(np.asarray(feat_mask, dtype=bool))[0]
+    n_feat = int(feat_idx.size)
+    if n_feat == 0:
+        raise ValueError("make_graph: no features selected")
+    cm = np.full(csr.n_cols, -1, dtype=np.int32)
+    cm[feat_idx] = np.arange(n_feat, dtype=np.int32)
+    col_map = torch.from_numpy(cm).to(dev)
+    n_local = csr.n_rows if cell_idx is None else int(cell_idx.numel())
+
+    # ---- normalisation scalars, mu, sigma (collective 2a) ----
+    row_sum, mu_d, sigma_d, n_total = normalise_stats(csr, cell_idx, col_map, n_feat, comm, log_transform,
+                                                      renormalize_subset, n_counts)
+    if mu is not None:  # run_mapping reuses the reference's mu / sigma
+        mu_d, sigma_d = mu, sigma
+    counts = comm.allgather_counts(n_local, dev)
+    row_offset = int(sum(counts[: comm.rank]))
+    k = min(k, n_total - 1)  # scarf/ann.py:85-86
+    dims = clamp_dims(dims, n_total, batch_size)
+    mark("stats")
+
+    # ---- Z (K1) ----
+    ldz = round_up(n_feat, 128)
+    n_pad = round_up(max(n_local, 1), lib.GRAM_SLAB)
+    z = torch.empty((n_pad, ldz), dtype=torch.float32, device=dev)
+    z[n_local:].zero_()
+    ops.csr_norm_scale(csr, cell_idx, col_map, n_feat, row_sum, z, SF, log_transform, mu_d, sigma_d)
+    mark("normalise")
+
+    # ---- PCA: Gram (K2, collective 2b) + eigensolve (K3) ----
+    if loadings is None:
+        g_fx = ops.gram_accumulate(z, n_pad, n_feat, mode=gram_mode)
+        comm.allreduce_sum_(g_fx)
+        mark("gram")
+        cov = g_fx.to(torch.float64) * (2.0 ** -lib.GRAM_SHIFT / max(n_total - 1, 1))
+        evals, load = eig_topk(cov, dims)
+        mark("eig")
+    else:
+        load, evals = loadings, torch.zeros(dims, dtype=torch.float64, device=dev)
+    ldv = round_up(dims, 4)
+    v32 = torch.zeros((n_feat, ldv), dtype=torch.float32, device=dev)
+    v32[:, :dims] = load.to(torch.float32)
+
+    # ---- embedding (K4) + exchange (collective 3) ----
+    y = ops.project(z, n_local, n_feat, v32, dims)
+    del z
+    y_all = comm.allgather_rows(y, counts)
+    mark("project")
+
+    # ---- exact kNN (K5) ----
+    idx, dist = ops.knn_l2(y, y_all, dims, k, self_offset=row_offset, method=knn_method)
+    mark("knn")
+
+    # ---- edge weights (K6, collective 4) ----
+    edges, weights = smoothen_dists(idx, dist, lc, bw, row_offset, batch_size, n_total, comm)
+    mark("weights")
+
+    return GraphResult(n_total, row_offset, feat_idx, mu_d, sigma_d, load, evals, y, dims, k, idx, dist, edges,
+                       weights)
+
+
+def smoothen_dists(idx, dist, lc, bw, row_offset, chunk_size, n_total, comm: Comm | None = None):
+    """scarf/knn_utils.py:89-159 on device for rows [row_offset, row_offset + n) -> (edges, weights)."""
+    comm = comm or Comm()
+    n, k = idx.shape
+    n_chunks = (n_total + chunk_size - 1) // chunk_size
+    csum = ops.chunk_sums(dist, row_offset, chunk_size, n_chunks)
+    comm.allreduce_sum_(csum)
+    rows_in_chunk = torch.full((n_chunks,), float(chunk_size), dtype=torch.float64, device=idx.device)
+    rows_in_chunk[-1] = float(n_total - (n_chunks - 1) * chunk_size)
+    cmean = (csum / (rows_in_chunk * k)).to(torch.float32)
+    sigma, rho = ops.smooth_knn(dist, cmean, lc, bw, row_offset, chunk_size)
+    edges, weights, cmin, czero = ops.membership_coo(idx, dist, sigma, rho, row_offset, chunk_size, n_chunks)
+    comm.allreduce_min_(cmin), comm.allreduce_max_(czero)
+    sel = czero > 0
+    if bool(sel.any()):  # zero weights := min(1, smallest non-zero weight of the chunks that hold a zero)
+        floor = min(1.0, float(cmin[sel].min()))
+        ops.fill_zero_weights(weights, floor)
+    return edges, weights

@@ -1,0 +1,123 @@
+"""Host-side part of ``mark_hvgs``: trend removal and HVG choice on the per-gene statistics.
+
+O(G) work on ~30k numbers: it stays on the host like the reference's
+(scarf/metadata.py:586-617, scarf/feat_utils.py:11-45, scarf/assay.py:1014-1063); the per-gene
+statistics themselves come from the CSR kernels.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+
+DEFAULT_BLACKLIST = "^MT-|^RPS|^RPL|^MRPS|^MRPL|^CCN|^HLA-|^H2-|^HIST"  # scarf/datastore/datastore.py:235
+
+
+def _lowess(y, x, frac, it):
+    """Cleveland's robust LOWESS as statsmodels' ``lowess(endog, exog, frac, it, delta=0,
+    return_sorted=False)`` computes it (scarf/feat_utils.py:38-40), all windows evaluated at once."""
+    order = np.argsort(x, kind="stable")
+    x, y = x[order], y[order]
+    n = x.size
+    k = int(frac * n + 1e-10)
+    if not 2 <= k <= n:
+        raise ValueError("lowess: frac * n must be within [2, n]")
+    left = np.zeros(n, dtype=np.int64)
+    lo = 0
+    for i in range(n):  # the k-wide window slides right while x[i] is nearer to its far end
+        while lo + k < n and x[i] > 0.5 * (x[lo] + x[lo + k]):
+            lo += 1
+        left[i] = lo
+    first = np.arange(n)  # tied x reuse the fit of the first point of the run (delta = 0)
+    for i in range(1, n):
+        if x[i] == x[i - 1]:
+            first[i] = first[i - 1]
+    win = left[first][:, None] + np.arange(k)[None, :]
+    xs, ys = x[win], y[win]
+    xi = x[first][:, None]
+    radius = np.maximum(xi[:, 0] - xs[:, 0], xs[:, -1] - xi[:, 0])[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u = np.abs(xs - xi) / radius
+    tri = (1.0 - u ** 3) ** 3
+    tri[~np.isfinite(tri)] = 0.0
+    rw = np.ones(n)
+    fit = np.zeros(n)
+    for _ in range(it + 1):
+        w = tri * rw[win]
+        sw = w.sum(axis=1, keepdims=True)
+        ok = sw[:, 0] > 0
+        wn = np.divide(w, sw, out=np.zeros_like(w), where=sw > 0)
+        xm = (wn * xs).sum(axis=1, keepdims=True)
+        dx = xs - xm
+        sq = (wn * dx * dx).sum(axis=1, keepdims=True)
+        slope_ok = sq > 1e-12
+        p = np.where(slope_ok, wn * (1.0 + (xi - xm) * dx / np.where(slope_ok, sq, 1.0)), wn)
+        fit = np.where(ok, (p * ys).sum(axis=1), y[first])
+        r = np.abs(y - fit)
+        med = np.median(r)
+        r = (r > 0).astype(np.float64) if med == 0 else r / (6.0 * med)
+        r = np.minimum(r, 1.0)
+        rw = (1.0 - r * r) ** 2
+    out = np.empty(n)
+    out[order] = fit
+    return out
+
+
+def fit_lowess(a, b, n_bins=200, lowess_frac=0.1):
+    """scarf/feat_utils.py:11-45: bin log(a), take the min-log(b) gene per bin, LOWESS through those,
+    return exp(log b - fit(bin)) per gene."""
+    la, lb = np.log(a), np.log(b)
+    edges = np.histogram(la, bins=n_bins)[1]
+    edges[-1] += 0.1
+    which = np.searchsorted(edges, la, side="right") - 1  # edges[i] <= la < edges[i+1]
+    which[(which < 0) | (which >= n_bins)] = -1
+    bx, by, bins = [], [], []
+    for t in np.unique(which[which >= 0]):
+        members = np.where(which == t)[0]
+        g = members[np.argmin(lb[members])]
+        bins.append(t)
+        bx.append(la[g])
+        by.append(lb[g])
+    fit = _lowess(np.asarray(by), np.asarray(bx), lowess_frac, 100)
+    fit_of_bin = np.full(n_bins, np.nan)
+    fit_of_bin[np.asarray(bins)] = fit
+    out = np.zeros(la.size)
+    sel = which >= 0
+    out[sel] = np.exp(lb[sel] - fit_of_bin[which[sel]])
+    return out
+
+
+def remove_trend(avg, sigmas, n_bins=200, lowess_frac=0.1, fill_value=0.0):
+    """scarf/metadata.py:586-617."""
+    avg, sigmas = np.asarray(avg, dtype=np.float64), np.asarray(sigmas, dtype=np.float64)
+    ret = np.full(avg.size, float(fill_value))
+    pos = avg > 0
+    ret[pos] = fit_lowess(avg[pos], sigmas[pos], n_bins, lowess_frac)
+    return ret
+
+
+def choose_hvgs(normed_n, nz_mean, c_var, feat_I, gene_names=None, top_n=500, min_cells=0, max_cells=np.inf,
+                min_mean=-np.inf, max_mean=np.inf, min_var=None, max_var=np.inf, blacklist=DEFAULT_BLACKLIST):
+    """scarf/assay.py:1014-1063 + MetaData.multi_sift (scarf/metadata.py:483-533): strict bounds, then the
+    ``top_n`` largest corrected variances.  All vectors cover every gene (NaN outside ``feat_I``)."""
+    g = normed_n.size
+    if blacklist and gene_names is not None:
+        pat = re.compile(blacklist)
+        keep = np.fromiter((pat.search(str(x)) is None for x in gene_names), dtype=bool, count=g)
+    else:
+        keep = np.ones(g, dtype=bool)
+    # thresholds are given in log2 and only exponentiated when finite (scarf/assay.py:1014-1021)
+    min_mean = 2.0 ** min_mean if min_mean != -np.inf else min_mean
+    max_mean = 2.0 ** max_mean if max_mean != np.inf else max_mean
+    with np.errstate(invalid="ignore"):
+        idx = (normed_n > min_cells) & (normed_n < max_cells) & (nz_mean > min_mean) & (nz_mean < max_mean)
+        idx &= feat_I & keep
+        if top_n is not None:
+            n_valid = int(idx.sum())
+            if top_n > n_valid:
+                top_n = n_valid - 1
+            min_var = np.sort(c_var[idx])[::-1][top_n]
+        else:
+            min_var = 2.0 ** min_var
+        hv = idx & (c_var > min_var) & (c_var < (np.inf if top_n is not None else 2.0 ** max_var))
+    return hv

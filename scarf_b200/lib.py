@@ -1,0 +1,78 @@
+"""ctypes binding of ``libscarf_b200.so`` (the C-ABI declared in include/scarf_b200.h).
+
+This is the same stub a Scarf maintainer would add.  No fallback: a missing
+library is an ImportError that says how to build it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libscarf_b200.so")
+
+_p, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+
+# name -> (restype, argtypes); mirrors include/scarf_b200.h one to one
+SIGNATURES = {
+    "scf_version": (_i32, []),
+    "scf_last_error": (ctypes.c_char_p, []),
+    "scf_csr_row_sums": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "scf_csr_gene_stats": (_i32, [_p, _p, _p, _p, _i64, _i32, _p, _f64, _p, _p, _p, _p]),
+    "scf_csr_hvg_colstats": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _f64, _i32, _p, _p, _p]),
+    "scf_csr_norm_scale": (_i32, [_p, _p, _p, _p, _i64, _p, _i32, _p, _f64, _i32, _p, _p, _p, _p, _i64, _p]),
+    "scf_gram_accumulate": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _i32, _p]),
+    "scf_project": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _i32, _p, _i64, _p]),
+    "scf_knn_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32]),
+    "scf_knn_l2": (_i32, [_p, _i64, _p, _i64, _i32, _i64, _i32, _i64, _p, _p, _i32, _p, _i64, _p]),
+    "scf_chunk_sums": (_i32, [_p, _i64, _i32, _i64, _i64, _p, _p]),
+    "scf_smooth_knn": (_i32, [_p, _i64, _i32, _f32, _f32, _i64, _i64, _p, _p, _p, _p]),
+    "scf_membership_coo": (_i32, [_p, _p, _p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p]),
+    "scf_fill_zero_weights": (_i32, [_p, _i64, _f32, _p]),
+}
+
+COLSTAT_SHIFT = 34
+GRAM_SHIFT = 36
+GRAM_SLAB = 2048
+
+
+class ScarfB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  scarf_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+_lib = _load()
+
+
+def version() -> int:
+    return _lib.scf_version()
+
+
+LAUNCHES = {"n": 0}  # kernel launches issued through the C-ABI (bench.py reports it as gpu_launches)
+_LAUNCHES_PER_CALL = {"scf_knn_l2": 1}
+
+
+def call(name: str, *args):
+    """Calls a status-returning entry point and raises with the library's error text."""
+    rc = getattr(_lib, name)(*args)
+    LAUNCHES["n"] += _LAUNCHES_PER_CALL.get(name, 1)
+    if rc != 0:
+        msg = _lib.scf_last_error().decode("utf-8", "replace")
+        if rc > 0:
+            raise ValueError(f"{name}: {msg} (status {rc})")
+        raise ScarfB200Error(f"{name}: CUDA error {-rc}: {msg}")
+
+
+def raw(name: str):
+    return getattr(_lib, name)

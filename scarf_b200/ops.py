@@ -1,0 +1,200 @@
+"""Torch-tensor front end of the C-ABI: one function per kernel, device tensors in and out.
+
+Every function launches on the current torch CUDA stream and returns without synchronising.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import lib
+
+U32 = torch.int32  # uint32 counts are carried in int32 storage (same bits); only the kernels read them
+
+
+@dataclass
+class CsrDevice:
+    """Raw counts in CSR form on one GPU (what ``Assay.to_raw_sparse`` yields, scarf/assay.py:175-199)."""
+    indptr: torch.Tensor   # int64 [n_rows + 1]
+    indices: torch.Tensor  # int32 [nnz], ascending inside a row
+    data: torch.Tensor     # uint32 [nnz] in int32 storage
+    n_rows: int
+    n_cols: int
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indices.numel())
+
+    @property
+    def device(self):
+        return self.indptr.device
+
+    @staticmethod
+    def from_host(indptr, indices, data, shape, device="cuda", non_blocking=False) -> "CsrDevice":
+        import numpy as np
+
+        def as_t(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            return torch.from_numpy(a.view(np.int32) if dt == np.uint32 else a)
+
+        ip = as_t(indptr, np.int64).to(device, non_blocking=non_blocking)
+        ix = as_t(indices, np.int32).to(device, non_blocking=non_blocking)
+        dv = as_t(data, np.uint32).to(device, non_blocking=non_blocking)
+        return CsrDevice(ip, ix, dv, int(shape[0]), int(shape[1]))
+
+    @staticmethod
+    def from_scipy(m, device="cuda") -> "CsrDevice":
+        m = m.tocsr()
+        m.sort_indices()
+        return CsrDevice.from_host(m.indptr, m.indices, m.data, m.shape, device)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device-resident contiguous tensor required"
+    return t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------ K0
+def csr_row_sums(csr: CsrDevice, row_ids=None, col_map=None):
+    """(sum float64, nnz int32) per selected row over the columns with col_map >= 0 (all if None)."""
+    _chk(row_ids, torch.int64, "row_ids"), _chk(col_map, torch.int32, "col_map")
+    n = csr.n_rows if row_ids is None else int(row_ids.numel())
+    s = torch.empty(n, dtype=torch.float64, device=csr.device)
+    c = torch.empty(n, dtype=torch.int32, device=csr.device)
+    lib.call("scf_csr_row_sums", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
+             _ptr(col_map), _ptr(s), _ptr(c), _stream())
+    return s, c
+
+
+def csr_gene_stats(csr: CsrDevice, row_ids=None, row_div=None, sf=1000.0, out=None, with_moments=True):
+    """Per-gene (nnz uint64-in-int64, sum f64, sumsq f64) of sf*c/row_div over the selected rows; accumulates into out."""
+    _chk(row_ids, torch.int64, "row_ids"), _chk(row_div, torch.float64, "row_div")
+    n = csr.n_rows if row_ids is None else int(row_ids.numel())
+    if out is None:
+        nnz = torch.zeros(csr.n_cols, dtype=torch.int64, device=csr.device)
+        sm = torch.zeros(csr.n_cols, dtype=torch.float64, device=csr.device) if with_moments else None
+        sq = torch.zeros(csr.n_cols, dtype=torch.float64, device=csr.device) if with_moments else None
+    else:
+        nnz, sm, sq = out
+    lib.call("scf_csr_gene_stats", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
+             csr.n_cols, _ptr(row_div), float(sf), _ptr(nnz), _ptr(sm), _ptr(sq), _stream())
+    return nnz, sm, sq
+
+
+# ------------------------------------------------------------------------------------------ K1
+def csr_hvg_colstats(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, sf=1000.0, log_transform=True, out=None):
+    """int64 fixed-point (sum x, sum x^2) per selected column; divide by 2**lib.COLSTAT_SHIFT."""
+    n = csr.n_rows if row_ids is None else int(row_ids.numel())
+    if out is None:
+        out = (torch.zeros(n_cols, dtype=torch.int64, device=csr.device),
+               torch.zeros(n_cols, dtype=torch.int64, device=csr.device))
+    lib.call("scf_csr_hvg_colstats", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
+             _ptr(col_map), _ptr(row_sum), float(sf), int(bool(log_transform)), _ptr(out[0]), _ptr(out[1]), _stream())
+    return out
+
+
+def csr_norm_scale(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, z, sf=1000.0, log_transform=True, mu=None,
+                   sigma=None, missing_fill=None):
+    """Writes rows [0, n_sel) of the float32 matrix z (row stride z.stride(0)) with (x - mu)/sigma."""
+    n = csr.n_rows if row_ids is None else int(row_ids.numel())
+    _chk(z, torch.float32, "z"), _chk(mu, torch.float64, "mu"), _chk(sigma, torch.float64, "sigma")
+    assert z.dim() == 2 and z.stride(1) == 1 and z.shape[0] >= n and z.is_cuda
+    lib.call("scf_csr_norm_scale", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
+             _ptr(col_map), int(n_cols), _ptr(row_sum), float(sf), int(bool(log_transform)), _ptr(mu), _ptr(sigma),
+             _ptr(missing_fill), z.data_ptr(), int(z.stride(0)), _stream())
+    return z
+
+
+# ------------------------------------------------------------------------------------------ K2 / K4
+def gram_accumulate(z, n_rows, n_cols, g_fx=None, mode=0):
+    """g_fx (int64 [n_cols, n_cols], << lib.GRAM_SHIFT) += Z[:n_rows, :n_cols]^T Z[:n_rows, :n_cols]."""
+    assert z.dtype == torch.float32 and z.stride(1) == 1
+    if g_fx is None:
+        g_fx = torch.zeros((n_cols, n_cols), dtype=torch.int64, device=z.device)
+    lib.call("scf_gram_accumulate", z.data_ptr(), int(z.stride(0)), int(n_rows), int(n_cols), _ptr(g_fx),
+             int(g_fx.stride(0)), int(mode), _stream())
+    return g_fx
+
+
+def project(z, n_rows, n_cols, v, dims, y=None, ldy=None):
+    """y[:n_rows, :dims] = z[:n_rows, :n_cols] @ v[:n_cols, :dims]; pad columns of y are zeroed."""
+    assert z.dtype == torch.float32 and v.dtype == torch.float32 and v.stride(1) == 1
+    if y is None:
+        ldy = ldy or round_up(dims, 32)
+        y = torch.empty((n_rows, ldy), dtype=torch.float32, device=z.device)
+    lib.call("scf_project", z.data_ptr(), int(z.stride(0)), int(n_rows), int(n_cols), v.data_ptr(), int(v.stride(0)),
+             int(dims), y.data_ptr(), int(y.stride(0)), _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------ K5
+def knn_l2(q, ref, dim, k, self_offset=-1, method=0):
+    """Exact kNN (squared L2).  q, ref: float32 [n, ld] sharing the row stride.  -> (int64 idx, float32 dist)."""
+    assert q.dtype == torch.float32 and ref.dtype == torch.float32
+    assert q.stride(1) == 1 and ref.stride(1) == 1 and q.stride(0) == ref.stride(0)
+    nq, nref = int(q.shape[0]), int(ref.shape[0])
+    idx = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    dist = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    ws_bytes = int(lib.raw("scf_knn_workspace_bytes")(nq, nref, int(dim), int(k), int(method)))
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=q.device)
+    lib.call("scf_knn_l2", q.data_ptr(), nq, ref.data_ptr(), nref, int(dim), int(q.stride(0)), int(k),
+             int(self_offset), idx.data_ptr(), dist.data_ptr(), int(method), ws.data_ptr(), ws_bytes, _stream())
+    return idx, dist
+
+
+# ------------------------------------------------------------------------------------------ K6
+def chunk_sums(dist, row_offset, chunk_size, n_chunks_total):
+    """float64 sum of the distances of every chunk this shard touches (other entries stay 0)."""
+    n, k = dist.shape
+    out = torch.zeros(n_chunks_total, dtype=torch.float64, device=dist.device)
+    lib.call("scf_chunk_sums", dist.data_ptr(), n, k, int(row_offset), int(chunk_size), out.data_ptr(), _stream())
+    return out
+
+
+def smooth_knn(dist, chunk_mean, lc=1.0, bw=1.5, row_offset=0, chunk_size=1000):
+    """umap smooth_knn_dist per row -> (sigma, rho) float32."""
+    n, k = dist.shape
+    assert dist.dtype == torch.float32 and dist.is_contiguous() and chunk_mean.dtype == torch.float32
+    sigma = torch.empty(n, dtype=torch.float32, device=dist.device)
+    rho = torch.empty(n, dtype=torch.float32, device=dist.device)
+    lib.call("scf_smooth_knn", dist.data_ptr(), n, k, float(lc), float(bw), int(row_offset), int(chunk_size),
+             chunk_mean.data_ptr(), sigma.data_ptr(), rho.data_ptr(), _stream())
+    return sigma, rho
+
+
+def membership_coo(idx, dist, sigma, rho, row_offset, chunk_size, n_chunks_total):
+    """compute_membership_strengths + COO rows -> edges int64 [n*k,2], weights float32 [n*k],
+    per-chunk (min non-zero weight, has-zero flag) indexed by global chunk id."""
+    n, k = idx.shape
+    dev = idx.device
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and dist.is_contiguous()
+    edges = torch.empty((n * k, 2), dtype=torch.int64, device=dev)
+    weights = torch.empty(n * k, dtype=torch.float32, device=dev)
+    cmin = torch.full((n_chunks_total,), math.inf, dtype=torch.float32, device=dev)
+    czero = torch.zeros(n_chunks_total, dtype=torch.int32, device=dev)
+    lib.call("scf_membership_coo", idx.data_ptr(), dist.data_ptr(), sigma.data_ptr(), rho.data_ptr(), n, k,
+             int(row_offset), int(chunk_size), edges.data_ptr(), weights.data_ptr(), cmin.data_ptr(),
+             czero.data_ptr(), _stream())
+    return edges, weights, cmin, czero
+
+
+def fill_zero_weights(weights, floor):
+    lib.call("scf_fill_zero_weights", weights.data_ptr(), int(weights.numel()), float(floor), _stream())
+    return weights

@@ -1,0 +1,244 @@
+"""GPU parity tests: every kernel of the path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs (and against the reference's PBMC goldens).  Bars: bit-exact for indices / integer
+work, stated tolerances for floating point (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+
+    from scarf_b200 import graph, ops, synth
+
+    torch.cuda.set_device(0)
+    return {"torch": torch, "graph": graph, "ops": ops, "synth": synth}
+
+
+@pytest.fixture(scope="module")
+def synth_small(gpu):
+    """3000 cells x 6000 genes, 40 planted factors; cells 0 and 17 emptied, cell 5 without any HVG-able count."""
+    m = gpu["synth"].make_counts_scipy(3000, 6000, 40, seed=11).tolil()
+    m[0, :] = 0
+    m[17, :] = 0
+    m = m.tocsr().astype(np.uint32)
+    m.eliminate_zeros()
+    m.sort_indices()
+    return m
+
+
+def _dev(gpu, m):
+    return gpu["ops"].CsrDevice.from_scipy(m, "cuda:0")
+
+
+def test_row_sums_and_ncells(gpu, synth_small):
+    from oracle import pipeline as P
+
+    torch, graph, ops = gpu["torch"], gpu["graph"], gpu["ops"]
+    csr = _dev(gpu, synth_small)
+    n_counts, n_feat = graph.cell_totals(csr)
+    oc, of = P.cell_totals(synth_small)
+    assert np.array_equal(n_counts.cpu().numpy(), oc) and np.array_equal(n_feat.cpu().numpy(), of.astype(np.int32))
+    assert np.array_equal(graph.gene_ncells(csr).cpu().numpy(), P.gene_ncells(synth_small))
+    # subset of rows + column subset
+    rows = torch.arange(5, 2000, 3, device="cuda")
+    cmap = np.full(6000, -1, dtype=np.int32)
+    cols = np.arange(100, 6000, 7)
+    cmap[cols] = np.arange(cols.size)
+    s, c = ops.csr_row_sums(csr, rows, torch.from_numpy(cmap).cuda())
+    sub = synth_small[rows.cpu().numpy()][:, cols]
+    assert np.array_equal(s.cpu().numpy(), np.asarray(sub.sum(1)).ravel().astype(np.float64))
+    assert np.array_equal(c.cpu().numpy(), np.asarray((sub > 0).sum(1)).ravel())
+
+
+def test_gene_stats_and_hvgs(gpu, synth_small):
+    from oracle import pipeline as P
+
+    torch, graph = gpu["torch"], gpu["graph"]
+    csr = _dev(gpu, synth_small)
+    n_counts, n_feat = graph.cell_totals(csr)
+    keep = (n_feat > 10).cpu().numpy()  # the two emptied cells drop out, like the reference's default filter
+    cell_idx = np.where(keep)[0]
+    feat_I = (graph.gene_ncells(csr) > 20).cpu().numpy()
+    st = graph.hvg_gene_stats(csr, torch.from_numpy(cell_idx).cuda(), n_counts, synth_small.shape[0])
+    so = P.gene_stats(synth_small, cell_idx, np.arange(6000), n_counts.cpu().numpy(), synth_small.shape[0])
+    for key in ("normed_n", "normed_tot", "sigmas", "avg", "nz_mean"):
+        np.testing.assert_allclose(st[key], so[key], rtol=1e-9, atol=1e-12, err_msg=key)
+    hv = graph.mark_hvgs_csr(csr, torch.from_numpy(cell_idx).cuda(), feat_I, n_counts, synth_small.shape[0], top_n=500)
+    hv_o = P.mark_hvgs(synth_small, cell_idx, feat_I, top_n=500)
+    assert hv.sum() == 500 and np.array_equal(hv, hv_o)
+
+
+def test_hvgs_pbmc_golden(gpu, pbmc):
+    """mark_hvgs(top_n=100) on the reference's PBMC fixture: same HVG set as the oracle chain that
+    reproduces knn_indices.npy (tests/test_oracle_golden.py)."""
+    from oracle import pipeline as P
+
+    torch, graph = gpu["torch"], gpu["graph"]
+    csr = _dev(gpu, pbmc["counts"])
+    n_counts, _ = graph.cell_totals(csr)
+    feat_I = (graph.gene_ncells(csr) > 20).cpu().numpy()
+    cell_idx = torch.from_numpy(pbmc["cell_idx"]).cuda()
+    hv = graph.mark_hvgs_csr(csr, cell_idx, feat_I, n_counts, 892, gene_names=pbmc["names"], top_n=100)
+    hv_o = P.mark_hvgs(pbmc["counts"], pbmc["cell_idx"], feat_I, gene_names=pbmc["names"], top_n=100)
+    assert np.array_equal(hv, hv_o)
+
+
+@pytest.fixture(scope="module")
+def chain(gpu, synth_small):
+    """GPU make_graph + oracle intermediates on the same matrix / HVG set."""
+    from oracle import pipeline as P
+
+    torch, graph = gpu["torch"], gpu["graph"]
+    csr = _dev(gpu, synth_small)
+    n_counts, n_feat = graph.cell_totals(csr)
+    cell_idx = np.where((n_feat > 10).cpu().numpy())[0]
+    feat_I = (graph.gene_ncells(csr) > 20).cpu().numpy()
+    hv = P.mark_hvgs(synth_small, cell_idx, feat_I, top_n=500)
+    res = graph.make_graph_csr(csr, torch.from_numpy(cell_idx).cuda(), hv, dims=20, k=11, gram_mode=0, knn_method=0)
+    torch.cuda.synchronize()
+    x = P.normed_hvg(synth_small, cell_idx, np.where(hv)[0])
+    mu, sigma = P.mu_sigma(x)
+    return {"res": res, "x": x, "mu": mu, "sigma": sigma, "hv": hv, "cell_idx": cell_idx, "csr": csr}
+
+
+def test_normalised_values(gpu, chain, synth_small):
+    """lib-size normalise + log1p + HVG gather: 1e-5 relative (north_star); float32 output gives ~1e-7."""
+    torch, ops = gpu["torch"], gpu["ops"]
+    hv, cell_idx, csr = chain["hv"], chain["cell_idx"], chain["csr"]
+    cm = np.full(csr.n_cols, -1, dtype=np.int32)
+    cm[np.where(hv)[0]] = np.arange(hv.sum())
+    cmap = torch.from_numpy(cm).cuda()
+    rows = torch.from_numpy(cell_idx).cuda()
+    s, _ = ops.csr_row_sums(csr, rows, cmap)
+    z = torch.full((len(cell_idx), 512), 7.0, dtype=torch.float32, device="cuda")
+    ops.csr_norm_scale(csr, rows, cmap, int(hv.sum()), s, z)
+    xg = z.cpu().numpy()
+    assert np.all(xg[:, 500:] == 0)
+    np.testing.assert_allclose(xg[:, :500], chain["x"], rtol=1e-5, atol=1e-7)
+    assert (chain["x"].sum(1) == 0).sum() >= 0
+
+
+def test_mu_sigma(chain):
+    res = chain["res"]
+    np.testing.assert_allclose(res.mu.cpu().numpy(), chain["mu"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(res.sigma.cpu().numpy(), chain["sigma"], rtol=1e-8, atol=1e-12)
+
+
+def test_pca_subspace_and_embedding(chain):
+    """Exact covariance-eig oracle: principal angles <= 1e-4 rad on every kept component,
+    sign-aligned embedding within 1e-3 absolute."""
+    from oracle import pipeline as P
+
+    res = chain["res"]
+    z = (chain["x"] - chain["mu"]) / chain["sigma"]
+    load_o, ev_o = P.exact_pca_loadings(z, res.dims)
+    load_g = res.loadings.cpu().numpy()
+    cosines = np.abs(np.sum(load_o * load_g, axis=0))
+    assert np.all(np.arccos(np.clip(cosines, 0, 1)) < 1e-4), cosines
+    assert np.all(np.sum(load_o * load_g, axis=0) > 0), "sign rule differs"
+    np.testing.assert_allclose(res.eigenvalues.cpu().numpy(), ev_o, rtol=1e-5)
+    y_o = z @ load_o
+    y_g = res.embedding[:, : res.dims].cpu().numpy()
+    assert np.abs(y_g - y_o).max() < 1e-3
+    assert np.all(res.embedding[:, res.dims:].cpu().numpy() == 0)
+
+
+def test_knn_bit_exact_on_embedding(chain):
+    """kNN indices and float32 distances bit-exact vs the oracle's exact search on the same embedding."""
+    from oracle import pipeline as P
+
+    res = chain["res"]
+    y = res.embedding[:, : res.dims].cpu().numpy()
+    idx_o, dist_o = P.exact_knn(y, y, res.k, self_offset=0)
+    assert np.array_equal(res.indices.cpu().numpy().astype(np.uint64), idx_o)
+    assert np.array_equal(res.distances.cpu().numpy(), dist_o)
+
+
+def test_weights_vs_oracle(chain):
+    from oracle import pipeline as P
+
+    res = chain["res"]
+    idx, dist = res.indices.cpu().numpy().astype(np.uint64), res.distances.cpu().numpy().astype(np.float64)
+    edges_o, w_o = P.smoothen_dists(idx, dist, 1.0, 1.5, 1000)
+    assert np.array_equal(res.edges.cpu().numpy().astype(np.uint64), edges_o)
+    assert np.abs(res.weights.cpu().numpy().astype(np.float64) - w_o).max() < 1e-5
+
+
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("nq,nref,dim,k,self_offset", [
+    (700, 700, 5, 4, 0), (1000, 5000, 25, 11, 1234), (333, 4097, 50, 21, -1), (129, 1000, 100, 3, -1),
+    (64, 65, 11, 64, 0), (1, 300, 33, 7, 0)])
+def test_knn_cases(gpu, method, nq, nref, dim, k, self_offset):
+    """Ragged sizes, duplicates (ties broken by index), k up to nref-1, run_mapping mode (self_offset=-1)."""
+    from oracle import pipeline as P
+
+    torch, ops = gpu["torch"], gpu["ops"]
+    rng = np.random.default_rng(nq + dim)
+    ref = rng.normal(size=(nref, dim)).astype(np.float32) * rng.uniform(0.5, 3.0, size=dim).astype(np.float32)
+    ref[nref // 2] = ref[3]           # exact duplicates
+    ref[nref // 3: nref // 3 + 5] = ref[7]
+    if self_offset >= 0:
+        q = ref[self_offset: self_offset + nq].copy()
+    else:
+        q = rng.normal(size=(nq, dim)).astype(np.float32)
+        q[0] = ref[7]
+    ld = ops.round_up(dim, 32)
+    rp = torch.zeros((nref, ld), dtype=torch.float32, device="cuda")
+    rp[:, :dim] = torch.from_numpy(ref).cuda()
+    qp = torch.zeros((nq, ld), dtype=torch.float32, device="cuda")
+    qp[:, :dim] = torch.from_numpy(q).cuda()
+    idx, dist = ops.knn_l2(qp, rp, dim, k, self_offset=self_offset, method=method)
+    idx_o, dist_o = P.exact_knn(q, ref, k, self_offset=self_offset)
+    assert np.array_equal(idx.cpu().numpy().astype(np.uint64), idx_o)
+    assert np.array_equal(dist.cpu().numpy(), dist_o)
+
+
+def test_weights_pbmc_golden(gpu, pbmc):
+    """K6 on the reference's own knn_indices / knn_distances -> knn_weights.npy (test_datastore.py:76-79, 1e-5)."""
+    torch, graph = gpu["torch"], gpu["graph"]
+    idx = torch.from_numpy(pbmc["indices"].astype(np.int64)).cuda()
+    dist = torch.from_numpy(pbmc["distances"].astype(np.float32)).cuda()
+    edges, w = graph.smoothen_dists(idx, dist, 1.0, 1.5, 0, 1000, 808)
+    assert np.abs(w.cpu().numpy().astype(np.float64) - pbmc["weights"]).max() < 1e-5
+    e = edges.cpu().numpy()
+    assert np.array_equal(e[:, 0], np.repeat(np.arange(808), 11)) and np.array_equal(e[:, 1], pbmc["indices"].ravel())
+
+
+def test_weights_chunk_quirks(gpu):
+    """Chunk-local 'neighbour == i' zeroing + floor, zero distances, sharded call == whole call."""
+    from oracle import pipeline as P
+
+    torch, graph = gpu["torch"], gpu["graph"]
+    rng = np.random.default_rng(3)
+    n, k, cs = 2500, 11, 1000
+    dist = np.sort(rng.gamma(2.0, 2.0, size=(n, k)).astype(np.float32), axis=1)
+    dist[5, :3] = 0.0
+    dist[1200] = 0.0
+    idx = rng.integers(0, n, size=(n, k)).astype(np.int64)
+    idx[1007, 4] = 7      # global id == chunk-local row id -> weight 0 -> floored
+    idx[2100, 0] = 100
+    edges_o, w_o = P.smoothen_dists(idx.astype(np.uint64), dist.astype(np.float64), 1.0, 1.5, cs)
+    e, w = graph.smoothen_dists(torch.from_numpy(idx).cuda(), torch.from_numpy(dist).cuda(), 1.0, 1.5, 0, cs, n)
+    assert np.array_equal(e.cpu().numpy().astype(np.uint64), edges_o)
+    assert np.abs(w.cpu().numpy().astype(np.float64) - w_o).max() < 1e-5
+    assert (w_o == 0).sum() == 0
+
+
+def test_full_chain_pbmc_golden(gpu, pbmc):
+    """mark_hvgs(top_n=100) -> make_graph(dims=11,k=11) on the PBMC fixture vs the reference goldens.
+    The GPU path uses exact PCA + exact kNN where the reference used IncrementalPCA + HNSW, so the pin is
+    a neighbour-set recall."""
+    torch, graph = gpu["torch"], gpu["graph"]
+    csr = _dev(gpu, pbmc["counts"])
+    n_counts, _ = graph.cell_totals(csr)
+    feat_I = (graph.gene_ncells(csr) > 20).cpu().numpy()
+    cell_idx = torch.from_numpy(pbmc["cell_idx"]).cuda()
+    hv = graph.mark_hvgs_csr(csr, cell_idx, feat_I, n_counts, 892, gene_names=pbmc["names"], top_n=100)
+    res = graph.make_graph_csr(csr, cell_idx, hv, dims=11, k=11)
+    idx = res.indices.cpu().numpy()
+    recall = np.mean([len(set(a) & set(b)) / 11 for a, b in zip(idx, pbmc["indices"].astype(np.int64))])
+    assert recall > 0.99, recall

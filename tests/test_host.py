@@ -1,0 +1,135 @@
+"""CPU-only tests: C-ABI surface, host logic (HVG selection, sharding, collectives over gloo), generator."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    """libscarf_b200.so loads without a GPU and exports exactly what include/scarf_b200.h declares."""
+    from scarf_b200 import lib
+
+    header = open(os.path.join(ROOT, "include", "scarf_b200.h")).read()
+    declared = set(re.findall(r"\b(scf_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    so = ctypes.CDLL(lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(so, name), name
+    assert lib.version() == 100
+
+
+def test_abi_argument_errors_do_not_need_a_gpu():
+    from scarf_b200 import lib
+
+    with pytest.raises(ValueError, match="null pointer"):
+        lib.call("scf_csr_row_sums", None, None, None, None, 0, None, None, None, None)
+    with pytest.raises(ValueError, match="method"):
+        lib.call("scf_knn_l2", 8, 1, 8, 10, 4, 4, 2, -1, 8, 8, 7, None, 0, None)
+    assert b"method" in lib.raw("scf_last_error")()
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No CPU fallback: importing the binding without the built library is an ImportError."""
+    code = ("import importlib.util, sys; spec = importlib.util.spec_from_file_location('lib', sys.argv[1]);"
+            "m = importlib.util.module_from_spec(spec); m.__file__ = sys.argv[2]; spec.loader.exec_module(m)")
+    fake = tmp_path / "scarf_b200"
+    fake.mkdir()
+    src = open(os.path.join(ROOT, "scarf_b200", "lib.py")).read()
+    (fake / "lib.py").write_text(src)
+    r = subprocess.run([sys.executable, "-c", code, str(fake / "lib.py"), str(fake / "lib.py")], capture_output=True,
+                       text=True)
+    assert r.returncode != 0 and "ImportError" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_hvg_host_logic_matches_oracle(pbmc):
+    """Product LOWESS / HVG choice (scarf_b200/hvg.py) vs the oracle restatement on the PBMC statistics."""
+    from oracle import pipeline as P
+    from scarf_b200 import hvg
+
+    counts, cell_idx = pbmc["counts"], pbmc["cell_idx"]
+    feat_I = P.gene_ncells(counts) > 20
+    n_counts, _ = P.cell_totals(counts)
+    hv_o, st = P.mark_hvgs(counts, cell_idx, feat_I, gene_names=pbmc["names"], top_n=100, return_stats=True)
+    c_var = np.full(counts.shape[1], np.nan)
+    c_var[feat_I] = hvg.remove_trend(st["avg"][feat_I], st["sigmas"][feat_I])
+    np.testing.assert_allclose(c_var[feat_I], st["c_var"][feat_I], rtol=1e-10)
+    hv = hvg.choose_hvgs(st["normed_n"], st["nz_mean"], c_var, feat_I, pbmc["names"], 100, int(0.01 * 892))
+    assert np.array_equal(hv, hv_o)
+    # blacklist really removes genes (the reference's default regex)
+    assert not any(str(n).startswith(("MT-", "RPS", "RPL")) for n in pbmc["names"][hv])
+
+
+def test_lowess_ties_and_small_windows():
+    from oracle.lowess import lowess as lowess_o
+    from scarf_b200.hvg import _lowess
+
+    rng = np.random.default_rng(5)
+    x = np.sort(rng.normal(size=60))
+    x[10] = x[9]
+    x[30:33] = x[30]
+    y = np.sin(x) + 0.1 * rng.normal(size=60)
+    y[20] += 3.0  # outlier exercises the robustness iterations
+    np.testing.assert_allclose(_lowess(y, x, 0.2, 100), lowess_o(y, x, frac=0.2, it=100), rtol=1e-9, atol=1e-12)
+
+
+def test_shard_plan():
+    from scarf_b200.dist import ShardPlan
+
+    p = ShardPlan.make(100_000, 8, 1000)
+    assert p.starts[0] == 0 and p.stops[-1] == 100_000
+    assert all(a == b for a, b in zip(p.stops[:-1], p.starts[1:]))
+    assert all(s % 1000 == 0 for s in p.starts)
+    assert max(b - a for a, b in zip(p.starts, p.stops)) - min(b - a for a, b in zip(p.starts, p.stops)) <= 1000
+    p = ShardPlan.make(2500, 4, 1000)  # fewer chunks than ranks: trailing ranks are empty
+    assert [b - a for a, b in zip(p.starts, p.stops)] == [1000, 1000, 500, 0]
+
+
+def test_synth_shards_are_slices_of_the_global_matrix():
+    from scarf_b200 import synth
+
+    full = synth.make_counts_scipy(900, 500, 8, seed=3, block=300)
+    part = synth.make_counts_scipy(300, 500, 8, seed=3, block=300, row_start=600)
+    assert (full[600:] != part).nnz == 0
+    assert full.indices.dtype == np.int32 and np.all(np.diff(full.indptr) > 0)
+    assert full.has_sorted_indices
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as td
+sys.path.insert(0, sys.argv[1])
+from scarf_b200.dist import Comm, ShardPlan
+td.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+c = Comm()
+plan = ShardPlan.make(2500, 2, 1000)
+a, b = plan.rows(c.rank)
+rows = torch.arange(a, b, dtype=torch.float32)[:, None] * torch.ones(1, 3)
+counts = c.allgather_counts(b - a, "cpu")
+assert counts == [2000, 500], counts
+allr = c.allgather_rows(rows, counts)
+assert allr.shape == (2500, 3) and torch.equal(allr[:, 0], torch.arange(2500, dtype=torch.float32))
+g = torch.full((4,), 2 ** 40 + c.rank, dtype=torch.int64)
+c.allreduce_sum_(g)
+assert int(g[0]) == 2 ** 41 + 1            # int64 fixed-point sums are exact
+m = torch.tensor([1.0 + c.rank, 5.0 - c.rank]); c.allreduce_min_(m); assert m.tolist() == [1.0, 4.0]
+z = torch.tensor([c.rank], dtype=torch.int32); c.allreduce_max_(z); assert int(z) == 1
+c.barrier(); td.destroy_process_group(); print("ok")
+'''
+
+
+def test_comm_world2_gloo(tmp_path):
+    """The N>1 host logic (uneven all-gather, exact int64 all-reduce, min/max floor exchange) on CPU over gloo."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29600 + os.getpid() % 300)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0 and "ok" in out, err
