@@ -97,6 +97,9 @@ int32_t scf_project(const float* z, int64_t ldz, int64_t n_rows, int32_t n_cols,
  * exact FP64 re-rank with a proven guard band (rows that fail the guard are recomputed by
  * method 0 inside the same call).  workspace: scf_knn_workspace_bytes(nq, nref, dim, k, method). */
 int64_t scf_knn_workspace_bytes(int64_t nq, int64_t nref, int32_t dim, int32_t k, int32_t method);
+/* diagnostics: byte offset inside the workspace of an int32 that, after scf_knn_l2(method 1), holds the
+ * number of query rows whose guard band could not be proven (recomputed by method 0); -1 if n/a. */
+int64_t scf_knn_fail_count_offset(int64_t nq, int64_t nref, int32_t dim, int32_t k, int32_t method);
 int32_t scf_knn_l2(const float* q, int64_t nq, const float* ref, int64_t nref, int32_t dim,
                    int64_t ld, int32_t k, int64_t self_offset, int64_t* out_idx, float* out_dist,
                    int32_t method, void* workspace, int64_t workspace_bytes, void* stream);

@@ -23,3 +23,33 @@ int32_t scf_check_launch(const char* what) {
 
 extern "C" int32_t scf_version(void) { return SCF_VERSION; }
 extern "C" const char* scf_last_error(void) { return g_err; }
+
+// ---- TMA descriptor helper shared by the tcgen05 kernels ----
+#include "tc_common.cuh"
+int32_t scf_make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_cols, uint32_t box_rows) {
+  static scf_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+      scf_set_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+      return e != cudaSuccess ? -(int32_t)e : -999;
+    }
+    fn = (scf_encode_tiled_fn)p;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    scf_set_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+    return -(int32_t)r - 10000;
+  }
+  return 0;
+}

@@ -12,9 +12,12 @@ namespace {
 constexpr int TQ = 64, TR = 64, DK = 32;
 
 // dynamic smem layout: Qs[dim_pad][TQ] | Rs[DK][TR+1] | Ds[TQ][TR+1] | Ld[TQ][k] | Li[TQ][k]
+// q_ids (nullable): list of query rows to compute (results go to those rows); n_ids_dev (nullable): device
+// scalar holding the length of that list (the tcgen05 path's fail list, no host round trip).
 __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict__ q, const int64_t* __restrict__ q_ids,
-                                                        int64_t nq, const float* __restrict__ ref, int64_t nref,
-                                                        int dim, int64_t ld, int k, int64_t self_offset,
+                                                        const int* __restrict__ n_ids_dev, int64_t nq,
+                                                        const float* __restrict__ ref, int64_t nref, int dim,
+                                                        int64_t ld, int64_t ldr, int k, int64_t self_offset,
                                                         int64_t* __restrict__ out_idx, float* __restrict__ out_dist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int dim_pad = (dim + DK - 1) / DK * DK;
@@ -24,7 +27,9 @@ __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict_
   float* Ld = Ds + TQ * (TR + 1);
   int* Li = reinterpret_cast<int*>(Ld + (size_t)TQ * k);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int64_t q0 = (int64_t)blockIdx.x * TQ;
+  if (n_ids_dev) nq = *n_ids_dev;
+ for (int64_t q0 = (int64_t)blockIdx.x * TQ; q0 < nq; q0 += (int64_t)gridDim.x * TQ) {
+  __syncthreads();  // previous tile's lists / Qs fully consumed
   // query tile, transposed, zero padded
   for (int e = tid; e < dim_pad * TQ; e += 256) {
     const int t = e % dim_pad, qq = e / dim_pad;
@@ -50,7 +55,7 @@ __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict_
       for (int e = tid; e < TR * DK; e += 256) {
         const int t = e % DK, rr = e / DK;
         float v = 0.f;
-        if (r0 + rr < nref && t0 + t < dim) v = __ldg(ref + (r0 + rr) * ld + t0 + t);
+        if (r0 + rr < nref && t0 + t < dim) v = __ldg(ref + (r0 + rr) * ldr + t0 + t);
         Rs[t * (TR + 1) + rr] = v;
       }
       __syncthreads();
@@ -105,6 +110,7 @@ __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict_
       out_dist[qi * k + p] = p < cnt ? Ld[(size_t)tid * k + p] : FLT_MAX;
     }
   }
+ }
 }
 
 }  // namespace
@@ -114,9 +120,9 @@ size_t knn_exact_smem(int dim, int k) {
   return sizeof(float) * ((size_t)dim_pad * TQ + DK * (TR + 1) + TQ * (TR + 1)) + (size_t)TQ * k * 8;
 }
 
-int32_t knn_exact_launch(const float* q, const int64_t* q_ids, int64_t nq, const float* ref, int64_t nref, int dim,
-                         int64_t ld, int k, int64_t self_offset, int64_t* out_idx, float* out_dist,
-                         cudaStream_t stream) {
+int32_t knn_exact_launch(const float* q, const int64_t* q_ids, const int* n_ids_dev, int64_t nq, const float* ref,
+                         int64_t nref, int dim, int64_t ld, int64_t ldr, int k, int64_t self_offset, int64_t* out_idx,
+                         float* out_dist, cudaStream_t stream) {
   if (nq == 0) return 0;
   const size_t smem = knn_exact_smem(dim, k);
   if (smem > 227 * 1024) {
@@ -128,7 +134,10 @@ int32_t knn_exact_launch(const float* q, const int64_t* q_ids, int64_t nq, const
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
-  knn_exact_kernel<<<(unsigned)((nq + TQ - 1) / TQ), 256, smem, stream>>>(q, q_ids, nq, ref, nref, dim, ld, k,
-                                                                         self_offset, out_idx, out_dist);
+  // with a device-side count the grid is a fixed persistent size and every CTA strides over the list
+  const int64_t tiles = (nq + TQ - 1) / TQ;
+  const unsigned grid = (unsigned)(n_ids_dev ? (tiles < 4 * SCF_NUM_SMS ? tiles : 4 * SCF_NUM_SMS) : tiles);
+  knn_exact_kernel<<<grid, 256, smem, stream>>>(q, q_ids, n_ids_dev, nq, ref, nref, dim, ld, ldr, k, self_offset,
+                                                out_idx, out_dist);
   return scf_check_launch("scf_knn_l2(exact)");
 }

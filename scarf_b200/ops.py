@@ -145,8 +145,9 @@ def project(z, n_rows, n_cols, v, dims, y=None, ldy=None):
 
 
 # ------------------------------------------------------------------------------------------ K5
-def knn_l2(q, ref, dim, k, self_offset=-1, method=0):
-    """Exact kNN (squared L2).  q, ref: float32 [n, ld] sharing the row stride.  -> (int64 idx, float32 dist)."""
+def knn_l2(q, ref, dim, k, self_offset=-1, method=0, stats=None):
+    """Exact kNN (squared L2).  q, ref: float32 [n, ld] sharing the row stride.  -> (int64 idx, float32 dist).
+    ``stats`` (optional dict) receives ``guard_fail_rows`` as a device scalar tensor (method 1)."""
     assert q.dtype == torch.float32 and ref.dtype == torch.float32
     assert q.stride(1) == 1 and ref.stride(1) == 1 and q.stride(0) == ref.stride(0)
     nq, nref = int(q.shape[0]), int(ref.shape[0])
@@ -156,6 +157,9 @@ def knn_l2(q, ref, dim, k, self_offset=-1, method=0):
     ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=q.device)
     lib.call("scf_knn_l2", q.data_ptr(), nq, ref.data_ptr(), nref, int(dim), int(q.stride(0)), int(k),
              int(self_offset), idx.data_ptr(), dist.data_ptr(), int(method), ws.data_ptr(), ws_bytes, _stream())
+    if stats is not None:
+        off = int(lib.raw("scf_knn_fail_count_offset")(nq, nref, int(dim), int(k), int(method)))
+        stats["guard_fail_rows"] = ws[off:off + 4].view(torch.int32).clone() if off >= 0 else None
     return idx, dist
 
 
