@@ -14,26 +14,31 @@
 //                          provably farther than the k-th kept neighbour, else the row goes on the fail list.
 //   kernel 4 (knn_exact)   FP64 brute force for the fail list (device-side count, no host round trip).
 #include <float.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "knn_common.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int BM = 128;        // queries per CTA (= TMEM lanes)
-constexpr int BN = 256;        // references per MMA / accumulator tile (TMEM columns)
+__device__ unsigned long long g_dbg[8];  // SCF_KNN_FLAGS & 16: event counters (developer diagnostics)
+
+constexpr int BM = 128;        // queries per MMA (= TMEM lanes)
+constexpr int QT = 2;          // query tiles per CTA: both reuse every reference tile staged in shared memory
+constexpr int BN = 128;        // references per MMA / accumulator tile (TMEM columns)
 constexpr int KCH = 32;        // float32 per 128-byte swizzle row
 constexpr int A_CHUNK_BYTES = BM * 128;
 constexpr int B_STAGE_BYTES = BN * 128;
-constexpr int NTHREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
+constexpr int NTHREADS = 320;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue
+constexpr int NLISTS = QT * BM;  // one candidate list per query row of the CTA
 constexpr float PAD_NORM = 1e30f;
 
-// error model of the tensor-core score (see DESIGN.md "kNN guard band"):
-//   inputs rounded to TF32 (RN, rel 2^-11 each) -> |2 a.b - 2 a~.b~| <= 2 (2*2^-11 + 2^-22) |a||b|
-//   FP32 accumulation of <= 131 terms, any order, truncating adder (2^-23 per add, x4 margin)
-//   -> 2^-14 (2|a||b| + |b|^2)
-__device__ __host__ inline double eps_c1() { return 2.0 * (2.0 * 0x1p-11 + 0x1p-22) + 0x1p-13; }
-__device__ __host__ inline double eps_c2() { return 0x1p-14 + 0x1p-28; }
+// error model of the tensor-core score (see DESIGN.md "kNN guard band"), a~ = tf32(a), da = a - a~ (known exactly):
+//   |2 a.b - 2 a~.b~| = 2 |da.b + a~.db| <= 2 (|da| |b| + |a| |db|)      with |da| per query, max |b|, max |db|
+//   tf32 x tf32 products are exact in FP32; accumulation of <= 131 terms in any order with a truncating adder
+//   (2^-23 per add, x4 margin) -> 2^-14 (2|a||b| + |b|^2); the |b|^2 split leaves < 2^-28 |b|^2
+__device__ __host__ inline double eps_acc() { return 0x1p-14 + 0x1p-28; }
 
 __device__ __forceinline__ float to_tf32_rn(float x) {
   uint32_t r;
@@ -48,28 +53,32 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const float* __restrict__
                                                        const float* __restrict__ ref, int64_t nref, int64_t nr_pad,
                                                        int dim, int64_t ld, int kp, float* __restrict__ qop,
                                                        float* __restrict__ rop, double* __restrict__ qnorm2,
-                                                       float* __restrict__ bmax) {
+                                                       float* __restrict__ qerr, float* __restrict__ bmax) {
   const int lane = threadIdx.x & 31;
   const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
-  float local_bmax = 0.f;
+  float local_bmax = 0.f, local_dbmax = 0.f;  // bmax[0] = max |b|, bmax[1] = max |b - tf32(b)|
   for (int64_t r = w0; r < nq_pad + nr_pad; r += nw) {
     const bool is_q = r < nq_pad;
     const int64_t row = is_q ? r : r - nq_pad;
     const bool live = is_q ? row < nq : row < nref;
     const float* src = (is_q ? q : ref) + row * ld;
     float* dst = (is_q ? qop : rop) + row * kp;
-    double n2 = 0.0;
+    double n2 = 0.0, e2 = 0.0;
     for (int t = lane; t < kp; t += 32) {
       if (t >= dim && t < dim + 3) continue;  // the three augmentation slots are written below
       float v = 0.f;
       if (live && t < dim) {
         const float x = src[t];
+        const float xr = to_tf32_rn(x);
+        const double dx = (double)x - (double)xr;
         n2 += (double)x * (double)x;
-        v = is_q ? to_tf32_rn(x) : -2.f * to_tf32_rn(x);
+        e2 += dx * dx;
+        v = is_q ? xr : -2.f * xr;
       }
       dst[t] = v;
     }
     n2 = warp_sum(n2);
+    e2 = warp_sum(e2);
     if (lane < 3) {
       float aug = 0.f;
       if (is_q) {
@@ -85,100 +94,146 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const float* __restrict__
       dst[dim + lane] = aug;
     }
     if (lane == 0 && live) {
-      if (is_q)
+      if (is_q) {
         qnorm2[row] = n2;
-      else
+        qerr[row] = (float)sqrt(e2) * 1.0000002f;
+      } else {
         local_bmax = fmaxf(local_bmax, (float)sqrt(n2) * 1.0000002f);
+        local_dbmax = fmaxf(local_dbmax, (float)sqrt(e2) * 1.0000002f);
+      }
     }
   }
   if (lane == 0 && local_bmax > 0.f) atomicMax(reinterpret_cast<int*>(bmax), __float_as_int(local_bmax));
+  if (lane == 0 && local_dbmax > 0.f) atomicMax(reinterpret_cast<int*>(bmax + 1), __float_as_int(local_dbmax));
 }
 
 // ---------------------------------------------------------------------------------------------- main
-// Per-thread UNSORTED candidate list in shared memory, entry e of row r at [e * BM + r] (conflict free).
-// thr = largest kept score, pmax = its slot: a new candidate overwrites that slot, then the maximum is
-// recomputed with kc independent loads (no dependent insertion-sort chain).
-__device__ __forceinline__ void list_replace_max(float* ls, int* li, int row, int kc, float s, int j, float& thr,
-                                                 int& pmax) {
-  ls[pmax * BM + row] = s;
-  li[pmax * BM + row] = j;
-  float mx = ls[row];
-  int pm = 0;
-#pragma unroll 4
-  for (int e = 1; e < kc; ++e) {
-    const float x = ls[e * BM + row];
-    if (x > mx) mx = x, pm = e;
+// Per-thread UNSORTED candidate list: the KC scores live in registers, the ids in shared memory (entry e of
+// list l at [e * NLISTS + l], conflict free).  The slot number is carried in the low mantissa bits of every kept
+// score (<= 31 ulp perturbation; the threshold is rounded down past the tag, so every rejected score is >= thr),
+// so one FMNMX3 tree yields both the largest kept score and the slot that holds it: a new candidate overwrites it.
+template <int KC>
+struct CandList {
+  static constexpr uint32_t SLOT_MASK = KC - 1;
+  float r[KC];
+  float tmax;  // largest kept (tagged) score: its low bits name the slot
+  float thr;   // comparison threshold: tmax with the tag rounded DOWN, so scores equal to a kept one never pass
+  template <int LO, int N>
+  __device__ __forceinline__ float max_tree() const {  // ternary tree over r[LO .. LO+N) -> FMNMX3
+    if constexpr (N == 1) {
+      return r[LO];
+    } else if constexpr (N == 2) {
+      return fmaxf(r[LO], r[LO + 1]);
+    } else {
+      constexpr int A = (N + 2) / 3, B = (N - A + 1) / 2, C = N - A - B;
+      return fmaxf(fmaxf(max_tree<LO, A>(), max_tree<LO + A, B>()), max_tree<LO + A + B, C>());
+    }
   }
-  thr = mx;
-  pmax = pm;
+  __device__ __forceinline__ void recompute() {
+    tmax = max_tree<0, KC>();
+    const uint32_t b = __float_as_uint(tmax);
+    thr = __uint_as_float((b & 0x80000000u) ? (b | SLOT_MASK) : (b & ~SLOT_MASK));
+  }
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int e = 0; e < KC; ++e) r[e] = __uint_as_float((0x7F7FFFFFu & ~SLOT_MASK) | (uint32_t)e);
+    recompute();
+  }
+  __device__ __forceinline__ void replace_max(float s, int j, int* li_slot) {
+    const uint32_t pmax = __float_as_uint(tmax) & SLOT_MASK;
+    li_slot[pmax * NLISTS] = j;
+    const float tagged = __uint_as_float((__float_as_uint(s) & ~SLOT_MASK) | pmax);
+    const uint32_t onehot = 1u << pmax;  // selects, not a dynamically indexed store (keeps r[] in registers)
+#pragma unroll
+    for (int e = 0; e < KC; ++e) r[e] = (onehot & (1u << e)) ? tagged : r[e];
+    recompute();
+  }
+};
+
+__device__ __forceinline__ float min8(const uint32_t* v) {
+  const float a = fminf(fminf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
+  const float b = fminf(fminf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
+  return fminf(fminf(a, b), fminf(__uint_as_float(v[6]), __uint_as_float(v[7])));
 }
 
-// v[c] for a runtime c in [0,32): 31 selects instead of a local-memory round trip
-__device__ __forceinline__ float select32(const uint32_t (&v)[32], int c) {
-  uint32_t a[16], b[8], d[4], e[2];
+// One 32-column chunk of one query row.  Group-of-8 minima prefilter (FMNMX3); rows with a candidate stage the
+// values of their hit groups in shared memory ([column][thread], conflict free) and set a 32-bit hit mask; then
+// every lane drains its own hits concurrently from the staged copy (dynamic column index without local memory).
+// All branches that contain warp votes are warp-uniform.  Returns after the registers v are dead, so the caller
+// can issue the next TMEM load before calling drain_hits().
+template <int KC>
+__device__ __forceinline__ uint32_t stage_hits(const uint32_t (&v)[32], float thr, float* st_slot, int dbg) {
+  if (dbg & 8) return 0u;  // timing experiment: TMEM traffic only
+  float g[4];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = (c & 1) ? v[2 * i + 1] : v[2 * i];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = (c & 2) ? a[2 * i + 1] : a[2 * i];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) d[i] = (c & 4) ? b[2 * i + 1] : b[2 * i];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) e[i] = (c & 8) ? d[2 * i + 1] : d[2 * i];
-  return __uint_as_float((c & 16) ? e[1] : e[0]);
-}
-
-// One 32-column chunk of one query row: block-min prefilter, then every lane drains its own hits concurrently.
-__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int jbase, float* ls, int* li, int row, int kc,
-                                           float& thr, int& pmax) {
-  float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]),
-        m3 = __uint_as_float(v[3]);
-#pragma unroll
-  for (int c = 4; c < 32; c += 4) {
-    m0 = fminf(m0, __uint_as_float(v[c]));
-    m1 = fminf(m1, __uint_as_float(v[c + 1]));
-    m2 = fminf(m2, __uint_as_float(v[c + 2]));
-    m3 = fminf(m3, __uint_as_float(v[c + 3]));
-  }
-  const float m = fminf(fminf(m0, m1), fminf(m2, m3));
-  if (!__any_sync(SCF_FULL, m < thr)) return;  // warp-uniform: no candidate in this chunk for any row
+  for (int i = 0; i < 4; ++i) g[i] = min8(v + 8 * i);
+  const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
+  if (!__any_sync(SCF_FULL, m < thr) || (dbg & 4)) return 0u;  // no candidate in this chunk for any row of the warp
+  const bool cnt = (dbg & 16) && (threadIdx.x & 31) == 0;
+  if (cnt) atomicAdd(&g_dbg[0], 1ull);
   uint32_t mask = 0;
-  if (m < thr) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) mask |= (__uint_as_float(v[c]) < thr) ? (1u << c) : 0u;
+  for (int i = 0; i < 4; ++i) {
+    if (!__any_sync(SCF_FULL, g[i] < thr)) continue;
+    if (cnt) atomicAdd(&g_dbg[1], 1ull);
+    if (g[i] < thr) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float x = __uint_as_float(v[8 * i + c]);
+        if (x < thr) {
+          st_slot[(8 * i + c) * NLISTS] = x;
+          mask |= 1u << (8 * i + c);
+        }
+      }
+    }
   }
+  return mask;
+}
+
+template <int KC>
+__device__ __forceinline__ void drain_hits(uint32_t mask, int jbase, CandList<KC>& cl, int* li_slot,
+                                           const float* st_slot, int dbg) {
+  const bool cnt = (dbg & 16) && (threadIdx.x & 31) == 0;
   while (__any_sync(SCF_FULL, mask != 0u)) {
+    if (cnt) atomicAdd(&g_dbg[2], 1ull);
     if (mask) {
       const int c = __ffs(mask) - 1;
       mask &= mask - 1;
-      const float s = select32(v, c);
-      if (s < thr) list_replace_max(ls, li, row, kc, s, jbase + c, thr, pmax);
+      const float sc = st_slot[c * NLISTS];
+      if (sc < cl.thr) {
+        if (dbg & 16) atomicAdd(&g_dbg[3], 1ull);
+        cl.replace_max(sc, jbase + c, li_slot);
+      }
     }
   }
 }
 
 struct KnnTcParams {
   int kchunks;          // Kp / 32
+  int ksteps_last;      // 8-wide K steps that hold data in the last chunk (all-zero padding steps are skipped)
   int stages;           // B pipeline depth
-  int kc;               // candidates kept per (query, split)
   int n_ref_tiles;      // nr_pad / BN
   int tiles_per_split;
   int nsplit;
-  float* cand_score;    // [nq_pad, nsplit, kc]  (unsorted)
+  float* cand_score;    // [nq_pad, nsplit, KC]  (unsorted)
   int* cand_idx;
   float* cand_tau;      // [nq_pad, nsplit]  largest kept score = lower bound of every rejected score
+  int nq;               // live query rows (pad rows keep nothing)
+  int flags;            // developer switches (SCF_KNN_FLAGS): 2 = back off in waits, 4/8 = timing experiments, 16 = counters
 };
 
+template <int KC>
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                              const __grid_constant__ CUtensorMap tmap_r,
                                                              const KnnTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // the 128-byte swizzle is a function of the shared-memory address: tiles must sit on 1024-byte boundaries
   unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* sA = smem;
-  unsigned char* sB = sA + (size_t)p.kchunks * A_CHUNK_BYTES;
-  float* ls = reinterpret_cast<float*>(sB + (size_t)p.stages * B_STAGE_BYTES);
-  int* li = reinterpret_cast<int*>(ls + (size_t)p.kc * BM);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)p.kc * BM);
+  unsigned char* sA = smem;                                             // [QT][kchunks][128 rows x 128 B]
+  unsigned char* sB = sA + (size_t)QT * p.kchunks * A_CHUNK_BYTES;      // [stages][128 rows x 128 B]
+  int* li = reinterpret_cast<int*>(sB + (size_t)p.stages * B_STAGE_BYTES);  // candidate ids [KC][NLISTS]
+  float* st = reinterpret_cast<float*>(li + (size_t)KC * NLISTS);           // staged chunk values [32][NLISTS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(st + (size_t)32 * NLISTS);
   uint64_t* a_full = bars;
   uint64_t* full = bars + 1;
   uint64_t* empty = full + p.stages;
@@ -187,7 +242,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BM;
+  const uint32_t backoff = (p.flags & 2) ? 32u : 0u;
+  const int q0 = blockIdx.x * (QT * BM);
   const int split = blockIdx.y;
   const int tile_begin = split * p.tiles_per_split;
   const int tile_end = min(tile_begin + p.tiles_per_split, p.n_ref_tiles);
@@ -201,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tmem_full + a, 1);
-      tc::mbar_init(tmem_empty + a, BM);
+      tc::mbar_init(tmem_empty + a, NLISTS);
     }
     tc::fence_barrier_init();
   }
@@ -209,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     tc::tma_prefetch_desc(&tmap_q);
     tc::tma_prefetch_desc(&tmap_r);
   }
-  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);  // 2 buffers x QT tiles x 128 columns
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -218,14 +274,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      tc::mbar_expect_tx(a_full, (uint32_t)(p.kchunks * A_CHUNK_BYTES));
-      for (int c = 0; c < p.kchunks; ++c) tc::tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmap_q, a_full, c * KCH, q0);
+      tc::mbar_expect_tx(a_full, (uint32_t)(QT * p.kchunks * A_CHUNK_BYTES));
+      for (int t = 0; t < QT; ++t)
+        for (int c = 0; c < p.kchunks; ++c)
+          tc::tma_load_2d(sA + (size_t)(t * p.kchunks + c) * A_CHUNK_BYTES, &tmap_q, a_full, c * KCH, q0 + t * BM);
       int it = 0;
       for (int t = tile_begin; t < tile_end; ++t)
         for (int c = 0; c < p.kchunks; ++c, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          tc::mbar_wait(empty + s, ph ^ 1u);
+          tc::mbar_wait(empty + s, ph ^ 1u, backoff);
           tc::mbar_expect_tx(full + s, B_STAGE_BYTES);
           tc::tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmap_r, full + s, c * KCH, t * BN);
         }
@@ -240,62 +298,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
       for (int lt = 0; lt < ntiles; ++lt) {
         const int acc = lt & 1;
         const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
-        tc::mbar_wait(tmem_empty + acc, acc_ph ^ 1u);
+        tc::mbar_wait(tmem_empty + acc, acc_ph ^ 1u, backoff);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int c = 0; c < p.kchunks; ++c, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          tc::mbar_wait(full + s, ph);
+          tc::mbar_wait(full + s, ph, backoff);
           tc::tc_fence_after();
-          const uint64_t da = tc::umma_desc_k_sw128(sA + (size_t)c * A_CHUNK_BYTES);
           const uint64_t db = tc::umma_desc_k_sw128(sB + (size_t)s * B_STAGE_BYTES);
+          const int nk = c + 1 == p.kchunks ? p.ksteps_last : KCH / 8;
 #pragma unroll
-          for (int kk = 0; kk < KCH / 8; ++kk)  // K = 8 tf32 = 32 bytes per instruction: +2 in 16-byte units
-            tc::umma_tf32(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (c | kk) != 0);
+          for (int t = 0; t < QT; ++t) {
+            const uint64_t da = tc::umma_desc_k_sw128(sA + (size_t)(t * p.kchunks + c) * A_CHUNK_BYTES);
+            const uint32_t d_tmem = tmem_base + (uint32_t)((acc * QT + t) * BN);
+#pragma unroll
+            for (int kk = 0; kk < KCH / 8; ++kk)  // K = 8 tf32 = 32 bytes per instruction: +2 in 16-byte units
+              if (kk < nk) tc::umma_tf32(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (c | kk) != 0);
+          }
           tc::umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
         }
-        tc::umma_commit(tmem_full + acc);  // accumulator complete
+        tc::umma_commit(tmem_full + acc);  // both accumulators of this reference tile complete
       }
     }
   } else {
-    // ===================== epilogue: top-k' per query row =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    // ===================== epilogue: one query row per thread, top-k' of the whole reference range ===========
+    const int quarter = warp & 3;      // TMEM lane quarter this warp may read
+    const int qt = (warp - 2) >> 2;    // which of the CTA's query tiles
     const int row = quarter * 32 + lane;
-    for (int e = 0; e < p.kc; ++e) {
-      ls[e * BM + row] = FLT_MAX;
-      li[e * BM + row] = -1;
-    }
-    float thr = FLT_MAX;
-    int pmax = 0;
+    int* li_slot = li + qt * BM + row;
+    float* st_slot = st + qt * BM + row;
+    CandList<KC> cl;
+    cl.init();
+    if (q0 + qt * BM + row >= p.nq) cl.thr = -FLT_MAX;  // pad row: never a candidate
+#pragma unroll
+    for (int e = 0; e < KC; ++e) li_slot[e * NLISTS] = -1;
     for (int lt = 0; lt < ntiles; ++lt) {
       const int acc = lt & 1;
       const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
       tc::mbar_wait(tmem_full + acc, acc_ph);
       tc::tc_fence_after();
       const int j0 = (tile_begin + lt) * BN;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      uint32_t v0[32], v1[32];
-      tc::tmem_ld32(t_row, v0);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
+      uint32_t v[32];
+      tc::tmem_ld32(t_row, v);
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; cc += 2) {  // TMEM load of the next chunk overlaps the scan of this one
+      for (int cc = 0; cc < BN / 32; ++cc) {
         tc::tmem_ld_wait();
-        tc::tmem_ld32(t_row + (uint32_t)((cc + 1) * 32), v1);
-        scan_chunk(v0, j0 + cc * 32, ls, li, row, p.kc, thr, pmax);
-        tc::tmem_ld_wait();
-        if (cc + 2 < BN / 32) tc::tmem_ld32(t_row + (uint32_t)((cc + 2) * 32), v0);
-        scan_chunk(v1, j0 + (cc + 1) * 32, ls, li, row, p.kc, thr, pmax);
+        const uint32_t mask = stage_hits<KC>(v, cl.thr, st_slot, p.flags);
+        // v is dead: the TMEM load of the next chunk overlaps the drain of this one
+        if (cc + 1 < BN / 32) tc::tmem_ld32(t_row + (uint32_t)((cc + 1) * 32), v);
+        drain_hits<KC>(mask, j0 + cc * 32, cl, li_slot, st_slot, p.flags);
       }
       tc::tc_fence_before();
       tc::mbar_arrive(tmem_empty + acc);
     }
-    // candidates out: [query, split, kc]
-    const size_t base = ((size_t)(q0 + row) * p.nsplit + split) * p.kc;
-    for (int e = 0; e < p.kc; ++e) {
-      p.cand_score[base + e] = ls[e * BM + row];
-      p.cand_idx[base + e] = li[e * BM + row];
+    // candidates out: [query, split, KC]
+    const size_t sub = (size_t)(q0 + qt * BM + row) * p.nsplit + split;
+#pragma unroll
+    for (int e = 0; e < KC; ++e) {
+      p.cand_score[sub * KC + e] = cl.r[e];
+      p.cand_idx[sub * KC + e] = li_slot[e * NLISTS];
     }
-    p.cand_tau[(size_t)(q0 + row) * p.nsplit + split] = thr;
+    p.cand_tau[sub] = cl.thr;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -315,6 +379,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
                                                          const int* __restrict__ cand_idx,
                                                          const float* __restrict__ cand_tau,
                                                          const double* __restrict__ qnorm2,
+                                                         const float* __restrict__ qerr,
                                                          const float* __restrict__ bmax, int64_t* __restrict__ out_idx,
                                                          float* __restrict__ out_dist, int64_t* __restrict__ fail_ids,
                                                          int* __restrict__ fail_count) {
@@ -375,8 +440,8 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   if (lane == 0) {
     bool ok = enough;
     if (ok && tau < 1e29f) {  // lists were full: something was rejected, prove it is farther than the k-th kept
-      const double an2 = qnorm2[qi], bm = (double)*bmax;
-      const double eps = eps_c1() * sqrt(an2) * bm + eps_c2() * bm * bm;
+      const double an2 = qnorm2[qi], an = sqrt(an2), bm = (double)bmax[0], dbm = (double)bmax[1];
+      const double eps = 2.0 * ((double)qerr[qi] * bm + an * dbm) * (1.0 + 1e-6) + eps_acc() * (2.0 * an * bm + bm * bm);
       const double lower = ((double)tau - eps + an2) * (1.0 - 1e-12);  // bound on any rejected exact distance
       const float dk = __uint_as_float((unsigned)(last >> 32));
       ok = lower > 0.0 && dk < __double2float_rd(lower);  // strict: a tie would be decided by the index
@@ -389,7 +454,6 @@ int pick_kc(int k) {
   const int need = k + 1;  // the query itself may be among the candidates
   if (need <= 12) return 16;
   if (need <= 25) return 32;
-  if (need <= 50) return 64;
   return 0;
 }
 
@@ -398,34 +462,31 @@ struct Plan {
   int64_t nq_pad, nr_pad;
   size_t smem;
   // workspace offsets (bytes)
-  size_t off_qop, off_rop, off_qn, off_cs, off_ci, off_tau, off_fail, off_misc, total;
+  size_t off_qop, off_rop, off_qn, off_qe, off_cs, off_ci, off_tau, off_fail, off_misc, off_fix, total;
 };
 
 bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.kc = pick_kc(k);
   pl.kp = (dim + 3 + KCH - 1) / KCH * KCH;
   pl.kchunks = pl.kp / KCH;
-  if (pl.kc == 0 || pl.kchunks > 4) return false;  // k > 48 or dim > 125: method 0 handles those
-  pl.nq_pad = (nq + BM - 1) / BM * BM;
+  if (pl.kc == 0 || pl.kchunks > 4) return false;  // k > 24 or dim > 125: method 0 handles those
+  pl.nq_pad = (nq + QT * BM - 1) / (QT * BM) * (QT * BM);
   pl.nr_pad = (nref + BN - 1) / BN * BN;
   pl.n_ref_tiles = (int)(pl.nr_pad / BN);
-  const int64_t qtiles = pl.nq_pad / BM;
-  // reference splits: fill the 148 SMs evenly (1 CTA per SM), keep >= 4 tiles per split, <= 8 splits
-  int best_s = 1;
-  double best_eff = 0.0;
-  for (int s = 1; s <= 8 && s * 4 <= std::max(pl.n_ref_tiles, 4) && s * pl.kc <= 32 * MAXU; ++s) {
-    const int64_t ctas = qtiles * s;
-    const double eff = (double)ctas / (double)((ctas + SCF_NUM_SMS - 1) / SCF_NUM_SMS * SCF_NUM_SMS);
-    if (eff > best_eff + 0.03) best_eff = eff, best_s = s;
-  }
-  pl.nsplit = best_s;
-  pl.tiles_per_split = (pl.n_ref_tiles + pl.nsplit - 1) / pl.nsplit;
+  const int64_t ctas = pl.nq_pad / (QT * BM);
+  // One candidate list per query over the WHOLE reference range keeps the number of list updates at
+  // k' ln(N/k'); the references are split across CTAs only when there are too few query tiles to fill the GPU.
+  int s = 1;
+  if (ctas < SCF_NUM_SMS) s = (int)std::min<int64_t>((SCF_NUM_SMS + ctas - 1) / ctas, 8);
+  s = std::max(1, std::min(s, pl.n_ref_tiles / 8));
+  while (s > 1 && s * pl.kc > 32 * MAXU) --s;
+  pl.tiles_per_split = (pl.n_ref_tiles + s - 1) / s;
   pl.nsplit = (pl.n_ref_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split;
   auto smem_for = [&](int stages) {
-    return (size_t)pl.kchunks * A_CHUNK_BYTES + (size_t)stages * B_STAGE_BYTES + (size_t)pl.kc * BM * 8 +
-           (size_t)(1 + 2 * stages + 4) * 8 + 16;
+    return (size_t)QT * pl.kchunks * A_CHUNK_BYTES + (size_t)stages * B_STAGE_BYTES + (size_t)pl.kc * NLISTS * 4 +
+           (size_t)32 * NLISTS * 4 + (size_t)(1 + 2 * stages + 4) * 8 + 64;
   };
-  pl.stages = 4;
+  pl.stages = 6;
   while (pl.stages > 2 && smem_for(pl.stages) + 1024 > 227 * 1024) --pl.stages;
   pl.smem = smem_for(pl.stages) + 1024;  // slack for the 1024-byte alignment of the swizzled tiles
   if (pl.smem > 227 * 1024) return false;
@@ -434,11 +495,13 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.off_qop = o, o = al(o + (size_t)pl.nq_pad * pl.kp * 4);
   pl.off_rop = o, o = al(o + (size_t)pl.nr_pad * pl.kp * 4);
   pl.off_qn = o, o = al(o + (size_t)pl.nq_pad * 8);
+  pl.off_qe = o, o = al(o + (size_t)pl.nq_pad * 4);
   pl.off_cs = o, o = al(o + (size_t)pl.nq_pad * pl.nsplit * pl.kc * 4);
   pl.off_ci = o, o = al(o + (size_t)pl.nq_pad * pl.nsplit * pl.kc * 4);
   pl.off_tau = o, o = al(o + (size_t)pl.nq_pad * pl.nsplit * 4);
   pl.off_fail = o, o = al(o + (size_t)nq * 8);
   pl.off_misc = o, o = al(o + 256);
+  pl.off_fix = o, o = al(o + knn_exact_fix_scratch_bytes(k));
   pl.total = o;
   return true;
 }
@@ -461,7 +524,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
                       int64_t self_offset, int64_t* out_idx, float* out_dist, void* workspace,
                       int64_t workspace_bytes, cudaStream_t stream) {
   Plan pl;
-  if (!make_plan(nq, nref, dim, k, pl))  // k > 48 or dim > 125: outside the tensor-core kernel's shapes
+  if (!make_plan(nq, nref, dim, k, pl))  // k > 24 or dim > 125: outside the tensor-core kernel's shapes
     return knn_exact_launch(q, nullptr, nullptr, nq, ref, nref, dim, ld, ld, k, self_offset, out_idx, out_dist,
                             stream);
   if (!workspace || workspace_bytes < (int64_t)pl.total) {
@@ -472,6 +535,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   float* qop = (float*)(ws + pl.off_qop);
   float* rop = (float*)(ws + pl.off_rop);
   double* qn = (double*)(ws + pl.off_qn);
+  float* qe = (float*)(ws + pl.off_qe);
   float* cs = (float*)(ws + pl.off_cs);
   int* ci = (int*)(ws + pl.off_ci);
   float* ctau = (float*)(ws + pl.off_tau);
@@ -484,7 +548,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     return -(int32_t)e;
   }
   knn_prep_kernel<<<4 * SCF_NUM_SMS, 256, 0, stream>>>(q, nq, pl.nq_pad, ref, nref, pl.nr_pad, dim, ld, pl.kp, qop, rop,
-                                                       qn, bmax);
+                                                       qn, qe, bmax);
   int32_t rc = scf_check_launch("scf_knn_l2(prep)");
   if (rc) return rc;
   CUtensorMap tq, tr;
@@ -493,22 +557,39 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   rc = scf_make_tmap_2d_f32(&tr, rop, (uint64_t)pl.nr_pad, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BN);
   if (rc) return rc;
   KnnTcParams prm;
-  prm.kchunks = pl.kchunks, prm.stages = pl.stages, prm.kc = pl.kc, prm.n_ref_tiles = pl.n_ref_tiles;
+  prm.kchunks = pl.kchunks, prm.stages = pl.stages, prm.n_ref_tiles = pl.n_ref_tiles;
+  prm.nq = (int)nq;
+  prm.ksteps_last = ((dim + 3 + 7) / 8) - (pl.kchunks - 1) * (KCH / 8);
   prm.tiles_per_split = pl.tiles_per_split, prm.nsplit = pl.nsplit, prm.cand_score = cs, prm.cand_idx = ci, prm.cand_tau = ctau;
-  e = cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  {
+    const char* f = getenv("SCF_KNN_FLAGS");
+    prm.flags = f ? atoi(f) : 2;
+  }
+  auto kern = pl.kc == 16 ? knn_tc_kernel<16> : knn_tc_kernel<32>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) {
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
-  dim3 grid((unsigned)(pl.nq_pad / BM), (unsigned)pl.nsplit);
-  knn_tc_kernel<<<grid, NTHREADS, pl.smem, stream>>>(tq, tr, prm);
+  dim3 grid((unsigned)(pl.nq_pad / (QT * BM)), (unsigned)pl.nsplit);
+  kern<<<grid, NTHREADS, pl.smem, stream>>>(tq, tr, prm);
   rc = scf_check_launch("scf_knn_l2(tcgen05)");
   if (rc) return rc;
   knn_rerank_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(q, nq, ref, nref, dim, ld, k, self_offset, pl.kc,
-                                                                  pl.nsplit, cs, ci, ctau, qn, bmax, out_idx, out_dist,
+                                                                  pl.nsplit, cs, ci, ctau, qn, qe, bmax, out_idx, out_dist,
                                                                   fail_ids, fail_count);
   rc = scf_check_launch("scf_knn_l2(rerank)");
   if (rc) return rc;
-  return knn_exact_launch(q, fail_ids, fail_count, nq, ref, nref, dim, ld, ld, k, self_offset, out_idx, out_dist,
-                          stream);
+  if (prm.flags & 16) {
+    unsigned long long h[8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_dbg, sizeof(h));
+    const double chunks = (double)pl.nq_pad / 32.0 * (double)pl.nr_pad / 32.0;  // (32 rows x 32 columns) units
+    fprintf(stderr, "[knn dbg] nsplit %d kc %d warp-chunks %.3g hit-chunks %llu (%.1f%%) hit-groups %llu drain-iters %llu inserts %llu (%.1f / query)\n",
+            pl.nsplit, pl.kc, chunks, h[0], 100.0 * h[0] / chunks, h[1], h[2], h[3], (double)h[3] / (double)nq);
+    memset(h, 0, sizeof(h));
+    cudaMemcpyToSymbol(g_dbg, h, sizeof(h));
+  }
+  return knn_exact_fix_launch(q, fail_ids, fail_count, nq, ref, nref, dim, ld, k, self_offset, out_idx, out_dist,
+                              ws + pl.off_fix, stream);
 }

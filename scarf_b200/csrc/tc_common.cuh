@@ -33,11 +33,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug (wrong tx count, bad tensor map) must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (backoff_ns) __nanosleep(backoff_ns);  // waiting roles should not steal issue slots from working warps
     if ((++spins & 0x3FF) == 0 && clock64() - t0 > 8000000000LL) __trap();  // ~4 s
   }
 }

@@ -197,6 +197,32 @@ def test_knn_cases(gpu, method, nq, nref, dim, k, self_offset):
     assert np.array_equal(dist.cpu().numpy(), dist_o)
 
 
+@pytest.mark.parametrize("n_dup,n", [(60, 6000), (3000, 3000)])
+def test_knn_guard_failures_are_repaired(gpu, n_dup, n):
+    """Tight duplicate clusters make the tensor-core guard band unprovable (ties at distance 0): those rows must go
+    through the FP64 repair path (few rows: reference-split + merge; many rows: one item per tile) and still be
+    bit-exact."""
+    from oracle import pipeline as P
+
+    torch, ops = gpu["torch"], gpu["ops"]
+    rng = np.random.default_rng(n_dup)
+    dim, k = 20, 11
+    y = (rng.normal(size=(n, dim)) * 5).astype(np.float32)
+    if n_dup == n:
+        y = y[rng.integers(0, 30, size=n)]          # only 30 distinct vectors
+    else:
+        y[100:100 + n_dup] = y[100]                 # one cluster of identical points
+    yp = torch.zeros((n, 32), dtype=torch.float32, device="cuda")
+    yp[:, :dim] = torch.from_numpy(y).cuda()
+    st = {}
+    idx, dist = ops.knn_l2(yp, yp, dim, k, self_offset=0, method=1, stats=st)
+    fails = int(st["guard_fail_rows"].item())
+    assert fails >= n_dup
+    idx_o, dist_o = P.exact_knn(y, y, k, self_offset=0)
+    assert np.array_equal(idx.cpu().numpy().astype(np.uint64), idx_o)
+    assert np.array_equal(dist.cpu().numpy(), dist_o)
+
+
 def test_weights_pbmc_golden(gpu, pbmc):
     """K6 on the reference's own knn_indices / knn_distances -> knn_weights.npy (test_datastore.py:76-79, 1e-5)."""
     torch, graph = gpu["torch"], gpu["graph"]
