@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=4000, help="cells in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -209,7 +211,11 @@ def run_ours(args, cfg, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     lib.LAUNCHES["n"] = 0
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     ms_total = timed(lambda: step(csr, timers), args.steps)
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     launches = lib.LAUNCHES["n"]
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps

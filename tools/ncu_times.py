@@ -13,7 +13,7 @@ for r in rows[1:]:
     if len(r) <= iv:
         continue
     name = re.sub(r"\(.*", "", r[ik]).replace("void ", "").replace("<unnamed>::", "")
-    key = (name, r[ig] if ig is not None else "")
+    key = (name, (r[ig] if ig is not None else "") if "--by-grid" in sys.argv else "")
     a = agg.setdefault(key, [0, 0.0])
     a[0] += 1
     a[1] += float(r[iv].replace(",", ""))
