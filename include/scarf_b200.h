@@ -65,23 +65,29 @@ int32_t scf_csr_hvg_colstats(const int64_t* indptr, const int32_t* indices, cons
  * (plain normalised values, used by the parity tests of the normalisation itself).
  * missing_fill (nullable, float64[n_cols]): value of x for columns that do not exist in this
  * matrix at all (align_features fills them with 1.0, scarf/mapping_utils.py:208-211); a column
- * with missing_fill[j] == missing_fill[j] (not NaN) ignores the CSR and uses that x. */
+ * with missing_fill[j] == missing_fill[j] (not NaN) ignores the CSR and uses that x.
+ * z_lo (nullable, same shape / stride as z): Z - tf32_trunc(Z), the low plane of the 3xTF32 Gram. */
 int32_t scf_csr_norm_scale(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
                            const int64_t* row_ids, int64_t n_sel, const int32_t* col_map,
                            int32_t n_cols, const double* row_sum, double sf, int32_t log_transform,
                            const double* mu, const double* sigma, const double* missing_fill,
-                           float* z, int64_t ldz, void* stream);
+                           float* z, float* z_lo, int64_t ldz, void* stream);
 
-/* ---- K2: Gram accumulation  G += Z^T Z  (upper-left n_cols x n_cols, full square written) -----
+/* ---- K2: Gram accumulation  G += Z^T Z  (upper triangle m <= n of the n_cols x n_cols matrix) ---
  * Replaces the per-block SVD updates of sklearn IncrementalPCA.partial_fit driven by
  * AnnStream._fit_pca (scarf/ann.py:207-256) by the exact covariance route.
- * Rows are consumed in fixed slabs of SCF_GRAM_SLAB rows (float32 partials inside a slab, int64
- * fixed point << SCF_GRAM_SHIFT across slabs).  n_rows must be a multiple of SCF_GRAM_SLAB or the
- * tail rows of the last slab must be readable zeros (callers pad Z).  ldg = row stride of g_fx.
- * mode: 0 = FP32 SIMT, 1 = TF32 tcgen05, 3 = 3xTF32 tcgen05. */
-#define SCF_GRAM_SLAB 2048
-int32_t scf_gram_accumulate(const float* z, int64_t ldz, int64_t n_rows, int32_t n_cols,
-                            int64_t* g_fx, int64_t ldg, int32_t mode, void* stream);
+ * Rows are consumed in fixed slabs of SCF_GRAM_SLAB rows (one reference block, scarf/ann.py:187-189):
+ * float32 partial sums inside a slab, int64 fixed point << SCF_GRAM_SHIFT across slabs, so G is
+ * bit-identical however the slabs are spread over CTAs or GPUs (shards aligned to the slab size).
+ * Rows past n_rows are not read.  ldg = row stride of g_fx.  After the last accumulate call (and
+ * after the all-reduce between ranks) scf_gram_symmetrize copies the upper triangle into the lower.
+ * mode: 0 = FP32 SIMT, 1 = TF32 tcgen05, 3 = 3xTF32 tcgen05 (needs z_lo = Z - tf32_trunc(Z), the
+ * second plane scf_csr_norm_scale writes; same shape / stride as z; NULL otherwise).
+ * The tcgen05 modes need ldz % 32 == 0, an even ldg and 16-byte aligned z / z_lo / g_fx. */
+#define SCF_GRAM_SLAB 1000
+int32_t scf_gram_accumulate(const float* z, const float* z_lo, int64_t ldz, int64_t n_rows,
+                            int32_t n_cols, int64_t* g_fx, int64_t ldg, int32_t mode, void* stream);
+int32_t scf_gram_symmetrize(int64_t* g_fx, int32_t n_cols, int64_t ldg, void* stream);
 
 /* ---- K4: projection  Y[:, :dims] = Z @ V ;  Y[:, dims:ldy] = 0 ----------------------------------
  * AnnStream.reducer (scarf/ann.py:138): V = loadings (n_cols x dims, float32 row-major, stride ldv) */
@@ -127,6 +133,13 @@ int32_t scf_membership_coo(const int64_t* idx, const float* dist, const float* s
                            int32_t* chunk_has_zero, void* stream);
 /* zero weights := floor (scarf/knn_utils.py:154-158); floor is a host value */
 int32_t scf_fill_zero_weights(float* weights, int64_t n, float floor_value, void* stream);
+
+/* ---- host helper (no GPU work): robust LOWESS --------------------------------------------------
+ * statsmodels lowess(endog, exog, frac, it, delta=0, return_sorted=False) as called by fit_lowess
+ * (scarf/feat_utils.py:22,38-40) on the <= n_bins (200) binned (log mean, log variance) points of
+ * mark_hvgs' trend removal.  All pointers are HOST pointers; out[i] = fitted value at exog[i]. */
+int32_t scf_host_lowess(const double* endog, const double* exog, int64_t n, double frac, int32_t it,
+                        double* out);
 
 #ifdef __cplusplus
 }

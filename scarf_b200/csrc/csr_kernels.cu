@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const uint32_t* __restrict__ data,
     const int64_t* __restrict__ row_ids, int64_t n_sel, const int32_t* __restrict__ col_map, int n_cols,
     const double* __restrict__ row_sum, double sf, int log_transform, const double* __restrict__ mu,
-    const double* __restrict__ sigma, const double* __restrict__ missing_fill, float* __restrict__ z, int64_t ldz) {
+    const double* __restrict__ sigma, const double* __restrict__ missing_fill, float* __restrict__ z,
+    float* __restrict__ z_lo, int64_t ldz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_mu = reinterpret_cast<double*>(smem_raw);
   double* s_sigma = s_mu + ldz;
@@ -167,7 +168,21 @@ __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
     });
     __syncwarp();
     float4* dst = reinterpret_cast<float4*>(z + r * ldz);
-    for (int j = lane; j < nvec; j += 32) __stcs(dst + j, reinterpret_cast<const float4*>(buf)[j]);
+    if (z_lo) {  // low plane of the 3xTF32 split: what the tensor core's 19-bit read of z drops
+      float4* dlo = reinterpret_cast<float4*>(z_lo + r * ldz);
+      for (int j = lane; j < nvec; j += 32) {
+        const float4 v = reinterpret_cast<const float4*>(buf)[j];
+        float4 lo;
+        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        __stcs(dst + j, v);
+        __stcs(dlo + j, lo);
+      }
+    } else {
+      for (int j = lane; j < nvec; j += 32) __stcs(dst + j, reinterpret_cast<const float4*>(buf)[j]);
+    }
     __syncwarp();
   }
 }
@@ -223,8 +238,8 @@ extern "C" int32_t scf_csr_hvg_colstats(const int64_t* indptr, const int32_t* in
 extern "C" int32_t scf_csr_norm_scale(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
                                       const int64_t* row_ids, int64_t n_sel, const int32_t* col_map, int32_t n_cols,
                                       const double* row_sum, double sf, int32_t log_transform, const double* mu,
-                                      const double* sigma, const double* missing_fill, float* z, int64_t ldz,
-                                      void* stream) {
+                                      const double* sigma, const double* missing_fill, float* z, float* z_lo,
+                                      int64_t ldz, void* stream) {
   SCF_ARG(indptr && indices && data && col_map && row_sum && z, "null pointer");
   SCF_ARG(n_sel >= 0 && n_cols > 0 && ldz >= n_cols && (ldz & 3) == 0, "bad sizes (ldz must be a multiple of 4)");
   if (n_sel == 0) return 0;
@@ -238,6 +253,6 @@ extern "C" int32_t scf_csr_norm_scale(const int64_t* indptr, const int32_t* indi
   const int grid = grid_for((const void*)norm_scale_kernel, kThreads, smem);
   norm_scale_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(indptr, indices, data, row_ids, n_sel, col_map,
                                                                      n_cols, row_sum, sf, log_transform, mu, sigma,
-                                                                     missing_fill, z, ldz);
+                                                                     missing_fill, z, z_lo, ldz);
   return scf_check_launch("scf_csr_norm_scale");
 }

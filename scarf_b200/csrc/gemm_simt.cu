@@ -135,16 +135,23 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
 
 }  // namespace
 
-int32_t scf_gram_tc(const float* z, int64_t ldz, int64_t n_rows, int32_t n_cols, int64_t* g_fx, int64_t ldg,
-                    int32_t mode, cudaStream_t stream);
+int32_t scf_gram_tc(const float* z, const float* z_lo, int64_t ldz, int64_t n_rows, int32_t n_cols, int64_t* g_fx,
+                    int64_t ldg, int32_t mode, cudaStream_t stream);
+int32_t scf_gram_mirror(int64_t* g_fx, int32_t n_cols, int64_t ldg, cudaStream_t stream);
 
-extern "C" int32_t scf_gram_accumulate(const float* z, int64_t ldz, int64_t n_rows, int32_t n_cols, int64_t* g_fx,
-                                       int64_t ldg, int32_t mode, void* stream) {
+extern "C" int32_t scf_gram_symmetrize(int64_t* g_fx, int32_t n_cols, int64_t ldg, void* stream) {
+  SCF_ARG(g_fx, "null pointer");
+  SCF_ARG(n_cols > 0 && ldg >= n_cols, "bad sizes");
+  return scf_gram_mirror(g_fx, n_cols, ldg, (cudaStream_t)stream);
+}
+
+extern "C" int32_t scf_gram_accumulate(const float* z, const float* z_lo, int64_t ldz, int64_t n_rows,
+                                       int32_t n_cols, int64_t* g_fx, int64_t ldg, int32_t mode, void* stream) {
   SCF_ARG(z && g_fx, "null pointer");
   SCF_ARG(n_rows >= 0 && n_cols > 0 && ldz >= n_cols && (ldz & 3) == 0 && ldg >= n_cols, "bad sizes");
   SCF_ARG(mode == 0 || mode == 1 || mode == 3, "mode must be 0 (fp32), 1 (tf32) or 3 (3xtf32)");
   if (n_rows == 0) return 0;
-  if (mode != 0) return scf_gram_tc(z, ldz, n_rows, n_cols, g_fx, ldg, mode, (cudaStream_t)stream);
+  if (mode != 0) return scf_gram_tc(z, z_lo, ldz, n_rows, n_cols, g_fx, ldg, mode, (cudaStream_t)stream);
   const int n_tiles = (n_cols + GT - 1) / GT;
   const int64_t n_slabs = (n_rows + SCF_GRAM_SLAB - 1) / SCF_GRAM_SLAB;
   SCF_ARG(n_slabs <= 65535, "too many slabs for one launch (split the rows)");

@@ -8,13 +8,16 @@
 int32_t knn_exact_launch(const float* q, const int64_t* q_ids, const int* n_ids_dev, int64_t nq, const float* ref,
                          int64_t nref, int dim, int64_t ld, int64_t ldr, int k, int64_t self_offset, int64_t* out_idx,
                          float* out_dist, cudaStream_t stream);
-// fail-list repair used by method 1: rows q_ids[0 .. *n_ids_dev) are recomputed exactly
-constexpr int KNN_FIX_CAP = 2048;     // up to this many rows use reference-split work items
-constexpr int KNN_FIX_NSPLIT = 32;
-size_t knn_exact_fix_scratch_bytes(int k);
-int32_t knn_exact_fix_launch(const float* q, const int64_t* q_ids, const int* n_ids_dev, int64_t nq_max,
-                             const float* ref, int64_t nref, int dim, int64_t ld, int k, int64_t self_offset,
-                             int64_t* out_idx, float* out_dist, void* scratch, cudaStream_t stream);
+// fail-list repair used by method 1: rows q_ids[0 .. *n_ids_dev) are recomputed exactly.  q_keys[s] = (float32
+// distance bits << 32 | index) of row s's current k-th candidate (~0 = unknown): a threshold scan over the
+// references collects every key <= it; up to KNN_FIX_CAP rows are repaired that way, the rest (and overflowing
+// rows) by the FP64 tile kernel.
+constexpr int KNN_FIX_CAP = 16384;
+size_t knn_exact_fix_scratch_bytes(int64_t nq, int k);
+int32_t knn_exact_fix_launch(const float* q, const int64_t* q_ids, const unsigned long long* q_keys,
+                             const int* n_ids_dev, int64_t nq_max, const float* ref, int64_t nref, int dim, int64_t ld,
+                             int k, int64_t self_offset, int64_t* out_idx, float* out_dist, void* scratch,
+                             cudaStream_t stream);
 // method 1 (knn_tc.cu)
 int64_t knn_tc_workspace_bytes(int64_t nq, int64_t nref, int dim, int k);
 int64_t knn_tc_fail_count_offset(int64_t nq, int64_t nref, int dim, int k);

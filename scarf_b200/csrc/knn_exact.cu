@@ -4,6 +4,7 @@
 // It is the exactness anchor of the library: the tcgen05 path (knn_tc.cu) re-ranks its candidates with
 // the same arithmetic and sends every query whose guard band cannot be proven through this kernel.
 #include <float.h>
+#include <algorithm>
 #include "common.cuh"
 #include "knn_common.cuh"
 
@@ -14,17 +15,11 @@ constexpr int TQ = 64, TR = 64, DK = 32;
 // dynamic smem layout: Qs[dim_pad][TQ] | Rs[DK][TR+1] | Ds[TQ][TR+1] | Ld[TQ][k] | Li[TQ][k]
 // q_ids (nullable): list of query rows to compute (results go to those rows); n_ids_dev (nullable): device
 // scalar holding the length of that list (the tcgen05 path's fail list, no host round trip).
-// nsplit > 1: the references are cut into nsplit ranges, work item = (query tile, range), partial top-k lists go
-// to part_d / part_i [(tile * nsplit + range) * TQ + row][k] and knn_merge_kernel picks the final k: this keeps
-// all SMs busy when only a few query rows are recomputed.  gate: 0 = always run, 1 = run only if the device-side
-// count is <= gate_cap (split mode), 2 = run only if it is > gate_cap (one item per query tile).
 __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict__ q, const int64_t* __restrict__ q_ids,
                                                         const int* __restrict__ n_ids_dev, int64_t nq,
                                                         const float* __restrict__ ref, int64_t nref, int dim,
                                                         int64_t ld, int64_t ldr, int k, int64_t self_offset,
-                                                        int64_t* __restrict__ out_idx, float* __restrict__ out_dist,
-                                                        int nsplit, float* __restrict__ part_d,
-                                                        int* __restrict__ part_i, int gate, int gate_cap) {
+                                                        int64_t* __restrict__ out_idx, float* __restrict__ out_dist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int dim_pad = (dim + DK - 1) / DK * DK;
   float* Qs = reinterpret_cast<float*>(smem_raw);
@@ -34,13 +29,10 @@ __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict_
   int* Li = reinterpret_cast<int*>(Ld + (size_t)TQ * k);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   if (n_ids_dev) nq = *n_ids_dev;
-  if ((gate == 1 && nq > gate_cap) || (gate == 2 && nq <= gate_cap)) return;
   const int64_t n_qtiles = (nq + TQ - 1) / TQ;
-  const int64_t refs_per_split = ((nref + nsplit - 1) / nsplit + TR - 1) / TR * TR;
- for (int64_t item = blockIdx.x; item < n_qtiles * nsplit; item += gridDim.x) {
-  const int64_t q0 = (item / nsplit) * TQ;
-  const int sp = (int)(item % nsplit);
-  const int64_t ref_begin = sp * refs_per_split, ref_end = min(ref_begin + refs_per_split, nref);
+ for (int64_t item = blockIdx.x; item < n_qtiles; item += gridDim.x) {
+  const int64_t q0 = item * TQ;
+  const int64_t ref_begin = 0, ref_end = nref;
   __syncthreads();  // previous item's lists / Qs fully consumed
   // query tile, transposed, zero padded
   for (int e = tid; e < dim_pad * TQ; e += 256) {
@@ -116,60 +108,13 @@ __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict_
     // the next tile's first __syncthreads (after loading Rs) orders these reads of Ds before its rewrite
   }
   if (tid < TQ && q0 + tid < nq) {
-    if (nsplit == 1) {
-      const int64_t qi = q_ids ? q_ids[q0 + tid] : q0 + tid;
-      for (int p = 0; p < k; ++p) {
-        out_idx[qi * k + p] = p < cnt ? (int64_t)Li[(size_t)tid * k + p] : -1;
-        out_dist[qi * k + p] = p < cnt ? Ld[(size_t)tid * k + p] : FLT_MAX;
-      }
-    } else {
-      const size_t base = ((size_t)item * TQ + tid) * k;
-      for (int p = 0; p < k; ++p) {
-        part_i[base + p] = p < cnt ? Li[(size_t)tid * k + p] : -1;
-        part_d[base + p] = p < cnt ? Ld[(size_t)tid * k + p] : FLT_MAX;
-      }
+    const int64_t qi = q_ids ? q_ids[q0 + tid] : q0 + tid;
+    for (int p = 0; p < k; ++p) {
+      out_idx[qi * k + p] = p < cnt ? (int64_t)Li[(size_t)tid * k + p] : -1;
+      out_dist[qi * k + p] = p < cnt ? Ld[(size_t)tid * k + p] : FLT_MAX;
     }
   }
  }
-}
-
-// one warp per recomputed query: final k of the nsplit partial lists, ordered by (distance, index)
-__global__ void __launch_bounds__(256) knn_merge_kernel(const int64_t* __restrict__ q_ids,
-                                                        const int* __restrict__ n_ids_dev, int k, int nsplit,
-                                                        const float* __restrict__ part_d,
-                                                        const int* __restrict__ part_i, int64_t* __restrict__ out_idx,
-                                                        float* __restrict__ out_dist, int gate_cap) {
-  const int n = *n_ids_dev;
-  if (n > gate_cap) return;
-  const int lane = threadIdx.x & 31;
-  for (int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); w < n; w += (int64_t)gridDim.x * 8) {
-    const int64_t tile = w / TQ, rowi = w % TQ;
-    const int64_t qi = q_ids[w];
-    unsigned long long last = 0;  // keys are unique (distinct ids): strictly increasing picks
-    bool first = true;
-    for (int r = 0; r < k; ++r) {
-      unsigned long long best = ~0ull;
-      for (int c = lane; c < nsplit * k; c += 32) {
-        const int sp = c / k, e = c % k;
-        const size_t at = (((size_t)tile * nsplit + sp) * TQ + rowi) * k + e;
-        const int j = part_i[at];
-        if (j < 0) continue;
-        const unsigned long long key = ((unsigned long long)__float_as_uint(part_d[at]) << 32) | (unsigned)j;
-        if ((first || key > last) && key < best) best = key;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(SCF_FULL, best, o);
-        best = other < best ? other : best;
-      }
-      if (lane == 0) {
-        out_idx[qi * k + r] = best == ~0ull ? -1 : (int64_t)(best & 0xffffffffull);
-        out_dist[qi * k + r] = best == ~0ull ? FLT_MAX : __uint_as_float((unsigned)(best >> 32));
-      }
-      last = best;
-      first = false;
-    }
-  }
 }
 
 }  // namespace
@@ -204,35 +149,174 @@ int32_t knn_exact_launch(const float* q, const int64_t* q_ids, const int* n_ids_
   const int64_t tiles = (nq + TQ - 1) / TQ;
   const unsigned grid = (unsigned)(n_ids_dev ? (tiles < 4 * SCF_NUM_SMS ? tiles : 4 * SCF_NUM_SMS) : tiles);
   knn_exact_kernel<<<grid, 256, smem, stream>>>(q, q_ids, n_ids_dev, nq, ref, nref, dim, ld, ldr, k, self_offset,
-                                                out_idx, out_dist, 1, nullptr, nullptr, 0, 0);
+                                                out_idx, out_dist);
   return scf_check_launch("scf_knn_l2(exact)");
 }
 
-// Recompute the rows listed in q_ids[0 .. *n_ids_dev): few rows -> reference-split work items + merge,
-// many rows -> one work item per query tile.  scratch: knn_exact_fix_scratch_bytes(k).
-size_t knn_exact_fix_scratch_bytes(int k) { return (size_t)KNN_FIX_CAP * KNN_FIX_NSPLIT * k * 8; }
+// ---------------------------------------------------------------------------------------------------------
+// Repair of the rows the tcgen05 path could not prove (knn_tc.cu): the re-rank kernel leaves, per failed row,
+// the (distance, index) key of its current k-th candidate.  The true k nearest all have keys <= that key, so one
+// threshold scan over the references with the oracle's FP64 arithmetic collects them (normally k plus a handful);
+// a warp then picks the k smallest.  Rows whose list overflows (or that had fewer than k candidates, or that do not
+// fit the scratch) go through knn_exact_kernel.
+//   scratch: [FIX_ROWS] int cnt | [FIX_ROWS][FIX_LIST] u64 keys | [nq] i64 slow_ids | int slow_count
+namespace {
 
-int32_t knn_exact_fix_launch(const float* q, const int64_t* q_ids, const int* n_ids_dev, int64_t nq_max,
-                             const float* ref, int64_t nref, int dim, int64_t ld, int k, int64_t self_offset,
-                             int64_t* out_idx, float* out_dist, void* scratch, cudaStream_t stream) {
+constexpr int FIX_QG = 8;         // failed rows per work item (each staged reference is used FIX_QG times)
+constexpr int FIX_LIST = 256;     // collected keys per row
+constexpr int FIX_ROWS = KNN_FIX_CAP;
+constexpr int FIX_MAXDIM = 128;
+
+__global__ void __launch_bounds__(256) knn_fix_scan_kernel(const float* __restrict__ q, const int64_t* __restrict__ q_ids,
+                                                           const unsigned long long* __restrict__ q_keys,
+                                                           const int* __restrict__ n_ids_dev,
+                                                           const float* __restrict__ ref, int64_t nref, int dim,
+                                                           int64_t ld, int64_t self_offset, int refs_per_split,
+                                                           int nsplit, int* __restrict__ cnt,
+                                                           unsigned long long* __restrict__ lists) {
+  __shared__ double aq[FIX_QG][FIX_MAXDIM];
+  __shared__ unsigned long long kth[FIX_QG];
+  __shared__ long long selfs[FIX_QG];
+  const int n = min(*n_ids_dev, FIX_ROWS);
+  const int ngroups = (n + FIX_QG - 1) / FIX_QG;
+  for (int item = blockIdx.x; item < ngroups * nsplit; item += gridDim.x) {
+    const int g = item / nsplit, sp = item % nsplit;
+    __syncthreads();
+    for (int e = threadIdx.x; e < FIX_QG * dim; e += blockDim.x) {
+      const int qq = e / dim, t = e % dim;
+      const int slot = g * FIX_QG + qq;
+      aq[qq][t] = slot < n ? (double)q[q_ids[slot] * ld + t] : 0.0;
+    }
+    if (threadIdx.x < FIX_QG) {
+      const int slot = g * FIX_QG + threadIdx.x;
+      kth[threadIdx.x] = slot < n ? q_keys[slot] : 0ull;  // key 0: nothing passes
+      selfs[threadIdx.x] = (slot < n && self_offset >= 0) ? q_ids[slot] + self_offset : -1;
+    }
+    __syncthreads();
+    const int64_t r0 = (int64_t)sp * refs_per_split, r1 = min(r0 + (int64_t)refs_per_split, nref);
+    for (int64_t j = r0 + threadIdx.x; j < r1; j += blockDim.x) {
+      const float* b = ref + j * ld;
+      double acc[FIX_QG];
+#pragma unroll
+      for (int qq = 0; qq < FIX_QG; ++qq) acc[qq] = 0.0;
+      int t = 0;
+      for (; t + 4 <= dim; t += 4) {  // rows are 16-byte aligned (ld is a multiple of 4 floats, checked by the host)
+        const float4 v = __ldg(reinterpret_cast<const float4*>(b + t));
+        const double bv[4] = {(double)v.x, (double)v.y, (double)v.z, (double)v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int qq = 0; qq < FIX_QG; ++qq) {
+            const double df = __dsub_rn(aq[qq][t + u], bv[u]);
+            acc[qq] = __dadd_rn(acc[qq], __dmul_rn(df, df));
+          }
+      }
+      for (; t < dim; ++t) {
+        const double bvv = (double)__ldg(b + t);
+#pragma unroll
+        for (int qq = 0; qq < FIX_QG; ++qq) {
+          const double df = __dsub_rn(aq[qq][t], bvv);
+          acc[qq] = __dadd_rn(acc[qq], __dmul_rn(df, df));
+        }
+      }
+#pragma unroll
+      for (int qq = 0; qq < FIX_QG; ++qq) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint((float)acc[qq]) << 32) | (unsigned)j;
+        if (key <= kth[qq] && j != selfs[qq]) {
+          const int slot = g * FIX_QG + qq;
+          const int pos = atomicAdd(cnt + slot, 1);
+          if (pos < FIX_LIST) lists[(size_t)slot * FIX_LIST + pos] = key;
+        }
+      }
+    }
+  }
+}
+
+// one warp per failed row: the k smallest collected keys; rows that cannot be finished here go on the slow list
+__global__ void __launch_bounds__(256) knn_fix_select_kernel(const int64_t* __restrict__ q_ids,
+                                                             const int* __restrict__ n_ids_dev, int k,
+                                                             const int* __restrict__ cnt,
+                                                             const unsigned long long* __restrict__ lists,
+                                                             int64_t* __restrict__ out_idx, float* __restrict__ out_dist,
+                                                             int64_t* __restrict__ slow_ids, int* __restrict__ slow_count) {
+  const int nfail = *n_ids_dev;
+  const int lane = threadIdx.x & 31;
+  for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < nfail; w += gridDim.x * 8) {
+    const int c = w < FIX_ROWS ? cnt[w] : -1;
+    if (c < k || c > FIX_LIST) {  // overflow, beyond the scratch, or an unusable threshold
+      if (lane == 0) slow_ids[atomicAdd(slow_count, 1)] = q_ids[w];
+      continue;
+    }
+    const int64_t qi = q_ids[w];
+    unsigned long long key[FIX_LIST / 32];
+#pragma unroll
+    for (int u = 0; u < FIX_LIST / 32; ++u) {
+      const int e = lane + 32 * u;
+      key[u] = e < c ? lists[(size_t)w * FIX_LIST + e] : ~0ull;
+    }
+    for (int r = 0; r < k; ++r) {
+      unsigned long long best = key[0];
+#pragma unroll
+      for (int u = 1; u < FIX_LIST / 32; ++u) best = best < key[u] ? best : key[u];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(SCF_FULL, best, o);
+        best = other < best ? other : best;
+      }
+#pragma unroll
+      for (int u = 0; u < FIX_LIST / 32; ++u)
+        if (key[u] == best) key[u] = ~0ull;  // keys are unique (distinct reference ids)
+      if (lane == 0) {
+        out_idx[qi * k + r] = (int64_t)(best & 0xffffffffull);
+        out_dist[qi * k + r] = __uint_as_float((unsigned)(best >> 32));
+      }
+    }
+  }
+}
+
+}  // namespace
+
+size_t knn_exact_fix_scratch_bytes(int64_t nq, int k) {
+  (void)k;
+  return (size_t)FIX_ROWS * 4 + (size_t)FIX_ROWS * FIX_LIST * 8 + (size_t)nq * 8 + 256;
+}
+
+int32_t knn_exact_fix_launch(const float* q, const int64_t* q_ids, const unsigned long long* q_keys,
+                             const int* n_ids_dev, int64_t nq_max, const float* ref, int64_t nref, int dim, int64_t ld,
+                             int k, int64_t self_offset, int64_t* out_idx, float* out_dist, void* scratch,
+                             cudaStream_t stream) {
   if (nq_max == 0) return 0;
   size_t smem;
   int32_t rc = exact_prepare(dim, k, smem);
   if (rc) return rc;
-  float* part_d = (float*)scratch;
-  int* part_i = (int*)((unsigned char*)scratch + (size_t)KNN_FIX_CAP * KNN_FIX_NSPLIT * k * 4);
-  knn_exact_kernel<<<2 * SCF_NUM_SMS, 256, smem, stream>>>(q, q_ids, n_ids_dev, nq_max, ref, nref, dim, ld, ld, k,
-                                                           self_offset, out_idx, out_dist, KNN_FIX_NSPLIT, part_d,
-                                                           part_i, 1, KNN_FIX_CAP);
-  rc = scf_check_launch("scf_knn_l2(fix,split)");
-  if (rc) return rc;
-  knn_merge_kernel<<<SCF_NUM_SMS, 256, 0, stream>>>(q_ids, n_ids_dev, k, KNN_FIX_NSPLIT, part_d, part_i, out_idx,
-                                                    out_dist, KNN_FIX_CAP);
-  rc = scf_check_launch("scf_knn_l2(fix,merge)");
+  unsigned char* sc = (unsigned char*)scratch;
+  int* cnt = (int*)sc;
+  unsigned long long* lists = (unsigned long long*)(sc + (size_t)FIX_ROWS * 4);
+  int64_t* slow_ids = (int64_t*)(sc + (size_t)FIX_ROWS * 4 + (size_t)FIX_ROWS * FIX_LIST * 8);
+  int* slow_count = (int*)(sc + (size_t)FIX_ROWS * 4 + (size_t)FIX_ROWS * FIX_LIST * 8 + (size_t)nq_max * 8);
+  cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)FIX_ROWS * 4, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(slow_count, 0, 4, stream);
+  if (e != cudaSuccess) {
+    scf_set_error("scf_knn_l2(fix): %s", cudaGetErrorString(e));
+    return -(int32_t)e;
+  }
+  const bool scan_ok = dim <= FIX_MAXDIM && (ld & 3) == 0 && k <= FIX_LIST;
+  if (scan_ok) {
+    int refs_per_split = (int)std::max<int64_t>(1024, (nref + 63) / 64);
+    refs_per_split = (refs_per_split + 255) / 256 * 256;
+    const int nsplit = (int)((nref + refs_per_split - 1) / refs_per_split);
+    knn_fix_scan_kernel<<<4 * SCF_NUM_SMS, 256, 0, stream>>>(q, q_ids, q_keys, n_ids_dev, ref, nref, dim, ld,
+                                                             self_offset, refs_per_split, nsplit, cnt, lists);
+    rc = scf_check_launch("scf_knn_l2(fix,scan)");
+    if (rc) return rc;
+  }  // otherwise every count stays 0 < k and all failed rows take the slow path
+  knn_fix_select_kernel<<<SCF_NUM_SMS, 256, 0, stream>>>(q_ids, n_ids_dev, k, cnt, lists, out_idx, out_dist, slow_ids,
+                                                         slow_count);
+  rc = scf_check_launch("scf_knn_l2(fix,select)");
   if (rc) return rc;
   const int64_t tiles = (nq_max + TQ - 1) / TQ;
   const unsigned grid = (unsigned)(tiles < 4 * SCF_NUM_SMS ? tiles : 4 * SCF_NUM_SMS);
-  knn_exact_kernel<<<grid, 256, smem, stream>>>(q, q_ids, n_ids_dev, nq_max, ref, nref, dim, ld, ld, k, self_offset,
-                                                out_idx, out_dist, 1, nullptr, nullptr, 2, KNN_FIX_CAP);
-  return scf_check_launch("scf_knn_l2(fix,full)");
+  knn_exact_kernel<<<grid, 256, smem, stream>>>(q, slow_ids, slow_count, nq_max, ref, nref, dim, ld, ld, k, self_offset,
+                                                out_idx, out_dist);
+  return scf_check_launch("scf_knn_l2(fix,slow)");
 }

@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
                                                          const float* __restrict__ qerr,
                                                          const float* __restrict__ bmax, int64_t* __restrict__ out_idx,
                                                          float* __restrict__ out_dist, int64_t* __restrict__ fail_ids,
+                                                         unsigned long long* __restrict__ fail_keys,
                                                          int* __restrict__ fail_count) {
   const int lane = threadIdx.x & 31;
   const int64_t qi = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -446,7 +447,11 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
       const float dk = __uint_as_float((unsigned)(last >> 32));
       ok = lower > 0.0 && dk < __double2float_rd(lower);  // strict: a tie would be decided by the index
     }
-    if (!ok) fail_ids[atomicAdd(fail_count, 1)] = qi;
+    if (!ok) {  // the repair scans the references for every key <= the current k-th candidate's
+      const int slot = atomicAdd(fail_count, 1);
+      fail_ids[slot] = qi;
+      fail_keys[slot] = enough ? last : ~0ull;
+    }
   }
 }
 
@@ -462,7 +467,7 @@ struct Plan {
   int64_t nq_pad, nr_pad;
   size_t smem;
   // workspace offsets (bytes)
-  size_t off_qop, off_rop, off_qn, off_qe, off_cs, off_ci, off_tau, off_fail, off_misc, off_fix, total;
+  size_t off_qop, off_rop, off_qn, off_qe, off_cs, off_ci, off_tau, off_fail, off_fkey, off_misc, off_fix, total;
 };
 
 bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
@@ -500,8 +505,9 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.off_ci = o, o = al(o + (size_t)pl.nq_pad * pl.nsplit * pl.kc * 4);
   pl.off_tau = o, o = al(o + (size_t)pl.nq_pad * pl.nsplit * 4);
   pl.off_fail = o, o = al(o + (size_t)nq * 8);
+  pl.off_fkey = o, o = al(o + (size_t)nq * 8);
   pl.off_misc = o, o = al(o + 256);
-  pl.off_fix = o, o = al(o + knn_exact_fix_scratch_bytes(k));
+  pl.off_fix = o, o = al(o + knn_exact_fix_scratch_bytes(nq, k));
   pl.total = o;
   return true;
 }
@@ -540,6 +546,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   int* ci = (int*)(ws + pl.off_ci);
   float* ctau = (float*)(ws + pl.off_tau);
   int64_t* fail_ids = (int64_t*)(ws + pl.off_fail);
+  unsigned long long* fail_keys = (unsigned long long*)(ws + pl.off_fkey);
   int* fail_count = (int*)(ws + pl.off_misc);
   float* bmax = (float*)(ws + pl.off_misc + 64);
   cudaError_t e = cudaMemsetAsync(ws + pl.off_misc, 0, 256, stream);
@@ -577,7 +584,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   if (rc) return rc;
   knn_rerank_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(q, nq, ref, nref, dim, ld, k, self_offset, pl.kc,
                                                                   pl.nsplit, cs, ci, ctau, qn, qe, bmax, out_idx, out_dist,
-                                                                  fail_ids, fail_count);
+                                                                  fail_ids, fail_keys, fail_count);
   rc = scf_check_launch("scf_knn_l2(rerank)");
   if (rc) return rc;
   if (prm.flags & 16) {
@@ -590,6 +597,6 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     memset(h, 0, sizeof(h));
     cudaMemcpyToSymbol(g_dbg, h, sizeof(h));
   }
-  return knn_exact_fix_launch(q, fail_ids, fail_count, nq, ref, nref, dim, ld, k, self_offset, out_idx, out_dist,
-                              ws + pl.off_fix, stream);
+  return knn_exact_fix_launch(q, fail_ids, fail_keys, fail_count, nq, ref, nref, dim, ld, k, self_offset, out_idx,
+                              out_dist, ws + pl.off_fix, stream);
 }

@@ -98,16 +98,19 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(const void* smem_tile) {
   d |= (uint64_t)2 << 61;                                 // layout type SWIZZLE_128B          [61,64)
   return d;
 }
-// Same, MN-major operand (the MN index is contiguous in memory): rows of 128 B hold 32 consecutive
-// MN positions of one k; 8 consecutive k form a 1024-B swizzle atom.  LBO = byte distance between
-// 32-wide MN blocks, SBO = byte distance between 8-k groups.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(const void* smem_tile, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major operand of 32-bit (tf32) elements: the MN index is contiguous in memory.  The only layout the tensor
+// core accepts here is SWIZZLE_128B_BASE32B (layout type 1): rows of 128 B hold 32 consecutive MN positions of
+// one k, the 32-byte chunks of a row are XORed with (row % 4), 4 consecutive k form a 512-B atom
+// (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  LBO = byte distance between 32-wide MN blocks, SBO = byte
+// distance between 4-k atoms; one K = 8 instruction consumes two atoms.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(const void* smem_tile, uint32_t lbo_bytes,
+                                                            uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
   return d;
 }
 // Instruction descriptor for kind::tf32, FP32 accumulate, dense.

@@ -189,18 +189,19 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
 
     # ---- Z (K1) ----
     ldz = round_up(n_feat, 128)
-    n_pad = round_up(max(n_local, 1), lib.GRAM_SLAB)
-    z = torch.empty((n_pad, ldz), dtype=torch.float32, device=dev)
-    z[n_local:].zero_()
-    ops.csr_norm_scale(csr, cell_idx, col_map, n_feat, row_sum, z, SF, log_transform, mu_d, sigma_d)
+    z = torch.empty((max(n_local, 1), ldz), dtype=torch.float32, device=dev)
+    z_lo = torch.empty_like(z) if (gram_mode == 3 and loadings is None) else None
+    ops.csr_norm_scale(csr, cell_idx, col_map, n_feat, row_sum, z, SF, log_transform, mu_d, sigma_d, z_lo=z_lo)
     mark("normalise")
 
     # ---- PCA: Gram (K2, collective 2b) + eigensolve (K3) ----
     if loadings is None:
-        g_fx = ops.gram_accumulate(z, n_pad, n_feat, mode=gram_mode)
+        g_fx = ops.gram_accumulate(z, n_local, n_feat, mode=gram_mode, z_lo=z_lo)
         comm.allreduce_sum_(g_fx)
+        ops.gram_symmetrize(g_fx, n_feat)
+        del z_lo
         mark("gram")
-        cov = g_fx.to(torch.float64) * (2.0 ** -lib.GRAM_SHIFT / max(n_total - 1, 1))
+        cov = g_fx[:n_feat, :n_feat].to(torch.float64) * (2.0 ** -lib.GRAM_SHIFT / max(n_total - 1, 1))
         evals, load = eig_topk(cov, dims)
         mark("eig")
     else:

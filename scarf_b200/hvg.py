@@ -14,8 +14,21 @@ DEFAULT_BLACKLIST = "^MT-|^RPS|^RPL|^MRPS|^MRPL|^CCN|^HLA-|^H2-|^HIST"  # scarf/
 
 
 def _lowess(y, x, frac, it):
-    """Cleveland's robust LOWESS as statsmodels' ``lowess(endog, exog, frac, it, delta=0,
-    return_sorted=False)`` computes it (scarf/feat_utils.py:38-40), all windows evaluated at once."""
+    """statsmodels' ``lowess(endog, exog, frac, it, delta=0, return_sorted=False)`` (scarf/feat_utils.py:38-40)
+    through the library's native host routine (statsmodels' own is Cython); :func:`_lowess_numpy` is the
+    all-numpy statement of the same algorithm the tests compare it with."""
+    from . import lib
+
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(y)
+    lib.call("scf_host_lowess", y.ctypes.data, x.ctypes.data, int(y.size), float(frac), int(it), out.ctypes.data,
+             launches=0)
+    return out
+
+
+def _lowess_numpy(y, x, frac, it):
+    """Cleveland's robust LOWESS, all windows evaluated at once."""
     order = np.argsort(x, kind="stable")
     x, y = x[order], y[order]
     n = x.size
@@ -42,7 +55,11 @@ def _lowess(y, x, frac, it):
     tri[~np.isfinite(tri)] = 0.0
     rw = np.ones(n)
     fit = np.zeros(n)
+    prev_rw = None
     for _ in range(it + 1):
+        if prev_rw is not None and np.array_equal(rw, prev_rw):
+            break  # fixed point reached bit for bit: every later iteration would reproduce `fit`
+        prev_rw = rw
         w = tri * rw[win]
         sw = w.sum(axis=1, keepdims=True)
         ok = sw[:, 0] > 0
@@ -71,16 +88,15 @@ def fit_lowess(a, b, n_bins=200, lowess_frac=0.1):
     edges[-1] += 0.1
     which = np.searchsorted(edges, la, side="right") - 1  # edges[i] <= la < edges[i+1]
     which[(which < 0) | (which >= n_bins)] = -1
-    bx, by, bins = [], [], []
-    for t in np.unique(which[which >= 0]):
-        members = np.where(which == t)[0]
-        g = members[np.argmin(lb[members])]
-        bins.append(t)
-        bx.append(la[g])
-        by.append(lb[g])
-    fit = _lowess(np.asarray(by), np.asarray(bx), lowess_frac, 100)
+    # min-log(b) gene of every non-empty bin (first one on ties, like argmin over the bin's members)
+    order = np.lexsort((lb, which))
+    order = order[which[order] >= 0]
+    w_sorted = which[order]
+    firsts = order[np.r_[True, w_sorted[1:] != w_sorted[:-1]]] if order.size else order
+    bins = which[firsts]
+    fit = _lowess(lb[firsts], la[firsts], lowess_frac, 100)
     fit_of_bin = np.full(n_bins, np.nan)
-    fit_of_bin[np.asarray(bins)] = fit
+    fit_of_bin[bins] = fit
     out = np.zeros(la.size)
     sel = which >= 0
     out[sel] = np.exp(lb[sel] - fit_of_bin[which[sel]])

@@ -20,8 +20,9 @@ SIGNATURES = {
     "scf_csr_row_sums": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "scf_csr_gene_stats": (_i32, [_p, _p, _p, _p, _i64, _i32, _p, _f64, _p, _p, _p, _p]),
     "scf_csr_hvg_colstats": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _f64, _i32, _p, _p, _p]),
-    "scf_csr_norm_scale": (_i32, [_p, _p, _p, _p, _i64, _p, _i32, _p, _f64, _i32, _p, _p, _p, _p, _i64, _p]),
-    "scf_gram_accumulate": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _i32, _p]),
+    "scf_csr_norm_scale": (_i32, [_p, _p, _p, _p, _i64, _p, _i32, _p, _f64, _i32, _p, _p, _p, _p, _p, _i64, _p]),
+    "scf_gram_accumulate": (_i32, [_p, _p, _i64, _i64, _i32, _p, _i64, _i32, _p]),
+    "scf_gram_symmetrize": (_i32, [_p, _i32, _i64, _p]),
     "scf_project": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _i32, _p, _i64, _p]),
     "scf_knn_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32]),
     "scf_knn_fail_count_offset": (_i64, [_i64, _i64, _i32, _i32, _i32]),
@@ -30,11 +31,12 @@ SIGNATURES = {
     "scf_smooth_knn": (_i32, [_p, _i64, _i32, _f32, _f32, _i64, _i64, _p, _p, _p, _p]),
     "scf_membership_coo": (_i32, [_p, _p, _p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p]),
     "scf_fill_zero_weights": (_i32, [_p, _i64, _f32, _p]),
+    "scf_host_lowess": (_i32, [_p, _p, _i64, _f64, _i32, _p]),
 }
 
 COLSTAT_SHIFT = 34
 GRAM_SHIFT = 36
-GRAM_SLAB = 2048
+GRAM_SLAB = 1000
 
 
 class ScarfB200Error(RuntimeError):
@@ -64,10 +66,10 @@ LAUNCHES = {"n": 0}  # kernel launches issued through the C-ABI (bench.py report
 _LAUNCHES_PER_CALL = {"scf_knn_l2": 1}
 
 
-def call(name: str, *args):
+def call(name: str, *args, launches=None):
     """Calls a status-returning entry point and raises with the library's error text."""
     rc = getattr(_lib, name)(*args)
-    LAUNCHES["n"] += _LAUNCHES_PER_CALL.get(name, 1)
+    LAUNCHES["n"] += _LAUNCHES_PER_CALL.get(name, 1) if launches is None else launches
     if rc != 0:
         msg = _lib.scf_last_error().decode("utf-8", "replace")
         if rc > 0:

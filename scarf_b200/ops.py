@@ -111,25 +111,37 @@ def csr_hvg_colstats(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, sf=1000.
 
 
 def csr_norm_scale(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, z, sf=1000.0, log_transform=True, mu=None,
-                   sigma=None, missing_fill=None):
-    """Writes rows [0, n_sel) of the float32 matrix z (row stride z.stride(0)) with (x - mu)/sigma."""
+                   sigma=None, missing_fill=None, z_lo=None):
+    """Writes rows [0, n_sel) of the float32 matrix z (row stride z.stride(0)) with (x - mu)/sigma; ``z_lo``
+    (optional, same shape and stride) receives z - tf32_trunc(z) for the 3xTF32 Gram."""
     n = csr.n_rows if row_ids is None else int(row_ids.numel())
     _chk(z, torch.float32, "z"), _chk(mu, torch.float64, "mu"), _chk(sigma, torch.float64, "sigma")
     assert z.dim() == 2 and z.stride(1) == 1 and z.shape[0] >= n and z.is_cuda
+    if z_lo is not None:
+        assert z_lo.dtype == torch.float32 and z_lo.shape == z.shape and z_lo.stride() == z.stride()
     lib.call("scf_csr_norm_scale", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
              _ptr(col_map), int(n_cols), _ptr(row_sum), float(sf), int(bool(log_transform)), _ptr(mu), _ptr(sigma),
-             _ptr(missing_fill), z.data_ptr(), int(z.stride(0)), _stream())
+             _ptr(missing_fill), z.data_ptr(), z_lo.data_ptr() if z_lo is not None else None, int(z.stride(0)),
+             _stream())
     return z
 
 
 # ------------------------------------------------------------------------------------------ K2 / K4
-def gram_accumulate(z, n_rows, n_cols, g_fx=None, mode=0):
-    """g_fx (int64 [n_cols, n_cols], << lib.GRAM_SHIFT) += Z[:n_rows, :n_cols]^T Z[:n_rows, :n_cols]."""
+def gram_accumulate(z, n_rows, n_cols, g_fx=None, mode=0, z_lo=None):
+    """g_fx (int64, << lib.GRAM_SHIFT) += Z[:n_rows, :n_cols]^T Z[:n_rows, :n_cols], upper triangle; call
+    :func:`gram_symmetrize` after the last accumulation / all-reduce.  g_fx is allocated [ldz, ldz] so that the
+    tensor-core epilogue never needs to clip a row segment."""
     assert z.dtype == torch.float32 and z.stride(1) == 1
     if g_fx is None:
-        g_fx = torch.zeros((n_cols, n_cols), dtype=torch.int64, device=z.device)
-    lib.call("scf_gram_accumulate", z.data_ptr(), int(z.stride(0)), int(n_rows), int(n_cols), _ptr(g_fx),
-             int(g_fx.stride(0)), int(mode), _stream())
+        ld = round_up(n_cols, 32)
+        g_fx = torch.zeros((ld, ld), dtype=torch.int64, device=z.device)
+    lib.call("scf_gram_accumulate", z.data_ptr(), z_lo.data_ptr() if z_lo is not None else None, int(z.stride(0)),
+             int(n_rows), int(n_cols), _ptr(g_fx), int(g_fx.stride(0)), int(mode), _stream())
+    return g_fx
+
+
+def gram_symmetrize(g_fx, n_cols):
+    lib.call("scf_gram_symmetrize", _ptr(g_fx), int(n_cols), int(g_fx.stride(0)), _stream())
     return g_fx
 
 

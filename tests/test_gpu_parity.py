@@ -12,10 +12,10 @@ pytestmark = pytest.mark.gpu
 def gpu():
     import torch
 
-    from scarf_b200 import graph, ops, synth
+    from scarf_b200 import graph, lib, ops, synth
 
     torch.cuda.set_device(0)
-    return {"torch": torch, "graph": graph, "ops": ops, "synth": synth}
+    return {"torch": torch, "graph": graph, "ops": ops, "synth": synth, "lib": lib}
 
 
 @pytest.fixture(scope="module")
@@ -166,6 +166,74 @@ def test_weights_vs_oracle(chain):
     edges_o, w_o = P.smoothen_dists(idx, dist, 1.0, 1.5, 1000)
     assert np.array_equal(res.edges.cpu().numpy().astype(np.uint64), edges_o)
     assert np.abs(res.weights.cpu().numpy().astype(np.float64) - w_o).max() < 1e-5
+
+
+@pytest.mark.parametrize("n_rows,n_cols,ldz", [(3000, 500, 512), (1000, 100, 128), (2617, 1999, 2048), (8, 33, 64),
+                                               (5001, 300, 320)])
+def test_gram_tensor_core_modes(gpu, n_rows, n_cols, ldz):
+    """K2 on tcgen05 vs float64: 3xTF32 within FP32-accumulation error, plain TF32 within the 2^-10 truncation of the
+    operands; the FP32 SIMT path is the anchor; integer accumulation makes repeated calls bit-identical."""
+    torch, ops, lib = gpu["torch"], gpu["ops"], gpu["lib"]
+    g = torch.Generator(device="cuda").manual_seed(n_rows + n_cols)
+    z = torch.zeros((n_rows, ldz), dtype=torch.float32, device="cuda")
+    z[:, :n_cols] = torch.randn((n_rows, n_cols), generator=g, device="cuda") * \
+        (1.0 + 3.0 * torch.rand((1, n_cols), generator=g, device="cuda"))
+    z[:, :n_cols] += 0.3 * z[:, :1]  # correlated columns: off-diagonal entries of the order of the diagonal
+    z_lo = z - (z.view(torch.int32) & -8192).view(torch.float32)
+    ref = (z[:, :n_cols].double().T @ z[:, :n_cols].double()).cpu().numpy()
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    out = {}
+    for mode in (0, 1, 3):
+        gfx = ops.gram_accumulate(z, n_rows, n_cols, mode=mode, z_lo=z_lo if mode == 3 else None)
+        ops.gram_symmetrize(gfx, n_cols)
+        torch.cuda.synchronize()
+        gm = gfx[:n_cols, :n_cols].cpu().numpy().astype(np.float64) * 2.0 ** -lib.GRAM_SHIFT
+        assert np.array_equal(gm, gm.T)
+        assert np.all(gfx[n_cols:].cpu().numpy() == 0) and np.all(gfx[:, n_cols:].cpu().numpy() == 0)
+        out[mode] = np.abs(gm - ref) / scale
+    assert out[0].max() < 2e-6, out[0].max()
+    # tensor-core FP32 accumulation rounds toward zero: ~2^-24 per MMA over <= 375 chained MMAs per slab
+    assert out[3].max() < 5e-5, out[3].max()
+    assert out[1].max() < 2.5e-3, out[1].max()
+    again = ops.gram_accumulate(z, n_rows, n_cols, mode=3, z_lo=z_lo)
+    ops.gram_symmetrize(again, n_cols)
+    assert torch.equal(again, gfx)
+
+
+def test_gram_is_invariant_to_row_sharding(gpu):
+    """Slab-aligned shards accumulated one after another (as ranks would, then all-reduce) give the same integers."""
+    torch, ops = gpu["torch"], gpu["ops"]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    z = torch.zeros((7300, 256), dtype=torch.float32, device="cuda")
+    z[:, :200] = torch.randn((7300, 200), generator=g, device="cuda")
+    z_lo = z - (z.view(torch.int32) & -8192).view(torch.float32)
+    for mode in (1, 3, 0):
+        whole = ops.gram_accumulate(z, 7300, 200, mode=mode, z_lo=z_lo)
+        parts = None
+        for a, b in ((0, 3000), (3000, 4000), (4000, 7300)):
+            parts = ops.gram_accumulate(z[a:b], b - a, 200, g_fx=parts, mode=mode, z_lo=z_lo[a:b])
+        assert torch.equal(whole, parts), mode
+
+
+@pytest.mark.parametrize("gram_mode,knn_method", [(3, 1), (1, 1)])
+def test_chain_tensor_core_path(gpu, chain, gram_mode, knn_method):
+    """The production configuration (tcgen05 Gram + tcgen05 kNN) against the FP32-SIMT / FP64 anchor chain."""
+    torch, graph = gpu["torch"], gpu["graph"]
+    res0 = chain["res"]
+    res = graph.make_graph_csr(chain["csr"], torch.from_numpy(chain["cell_idx"]).cuda(), chain["hv"], dims=20, k=11,
+                               gram_mode=gram_mode, knn_method=knn_method)
+    l0, l1 = res0.loadings.cpu().numpy(), res.loadings.cpu().numpy()
+    cos = np.abs(np.sum(l0 * l1, axis=0))
+    tol = 1e-4 if gram_mode == 3 else 5e-3
+    assert np.all(np.arccos(np.clip(cos, 0, 1)) < tol), np.arccos(np.clip(cos, 0, 1)).max()
+    y0, y1 = res0.embedding.cpu().numpy(), res.embedding.cpu().numpy()
+    assert np.abs(y0 - y1).max() < (1e-3 if gram_mode == 3 else 5e-2)
+    # kNN must be exact on ITS OWN embedding whatever the Gram precision was
+    from oracle import pipeline as P
+    y = y1[:, : res.dims]
+    idx_o, dist_o = P.exact_knn(y, y, res.k, self_offset=0)
+    assert np.array_equal(res.indices.cpu().numpy().astype(np.uint64), idx_o)
+    assert np.array_equal(res.distances.cpu().numpy(), dist_o)
 
 
 @pytest.mark.parametrize("method", [0, 1])

@@ -68,7 +68,7 @@ def test_hvg_host_logic_matches_oracle(pbmc):
 
 def test_lowess_ties_and_small_windows():
     from oracle.lowess import lowess as lowess_o
-    from scarf_b200.hvg import _lowess
+    from scarf_b200.hvg import _lowess, _lowess_numpy
 
     rng = np.random.default_rng(5)
     x = np.sort(rng.normal(size=60))
@@ -77,6 +77,10 @@ def test_lowess_ties_and_small_windows():
     y = np.sin(x) + 0.1 * rng.normal(size=60)
     y[20] += 3.0  # outlier exercises the robustness iterations
     np.testing.assert_allclose(_lowess(y, x, 0.2, 100), lowess_o(y, x, frac=0.2, it=100), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(_lowess_numpy(y, x, 0.2, 100), lowess_o(y, x, frac=0.2, it=100), rtol=1e-9, atol=1e-12)
+    x2 = rng.gamma(2.0, 1.0, size=200)  # unsorted input, even n, the size mark_hvgs uses
+    y2 = np.log1p(x2) + 0.05 * rng.normal(size=200)
+    np.testing.assert_allclose(_lowess(y2, x2, 0.1, 100), lowess_o(y2, x2, frac=0.1, it=100), rtol=1e-9, atol=1e-12)
 
 
 def test_shard_plan():
