@@ -4,7 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # our arm  (torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's algorithm on host cores
 
-One "step" = mark_hvgs + make_graph on one synthetic CSR batch: raw CSR -> weighted kNN graph.
+One "step" = mark_hvgs + make_graph on one synthetic CSR batch: raw CSR -> weighted kNN graph.  As in the
+reference, the per-cell nCounts and the per-gene nCells mask `I` are attributes the DataStore computed when the
+store was created (scarf/datastore/base_datastore.py:324-401, scarf/assay.py:201-225): both arms receive them.
 `value`  : cells/s with the CSR shard already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same through the public API with HOST (pinned) CSR buffers, H2D + D2H inside the timed region.
 `roofline`: the dominant kernel (exact kNN) timed live with CUDA events on its launch stream.
@@ -33,13 +35,13 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cells", type=int, default=None, help="cells per GPU (overrides the workload)")
-    ap.add_argument("--gram-mode", type=int, default=int(os.environ.get("SCF_GRAM_MODE", "0")))
-    ap.add_argument("--knn-method", type=int, default=int(os.environ.get("SCF_KNN_METHOD", "0")))
+    ap.add_argument("--gram-mode", type=int, default=int(os.environ.get("SCF_GRAM_MODE", "3")))
+    ap.add_argument("--knn-method", type=int, default=int(os.environ.get("SCF_KNN_METHOD", "1")))
     ap.add_argument("--cpu-sample", type=int, default=4000, help="cells in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -58,7 +60,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -70,12 +72,15 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=open(self.path, "w"),
+                                          "-lms", "50", "-i", str(self.index)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples whose wall-clock stamp falls inside [t0, t1] (the timed region); all samples if none does."""
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -84,21 +89,28 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])), mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        os.unlink(self.path)
+        inside = [r for r in rows if t0 is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        use = inside or rows
+        reasons = set()
+        for r in use:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if use:
+            out = {"sm_mhz": statistics.median(r[1] for r in use), "sm_max_mhz": max(r[2] for r in use),
+                   "reasons": sorted(reasons), "samples": len(use),
+                   "window": "timed region" if inside else "whole run (no sample fell inside the timed region)"}
         return out
 
 
@@ -114,11 +126,11 @@ def cpu_reference_run(cfg, sample, threads):
 
     m = synth.make_counts_scipy(sample, cfg["genes"], cfg["factors"], seed=4466, block=2000)
     P.exact_knn(np.zeros((4, 2), np.float32), np.zeros((4, 2), np.float32), 1)  # builds/loads the C part untimed
+    cell_idx = np.arange(sample)
+    n_counts, _ = P.cell_totals(m)     # DataStore-creation attributes: outside the timed region on both arms
+    feat_I = P.gene_ncells(m) > 20
     t0 = time.perf_counter()
     with threadpool_limits(limits=threads):
-        cell_idx = np.arange(sample)
-        n_counts, _ = P.cell_totals(m)
-        feat_I = P.gene_ncells(m) > 20
         hv = P.mark_hvgs(m, cell_idx, feat_I, top_n=min(cfg["hvgs"], int(feat_I.sum()) - 1), n_counts=n_counts)
         P.make_graph(m, cell_idx, hv, dims=cfg["dims"], k=cfg["k"], pca="ipca", knn_threads=threads)
     return time.perf_counter() - t0, sample
@@ -183,10 +195,18 @@ def run_ours(args, cfg, rank, world, local_rank):
     nnz = csr.nnz
     timers = []
 
+    n_counts, _ = graph.cell_totals(csr)  # DataStore-creation attributes (see the module docstring)
+    feat_I = graph.gene_ncells(csr, comm) > 20  # bool device tensor
+    keep = torch.ones(cfg["genes"], dtype=torch.bool, device=dev)  # synthetic gene names never hit the blacklist
+    torch.cuda.synchronize()
+
     def step(c, tm=None):
-        n_counts, _ = graph.cell_totals(c)
-        feat_I = (graph.gene_ncells(c, comm) > 20).cpu().numpy()
-        hv = graph.mark_hvgs_csr(c, None, feat_I, n_counts, n_total, top_n=cfg["hvgs"], comm=comm)
+        if tm is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            tm.append(("step_start", e))
+        hv = graph.mark_hvgs_csr(c, None, feat_I, n_counts, n_total, top_n=cfg["hvgs"], comm=comm, as_tensor=True,
+                                 keep_mask=keep)
         return graph.make_graph_csr(c, None, hv, dims=cfg["dims"], k=cfg["k"], comm=comm, gram_mode=args.gram_mode,
                                     knn_method=args.knn_method, timers=tm)
 
@@ -210,22 +230,25 @@ def run_ours(args, cfg, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)  # nvidia-smi needs a moment before its first sample
     lib.LAUNCHES["n"] = 0
     if args.profiler_range:
         torch.cuda.profiler.start()
+    wall0 = time.time()
     ms_total = timed(lambda: step(csr, timers), args.steps)
+    wall1 = time.time()
     if args.profiler_range:
         torch.cuda.profiler.stop()
     launches = lib.LAUNCHES["n"]
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_step = ms_total / args.steps
     value = n_total / (ms_step / 1e3)
 
     # per-stage CUDA-event times of the timed steps (events were recorded on the launching stream)
     stage_ms = {}
     for (n0, a), (n1, b) in zip(timers[:-1], timers[1:]):
-        if n1 != "start":
-            stage_ms.setdefault(n1, []).append(a.elapsed_time(b))
+        if n1 != "step_start":
+            stage_ms.setdefault("mark_hvgs" if n1 == "start" else n1, []).append(a.elapsed_time(b))
     stage_ms = {k_: sum(v) / len(v) for k_, v in stage_ms.items()}
     pk = peaks()
     knn_ms = stage_ms.get("knn", float("nan"))

@@ -52,11 +52,13 @@ int32_t scf_csr_gene_stats(const int64_t* indptr, const int32_t* indices, const 
 /* ---- K1a: column sums of the normalised HVG matrix -------------------------------------------
  * x = log1p(sf*c/row_sum[r]) (log_transform) or sf*c/row_sum[r]   (scarf/assay.py:54-64,826)
  * accumulates sum x and sum x^2 per selected column as int64 fixed point (<< SCF_COLSTAT_SHIFT):
- * the mu / sigma block of make_graph (scarf/datastore/graph_datastore.py:767-796). */
+ * the mu / sigma block of make_graph (scarf/datastore/graph_datastore.py:767-796).
+ * sum_fx / sumsq_fx are [n_rep][n_cols]: CTAs spread their atomics over n_rep copies (same-address
+ * atomics serialise in L2); the caller adds the copies (integer adds: any order, same result). */
 int32_t scf_csr_hvg_colstats(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
                              const int64_t* row_ids, int64_t n_sel, const int32_t* col_map,
-                             const double* row_sum, double sf, int32_t log_transform,
-                             int64_t* sum_fx, int64_t* sumsq_fx, void* stream);
+                             const double* row_sum, double sf, int32_t log_transform, int32_t n_cols,
+                             int32_t n_rep, int64_t* sum_fx, int64_t* sumsq_fx, void* stream);
 
 /* ---- K1b: fused lib-size normalise -> log1p -> HVG gather -> z-scale --------------------------
  * Z[r, col_map[g]] = (x - mu)/sigma   (AnnStream.transform_z, scarf/ann.py:191-192; the dense

@@ -102,7 +102,11 @@ __global__ void __launch_bounds__(kThreads) hvg_colstats_kernel(const int64_t* _
                                                                 const int32_t* __restrict__ col_map,
                                                                 const double* __restrict__ row_sum, double sf,
                                                                 int log_transform, long long* __restrict__ sum_fx,
-                                                                long long* __restrict__ sumsq_fx) {
+                                                                long long* __restrict__ sumsq_fx, int n_cols,
+                                                                int n_rep) {
+  // same-address atomics serialise in L2: every CTA adds into one of n_rep copies of the H-long accumulators
+  sum_fx += (int64_t)(blockIdx.x % n_rep) * n_cols;
+  sumsq_fx += (int64_t)(blockIdx.x % n_rep) * n_cols;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
@@ -122,7 +126,12 @@ __global__ void __launch_bounds__(kThreads) hvg_colstats_kernel(const int64_t* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// smem: double mu[ldz], double inv-less sigma[ldz], float base[ldz], float rowbuf[kWarpsPerCta][ldz]
+// Z rows go straight to global memory: the warp first writes the "no count" row ((0 - mu)/sigma, identical for
+// every cell, kept in shared memory), then overwrites the <= n_hvg entries the cell really has.  Both are plain
+// stores that merge in L2, so HBM sees each Z row once; no per-warp row buffer means ~40 resident warps per SM to
+// cover the latency of the CSR stream.  smem: double mu[ldz] | double sigma[ldz] | float base[ldz] | float base_lo[ldz]
+__device__ __forceinline__ float tf32_low_part(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
 __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const uint32_t* __restrict__ data,
     const int64_t* __restrict__ row_ids, int64_t n_sel, const int32_t* __restrict__ col_map, int n_cols,
@@ -133,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
   double* s_mu = reinterpret_cast<double*>(smem_raw);
   double* s_sigma = s_mu + ldz;
   float* s_base = reinterpret_cast<float*>(s_sigma + ldz);
-  float* s_rows = s_base + ldz;
+  float* s_base_lo = s_base + ldz;
   for (int j = threadIdx.x; j < ldz; j += kThreads) {
     const double m = (j < n_cols && mu) ? mu[j] : 0.0;
     const double sd = (j < n_cols && sigma) ? sigma[j] : 1.0;
@@ -144,11 +153,12 @@ __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
     }
     s_mu[j] = m;
     s_sigma[j] = sd;
-    s_base[j] = j < n_cols ? (float)__ddiv_rn(x0 - m, sd) : 0.f;
+    const float b = j < n_cols ? (float)__ddiv_rn(x0 - m, sd) : 0.f;
+    s_base[j] = b;
+    s_base_lo[j] = tf32_low_part(b);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* buf = s_rows + (int64_t)warp * ldz;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + warp;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
   const int nvec = (int)(ldz >> 2);
@@ -157,33 +167,25 @@ __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
     const int64_t s = indptr[row], e = indptr[row + 1];
     double sc = row_sum[r];
     if (sc == 0.0) sc = 1.0;
-    for (int j = lane; j < nvec; j += 32)
-      reinterpret_cast<float4*>(buf)[j] = reinterpret_cast<const float4*>(s_base)[j];
-    __syncwarp();
+    float* zr = z + r * ldz;
+    float* zl = z_lo ? z_lo + r * ldz : nullptr;
+    for (int j = lane; j < nvec; j += 32) {
+      reinterpret_cast<float4*>(zr)[j] = reinterpret_cast<const float4*>(s_base)[j];
+      if (zl) reinterpret_cast<float4*>(zl)[j] = reinterpret_cast<const float4*>(s_base_lo)[j];
+    }
+    __syncwarp();  // orders the base row before the overwrites below (different lanes hit the same addresses)
     warp_row_scan(indices, data, s, e, lane, [&](int32_t g, uint32_t c) {
       const int col = __ldg(col_map + g);
       if (col < 0) return;
-      const double x = norm_value(c, sc, sf, log_transform != 0);
-      buf[col] = (float)__ddiv_rn(x - s_mu[col], s_sigma[col]);
-    });
-    __syncwarp();
-    float4* dst = reinterpret_cast<float4*>(z + r * ldz);
-    if (z_lo) {  // low plane of the 3xTF32 split: what the tensor core's 19-bit read of z drops
-      float4* dlo = reinterpret_cast<float4*>(z_lo + r * ldz);
-      for (int j = lane; j < nvec; j += 32) {
-        const float4 v = reinterpret_cast<const float4*>(buf)[j];
-        float4 lo;
-        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-        __stcs(dst + j, v);
-        __stcs(dlo + j, lo);
+      if (missing_fill) {  // a column the target matrix does not really have keeps its fill value
+        const double f = __ldg(missing_fill + col);
+        if (f == f) return;
       }
-    } else {
-      for (int j = lane; j < nvec; j += 32) __stcs(dst + j, reinterpret_cast<const float4*>(buf)[j]);
-    }
-    __syncwarp();
+      const double x = norm_value(c, sc, sf, log_transform != 0);
+      const float v = (float)__ddiv_rn(x - s_mu[col], s_sigma[col]);
+      zr[col] = v;
+      if (zl) zl[col] = tf32_low_part(v);  // what the tensor core's 19-bit read of z drops (3xTF32 low plane)
+    });
   }
 }
 
@@ -223,15 +225,15 @@ extern "C" int32_t scf_csr_gene_stats(const int64_t* indptr, const int32_t* indi
 
 extern "C" int32_t scf_csr_hvg_colstats(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
                                         const int64_t* row_ids, int64_t n_sel, const int32_t* col_map,
-                                        const double* row_sum, double sf, int32_t log_transform, int64_t* sum_fx,
-                                        int64_t* sumsq_fx, void* stream) {
+                                        const double* row_sum, double sf, int32_t log_transform, int32_t n_cols,
+                                        int32_t n_rep, int64_t* sum_fx, int64_t* sumsq_fx, void* stream) {
   SCF_ARG(indptr && indices && data && col_map && row_sum && sum_fx && sumsq_fx, "null pointer");
-  SCF_ARG(n_sel >= 0, "n_sel < 0");
+  SCF_ARG(n_sel >= 0 && n_cols > 0 && n_rep > 0, "bad sizes");
   if (n_sel == 0) return 0;
   const int grid = grid_for((const void*)hvg_colstats_kernel, kThreads, 0);
   hvg_colstats_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, row_ids, n_sel, col_map,
                                                                     row_sum, sf, log_transform, (long long*)sum_fx,
-                                                                    (long long*)sumsq_fx);
+                                                                    (long long*)sumsq_fx, n_cols, n_rep);
   return scf_check_launch("scf_csr_hvg_colstats");
 }
 
@@ -243,7 +245,7 @@ extern "C" int32_t scf_csr_norm_scale(const int64_t* indptr, const int32_t* indi
   SCF_ARG(indptr && indices && data && col_map && row_sum && z, "null pointer");
   SCF_ARG(n_sel >= 0 && n_cols > 0 && ldz >= n_cols && (ldz & 3) == 0, "bad sizes (ldz must be a multiple of 4)");
   if (n_sel == 0) return 0;
-  const size_t smem = (size_t)ldz * (8 + 8 + 4 + 4 * kWarpsPerCta);
+  const size_t smem = (size_t)ldz * (8 + 8 + 4 + 4);
   SCF_ARG(smem <= 227 * 1024, "ldz too large for the shared-memory row buffers");
   cudaError_t e = cudaFuncSetAttribute(norm_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {

@@ -16,20 +16,30 @@ extern "C" int32_t scf_host_lowess(const double* endog, const double* exog, int6
   std::vector<int64_t> order(n);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return exog[a] < exog[b]; });
-  std::vector<double> x(n), y(n), fit(n, 0.0), rw(n, 1.0), w(k), r(n), tmp(n);
+  std::vector<double> x(n), y(n), fit(n, 0.0), rw(n, 1.0), w(k), r(n), tmp(n), tri((size_t)n * k);
+  std::vector<int64_t> lefts(n);
   for (int64_t i = 0; i < n; ++i) x[i] = exog[order[i]], y[i] = endog[order[i]];
-  for (int32_t pass = 0; pass <= it; ++pass) {
-    int64_t left = 0, right = k, i = 0;
-    while (i < n) {
+  {  // windows and tricube weights do not change between the robustness passes
+    int64_t left = 0, right = k;
+    for (int64_t i = 0; i < n; ++i) {
       while (right < n && x[i] > 0.5 * (x[left] + x[right])) ++left, ++right;  // k nearest neighbours of x[i]
+      lefts[i] = left;
       const double radius = std::max(x[i] - x[left], x[right - 1] - x[i]);
-      double sw = 0.0;
       for (int64_t j = 0; j < k; ++j) {
         const double d = fabs(x[left + j] - x[i]) / radius;
         double t = 1.0 - d * d * d;
-        t = t * t * t;  // tricube
-        if (!isfinite(t)) t = 0.0;
-        w[j] = t * rw[left + j];
+        t = t * t * t;
+        tri[(size_t)i * k + j] = isfinite(t) ? t : 0.0;
+      }
+    }
+  }
+  for (int32_t pass = 0; pass <= it; ++pass) {
+    int64_t i = 0;
+    while (i < n) {
+      const int64_t left = lefts[i];
+      double sw = 0.0;
+      for (int64_t j = 0; j < k; ++j) {
+        w[j] = tri[(size_t)i * k + j] * rw[left + j];
         sw += w[j];
       }
       if (!(sw > 0.0)) {

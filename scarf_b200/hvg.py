@@ -137,3 +137,70 @@ def choose_hvgs(normed_n, nz_mean, c_var, feat_I, gene_names=None, top_n=500, mi
             min_var = 2.0 ** min_var
         hv = idx & (c_var > min_var) & (c_var < (np.inf if top_n is not None else 2.0 ** max_var))
     return hv
+
+
+# =============================================================================================
+# The same two steps on device tensors: the per-gene vectors stay on the GPU (they come from the CSR kernels), only
+# the <= n_bins binned points cross to the host for the LOWESS fit.  Used by graph.mark_hvgs_csr.
+# =============================================================================================
+def blacklist_keep_mask(gene_names, n_genes, blacklist=DEFAULT_BLACKLIST):
+    """bool numpy mask of the genes that survive the blacklist regex (static per dataset)."""
+    if blacklist and gene_names is not None:
+        pat = re.compile(blacklist)
+        return np.fromiter((pat.search(str(x)) is None for x in gene_names), dtype=bool, count=n_genes)
+    return np.ones(n_genes, dtype=bool)
+
+
+def remove_trend_device(avg, sigmas, n_bins=200, lowess_frac=0.1):
+    """:func:`remove_trend` on float64 device vectors (any device); returns a device vector."""
+    import torch
+
+    out = torch.zeros_like(avg)
+    pos = avg > 0
+    la, lb = torch.log(avg[pos]), torch.log(sigmas[pos])
+    if la.numel() == 0:
+        return out
+    lo_hi = torch.stack([la.min(), la.max()]).cpu().numpy()
+    # np.histogram's edges for `bins=n_bins` (linspace over the data range), last edge widened like the reference
+    first, last = (float(lo_hi[0]) - 0.5, float(lo_hi[1]) + 0.5) if lo_hi[0] == lo_hi[1] else (float(lo_hi[0]), float(lo_hi[1]))
+    edges = np.linspace(first, last, n_bins + 1, endpoint=True)
+    edges[-1] += 0.1
+    edges_t = torch.from_numpy(edges).to(la.device)
+    which = torch.bucketize(la, edges_t, right=True) - 1  # edges[i] <= la < edges[i+1]
+    valid = (which >= 0) & (which < n_bins)
+    which = torch.where(valid, which, torch.full_like(which, n_bins))  # invalid -> a bin past the end
+    # min-log(b) gene of every non-empty bin, first one on ties: stable sort by lb, then stable sort by bin
+    i1 = torch.argsort(lb, stable=True)
+    i2 = torch.argsort(which[i1], stable=True)
+    order = i1[i2]
+    w_sorted = which[order]
+    is_first = torch.ones_like(w_sorted, dtype=torch.bool)
+    is_first[1:] = w_sorted[1:] != w_sorted[:-1]
+    firsts = order[is_first & (w_sorted < n_bins)]
+    pts = torch.stack([which[firsts].to(torch.float64), la[firsts], lb[firsts]]).cpu().numpy()
+    fit = _lowess(pts[2], pts[1], lowess_frac, 100)
+    fit_of_bin = np.full(n_bins + 1, np.nan)
+    fit_of_bin[pts[0].astype(np.int64)] = fit
+    fit_t = torch.from_numpy(fit_of_bin).to(la.device)
+    val = torch.exp(lb - fit_t[which])
+    val = torch.where(valid, val, torch.zeros_like(val))
+    out[pos] = val
+    return out
+
+
+def choose_hvgs_device(normed_n, nz_mean, c_var, eligible, top_n=500, min_cells=0, max_cells=np.inf,
+                       min_mean=-np.inf, max_mean=np.inf, min_var=None, max_var=np.inf):
+    """:func:`choose_hvgs` on device vectors; ``eligible`` = feat_I & blacklist-keep (bool tensor)."""
+    import torch
+
+    min_mean = 2.0 ** min_mean if min_mean != -np.inf else min_mean
+    max_mean = 2.0 ** max_mean if max_mean != np.inf else max_mean
+    idx = (normed_n > min_cells) & (normed_n < max_cells) & (nz_mean > min_mean) & (nz_mean < max_mean) & eligible
+    if top_n is not None:
+        cv = torch.sort(c_var[idx], descending=True).values
+        n_valid = int(cv.numel())
+        if top_n > n_valid:
+            top_n = n_valid - 1
+        thr = cv[top_n]
+        return idx & (c_var > thr)
+    return idx & (c_var > 2.0 ** min_var) & (c_var < 2.0 ** max_var)

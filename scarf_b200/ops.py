@@ -99,15 +99,15 @@ def csr_gene_stats(csr: CsrDevice, row_ids=None, row_div=None, sf=1000.0, out=No
 
 
 # ------------------------------------------------------------------------------------------ K1
-def csr_hvg_colstats(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, sf=1000.0, log_transform=True, out=None):
+def csr_hvg_colstats(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, sf=1000.0, log_transform=True, n_rep=32):
     """int64 fixed-point (sum x, sum x^2) per selected column; divide by 2**lib.COLSTAT_SHIFT."""
     n = csr.n_rows if row_ids is None else int(row_ids.numel())
-    if out is None:
-        out = (torch.zeros(n_cols, dtype=torch.int64, device=csr.device),
-               torch.zeros(n_cols, dtype=torch.int64, device=csr.device))
+    acc = torch.zeros((2, n_rep, n_cols), dtype=torch.int64, device=csr.device)
     lib.call("scf_csr_hvg_colstats", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
-             _ptr(col_map), _ptr(row_sum), float(sf), int(bool(log_transform)), _ptr(out[0]), _ptr(out[1]), _stream())
-    return out
+             _ptr(col_map), _ptr(row_sum), float(sf), int(bool(log_transform)), int(n_cols), int(n_rep),
+             acc[0].data_ptr(), acc[1].data_ptr(), _stream())
+    tot = acc.sum(dim=1)
+    return tot[0], tot[1]
 
 
 def csr_norm_scale(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, z, sf=1000.0, log_transform=True, mu=None,

@@ -66,6 +66,27 @@ def test_hvg_host_logic_matches_oracle(pbmc):
     assert not any(str(n).startswith(("MT-", "RPS", "RPL")) for n in pbmc["names"][hv])
 
 
+def test_hvg_device_functions_match_host(pbmc):
+    """remove_trend_device / choose_hvgs_device (torch, here on CPU tensors) == the numpy statements."""
+    import torch
+
+    from oracle import pipeline as P
+    from scarf_b200 import hvg
+
+    counts, cell_idx = pbmc["counts"], pbmc["cell_idx"]
+    feat_I = P.gene_ncells(counts) > 20
+    hv_o, st = P.mark_hvgs(counts, cell_idx, feat_I, gene_names=pbmc["names"], top_n=100, return_stats=True)
+    t = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)) for k, v in st.items()}
+    fI = torch.from_numpy(feat_I)
+    c_var = torch.full((counts.shape[1],), float("nan"), dtype=torch.float64)
+    c_var[fI] = hvg.remove_trend_device(t["avg"][fI], t["sigmas"][fI])
+    ref = hvg.remove_trend(st["avg"][feat_I], st["sigmas"][feat_I])
+    np.testing.assert_allclose(c_var[fI].numpy(), ref, rtol=1e-12)
+    keep = torch.from_numpy(hvg.blacklist_keep_mask(pbmc["names"], counts.shape[1]))
+    hv = hvg.choose_hvgs_device(t["normed_n"], t["nz_mean"], c_var, fI & keep, 100, int(0.01 * 892))
+    assert np.array_equal(hv.numpy(), hv_o)
+
+
 def test_lowess_ties_and_small_windows():
     from oracle.lowess import lowess as lowess_o
     from scarf_b200.hvg import _lowess, _lowess_numpy
