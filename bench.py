@@ -58,6 +58,38 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
 
 
+def measure_tf32_peak(torch, dev):
+    """cuBLAS TF32 dense GEMM 8192^3, best of 10 (the method MEASURED_PEAKS.json uses for bf16): TFLOP/s."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((8192, 8192), device=dev, dtype=torch.float32)
+        b = torch.randn((8192, 8192), device=dev, dtype=torch.float32)
+        for _ in range(3):
+            a @ b
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full summary (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "ncu_full_summary.json")
+    if os.path.exists(p):
+        d = json.load(open(p)).get(kernel_key)
+        if d:
+            return d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0)
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -253,13 +285,19 @@ def run_ours(args, cfg, rank, world, local_rank):
     pk = peaks()
     knn_ms = stage_ms.get("knn", float("nan"))
     knn_flop = 2.0 * n_total * cfg["dims"] * n_local  # 2*N_ref*D per query, true D
-    tf32_peak = pk["bf16_tflops"] / 2.0
-    roofline = {"kernel": "scf_knn_l2 (exact kNN: distance contraction + top-k + FP64 re-rank)", "bound": "tensor",
-                "achieved": knn_flop / (knn_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": knn_flop / (knn_ms * 1e-3) / 1e12 / tf32_peak, "traffic": None,
-                "peak_note": f"TF32 dense = {pk['src']} cuBLAS bf16 {pk['bf16_tflops']} TFLOP/s / 2 "
-                             "(TF32 runs at half the bf16 rate; not measured separately)",
-                "ms_per_launch": knn_ms}
+    tf32_peak = measure_tf32_peak(torch, dev)
+    roofline = {"kernel": "scf_knn_l2 (exact kNN entry point: operand prep + tcgen05 distance contraction with fused "
+                          "top-k' + FP64 re-rank + guard repair; all of its launches are inside the timed span)",
+                "bound": "tensor", "achieved": knn_flop / (knn_ms * 1e-3) / 1e12, "peak": tf32_peak,
+                "unit": "TFLOP/s", "frac": knn_flop / (knn_ms * 1e-3) / 1e12 / tf32_peak,
+                "traffic": ncu_traffic("knn_tc_kernel"),
+                "peak_note": "TF32 dense peak measured in this run: cuBLAS TF32 GEMM 8192^3, best of 10 (burst); "
+                             f"MEASURED_PEAKS.json ({pk['src']}) has bf16 {pk['bf16_tflops']} TFLOP/s, HBM {pk['hbm_gbs']} GB/s",
+                "ms_per_launch": knn_ms,
+                "hbm_side": {k_: {"ms": stage_ms.get(k_), "algorithmic_GBs": v / (stage_ms[k_] * 1e-3) / 1e9,
+                                  "frac_of_hbm_peak": v / (stage_ms[k_] * 1e-3) / 1e9 / pk["hbm_gbs"]}
+                             for k_, v in (("normalise", 8.0 * nnz + 8.0 * n_local + 4.0 * 2048 * n_local *
+                                            (2 if args.gram_mode == 3 else 1)),) if stage_ms.get(k_)}}
     csr_bytes = 8.0 * nnz + 8.0 * (n_local + 1)
     stages = {k_: round(v, 4) for k_, v in stage_ms.items()}
 

@@ -220,12 +220,26 @@ struct KnnTcParams {
   float* cand_tau;      // [nq_pad, nsplit]  largest kept score = lower bound of every rejected score
   int nq;               // live query rows (pad rows keep nothing)
   int flags;            // developer switches (SCF_KNN_FLAGS): 2 = back off in waits, 4/8 = timing experiments, 16 = counters
+  // collect pass (repair of guard failures): query row r of this launch is failed row r of the fail list
+  const int* fail_count;   // device count of failed rows (rows >= min(count, FIXTC_ROWS) do nothing)
+  const float* fix_thr;    // [FIXTC_ROWS] score threshold: every reference scoring below it is collected
+  int* fix_cnt;            // [FIXTC_ROWS] collected so far
+  int* fix_list;           // [FIXTC_ROWS][FIXTC_CAP] reference ids
 };
 
-template <int KC>
+constexpr int FIXTC_ROWS = 8192;  // failed rows repaired by the tensor-core collect pass (the rest: FP64 scan)
+constexpr int FIXTC_CAP = 64;     // collected references per failed row
+constexpr int FIXTC_NSPLIT = 16;  // reference ranges per query tile in the collect pass
+
+template <int KC, bool COLLECT>
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                              const __grid_constant__ CUtensorMap tmap_r,
                                                              const KnnTcParams p) {
+  int n_fix = 0;
+  if constexpr (COLLECT) {  // whole CTA leaves before any barrier / TMEM setup when its query tile is empty
+    n_fix = min(*p.fail_count, FIXTC_ROWS);
+    if ((int)blockIdx.x * (QT * BM) >= n_fix) return;
+  }
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // the 128-byte swizzle is a function of the shared-memory address: tiles must sit on 1024-byte boundaries
   unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -327,39 +341,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     const int row = quarter * 32 + lane;
     int* li_slot = li + qt * BM + row;
     float* st_slot = st + qt * BM + row;
-    CandList<KC> cl;
-    cl.init();
-    if (q0 + qt * BM + row >= p.nq) cl.thr = -FLT_MAX;  // pad row: never a candidate
-#pragma unroll
-    for (int e = 0; e < KC; ++e) li_slot[e * NLISTS] = -1;
-    for (int lt = 0; lt < ntiles; ++lt) {
-      const int acc = lt & 1;
-      const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
-      tc::mbar_wait(tmem_full + acc, acc_ph);
-      tc::tc_fence_after();
-      const int j0 = (tile_begin + lt) * BN;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
-      uint32_t v[32];
-      tc::tmem_ld32(t_row, v);
+    if constexpr (COLLECT) {
+      // fixed per-row threshold, append-only: every reference whose score is below it goes on the row's list
+      const int slot = q0 + qt * BM + row;
+      const float thr = slot < n_fix ? p.fix_thr[slot] : -FLT_MAX;
+      for (int lt = 0; lt < ntiles; ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
+        tc::mbar_wait(tmem_full + acc, acc_ph);
+        tc::tc_fence_after();
+        const int j0 = (tile_begin + lt) * BN;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        tc::tmem_ld_wait();
-        const uint32_t mask = stage_hits<KC>(v, cl.thr, st_slot, p.flags);
-        // v is dead: the TMEM load of the next chunk overlaps the drain of this one
-        if (cc + 1 < BN / 32) tc::tmem_ld32(t_row + (uint32_t)((cc + 1) * 32), v);
-        drain_hits<KC>(mask, j0 + cc * 32, cl, li_slot, st_slot, p.flags);
-      }
-      tc::tc_fence_before();
-      tc::mbar_arrive(tmem_empty + acc);
-    }
-    // candidates out: [query, split, KC]
-    const size_t sub = (size_t)(q0 + qt * BM + row) * p.nsplit + split;
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          uint32_t v[32];
+          tc::tmem_ld32(t_row + (uint32_t)(cc * 32), v);
+          tc::tmem_ld_wait();
+          float g[4];
 #pragma unroll
-    for (int e = 0; e < KC; ++e) {
-      p.cand_score[sub * KC + e] = cl.r[e];
-      p.cand_idx[sub * KC + e] = li_slot[e * NLISTS];
+          for (int i = 0; i < 4; ++i) g[i] = min8(v + 8 * i);
+          const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
+          if (!__any_sync(SCF_FULL, m < thr)) continue;
+          if (m < thr) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (__uint_as_float(v[c]) < thr) {
+                const int pos = atomicAdd(p.fix_cnt + slot, 1);
+                if (pos < FIXTC_CAP) p.fix_list[(size_t)slot * FIXTC_CAP + pos] = j0 + cc * 32 + c;
+              }
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(tmem_empty + acc);
+      }
+    } else {
+    CandList<KC> cl;
+      cl.init();
+      if (q0 + qt * BM + row >= p.nq) cl.thr = -FLT_MAX;  // pad row: never a candidate
+  #pragma unroll
+      for (int e = 0; e < KC; ++e) li_slot[e * NLISTS] = -1;
+      for (int lt = 0; lt < ntiles; ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
+        tc::mbar_wait(tmem_full + acc, acc_ph);
+        tc::tc_fence_after();
+        const int j0 = (tile_begin + lt) * BN;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
+        uint32_t v[32];
+        tc::tmem_ld32(t_row, v);
+  #pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          tc::tmem_ld_wait();
+          const uint32_t mask = stage_hits<KC>(v, cl.thr, st_slot, p.flags);
+          // v is dead: the TMEM load of the next chunk overlaps the drain of this one
+          if (cc + 1 < BN / 32) tc::tmem_ld32(t_row + (uint32_t)((cc + 1) * 32), v);
+          drain_hits<KC>(mask, j0 + cc * 32, cl, li_slot, st_slot, p.flags);
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(tmem_empty + acc);
+      }
+      // candidates out: [query, split, KC]
+      const size_t sub = (size_t)(q0 + qt * BM + row) * p.nsplit + split;
+  #pragma unroll
+      for (int e = 0; e < KC; ++e) {
+        p.cand_score[sub * KC + e] = cl.r[e];
+        p.cand_idx[sub * KC + e] = li_slot[e * NLISTS];
+      }
+      p.cand_tau[sub] = cl.thr;
     }
-    p.cand_tau[sub] = cl.thr;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -383,7 +432,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
                                                          const float* __restrict__ bmax, int64_t* __restrict__ out_idx,
                                                          float* __restrict__ out_dist, int64_t* __restrict__ fail_ids,
                                                          unsigned long long* __restrict__ fail_keys,
-                                                         int* __restrict__ fail_count) {
+                                                         float* __restrict__ fix_thr, int* __restrict__ fail_count) {
   const int lane = threadIdx.x & 31;
   const int64_t qi = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (qi >= nq) return;
@@ -440,17 +489,109 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   }
   if (lane == 0) {
     bool ok = enough;
+    const double an2 = qnorm2[qi], an = sqrt(an2), bm = (double)bmax[0], dbm = (double)bmax[1];
+    const double eps = 2.0 * ((double)qerr[qi] * bm + an * dbm) * (1.0 + 1e-6) + eps_acc() * (2.0 * an * bm + bm * bm);
+    const float dk = __uint_as_float((unsigned)(last >> 32));
     if (ok && tau < 1e29f) {  // lists were full: something was rejected, prove it is farther than the k-th kept
-      const double an2 = qnorm2[qi], an = sqrt(an2), bm = (double)bmax[0], dbm = (double)bmax[1];
-      const double eps = 2.0 * ((double)qerr[qi] * bm + an * dbm) * (1.0 + 1e-6) + eps_acc() * (2.0 * an * bm + bm * bm);
       const double lower = ((double)tau - eps + an2) * (1.0 - 1e-12);  // bound on any rejected exact distance
-      const float dk = __uint_as_float((unsigned)(last >> 32));
       ok = lower > 0.0 && dk < __double2float_rd(lower);  // strict: a tie would be decided by the index
     }
-    if (!ok) {  // the repair scans the references for every key <= the current k-th candidate's
+    if (!ok) {
+      // Repair: every true neighbour has an exact distance <= dk, hence a tensor-core score below
+      // dk - |a|^2 + eps; the collect pass gathers exactly those references (or, if there were fewer than k
+      // candidates, the FP64 scan takes the row).
       const int slot = atomicAdd(fail_count, 1);
       fail_ids[slot] = qi;
       fail_keys[slot] = enough ? last : ~0ull;
+      if (slot < FIXTC_ROWS) {
+        const double t = (double)dk * (1.0 + 0x1p-22) - an2 + eps;
+        fix_thr[slot] = enough ? __double2float_ru(t + fabs(t) * 1e-9) : FLT_MAX;
+      }
+    }
+  }
+}
+
+// rows of the augmented query operand of the failed queries, compacted for the collect pass
+__global__ void __launch_bounds__(256) knn_fix_gather_kernel(const float* __restrict__ qop, int kp,
+                                                             const int64_t* __restrict__ fail_ids,
+                                                             const int* __restrict__ fail_count,
+                                                             float* __restrict__ qfix) {
+  const int n = min(*fail_count, FIXTC_ROWS);
+  const int lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += gridDim.x * 8) {
+    const float* src = qop + fail_ids[r] * kp;
+    for (int t = lane; t < kp; t += 32) qfix[(size_t)r * kp + t] = src[t];
+  }
+}
+
+// one warp per failed row: the oracle's FP64 distance of every collected reference, k smallest by (distance, index);
+// rows that cannot be finished here (list overflow, too few entries, beyond the collect capacity) are handed on
+__global__ void __launch_bounds__(256) knn_fix_finish_kernel(const float* __restrict__ q, const float* __restrict__ ref,
+                                                             int dim, int64_t ld, int k, int64_t self_offset,
+                                                             const int64_t* __restrict__ fail_ids,
+                                                             const unsigned long long* __restrict__ fail_keys,
+                                                             const int* __restrict__ fail_count,
+                                                             const int* __restrict__ fix_cnt,
+                                                             const int* __restrict__ fix_list,
+                                                             int64_t* __restrict__ out_idx, float* __restrict__ out_dist,
+                                                             int64_t* __restrict__ rest_ids,
+                                                             unsigned long long* __restrict__ rest_keys,
+                                                             int* __restrict__ rest_count) {
+  const int nfail = *fail_count;
+  const int lane = threadIdx.x & 31;
+  for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < nfail; w += gridDim.x * 8) {
+    const int64_t qi = fail_ids[w];
+    const int c = w < FIXTC_ROWS ? fix_cnt[w] : -1;
+    bool done = false;
+    if (c >= k && c <= FIXTC_CAP) {
+      const int64_t self = self_offset >= 0 ? qi + self_offset : -1;
+      const float* a = q + qi * ld;
+      unsigned long long key[FIXTC_CAP / 32];
+      int live = 0;
+#pragma unroll
+      for (int u = 0; u < FIXTC_CAP / 32; ++u) {
+        key[u] = ~0ull;
+        const int e = lane + 32 * u;
+        if (e < c) {
+          const int j = fix_list[(size_t)w * FIXTC_CAP + e];
+          if (j != self) {
+            const float* b = ref + (int64_t)j * ld;
+            double acc = 0.0;
+            for (int t = 0; t < dim; ++t) {
+              const double df = __dsub_rn((double)a[t], (double)__ldg(b + t));
+              acc = __dadd_rn(acc, __dmul_rn(df, df));
+            }
+            key[u] = ((unsigned long long)__float_as_uint((float)acc) << 32) | (unsigned)j;
+            ++live;
+          }
+        }
+      }
+      live = warp_sum(live);
+      if (live >= k) {
+        done = true;
+        for (int r = 0; r < k; ++r) {
+          unsigned long long best = key[0];
+#pragma unroll
+          for (int u = 1; u < FIXTC_CAP / 32; ++u) best = best < key[u] ? best : key[u];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(SCF_FULL, best, o);
+            best = other < best ? other : best;
+          }
+#pragma unroll
+          for (int u = 0; u < FIXTC_CAP / 32; ++u)
+            if (key[u] == best) key[u] = ~0ull;
+          if (lane == 0) {
+            out_idx[qi * k + r] = (int64_t)(best & 0xffffffffull);
+            out_dist[qi * k + r] = __uint_as_float((unsigned)(best >> 32));
+          }
+        }
+      }
+    }
+    if (!done && lane == 0) {
+      const int slot = atomicAdd(rest_count, 1);
+      rest_ids[slot] = qi;
+      rest_keys[slot] = fail_keys[w];
     }
   }
 }
@@ -467,7 +608,8 @@ struct Plan {
   int64_t nq_pad, nr_pad;
   size_t smem;
   // workspace offsets (bytes)
-  size_t off_qop, off_rop, off_qn, off_qe, off_cs, off_ci, off_tau, off_fail, off_fkey, off_misc, off_fix, total;
+  size_t off_qop, off_rop, off_qn, off_qe, off_cs, off_ci, off_tau, off_fail, off_fkey, off_misc, off_fix, off_qfix,
+      off_fthr, off_fcnt, off_flist, off_rest, off_rkey, total;
 };
 
 bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
@@ -508,6 +650,12 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.off_fkey = o, o = al(o + (size_t)nq * 8);
   pl.off_misc = o, o = al(o + 256);
   pl.off_fix = o, o = al(o + knn_exact_fix_scratch_bytes(nq, k));
+  pl.off_qfix = o, o = al(o + (size_t)FIXTC_ROWS * pl.kp * 4);
+  pl.off_fthr = o, o = al(o + (size_t)FIXTC_ROWS * 4);
+  pl.off_fcnt = o, o = al(o + (size_t)FIXTC_ROWS * 4);
+  pl.off_flist = o, o = al(o + (size_t)FIXTC_ROWS * FIXTC_CAP * 4);
+  pl.off_rest = o, o = al(o + (size_t)nq * 8);
+  pl.off_rkey = o, o = al(o + (size_t)nq * 8);
   pl.total = o;
   return true;
 }
@@ -549,7 +697,15 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   unsigned long long* fail_keys = (unsigned long long*)(ws + pl.off_fkey);
   int* fail_count = (int*)(ws + pl.off_misc);
   float* bmax = (float*)(ws + pl.off_misc + 64);
+  int* rest_count = (int*)(ws + pl.off_misc + 128);
+  float* qfix = (float*)(ws + pl.off_qfix);
+  float* fix_thr = (float*)(ws + pl.off_fthr);
+  int* fix_cnt = (int*)(ws + pl.off_fcnt);
+  int* fix_list = (int*)(ws + pl.off_flist);
+  int64_t* rest_ids = (int64_t*)(ws + pl.off_rest);
+  unsigned long long* rest_keys = (unsigned long long*)(ws + pl.off_rkey);
   cudaError_t e = cudaMemsetAsync(ws + pl.off_misc, 0, 256, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(fix_cnt, 0, (size_t)FIXTC_ROWS * 4, stream);
   if (e != cudaSuccess) {
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
@@ -572,7 +728,8 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     const char* f = getenv("SCF_KNN_FLAGS");
     prm.flags = f ? atoi(f) : 2;
   }
-  auto kern = pl.kc == 16 ? knn_tc_kernel<16> : knn_tc_kernel<32>;
+  prm.fail_count = nullptr, prm.fix_thr = nullptr, prm.fix_cnt = nullptr, prm.fix_list = nullptr;
+  auto kern = pl.kc == 16 ? knn_tc_kernel<16, false> : knn_tc_kernel<32, false>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) {
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
@@ -584,7 +741,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   if (rc) return rc;
   knn_rerank_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(q, nq, ref, nref, dim, ld, k, self_offset, pl.kc,
                                                                   pl.nsplit, cs, ci, ctau, qn, qe, bmax, out_idx, out_dist,
-                                                                  fail_ids, fail_keys, fail_count);
+                                                                  fail_ids, fail_keys, fix_thr, fail_count);
   rc = scf_check_launch("scf_knn_l2(rerank)");
   if (rc) return rc;
   if (prm.flags & 16) {
@@ -597,6 +754,33 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     memset(h, 0, sizeof(h));
     cudaMemcpyToSymbol(g_dbg, h, sizeof(h));
   }
-  return knn_exact_fix_launch(q, fail_ids, fail_keys, fail_count, nq, ref, nref, dim, ld, k, self_offset, out_idx,
+  // ---- repair of the rows whose guard could not be proven: tensor-core collect pass, then FP64 on the few left ----
+  knn_fix_gather_kernel<<<SCF_NUM_SMS, 256, 0, stream>>>(qop, pl.kp, fail_ids, fail_count, qfix);
+  rc = scf_check_launch("scf_knn_l2(fix,gather)");
+  if (rc) return rc;
+  CUtensorMap tf;
+  rc = scf_make_tmap_2d_f32(&tf, qfix, (uint64_t)FIXTC_ROWS, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BM);
+  if (rc) return rc;
+  KnnTcParams fp = prm;
+  fp.nq = FIXTC_ROWS;
+  fp.nsplit = std::max(1, std::min(FIXTC_NSPLIT, pl.n_ref_tiles));
+  fp.tiles_per_split = (pl.n_ref_tiles + fp.nsplit - 1) / fp.nsplit;
+  fp.nsplit = (pl.n_ref_tiles + fp.tiles_per_split - 1) / fp.tiles_per_split;
+  fp.fail_count = fail_count, fp.fix_thr = fix_thr, fp.fix_cnt = fix_cnt, fp.fix_list = fix_list;
+  auto fkern = knn_tc_kernel<16, true>;
+  e = cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (e != cudaSuccess) {
+    scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
+    return -(int32_t)e;
+  }
+  fkern<<<dim3(FIXTC_ROWS / (QT * BM), (unsigned)fp.nsplit), NTHREADS, pl.smem, stream>>>(tf, tr, fp);
+  rc = scf_check_launch("scf_knn_l2(fix,collect)");
+  if (rc) return rc;
+  knn_fix_finish_kernel<<<SCF_NUM_SMS, 256, 0, stream>>>(q, ref, dim, ld, k, self_offset, fail_ids, fail_keys, fail_count,
+                                                         fix_cnt, fix_list, out_idx, out_dist, rest_ids, rest_keys,
+                                                         rest_count);
+  rc = scf_check_launch("scf_knn_l2(fix,finish)");
+  if (rc) return rc;
+  return knn_exact_fix_launch(q, rest_ids, rest_keys, rest_count, nq, ref, nref, dim, ld, k, self_offset, out_idx,
                               out_dist, ws + pl.off_fix, stream);
 }

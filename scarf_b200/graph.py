@@ -158,9 +158,8 @@ def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
     ``b = 2*dims + 64`` wide block: a degree-``degree`` polynomial of C (GEMMs) that damps everything below the
     block's smallest Ritz value, a Householder QR, and a Rayleigh-Ritz step.  It stops when every kept pair has a
     residual ``|C v - lambda v| <= tol * lambda_max`` (angle to the exact eigenvector <= residual / eigengap).
-    The Ritz values predict how many filter rounds are still needed; those run back to back before the next
-    Rayleigh-Ritz check.  When they show no usable gap after the block (prediction beyond the budget), or for
-    small matrices, the full ``eigh`` runs instead -- same answer, more time."""
+    When the measured residual reduction says the remaining budget cannot reach ``tol`` (no usable gap after the
+    block), or for small matrices, the full ``eigh`` runs instead -- same answer, more time."""
     h = cov.shape[0]
     b = 2 * dims + 64
     if h < 4 * b:
@@ -183,24 +182,20 @@ def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
             stats["eig_rounds"], stats["eig_residual"] = rounds, res
         if res <= tol:
             return _finish_eig(wt, v, dims)
-        # per-degree error reduction predicted from the Ritz values: exp(acosh(1 + 2 gap)), gap = (th_d - cut) / cut
-        gap = max((th_d - th_min) / max(th_min, 1e-300), 0.0)
-        rate = math.acosh(1.0 + 2.0 * gap) if gap > 0 else 0.0
-        need = math.log(res / tol) / rate if rate > 0 else math.inf
-        if prev_res is not None:  # trust the measured reduction per degree over the Ritz-value prediction
-            seen = math.log(max(prev_res / res, 1.0 + 1e-12)) / prev_deg
-            need = max(need, math.log(res / tol) / seen)
         # From a random start a column mixes all eigenvectors and a high degree would bury the weak ones under the
         # rounding noise of the strong ones (T_m grows like 70^m between them); once the block is rotated to Ritz
-        # vectors each column is dominated by its own eigenvector and the degree can double.
-        plan = [degree] if rounds == 0 else [2 * degree] * min(max(int(math.ceil(need / (2 * degree))), 1), 2)
-        if rounds + len(plan) > max_rounds or need > 2 * degree * (max_rounds - rounds) * 1.5:
+        # vectors each column is dominated by its own eigenvector and the degree can double.  A Rayleigh-Ritz
+        # rotation precedes EVERY filter application for the same reason.
+        m = degree if rounds == 0 else 2 * degree
+        if prev_res is not None:  # measured reduction per degree of the last round -> rounds still needed
+            seen = math.log(max(prev_res / res, 1.0 + 1e-12)) / prev_deg
+            if math.log(res / tol) / seen > 2.0 * m * (max_rounds - rounds):
+                break
+        if rounds >= max_rounds:
             break
-        q = q @ s
-        for m in plan:  # the cut / top estimates stay valid (Ritz values only move outwards)
-            q, _ = torch.linalg.qr(_cheb_filter(cov, q, m, th_min, th_max))
-        rounds += len(plan)
-        prev_res, prev_deg = res, sum(plan)
+        q, _ = torch.linalg.qr(_cheb_filter(cov, q @ s, m, th_min, th_max))
+        rounds += 1
+        prev_res, prev_deg = res, m
     w, v = torch.linalg.eigh(cov)
     if stats is not None:
         stats["eig_rounds"] = -1 - rounds
