@@ -472,3 +472,56 @@ def make_graph(counts, cell_idx, hvg_mask, dims=11, k=11, lc=1.0, bw=1.5, batch_
     if return_all:
         out.update({"x": x, "mu": mu, "sigma": sigma, "loadings": loadings, "embedding": y})
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# A.8  run_mapping                     scarf/mapping_utils.py:98-214, scarf/datastore/mapping_datastore.py:95-208
+# ----------------------------------------------------------------------------------------------
+def order_features(source_ids, target_ids, source_feat_ids):
+    """``_order_features`` with exclude_missing=False, filter_null=False (the defaults, mapping_utils.py:98-145):
+    for every source feature used by the graph, its column in the target matrix or -1 when the target lacks it."""
+    pos = {v: i for i, v in enumerate(target_ids)}
+    wanted = set(source_feat_ids)
+    s_idx = np.array([i for i, v in enumerate(source_ids) if v in wanted], dtype=np.int64)
+    t_re_idx = np.array([pos.get(source_ids[i], -1) for i in s_idx], dtype=np.int64)
+    if np.all(t_re_idx == -1):
+        raise ValueError("ERROR: None of the features from reference were found in the target data")
+    return s_idx, t_re_idx
+
+
+def aligned_target(target_counts, target_cell_idx, t_re_idx, sf=1000, log_transform=True, renormalize_subset=True,
+                   n_counts=None):
+    """``align_features`` (mapping_utils.py:186-213): the target normalised over the features it shares with the
+    source (``target.normed(cells, sorted_t_idx, **source subset_params)``), columns in the SOURCE order, features
+    the target lacks filled with 1.0."""
+    present = t_re_idx != -1
+    sorted_t_idx = np.array(sorted(t_re_idx[present]))
+    normed = normed_hvg(target_counts, target_cell_idx, sorted_t_idx, sf, log_transform, renormalize_subset, n_counts)
+    unsorter = np.argsort(np.argsort(t_re_idx[present]))
+    a = np.ones((normed.shape[0], t_re_idx.size))
+    a[:, np.where(present)[0]] = normed[:, unsorter]
+    return a
+
+
+def run_mapping(ref_embedding, loadings, mu, sigma, target_x, save_k=3, ref_mu=True, ref_sigma=True, nthreads=0):
+    """The projection loop (mapping_datastore.py:177-208): z-scale the aligned target with the reference's mu /
+    sigma (or the target's own when ``ref_mu`` / ``ref_sigma`` are False), embed with the reference loadings, query
+    the reference index for ``save_k`` neighbours -- no self handling.  Exact search stands in for hnswlib."""
+    if not ref_mu:
+        mu = clean_array(target_x.mean(axis=0))
+    if not ref_sigma:
+        sigma = clean_array(target_x.std(axis=0), 1)
+    y_q = ((target_x - mu) / sigma) @ loadings
+    idx, dist = exact_knn(y_q.astype(np.float32), np.asarray(ref_embedding, dtype=np.float32), save_k, self_offset=-1,
+                          nthreads=nthreads)
+    return idx, dist.astype(np.float64), y_q
+
+
+def mapping_score(indices, distances, n_ref, multiplier=1000.0, per_k=True):
+    """``get_mapping_score`` with the defaults (mapping_datastore.py:255-285), one group; ``per_k=False`` reproduces
+    the normalisation the reference's stored golden (cell_attributes.csv: mapping_scores) was generated with."""
+    w = 1.0 / (np.log1p(distances) + 1.0)
+    ms = np.zeros(n_ref)
+    np.add.at(ms, np.asarray(indices, dtype=np.int64).ravel(), w.ravel())
+    ms = multiplier * ms / (indices.shape[0] * (indices.shape[1] if per_k else 1))
+    return np.log1p(ms)

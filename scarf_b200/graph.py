@@ -97,6 +97,7 @@ class GraphResult:
     loadings: torch.Tensor  # float64 [H, dims]
     eigenvalues: torch.Tensor
     embedding: torch.Tensor  # float32 [n_local, ldy] (pad columns zero) -- what hnswlib would have indexed
+    embedding_all: torch.Tensor  # the embedding of ALL selected cells (== embedding on one GPU): run_mapping's index
     dims: int
     k: int
     indices: torch.Tensor    # int64 [n_local, k]
@@ -302,8 +303,8 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
     edges, weights = smoothen_dists(idx, dist, lc, bw, row_offset, batch_size, n_total, comm)
     mark("weights")
 
-    return GraphResult(n_total, row_offset, feat_idx_t.cpu().numpy(), mu_d, sigma_d, load, evals, y, dims, k, idx, dist,
-                       edges, weights)
+    return GraphResult(n_total, row_offset, feat_idx_t.cpu().numpy(), mu_d, sigma_d, load, evals, y, y_all, dims, k,
+                       idx, dist, edges, weights)
 
 
 def smoothen_dists(idx, dist, lc, bw, row_offset, chunk_size, n_total, comm: Comm | None = None):
@@ -324,3 +325,77 @@ def smoothen_dists(idx, dist, lc, bw, row_offset, chunk_size, n_total, comm: Com
         floor = min(1.0, float(cmin[sel].min()))
         ops.fill_zero_weights(weights, floor)
     return edges, weights
+
+
+# =============================================================================================
+# run_mapping
+# =============================================================================================
+@dataclass
+class MappingResult:
+    indices: torch.Tensor     # int64 [nq_local, save_k] ids of reference cells (global selected-row ids)
+    distances: torch.Tensor   # float32 [nq_local, save_k] squared L2
+    embedding: torch.Tensor   # float32 [nq_local, ld] target cells in the reference's PCA space
+    mu: torch.Tensor
+    sigma: torch.Tensor
+
+
+def run_mapping_csr(target: CsrDevice, target_cell_idx, t_col_of_feature, ref_mu, ref_sigma, ref_loadings,
+                    ref_embedding_all, dims, save_k=3, use_ref_mu=True, use_ref_sigma=True, log_transform=True,
+                    renormalize_subset=True, n_counts=None, comm: Comm | None = None) -> MappingResult:
+    """MappingDatastore.run_mapping's numeric core (scarf/datastore/mapping_datastore.py:118-208 with
+    mapping_utils.align_features :148-214) for this rank's target cells.
+
+    ``t_col_of_feature``: int array [H], for every feature of the reference graph (source order) its column in the
+    target matrix or -1 when the target lacks it (``_order_features``, exclude_missing=False); such features get
+    the value 1.0 before z-scaling (mapping_utils.py:208).  The target is normalised with the reference's
+    ``subset_params`` over the features it shares with the source.  ``ref_embedding_all`` is the reference embedding
+    of ALL reference cells (every rank holds it after make_graph's all-gather); no self handling in the query.
+    ``use_ref_mu`` / ``use_ref_sigma`` False: z-scale with the target's own column mean / std instead
+    (mapping_datastore.py:177-190)."""
+    comm = comm or Comm()
+    dev = target.device
+    t_col = np.asarray(t_col_of_feature, dtype=np.int64)
+    n_feat = int(t_col.size)
+    present = t_col >= 0
+    if not present.any():
+        raise ValueError("ERROR: None of the features from reference were found in the target data")
+    cm = np.full(target.n_cols, -1, dtype=np.int32)
+    cm[t_col[present]] = np.where(present)[0].astype(np.int32)
+    col_map = torch.from_numpy(cm).to(dev)
+    fill = np.where(present, np.nan, 1.0)
+    missing_fill = torch.from_numpy(fill).to(dev) if (~present).any() else None
+    n_local = target.n_rows if target_cell_idx is None else int(target_cell_idx.numel())
+    if renormalize_subset:
+        row_sum, _ = ops.csr_row_sums(target, target_cell_idx, col_map)
+    else:
+        row_sum = (n_counts[target_cell_idx] if target_cell_idx is not None else n_counts).contiguous()
+    mu_d, sigma_d = ref_mu, ref_sigma
+    if not (use_ref_mu and use_ref_sigma):
+        sx, sxx = ops.csr_hvg_colstats(target, target_cell_idx, col_map, n_feat, row_sum, SF, log_transform)
+        n = n_local
+        if comm.world > 1:
+            cnt = torch.tensor([n_local], dtype=torch.int64, device=dev)
+            comm.allreduce_sum_(sx), comm.allreduce_sum_(sxx), comm.allreduce_sum_(cnt)
+            n = int(cnt.item())
+        scale = 2.0 ** -lib.COLSTAT_SHIFT
+        mean = sx.to(torch.float64) * scale / n
+        var = torch.clamp(sxx.to(torch.float64) * scale / n - mean * mean, min=0.0)
+        miss = torch.from_numpy(~present).to(dev)
+        mean = torch.where(miss, torch.ones_like(mean), mean)  # a column of ones: mean 1, std 0
+        var = torch.where(miss, torch.zeros_like(var), var)
+        if not use_ref_mu:
+            mu_d = clean_array(mean)
+        if not use_ref_sigma:
+            sigma_d = clean_array(torch.sqrt(var), 1.0)
+    ldz = round_up(n_feat, 128)
+    z = torch.empty((max(n_local, 1), ldz), dtype=torch.float32, device=dev)
+    ops.csr_norm_scale(target, target_cell_idx, col_map, n_feat, row_sum, z, SF, log_transform, mu_d, sigma_d,
+                       missing_fill=missing_fill)
+    ldv = round_up(dims, 4)
+    v32 = torch.zeros((n_feat, ldv), dtype=torch.float32, device=dev)
+    v32[:, :dims] = ref_loadings[:, :dims].to(torch.float32)
+    y = ops.project(z, n_local, n_feat, v32, dims, ldy=int(ref_embedding_all.stride(0)))
+    del z
+    save_k = min(save_k, int(ref_embedding_all.shape[0]))
+    idx, dist = ops.knn_l2(y, ref_embedding_all, dims, save_k, self_offset=-1, method=1)
+    return MappingResult(idx, dist, y, mu_d, sigma_d)

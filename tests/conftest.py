@@ -43,4 +43,5 @@ def pbmc():
         "indices": np.load(os.path.join(GOLDEN, "pbmc_knn_indices.npy")),
         "distances": np.load(os.path.join(GOLDEN, "pbmc_knn_distances.npy")),
         "weights": np.load(os.path.join(GOLDEN, "pbmc_knn_weights.npy")),
+        "mapping_scores": np.load(os.path.join(GOLDEN, "pbmc_mapping_scores.npy")),
     }

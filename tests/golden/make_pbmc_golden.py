@@ -10,6 +10,7 @@ Inputs (reference, read-only):
 Outputs:
   pbmc_counts.npz   CSR of the raw counts (+ gene names, kept cell ids)
   pbmc_knn_indices.npy / pbmc_knn_distances.npy / pbmc_knn_weights.npy   copies of the goldens
+  pbmc_mapping_scores.npy   cell_attributes.csv column mapping_scores (run_mapping self-map, save_k=3)
 """
 import os
 import tarfile
@@ -36,4 +37,6 @@ np.savez_compressed(os.path.join(OUT, "pbmc_counts.npz"), indptr=counts.indptr.a
                     shape=np.array(counts.shape), names=names.astype("U"), cell_idx=attrs.index.values.astype(np.int64))
 for f in ("indices", "distances", "weights"):
     np.save(os.path.join(OUT, f"pbmc_knn_{f}.npy"), np.load(os.path.join(REF, f"knn_{f}.npy")))
+# run_mapping golden (test_datastore.py:160-163): self-mapping scores of the 808 cells
+np.save(os.path.join(OUT, "pbmc_mapping_scores.npy"), attrs.mapping_scores.values.astype(np.float64))
 print("ok", counts.shape, counts.nnz)

@@ -336,3 +336,61 @@ def test_full_chain_pbmc_golden(gpu, pbmc):
     idx = res.indices.cpu().numpy()
     recall = np.mean([len(set(a) & set(b)) / 11 for a, b in zip(idx, pbmc["indices"].astype(np.int64))])
     assert recall > 0.99, recall
+
+
+@pytest.mark.parametrize("use_ref", [True, False])
+def test_run_mapping_vs_oracle(gpu, chain, use_ref):
+    """run_mapping numeric core: target with permuted gene order and 7 % of the reference HVGs missing (filled with
+    1.0), reference mu/sigma/loadings (or the target's own mu/sigma); embedding vs the float64 oracle 1e-3, neighbour
+    ids and float32 distances bit-exact vs exact search on the same embeddings."""
+    from oracle import pipeline as P
+
+    torch, graph, synth = gpu["torch"], gpu["graph"], gpu["synth"]
+    res = chain["res"]
+    tgt = synth.make_counts_scipy(1500, 6000, 40, seed=12)
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(6000)                      # target column c holds source gene perm[c]
+    keep = np.ones(6000, dtype=bool)
+    hv_idx = np.where(chain["hv"])[0]
+    keep[rng.choice(hv_idx, size=35, replace=False)] = False   # the target lacks 35 of the 500 reference HVGs
+    cols = perm[keep[perm]]
+    tgt_sub = tgt[:, cols].tocsr()
+    tgt_sub.sort_indices()
+    source_ids = np.arange(6000)
+    s_idx, t_re = P.order_features(source_ids, cols, hv_idx)
+    assert (t_re == -1).sum() == 35
+    cell_idx = np.arange(5, 1400)
+    xt = P.aligned_target(tgt_sub, cell_idx, t_re)
+    load = res.loadings.cpu().numpy()
+    y_ref = res.embedding[:, : res.dims].cpu().numpy()
+    idx_o, dist_o, yq_o = P.run_mapping(y_ref, load, res.mu.cpu().numpy(), res.sigma.cpu().numpy(), xt, save_k=3,
+                                        ref_mu=use_ref, ref_sigma=use_ref)
+    m = graph.run_mapping_csr(_dev(gpu, tgt_sub), torch.from_numpy(cell_idx).cuda(), t_re, res.mu, res.sigma,
+                              res.loadings, res.embedding_all, res.dims, save_k=3, use_ref_mu=use_ref,
+                              use_ref_sigma=use_ref)
+    yq = m.embedding[:, : res.dims].cpu().numpy()
+    assert np.abs(yq - yq_o).max() < 1e-3
+    idx_e, dist_e = P.exact_knn(yq, y_ref, 3, self_offset=-1)
+    assert np.array_equal(m.indices.cpu().numpy().astype(np.uint64), idx_e)
+    assert np.array_equal(m.distances.cpu().numpy(), dist_e)
+    assert (m.indices.cpu().numpy() == idx_o.astype(np.int64)).mean() > 0.99  # same neighbours as the all-float64 path
+
+
+def test_run_mapping_pbmc_golden(gpu, pbmc):
+    """Self-map of the PBMC fixture (fixtures_datastore.py:146-153) -> mapping_scores golden (see
+    tests/test_oracle_golden.py::test_run_mapping_golden for the normalisation of the stored column)."""
+    from oracle import pipeline as P
+
+    torch, graph = gpu["torch"], gpu["graph"]
+    csr = _dev(gpu, pbmc["counts"])
+    n_counts, _ = graph.cell_totals(csr)
+    feat_I = (graph.gene_ncells(csr) > 20).cpu().numpy()
+    cell_idx = torch.from_numpy(pbmc["cell_idx"]).cuda()
+    hv = graph.mark_hvgs_csr(csr, cell_idx, feat_I, n_counts, 892, gene_names=pbmc["names"], top_n=100)
+    res = graph.make_graph_csr(csr, cell_idx, hv, dims=11, k=11, gram_mode=3, knn_method=1)
+    t_re = np.where(hv)[0]
+    m = graph.run_mapping_csr(csr, cell_idx, t_re, res.mu, res.sigma, res.loadings, res.embedding_all, res.dims, 3)
+    idx = m.indices.cpu().numpy()
+    assert np.array_equal(idx[:, 0], np.arange(808))
+    sc = P.mapping_score(idx, m.distances.cpu().numpy().astype(np.float64), 808, per_k=False)
+    assert (np.abs(sc - pbmc["mapping_scores"]) < 1e-2).mean() > 0.98

@@ -78,3 +78,39 @@ def test_sign_rule_matches_sklearn_svd_flip():
     u, s, vt = np.linalg.svd(rng.normal(size=(40, 12)), full_matrices=False)
     _, vt_f = svd_flip(u, vt, u_based_decision=False)
     assert np.allclose(P.sign_rule(vt), vt_f)
+
+
+def test_run_mapping_golden(pbmc, pbmc_oracle):
+    """run_mapping self-map (fixtures_datastore.py:146-153, save_k=3) -> cell_attributes.csv: mapping_scores
+    (test_datastore.py:160-163, tolerance 1e-2).  The stored golden predates the division by save_k that
+    get_mapping_score does today (mapping_datastore.py:282), hence per_k=False; exact PCA / exact search differ from
+    IncrementalPCA / hnswlib on a handful of neighbour lists, so the pin is the fraction of cells within tolerance."""
+    counts, cell_idx = pbmc["counts"], pbmc["cell_idx"]
+    ids = np.arange(counts.shape[1])
+    s_idx, t_re = P.order_features(ids, ids, np.where(pbmc_oracle["hvgs"])[0])
+    assert np.array_equal(s_idx, np.where(pbmc_oracle["hvgs"])[0]) and np.array_equal(t_re, s_idx)
+    xt = P.aligned_target(counts, cell_idx, t_re)
+    assert np.array_equal(xt, pbmc_oracle["x"])  # self-map: the aligned target IS the reference's normalised data
+    idx, dist, _ = P.run_mapping(pbmc_oracle["embedding"], pbmc_oracle["loadings"], pbmc_oracle["mu"],
+                                 pbmc_oracle["sigma"], xt, save_k=3)
+    assert np.array_equal(idx[:, 0], np.arange(len(cell_idx), dtype=idx.dtype))  # every cell finds itself first
+    sc = P.mapping_score(idx, dist, len(cell_idx), per_k=False)
+    assert (np.abs(sc - pbmc["mapping_scores"]) < 1e-2).mean() > 0.98
+
+
+def test_aligned_target_missing_features_and_order():
+    """Features the target lacks become columns of 1.0; present ones follow the SOURCE order (mapping_utils.py:200-211)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(0)
+    t = sp.csr_matrix(rng.poisson(1.0, size=(6, 9)).astype(np.uint32))
+    source_ids = np.array(["g%d" % i for i in range(12)])
+    target_ids = np.array(["g7", "g2", "x1", "g5", "g0", "x2", "g9", "g3", "x3"])
+    s_idx, t_re = P.order_features(source_ids, target_ids, source_ids[[0, 2, 4, 5, 9, 11]])
+    assert s_idx.tolist() == [0, 2, 4, 5, 9, 11] and t_re.tolist() == [4, 1, -1, 3, 6, -1]
+    a = P.aligned_target(t, np.arange(6), t_re)
+    assert np.all(a[:, [2, 5]] == 1.0)
+    dense = t.toarray().astype(np.float64)
+    sub = dense[:, [4, 1, 3, 6]]
+    tot = sub.sum(1, keepdims=True)
+    tot[tot == 0] = 1
+    np.testing.assert_allclose(a[:, [0, 1, 3, 4]], np.log1p(1000 * sub / tot), rtol=1e-12)
