@@ -1,0 +1,550 @@
+"""Scarf-compatible front end of the path: ``DataStore.mark_hvgs`` / ``make_graph`` / ``run_mapping`` /
+``load_graph`` with the reference's signatures, defaults, parameter resolution, error behaviour and Zarr layout
+(SURVEY.md 8(b), App. B), computing on the GPU through the C-ABI.
+
+What mirrors what (paths relative to the reference checkout):
+  DataStore.__init__      scarf/datastore/base_datastore.py:77,324-401 + scarf/assay.py:201-225 (nCounts, nFeatures,
+                          nCells, the cell / feature ``I`` columns)
+  mark_hvgs               scarf/datastore/datastore.py:223-314 -> scarf/assay.py:945-1074
+  make_graph              scarf/datastore/graph_datastore.py:513-1020 (+ _set_graph_params :63-363)
+  run_mapping             scarf/datastore/mapping_datastore.py:31-209 (+ mapping_utils.align_features :148-214)
+  load_graph              scarf/datastore/graph_datastore.py:474-511,1022-1075
+
+Differences that are deliberate (and documented in DESIGN.md): raw counts enter as CSR (``from_csr``) and are kept
+as three 1-D arrays under ``<assay>/counts_csr`` instead of the reference's dense chunked ``counts`` array; the
+``ann__...`` group holds the float32 embedding (``embedding``) in place of hnswlib's ``ann_idx`` file; arrays are
+written uncompressed; options the GPU path does not implement raise ``NotImplementedError`` (no CPU fallback).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import graph
+from . import hvg as hvg_host
+from . import ops
+from .dist import Comm
+from .ops import CsrDevice
+from .zarr_store import Group, open_group
+
+__all__ = ["DataStore", "AnnStream", "MetaData", "RNAassay"]
+
+
+class MetaData:
+    """Column store for cell / feature attributes (scarf/metadata.py): boolean key columns select subsets."""
+
+    def __init__(self, zgrp: Group):
+        self.z = zgrp
+        self.N = int(self.z["I"].shape[0])
+
+    @property
+    def columns(self):
+        return self.z.keys()
+
+    def get_dtype(self, column):
+        return self.z[column].dtype.type if self.z[column].dtype.kind != "b" else bool
+
+    def fetch_all(self, column):
+        if column not in self.z:
+            raise KeyError(f"ERROR: {column} not found in MetaData")
+        return self.z[column][:]
+
+    def active_index(self, key):
+        col = self.fetch_all(key)
+        if col.dtype != bool:
+            raise ValueError(f"ERROR: {key} is not of boolean type. Cannot perform fetch operation")
+        return np.where(col)[0]
+
+    def fetch(self, column, key="I"):
+        return self.fetch_all(column)[self.active_index(key)]
+
+    def insert(self, column_name, values, fill_value=np.nan, key="I", overwrite=False):
+        """metadata.py:395-433: ``values`` covers the rows where ``key`` is True; the rest get ``fill_value``."""
+        if column_name in ("I", "ids", "names"):
+            raise ValueError(f"ERROR: {column_name} is a protected column name in MetaData class.")
+        if column_name in self.z and not overwrite:
+            raise ValueError(f"ERROR: {column_name} already exists. Please set `overwrite` to True to overwrite.")
+        values = np.asarray(values)
+        idx = self.active_index(key)
+        if len(values) != len(idx):
+            raise ValueError(f"ERROR: `values` are of incorrect length: {len(values)} for {len(idx)} active rows")
+        full = np.full(self.N, fill_value, dtype=values.dtype if values.dtype.kind in "bU" else np.float64)
+        if values.dtype.kind == "b":
+            full = np.zeros(self.N, dtype=bool) | bool(fill_value)
+        full[idx] = values
+        a = self.z.create_dataset(column_name, full.shape, full.dtype, (100000,))
+        a[:] = full
+
+
+class RNAassay:
+    """The raw counts of one assay on the device plus its feature table (scarf/assay.py: RNAassay)."""
+
+    def __init__(self, zroot: Group, name: str, cells: MetaData, device):
+        self.name, self.z, self.cells = name, zroot[name], cells
+        self.feats = MetaData(self.z["featureData"])
+        self.sf = 1000  # scarf/assay.py:776
+        g = self.z["counts_csr"]
+        shape = tuple(g.attrs["shape"])
+        self.csr = CsrDevice.from_host(g["indptr"][:], g["indices"][:], g["data"][:], shape, device)
+
+    @property
+    def nCounts(self):
+        return self.cells.fetch_all(f"{self.name}_nCounts")
+
+
+class _KMeans:
+    def __init__(self, centers):
+        self.cluster_centers_ = centers
+
+
+class _ExactIndex:
+    """Stands where hnswlib's Index stood (scarf/ann.py:14-28): exact search on the stored embedding."""
+
+    def __init__(self, embedding: torch.Tensor, dims: int):
+        self.embedding, self.dims = embedding, dims
+
+    def knn_query(self, a, k: int = 1):
+        a = np.atleast_2d(np.asarray(a, dtype=np.float32))
+        q = torch.zeros((a.shape[0], self.embedding.stride(0)), dtype=torch.float32, device=self.embedding.device)
+        q[:, : a.shape[1]] = torch.from_numpy(a).to(q.device)
+        idx, dist = ops.knn_l2(q, self.embedding, self.dims, k, self_offset=-1, method=1)
+        return idx.cpu().numpy().astype(np.uint64), dist.cpu().numpy()
+
+    def save_index(self, path):
+        np.save(path + ".npy", self.embedding[:, : self.dims].cpu().numpy())
+
+
+class AnnStream:
+    """What ``make_graph(return_ann_object=True)`` hands back (scarf/ann.py:55): same attribute names."""
+
+    def __init__(self, res: graph.GraphResult, k: int, kmeans=None, labels=None):
+        self.k, self.method, self.dims = k, "pca", res.dims
+        self.mu, self.sigma = res.mu.cpu().numpy(), res.sigma.cpu().numpy()
+        self.loadings = res.loadings.cpu().numpy()
+        self.nCells, self.nFeats = res.n_cells, int(res.mu.numel())
+        self.harmonizedData, self.data = None, None
+        self.annIdx = _ExactIndex(res.embedding_all, res.dims)
+        self.kmeans, self.clusterLabels = kmeans, labels
+        self._res = res
+
+    def reducer(self, x):
+        """``transform_z(x).dot(loadings)`` (scarf/ann.py:138,191-192); accepts a block or one row."""
+        x = np.asarray(x, dtype=np.float64)
+        return ((x - self.mu) / self.sigma).dot(self.loadings)
+
+    def transform_ann(self, a, k=None, self_indices=None):
+        """scarf/ann.py:194-205: query ``k`` (+1 and drop self when ``self_indices`` is given)."""
+        k = self.k if k is None else k
+        if self_indices is None:
+            return self.annIdx.knn_query(a, k)
+        i, d = self.annIdx.knn_query(a, k + 1)
+        from .graph import fix_knn_query
+
+        return fix_knn_query(i, d, np.asarray(self_indices))
+
+
+class DataStore:
+    """A Scarf-style datastore whose graph path runs on B200.  Create with :meth:`from_csr`, reopen by path."""
+
+    def __init__(self, zarr_loc: str, default_assay: str = "RNA", device="cuda", comm: Optional[Comm] = None,
+                 mode: str = "r+"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("scarf_b200.DataStore needs a CUDA device: the path has no CPU fallback")
+        self.zw = open_group(zarr_loc, mode)
+        self.z = self.zw
+        self._defaultAssay = default_assay
+        self.device = torch.device(device)
+        self.comm = comm
+        self.cells = MetaData(self.zw["cellData"])
+        self._assays = {}
+        setattr(self, default_assay, self._get_assay(default_assay))
+
+    # ---------------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_csr(cls, zarr_loc: str, counts, feature_ids, feature_names=None, cell_ids=None, assay_name="RNA",
+                 min_features_per_cell: int = 10, min_cells_per_feature: int = 20, device="cuda", **kw):
+        """Ingest raw counts given as CSR (scipy) -- the role of ``SparseToZarr`` + the first ``DataStore(...)`` open
+        (scarf/writers.py:645-772, base_datastore.py:324-401, assay.py:201-225): writes cellData / featureData with
+        ids, names, ``I``, ``<assay>_nCounts``, ``<assay>_nFeatures``, ``nCells`` computed on the GPU."""
+        counts = counts.tocsr()
+        counts.sort_indices()
+        n, g = counts.shape
+        root = open_group(zarr_loc, "w")
+        dev = torch.device(device)
+        csr = CsrDevice.from_scipy(counts, dev)
+        n_counts, n_feats = graph.cell_totals(csr)
+        n_cells = graph.gene_ncells(csr)
+        cg = root.create_group("cellData")
+        cell_ids = np.asarray(cell_ids if cell_ids is not None else [f"c{i}" for i in range(n)]).astype("U")
+        feature_ids = np.asarray(feature_ids).astype("U")
+        feature_names = np.asarray(feature_names if feature_names is not None else feature_ids).astype("U")
+        nf = n_feats.cpu().numpy().astype(np.float64)
+
+        def put(grp, name, arr):
+            a = grp.create_dataset(name, arr.shape, arr.dtype, (100000,))
+            a[:] = arr
+
+        put(cg, "ids", cell_ids), put(cg, "names", cell_ids)
+        put(cg, "I", nf > min_features_per_cell)  # base_datastore.py:389-399
+        put(cg, f"{assay_name}_nCounts", n_counts.cpu().numpy())
+        put(cg, f"{assay_name}_nFeatures", nf)
+        ag = root.create_group(assay_name)
+        ag.attrs["is_assay"] = True
+        ag.attrs["misc"] = {"sf": 1000}
+        fg = ag.create_group("featureData")
+        nc = n_cells.cpu().numpy().astype(np.float64)
+        put(fg, "ids", feature_ids), put(fg, "names", feature_names)
+        put(fg, "I", nc > min_cells_per_feature)  # assay.py:225
+        put(fg, "nCells", nc)
+        rg = ag.create_group("counts_csr")
+        rg.attrs["shape"] = [int(n), int(g)]
+        put(rg, "indptr", counts.indptr.astype(np.int64))
+        put(rg, "indices", counts.indices.astype(np.int32))
+        put(rg, "data", counts.data.astype(np.uint32))
+        return cls(zarr_loc, default_assay=assay_name, device=device, **kw)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _get_assay(self, from_assay):
+        if from_assay not in self._assays:
+            if from_assay not in self.zw or "counts_csr" not in self.zw[from_assay]:
+                raise ValueError(f"ERROR: Assay {from_assay} was not found.")
+            self._assays[from_assay] = RNAassay(self.zw, from_assay, self.cells, self.device)
+        return self._assays[from_assay]
+
+    def _get_latest_keys(self, from_assay, cell_key, feat_key):
+        """graph_datastore.py / base: fall back on the keys the latest make_graph stored on the assay group."""
+        if from_assay is None:
+            from_assay = self._defaultAssay
+        a = self.zw[from_assay].attrs
+        if cell_key is None:
+            cell_key = a.get("latest_cell_key", "I")
+        if feat_key is None:
+            feat_key = a.get("latest_feat_key")
+            if feat_key is None:
+                raise ValueError("ERROR: No graph has been made yet: `feat_key` is unknown")
+        return from_assay, cell_key, feat_key
+
+    # ---------------------------------------------------------------------------------------------------------
+    def mark_hvgs(self, from_assay: Optional[str] = None, cell_key: str = "I", min_cells: Optional[int] = None,
+                  top_n: int = 500, min_var: float = -np.inf, max_var: float = np.inf, min_mean: float = -np.inf,
+                  max_mean: float = np.inf, n_bins: int = 200, lowess_frac: float = 0.1,
+                  blacklist: str = hvg_host.DEFAULT_BLACKLIST, show_plot: bool = False,
+                  hvg_key_name: str = "hvgs", **plot_kwargs) -> None:
+        """scarf/datastore/datastore.py:223-314.  Stores ``<cell_key>__<hvg_key_name>`` (bool) and the statistics
+        columns of ``set_summary_stats`` in the feature table."""
+        if cell_key not in self.cells.columns:
+            raise ValueError(f"ERROR: cell_key {cell_key} not found in cell metadata")
+        if from_assay is None:
+            from_assay = self._defaultAssay
+        assay = self._get_assay(from_assay)
+        if not isinstance(assay, RNAassay):
+            raise TypeError(f"ERROR: This method of feature selection can only be applied to RNAassay type of assay.")
+        if min_cells is None:
+            min_cells = int(0.01 * self.cells.N)  # datastore.py:291
+        cells = torch.from_numpy(self.cells.active_index(cell_key)).to(self.device)
+        n_counts = torch.from_numpy(assay.nCounts).to(self.device)
+        feat_I = assay.feats.fetch_all("I")
+        mask, st = graph.mark_hvgs_csr(assay.csr, cells, feat_I, n_counts, self.cells.N,
+                                       gene_names=assay.feats.fetch_all("names"), top_n=top_n, min_cells=min_cells,
+                                       min_mean=min_mean, max_mean=max_mean, n_bins=n_bins, lowess_frac=lowess_frac,
+                                       blacklist=blacklist, comm=self.comm, return_stats=True)
+        ident = f"{cell_key}__"
+        for name, col in (("normed_tot", "normed_tot"), ("avg", "avg"), ("nz_mean", "nz_mean"),
+                          ("sigmas", "sigmas"), ("normed_n", "normed_n"), ("c_var", f"c_var__{n_bins}__{lowess_frac}")):
+            assay.feats.insert(ident + col, st[name][feat_I], overwrite=True)  # assay.py:884-897, metadata.py:612
+        assay.feats.insert(ident + hvg_key_name, mask[feat_I], fill_value=False, overwrite=True)
+        return None
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _set_graph_params(self, from_assay, cell_key, feat_key, log_transform=None, renormalize_subset=None,
+                          reduction_method="auto", dims=None, pca_cell_key=None, ann_metric=None, ann_efc=None,
+                          ann_ef=None, ann_m=None, rand_state=None, k=None, n_centroids=None, local_connectivity=None,
+                          bandwidth=None) -> tuple:
+        """graph_datastore.py:63-363: every ``None`` resolves as explicit -> value cached by the latest run in the
+        same branch of the Zarr tree -> default."""
+        dv = {"log_transform": True, "renormalize_subset": True, "dims": 11, "ann_metric": "l2", "rand_state": 4466,
+              "k": 11, "n_centroids": 1000, "local_connectivity": 1.0, "bandwidth": 1.5}
+        zw = self.zw
+        normed_loc = f"{from_assay}/normed__{cell_key}__{feat_key}"
+        cached = zw[normed_loc].attrs.get("subset_params") if normed_loc in zw else None
+        if log_transform is None:
+            log_transform = cached["log_transform"] if cached else dv["log_transform"]
+        if renormalize_subset is None:
+            renormalize_subset = cached["renormalize_subset"] if cached else dv["renormalize_subset"]
+        log_transform, renormalize_subset = bool(log_transform), bool(renormalize_subset)
+        c_dims = c_pca = None
+        if normed_loc in zw and "latest_reduction" in zw[normed_loc].attrs:
+            c_dims, c_pca = zw[normed_loc].attrs["latest_reduction"].rsplit("__", 2)[1:]
+        if dims is None:
+            dims = int(c_dims) if c_dims is not None else dv["dims"]
+        if pca_cell_key is None:
+            pca_cell_key = c_pca if c_pca is not None else cell_key
+        else:
+            if pca_cell_key not in self.cells.columns:
+                raise ValueError(f"ERROR: `pca_use_cell_key` {pca_cell_key} does not exist in cell metadata")
+            if self.cells.get_dtype(pca_cell_key) != bool:
+                raise TypeError("ERROR: Type of `pca_use_cell_key` column in cell metadata should be `bool`")
+        dims = int(dims)
+        reduction_method = reduction_method.lower()
+        if reduction_method not in ["pca", "lsi", "auto", "custom"]:
+            raise ValueError("ERROR: Please choose either 'pca' or 'lsi' as reduction method")
+        if reduction_method == "auto":
+            reduction_method = "pca"  # RNAassay (graph_datastore.py:49-61)
+        reduction_loc = f"{normed_loc}/reduction__{reduction_method}__{dims}__{pca_cell_key}"
+        c = [None] * 5
+        if reduction_loc in zw and "latest_ann" in zw[reduction_loc].attrs:
+            c = zw[reduction_loc].attrs["latest_ann"].rsplit("/", 1)[1].split("__")[1:]
+        if ann_metric is None:
+            ann_metric = c[0] if c[0] is not None else dv["ann_metric"]
+        if ann_efc is None and c[1] is not None:
+            ann_efc = int(c[1])
+        if ann_ef is None and c[2] is not None:
+            ann_ef = int(c[2])
+        if ann_m is None:
+            ann_m = int(c[3]) if c[3] is not None else min(max(48, int(dims * 1.5)), 64)
+        if rand_state is None:
+            rand_state = int(c[4]) if c[4] is not None else dv["rand_state"]
+        ann_metric, ann_m, rand_state = str(ann_metric), int(ann_m), int(rand_state)
+        if k is None:
+            k = dv["k"]
+            if reduction_loc in zw and "latest_ann" in zw[reduction_loc].attrs:
+                ann_loc = zw[reduction_loc].attrs["latest_ann"]
+                if ann_loc in zw and "latest_knn" in zw[ann_loc].attrs:
+                    k = int(zw[ann_loc].attrs["latest_knn"].rsplit("__", 1)[1])
+        k = int(k)
+        ann_ef = int(min(100, max(k * 3, 50)) if ann_ef is None else ann_ef)
+        ann_efc = int(min(100, max(k * 3, 50)) if ann_efc is None else ann_efc)
+        ann_loc = f"{reduction_loc}/ann__{ann_metric}__{ann_efc}__{ann_ef}__{ann_m}__{rand_state}"
+        knn_loc = f"{ann_loc}/knn__{k}"
+        if n_centroids is None:
+            n_centroids = dv["n_centroids"]
+            if reduction_loc in zw and "latest_kmeans" in zw[reduction_loc].attrs:
+                n_centroids = int(zw[reduction_loc].attrs["latest_kmeans"].split("/")[-1].split("__")[1])
+        n_centroids = int(n_centroids)
+        c_lc = c_bw = None
+        if knn_loc in zw and "latest_graph" in zw[knn_loc].attrs:
+            c_lc, c_bw = map(float, zw[knn_loc].attrs["latest_graph"].rsplit("/", 1)[1].split("__")[1:])
+        if local_connectivity is None:
+            local_connectivity = c_lc if c_lc is not None else dv["local_connectivity"]
+        if bandwidth is None:
+            bandwidth = c_bw if c_bw is not None else dv["bandwidth"]
+        return (log_transform, renormalize_subset, reduction_method, dims, pca_cell_key, ann_metric, ann_efc, ann_ef,
+                ann_m, rand_state, k, n_centroids, float(local_connectivity), float(bandwidth))
+
+    def make_graph(self, from_assay: Optional[str] = None, cell_key: Optional[str] = None,
+                   feat_key: Optional[str] = None, pca_cell_key: Optional[str] = None, reduction_method: str = "auto",
+                   dims: Optional[int] = None, k: Optional[int] = None, ann_metric: Optional[str] = None,
+                   ann_efc: Optional[int] = None, ann_ef: Optional[int] = None, ann_m: Optional[int] = None,
+                   ann_parallel: bool = False, rand_state: Optional[int] = None, n_centroids: Optional[int] = None,
+                   batch_size: Optional[int] = None, log_transform: Optional[bool] = None,
+                   renormalize_subset: Optional[bool] = None, local_connectivity: Optional[float] = None,
+                   bandwidth: Optional[float] = None, update_keys: bool = True, return_ann_object: bool = False,
+                   custom_loadings: Optional[np.ndarray] = None, feat_scaling: bool = True,
+                   lsi_skip_first: bool = True, harmonize: bool = False, batch_columns=None,
+                   show_elbow_plot: bool = False, ann_index_fetcher=None, ann_index_saver=None):
+        """graph_datastore.py:513-1020 on the GPU.  Same groups, array names, dtypes, chunking and ``latest_*``
+        attributes; a re-run with the same parameters finds its groups and only reloads (the Zarr tree is the
+        checkpoint)."""
+        if from_assay is None:
+            from_assay = self._defaultAssay
+        assay = self._get_assay(from_assay)
+        if batch_size is None:
+            batch_size = 1000  # assay.rawData.chunksize[0] of a reference store (writers.py:164-204)
+        if cell_key is None:
+            cell_key = "I"
+        if feat_key is None:
+            bool_cols = [x.split("__", 1) for x in assay.feats.columns
+                         if assay.feats.get_dtype(x) == bool and x != "I"]
+            bool_cols = " ".join(f"{x[1]}({x[0]})" for x in bool_cols)
+            raise ValueError(
+                "ERROR: You have to choose which features that should be used for graph construction. "
+                "Ideally you should have performed a feature selection step before making this graph. "
+                "Feature selection step adds a column to your feature table. \n"
+                f"You have following boolean columns in the feature metadata of assay {from_assay} which you can "
+                f"choose from: {bool_cols}\n The values in brackets indicate the cell_key for which the feat_key is "
+                "available. Choosing 'I' as `feat_key` means that you will use all the genes for graph creation.")
+        if custom_loadings is not None or reduction_method.lower() in ("lsi", "custom") or harmonize or \
+                not feat_scaling or ann_index_fetcher is not None or ann_index_saver is not None:
+            raise NotImplementedError("scarf_b200.make_graph implements reduction_method='pca' with feature scaling; "
+                                      "custom loadings, LSI, Harmony and custom index stores are not on the GPU path")
+        (log_transform, renormalize_subset, reduction_method, dims, pca_cell_key, ann_metric, ann_efc, ann_ef, ann_m,
+         rand_state, k, n_centroids, local_connectivity, bandwidth) = self._set_graph_params(
+            from_assay, cell_key, feat_key, log_transform, renormalize_subset, reduction_method, dims, pca_cell_key,
+            ann_metric, ann_efc, ann_ef, ann_m, rand_state, k, n_centroids, local_connectivity, bandwidth)
+        if ann_metric != "l2":
+            raise NotImplementedError("scarf_b200.make_graph implements ann_metric='l2' only")
+        if pca_cell_key != cell_key:
+            raise NotImplementedError("fitting the PCA on a different cell subset (`pca_cell_key`) is not implemented")
+        zw = self.zw
+        normed_loc = f"{from_assay}/normed__{cell_key}__{feat_key}"
+        reduction_loc = f"{normed_loc}/reduction__{reduction_method}__{dims}__{pca_cell_key}"
+        ann_loc = f"{reduction_loc}/ann__{ann_metric}__{ann_efc}__{ann_ef}__{ann_m}__{rand_state}"
+        knn_loc = f"{ann_loc}/knn__{k}"
+        kmeans_loc = f"{reduction_loc}/kmeans__{n_centroids}__{rand_state}"
+        graph_loc = f"{knn_loc}/graph__{local_connectivity}__{bandwidth}"
+
+        # ---- Assay.save_normalized_data bookkeeping (assay.py:400-478): subset hash / params, latest keys ----
+        cell_idx = self.cells.active_index(cell_key)
+        feat_col = cell_key + "__" + feat_key if feat_key != "I" else "I"
+        feat_mask = assay.feats.fetch_all(feat_col)
+        if feat_mask.dtype != bool:
+            raise ValueError(f"ERROR: {feat_col} is not of boolean type. Cannot perform fetch operation")
+        feat_idx = np.where(feat_mask)[0]
+        subset_hash = hashlib.md5((str(cell_idx.tolist()) + str(feat_idx.tolist())).encode()).hexdigest()
+        subset_params = {"log_transform": log_transform, "renormalize_subset": renormalize_subset}
+        if normed_loc in zw and (zw[normed_loc].attrs.get("subset_hash") != subset_hash or
+                                 zw[normed_loc].attrs.get("subset_params") != subset_params):
+            zw.create_group(normed_loc, overwrite=True)  # stale cache: everything below it is recomputed
+        if normed_loc not in zw:
+            zw.create_group(normed_loc)
+        zw[normed_loc].attrs["subset_hash"] = subset_hash
+        zw[normed_loc].attrs["subset_params"] = subset_params
+        if update_keys:
+            zw[from_assay].attrs["latest_cell_key"] = cell_key
+            zw[from_assay].attrs["latest_feat_key"] = feat_key
+
+        cached = all(x in zw for x in (reduction_loc, ann_loc, knn_loc, graph_loc, kmeans_loc)) and \
+            "embedding" in zw[ann_loc] and "mu" in zw[normed_loc]
+        if cached and not return_ann_object:
+            self._set_latest(normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc)
+            return None
+
+        cells_t = torch.from_numpy(cell_idx).to(self.device)
+        n_counts = torch.from_numpy(assay.nCounts).to(self.device)
+        res = graph.make_graph_csr(assay.csr, cells_t, feat_mask, dims=dims, k=k, lc=local_connectivity,
+                                   bw=bandwidth, batch_size=batch_size, log_transform=log_transform,
+                                   renormalize_subset=renormalize_subset, n_counts=n_counts, comm=self.comm,
+                                   gram_mode=3, knn_method=1)
+        centers, labels = graph.fit_kmeans(res.embedding_all, res.dims, max(n_centroids, 2), rand_state)
+        ann_obj = AnnStream(res, res.k, _KMeans(centers.cpu().numpy().astype(np.float64)),
+                            labels.cpu().numpy().astype(np.float64))
+        if self.comm is None or self.comm.rank == 0 or self.comm.world == 1:
+            self._write_graph(res, ann_obj, normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc,
+                              batch_size)
+        self._set_latest(normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc)
+        return ann_obj if return_ann_object else None
+
+    def _set_latest(self, normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc):
+        zw = self.zw  # graph_datastore.py:1003-1008
+        zw[normed_loc].attrs["latest_reduction"] = reduction_loc
+        zw[reduction_loc].attrs["latest_ann"] = ann_loc
+        zw[reduction_loc].attrs["latest_kmeans"] = kmeans_loc
+        zw[ann_loc].attrs["isHarmonized"] = False
+        zw[ann_loc].attrs["latest_knn"] = knn_loc
+        zw[knn_loc].attrs["latest_graph"] = graph_loc
+
+    def _write_graph(self, res, ann_obj, normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc,
+                     batch_size):
+        """Array names / dtypes / chunks of SURVEY.md App. B (single writer: with several ranks the caller gathers)."""
+        zw = self.zw
+        if self.comm is not None and self.comm.world > 1:
+            raise NotImplementedError("writing the store from a sharded run: gather the GraphResult rows on rank 0 "
+                                      "(rank r owns rows [start_r, stop_r) of every array)")
+
+        def put(loc, name, arr, chunks, dtype):
+            if loc not in zw:
+                zw.create_group(loc)
+            a = zw[loc].create_dataset(name, arr.shape, dtype, chunks)
+            a[:] = arr.astype(dtype)
+
+        n, k = res.indices.shape
+        put(normed_loc, "mu", ann_obj.mu, (100000,), "f8")            # graph_datastore.py:778-796
+        put(normed_loc, "sigma", ann_obj.sigma, (100000,), "f8")
+        put(reduction_loc, "reduction", ann_obj.loadings, (batch_size, ann_obj.loadings.shape[0]), "f8")  # :921-928
+        put(ann_loc, "embedding", res.embedding_all[:, : res.dims].cpu().numpy(), (batch_size,), "f4")
+        put(kmeans_loc, "cluster_centers", ann_obj.kmeans.cluster_centers_, (1000, 1000), "f8")           # :958-976
+        put(kmeans_loc, "cluster_labels", ann_obj.clusterLabels, (100000,), "f8")
+        put(knn_loc, "indices", res.indices.cpu().numpy(), (batch_size,), "u8")                          # knn_utils.py:54-59
+        put(knn_loc, "distances", res.distances.cpu().numpy(), (batch_size,), "f8")
+        put(graph_loc, "edges", res.edges.cpu().numpy(), (batch_size * k,), "u8")                        # knn_utils.py:108-117
+        put(graph_loc, "weights", res.weights.cpu().numpy(), (batch_size * k,), "f8")
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _get_latest_graph_loc(self, from_assay, cell_key, feat_key):
+        """graph_datastore.py:379-397."""
+        normed_loc = f"{from_assay}/normed__{cell_key}__{feat_key}"
+        reduction_loc = self.zw[normed_loc].attrs["latest_reduction"]
+        ann_loc = self.zw[reduction_loc].attrs["latest_ann"]
+        knn_loc = self.zw[ann_loc].attrs["latest_knn"]
+        return self.zw[knn_loc].attrs["latest_graph"]
+
+    def load_graph(self, from_assay: Optional[str] = None, cell_key: Optional[str] = None,
+                   feat_key: Optional[str] = None, symmetric: bool = True, upper_only: bool = True,
+                   use_k: Optional[int] = None, graph_loc: Optional[str] = None):
+        """graph_datastore.py:1022-1075 + _store_to_sparse :474-511 -> scipy CSR."""
+        from scipy.sparse import csr_matrix, triu
+
+        from_assay, cell_key, feat_key = self._get_latest_keys(from_assay, cell_key, feat_key)
+        if graph_loc is None:
+            graph_loc = self._get_latest_graph_loc(from_assay, cell_key, feat_key)
+        if graph_loc not in self.zw:
+            raise ValueError(f"{graph_loc} not found in zarr location {self.zw.path}. Run `make_graph` for assay "
+                             f"{from_assay}")
+        knn_loc = graph_loc.rsplit("/", 1)[0]
+        n_cells, k = self.zw[knn_loc]["indices"].shape
+        store = self.zw[graph_loc]
+        edges, weights = store["edges"][:], store["weights"][:]
+        if use_k is not None and 0 < use_k < k:  # the first use_k of every row's k entries
+            keep = (np.arange(edges.shape[0]) % k) < use_k
+            edges, weights = edges[keep], weights[keep]
+        g = csr_matrix((weights, (edges[:, 0].astype(np.int64), edges[:, 1].astype(np.int64))),
+                       shape=(n_cells, n_cells))
+        if symmetric:
+            g = g + g.T - g.multiply(g.T)  # graph_datastore.py:1067-1070
+            if upper_only:
+                g = triu(g)
+        return g.tocsr()
+
+    # ---------------------------------------------------------------------------------------------------------
+    def run_mapping(self, target_assay: RNAassay, target_name: str, target_feat_key: str,
+                    from_assay: Optional[str] = None, cell_key: str = "I", feat_key: Optional[str] = None,
+                    save_k: int = 3, batch_size: int = 1000, ref_mu: bool = True, ref_sigma: bool = True,
+                    run_coral: bool = False, exclude_missing: bool = False, filter_null: bool = False,
+                    feat_scaling: bool = True, ann_index_fetcher=None, ann_index_saver=None,
+                    target_cell_key: str = "I") -> None:
+        """mapping_datastore.py:31-209: project the cells of ``target_assay`` onto this store's graph and store
+        ``projections/<target_name>/{indices (u8), distances (f8)}``."""
+        from_assay, cell_key, feat_key = self._get_latest_keys(from_assay, cell_key, feat_key)
+        source = self._get_assay(from_assay)
+        if type(target_assay) != type(source):
+            raise TypeError(f"ERROR: Source assay ({type(source)}) and target assay ({type(target_assay)}) are of "
+                            "different types. Mapping can only be performed between same assay types")
+        if target_feat_key == feat_key:
+            raise ValueError(f"ERROR: `target_feat_key` cannot be sample as `feat_key`: {feat_key}")
+        if run_coral or exclude_missing or filter_null or not feat_scaling:
+            raise NotImplementedError("scarf_b200.run_mapping implements the default path (no CORAL, "
+                                      "exclude_missing=False, filter_null=False, feat_scaling=True)")
+        target_assay.sf = source.sf
+        feat_col = cell_key + "__" + feat_key if feat_key != "I" else "I"
+        s_ids = source.feats.fetch_all("ids")
+        s_feat_idx = np.where(source.feats.fetch_all(feat_col))[0]
+        pos = {v: i for i, v in enumerate(target_assay.feats.fetch_all("ids"))}
+        t_col = np.array([pos.get(s_ids[i], -1) for i in s_feat_idx], dtype=np.int64)  # mapping_utils.py:98-145
+        if np.all(t_col == -1):
+            raise ValueError("ERROR: None of the features from reference were found in the target data")
+        ann_obj = self.make_graph(from_assay=from_assay, cell_key=cell_key, feat_key=feat_key,
+                                  return_ann_object=True, update_keys=False)
+        if save_k > ann_obj.k:
+            save_k = ann_obj.k
+        normed_loc = f"{from_assay}/normed__{cell_key}__{feat_key}"
+        params = self.zw[normed_loc].attrs["subset_params"]
+        res = ann_obj._res
+        t_cells = torch.from_numpy(target_assay.cells.active_index(target_cell_key)).to(self.device)
+        t_counts = torch.from_numpy(target_assay.nCounts).to(self.device)
+        m = graph.run_mapping_csr(target_assay.csr, t_cells, t_col, res.mu, res.sigma, res.loadings,
+                                  res.embedding_all, res.dims, save_k=save_k, use_ref_mu=ref_mu,
+                                  use_ref_sigma=ref_sigma, log_transform=params["log_transform"],
+                                  renormalize_subset=params["renormalize_subset"], n_counts=t_counts, comm=self.comm)
+        if "projections" not in self.zw[from_assay]:
+            self.zw[from_assay].create_group("projections")
+        store = self.zw[from_assay]["projections"].create_group(target_name, overwrite=True)
+        nc = int(t_cells.numel())
+        zi = store.create_dataset("indices", (nc, save_k), "u8", (batch_size,))
+        zd = store.create_dataset("distances", (nc, save_k), "f8", (batch_size,))
+        zi[:] = m.indices.cpu().numpy().astype(np.uint64)
+        zd[:] = m.distances.cpu().numpy().astype(np.float64)
+        return None

@@ -399,3 +399,50 @@ def run_mapping_csr(target: CsrDevice, target_cell_idx, t_col_of_feature, ref_mu
     save_k = min(save_k, int(ref_embedding_all.shape[0]))
     idx, dist = ops.knn_l2(y, ref_embedding_all, dims, save_k, self_offset=-1, method=1)
     return MappingResult(idx, dist, y, mu_d, sigma_d)
+
+
+# =============================================================================================
+# small pieces of the AnnStream contract
+# =============================================================================================
+def fix_knn_query(indices: np.ndarray, distances: np.ndarray, ref_idx: np.ndarray):
+    """scarf/ann.py:31-52: drop each query's own hit from a (k+1)-neighbour result -- column 0 when it is the query
+    itself, else wherever the query is found, else the last column.  Returns (indices, distances, n_not_first)."""
+    n, k1 = indices.shape
+    first = indices[:, 0] != ref_idx
+    pos = np.zeros(n, dtype=np.int64)
+    hit = indices == ref_idx[:, None]
+    found = hit.any(axis=1)
+    pos[found] = hit[found].argmax(axis=1)
+    pos[~found] = k1 - 1
+    keep = np.ones((n, k1), dtype=bool)
+    keep[np.arange(n), pos] = False
+    return indices[keep].reshape(n, k1 - 1), distances[keep].reshape(n, k1 - 1), int(first.sum())
+
+
+def fit_kmeans(embedding_all, dims, n_clusters, rand_state=4466, n_iter=10):
+    """The ``kmeans__<n>__<seed>`` arrays make_graph always writes (scarf/ann.py:328-346, read back by run_umap /
+    run_tsne for initialisation, graph_datastore.py:427-457).  The reference fits sklearn MiniBatchKMeans; its result
+    is not pinned by any reference test, so this is a deterministic Lloyd iteration on the GPU: seeded choice of
+    start rows, assignment = exact 1-nearest-centre search with the kNN kernel, update = segment means.  Every rank
+    holds the full embedding and gets identical centres and labels.  -> (centres float32 [n_clusters, dims],
+    labels int64 [n_cells])."""
+    n = int(embedding_all.shape[0])
+    n_clusters = int(max(2, min(n_clusters, n)))
+    dev = embedding_all.device
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(rand_state))
+    start = torch.sort(torch.randperm(n, generator=g)[:n_clusters]).values.to(dev)
+    ld = int(embedding_all.stride(0))
+    centres = embedding_all[start].clone()  # [n_clusters, ld], pad columns zero
+    labels = None
+    for it in range(n_iter + 1):
+        idx, _ = ops.knn_l2(embedding_all, centres, dims, 1, self_offset=-1, method=1)
+        labels = idx[:, 0]
+        if it == n_iter:
+            break
+        sums = torch.zeros((n_clusters, ld), dtype=torch.float64, device=dev)
+        sums.index_add_(0, labels, embedding_all.to(torch.float64))
+        cnt = torch.bincount(labels, minlength=n_clusters).to(torch.float64)
+        new = (sums / cnt.clamp(min=1.0)[:, None]).to(torch.float32)
+        centres = torch.where((cnt > 0)[:, None], new, centres).contiguous()  # an empty cluster keeps its centre
+    return centres[:, :dims].contiguous(), labels
