@@ -60,6 +60,23 @@ int32_t scf_csr_hvg_colstats(const int64_t* indptr, const int32_t* indices, cons
                              const double* row_sum, double sf, int32_t log_transform, int32_t n_cols,
                              int32_t n_rep, int64_t* sum_fx, int64_t* sumsq_fx, void* stream);
 
+/* ---- K1a' / K1b': the same two steps through a compact matrix ---------------------------------
+ * scf_csr_hvg_compact does K1a's pass and, in the same scan, writes the selected non-zero entries of
+ * every row as a small CSR of normalised values (out_col int32, out_x float64; row r occupies
+ * [row_off[r], row_off[r+1]), row_off = exclusive prefix sum of the out_nnz of scf_csr_row_sums).
+ * scf_hvg_dense_scale then produces exactly the Z (and z_lo) of scf_csr_norm_scale from that matrix
+ * without re-reading the raw counts or re-evaluating log1p: HBM sees 12 B per selected entry
+ * instead of 8 B per stored value.  make_graph uses this pair; scf_csr_norm_scale stays for callers
+ * that already know mu / sigma (run_mapping). */
+int32_t scf_csr_hvg_compact(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
+                            const int64_t* row_ids, int64_t n_sel, const int32_t* col_map,
+                            const double* row_sum, double sf, int32_t log_transform,
+                            const int64_t* row_off, int32_t* out_col, double* out_x, int32_t n_cols,
+                            int32_t n_rep, int64_t* sum_fx, int64_t* sumsq_fx, void* stream);
+int32_t scf_hvg_dense_scale(const int64_t* row_off, const int32_t* cols, const double* xs,
+                            int64_t n_sel, int32_t n_cols, const double* mu, const double* sigma,
+                            float* z, float* z_lo, int64_t ldz, void* stream);
+
 /* ---- K1b: fused lib-size normalise -> log1p -> HVG gather -> z-scale --------------------------
  * Z[r, col_map[g]] = (x - mu)/sigma   (AnnStream.transform_z, scarf/ann.py:191-192; the dense
  * row also gets (0 - mu)/sigma where the cell has no count).  Z is float32 row-major with row

@@ -149,6 +149,12 @@ def _cheb_filter(cov, x, degree, cut, top):
     return y
 
 
+def _orthonormalise(y):
+    """Orthonormal basis of range(y): Householder QR.  (Cholesky-QR is cheaper but breaks down here: after a filter
+    the unconverged tail columns of the block are dominated by leaked top eigenvectors and become nearly parallel.)"""
+    return torch.linalg.qr(y)[0]
+
+
 def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
     """K3: top-``dims`` eigenpairs of the symmetric PSD float64 matrix ``cov`` (replicated on every rank; the inputs
     are bit-identical after the integer all-reduce and the start block is seeded, so every rank gets the same
@@ -156,11 +162,11 @@ def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
 
     Only ``dims`` << H pairs are needed, so instead of a full tridiagonalisation (cuSOLVER syevd: ~28 ms at H = 2000
     on B200 -- two thousand dependent BLAS-2 panels) this runs Chebyshev-filtered subspace iteration on a
-    ``b = 2*dims + 64`` wide block: a degree-``degree`` polynomial of C (GEMMs) that damps everything below the
-    block's smallest Ritz value, a Householder QR, and a Rayleigh-Ritz step.  It stops when every kept pair has a
-    residual ``|C v - lambda v| <= tol * lambda_max`` (angle to the exact eigenvector <= residual / eigengap).
-    When the measured residual reduction says the remaining budget cannot reach ``tol`` (no usable gap after the
-    block), or for small matrices, the full ``eigh`` runs instead -- same answer, more time."""
+    ``b = 2*dims + 64`` wide block: a polynomial of C (GEMMs) that damps everything below the block's smallest Ritz
+    value, an orthonormalisation, and a Rayleigh-Ritz step.  It stops when every kept pair has a residual
+    ``|C v - lambda v| <= tol * lambda_max`` (angle to the exact eigenvector <= residual / eigengap).  When the
+    measured residual reduction says the remaining budget cannot reach ``tol`` (no usable gap after the block), or
+    for small matrices, the full ``eigh`` runs instead -- same answer, more time."""
     h = cov.shape[0]
     b = 2 * dims + 64
     if h < 4 * b:
@@ -169,8 +175,11 @@ def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
     g = torch.Generator(device=cov.device)
     g.manual_seed(4466)
     q = torch.randn((h, b), dtype=torch.float64, device=cov.device, generator=g)
-    q, _ = torch.linalg.qr(cov @ (cov @ q))
-    rounds, prev_res, prev_deg = 0, None, 0
+    # first filter without a Rayleigh-Ritz step: cut at the mean eigenvalue (the wanted ones lie above it),
+    # upper bound from the 1-norm
+    bounds = torch.stack([torch.diagonal(cov).sum() / h, cov.abs().sum(dim=0).max()]).tolist()
+    q = _orthonormalise(_cheb_filter(cov, q, degree, float(bounds[0]), float(bounds[1])))
+    rounds, prev_res, prev_deg = 1, None, 0
     while True:
         aq = cov @ q
         t = q.T @ aq
@@ -178,7 +187,7 @@ def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
         top, wt = s[:, -dims:], w[-dims:]
         v = q @ top
         res_t = (aq @ top - v * wt).norm(dim=0).max() / w[-1]
-        res, th_min, th_d, th_max = (float(x) for x in torch.stack([res_t, w[0], wt[0], w[-1]]).tolist())
+        res, th_min, th_max = (float(x) for x in torch.stack([res_t, w[0], w[-1]]).tolist())
         if stats is not None:
             stats["eig_rounds"], stats["eig_residual"] = rounds, res
         if res <= tol:
@@ -186,15 +195,15 @@ def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
         # From a random start a column mixes all eigenvectors and a high degree would bury the weak ones under the
         # rounding noise of the strong ones (T_m grows like 70^m between them); once the block is rotated to Ritz
         # vectors each column is dominated by its own eigenvector and the degree can double.  A Rayleigh-Ritz
-        # rotation precedes EVERY filter application for the same reason.
-        m = degree if rounds == 0 else 2 * degree
+        # rotation precedes EVERY further filter application for the same reason.
+        m = 2 * degree
         if prev_res is not None:  # measured reduction per degree of the last round -> rounds still needed
             seen = math.log(max(prev_res / res, 1.0 + 1e-12)) / prev_deg
             if math.log(res / tol) / seen > 2.0 * m * (max_rounds - rounds):
                 break
         if rounds >= max_rounds:
             break
-        q, _ = torch.linalg.qr(_cheb_filter(cov, q @ s, m, th_min, th_max))
+        q = _orthonormalise(_cheb_filter(cov, q @ s, m, th_min, th_max))
         rounds += 1
         prev_res, prev_deg = res, m
     w, v = torch.linalg.eigh(cov)
@@ -205,12 +214,13 @@ def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
 
 def normalise_stats(csr, cell_idx, col_map, n_feat, comm, log_transform=True, renormalize_subset=True,
                     n_counts=None):
-    """Row scalars + mu / sigma of the normalised feature matrix (graph_datastore.py:767-796)."""
-    if renormalize_subset:
-        row_sum, _ = ops.csr_row_sums(csr, cell_idx, col_map)  # scarf/assay.py:814-823
-    else:
+    """Row scalars, mu / sigma of the normalised feature matrix (graph_datastore.py:767-796) and -- from the same
+    scan -- the compact matrix of normalised values that :func:`ops.hvg_dense_scale` turns into Z."""
+    row_sum, row_nnz = ops.csr_row_sums(csr, cell_idx, col_map)  # scarf/assay.py:814-823
+    if not renormalize_subset:
         row_sum = (n_counts[cell_idx] if cell_idx is not None else n_counts).contiguous()
-    sx, sxx = ops.csr_hvg_colstats(csr, cell_idx, col_map, n_feat, row_sum, SF, log_transform)
+    row_off, cols, xs, sx, sxx = ops.csr_hvg_compact(csr, cell_idx, col_map, n_feat, row_sum, row_nnz, SF,
+                                                     log_transform)
     n_local = csr.n_rows if cell_idx is None else int(cell_idx.numel())
     n = n_local
     if comm.world > 1:
@@ -223,7 +233,7 @@ def normalise_stats(csr, cell_idx, col_map, n_feat, comm, log_transform=True, re
     var = torch.clamp(sxx.to(torch.float64) * scale / n - mean * mean, min=0.0)
     mu = clean_array(mean)
     sigma = clean_array(torch.sqrt(var), 1.0)
-    return row_sum, mu, sigma, int(n)
+    return (row_off, cols, xs), mu, sigma, int(n)
 
 
 def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, bw=1.5, batch_size=1000,
@@ -256,7 +266,7 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
     n_local = csr.n_rows if cell_idx is None else int(cell_idx.numel())
 
     # ---- normalisation scalars, mu, sigma (collective 2a) ----
-    row_sum, mu_d, sigma_d, n_total = normalise_stats(csr, cell_idx, col_map, n_feat, comm, log_transform,
+    compact, mu_d, sigma_d, n_total = normalise_stats(csr, cell_idx, col_map, n_feat, comm, log_transform,
                                                       renormalize_subset, n_counts)
     if mu is not None:  # run_mapping reuses the reference's mu / sigma
         mu_d, sigma_d = mu, sigma
@@ -270,7 +280,8 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
     ldz = round_up(n_feat, 128)
     z = torch.empty((max(n_local, 1), ldz), dtype=torch.float32, device=dev)
     z_lo = torch.empty_like(z) if (gram_mode == 3 and loadings is None) else None
-    ops.csr_norm_scale(csr, cell_idx, col_map, n_feat, row_sum, z, SF, log_transform, mu_d, sigma_d, z_lo=z_lo)
+    ops.hvg_dense_scale(*compact, n_feat, z, mu_d, sigma_d, z_lo=z_lo)
+    del compact
     mark("normalise")
 
     # ---- PCA: Gram (K2, collective 2b) + eigensolve (K3) ----

@@ -21,6 +21,8 @@ SIGNATURES = {
     "scf_csr_gene_stats": (_i32, [_p, _p, _p, _p, _i64, _i32, _p, _f64, _p, _p, _p, _p]),
     "scf_csr_hvg_colstats": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _f64, _i32, _i32, _i32, _p, _p, _p]),
     "scf_csr_norm_scale": (_i32, [_p, _p, _p, _p, _i64, _p, _i32, _p, _f64, _i32, _p, _p, _p, _p, _p, _i64, _p]),
+    "scf_csr_hvg_compact": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _f64, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p]),
+    "scf_hvg_dense_scale": (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i64, _p]),
     "scf_gram_accumulate": (_i32, [_p, _p, _i64, _i64, _i32, _p, _i64, _i32, _p]),
     "scf_gram_symmetrize": (_i32, [_p, _i32, _i64, _p]),
     "scf_project": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _i32, _p, _i64, _p]),

@@ -110,6 +110,34 @@ def csr_hvg_colstats(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, sf=1000.
     return tot[0], tot[1]
 
 
+def csr_hvg_compact(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, row_nnz, sf=1000.0, log_transform=True,
+                    n_rep=32):
+    """One scan: compact normalised matrix of the selected non-zero entries + fixed-point column sums.
+    ``row_nnz`` = int32 per-row count from :func:`csr_row_sums` with the same ``col_map``.
+    -> (row_off int64 [n+1], cols int32, xs float64, sum_fx, sumsq_fx)."""
+    n = csr.n_rows if row_ids is None else int(row_ids.numel())
+    row_off = torch.zeros(n + 1, dtype=torch.int64, device=csr.device)
+    torch.cumsum(row_nnz, dim=0, out=row_off[1:])
+    total = int(row_off[-1].item())
+    cols = torch.empty(max(total, 1), dtype=torch.int32, device=csr.device)
+    xs = torch.empty(max(total, 1), dtype=torch.float64, device=csr.device)
+    acc = torch.zeros((2, n_rep, n_cols), dtype=torch.int64, device=csr.device)
+    lib.call("scf_csr_hvg_compact", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
+             _ptr(col_map), _ptr(row_sum), float(sf), int(bool(log_transform)), _ptr(row_off), _ptr(cols), _ptr(xs),
+             int(n_cols), int(n_rep), acc[0].data_ptr(), acc[1].data_ptr(), _stream())
+    tot = acc.sum(dim=1)
+    return row_off, cols, xs, tot[0], tot[1]
+
+
+def hvg_dense_scale(row_off, cols, xs, n_cols, z, mu=None, sigma=None, z_lo=None):
+    """Z rows [0, n) (and z_lo) from the compact matrix of :func:`csr_hvg_compact`; same values as csr_norm_scale."""
+    n = int(row_off.numel()) - 1
+    assert z.dtype == torch.float32 and z.stride(1) == 1 and z.shape[0] >= n
+    lib.call("scf_hvg_dense_scale", _ptr(row_off), _ptr(cols), _ptr(xs), n, int(n_cols), _ptr(mu), _ptr(sigma),
+             z.data_ptr(), z_lo.data_ptr() if z_lo is not None else None, int(z.stride(0)), _stream())
+    return z
+
+
 def csr_norm_scale(csr: CsrDevice, row_ids, col_map, n_cols, row_sum, z, sf=1000.0, log_transform=True, mu=None,
                    sigma=None, missing_fill=None, z_lo=None):
     """Writes rows [0, n_sel) of the float32 matrix z (row stride z.stride(0)) with (x - mu)/sigma; ``z_lo``

@@ -122,6 +122,25 @@ def test_normalised_values(gpu, chain, synth_small):
     assert (chain["x"].sum(1) == 0).sum() >= 0
 
 
+def test_compact_path_equals_direct_path(gpu, chain):
+    """K1a' + K1b' (compact matrix) give bit for bit the column sums of K1a and the Z / z_lo of K1b."""
+    torch, ops = gpu["torch"], gpu["ops"]
+    hv, cell_idx, csr, res = chain["hv"], chain["cell_idx"], chain["csr"], chain["res"]
+    cm = np.full(csr.n_cols, -1, dtype=np.int32)
+    cm[np.where(hv)[0]] = np.arange(hv.sum())
+    cmap, rows, h = torch.from_numpy(cm).cuda(), torch.from_numpy(cell_idx).cuda(), int(hv.sum())
+    s, nnz = ops.csr_row_sums(csr, rows, cmap)
+    sx0, sxx0 = ops.csr_hvg_colstats(csr, rows, cmap, h, s)
+    row_off, cols, xs, sx1, sxx1 = ops.csr_hvg_compact(csr, rows, cmap, h, s, nnz)
+    assert torch.equal(sx0, sx1) and torch.equal(sxx0, sxx1)
+    assert int(row_off[-1]) == int(nnz.sum()) and bool((cols[: int(row_off[-1])] >= 0).all())
+    z0, l0 = torch.full((len(cell_idx), 512), 3.0, device="cuda"), torch.full((len(cell_idx), 512), 3.0, device="cuda")
+    z1, l1 = torch.full_like(z0, 5.0), torch.full_like(z0, 5.0)
+    ops.csr_norm_scale(csr, rows, cmap, h, s, z0, mu=res.mu, sigma=res.sigma, z_lo=l0)
+    ops.hvg_dense_scale(row_off, cols, xs, h, z1, res.mu, res.sigma, z_lo=l1)
+    assert torch.equal(z0, z1) and torch.equal(l0, l1)
+
+
 def test_mu_sigma(chain):
     res = chain["res"]
     np.testing.assert_allclose(res.mu.cpu().numpy(), chain["mu"], rtol=1e-8, atol=1e-12)
