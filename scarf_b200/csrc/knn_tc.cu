@@ -22,7 +22,10 @@
 
 namespace {
 
-__device__ unsigned long long g_dbg[8];  // SCF_KNN_FLAGS & 16: event counters (developer diagnostics)
+#ifndef SCF_KNN_DEBUG
+#define SCF_KNN_DEBUG 0  // compile-time developer switches for the epilogue: 4 / 8 = timing experiments, 16 = counters
+#endif
+__device__ unsigned long long g_dbg[8];  // SCF_KNN_DEBUG & 16: event counters (developer diagnostics)
 
 constexpr int BM = 128;        // queries per MMA (= TMEM lanes)
 constexpr int QT = 2;          // query tiles per CTA: both reuse every reference tile staged in shared memory
@@ -389,13 +392,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
         uint32_t v[32];
         tc::tmem_ld32(t_row, v);
-  #pragma unroll 1
+  #pragma unroll
         for (int cc = 0; cc < BN / 32; ++cc) {
           tc::tmem_ld_wait();
-          const uint32_t mask = stage_hits<KC>(v, cl.thr, st_slot, p.flags);
+          const uint32_t mask = stage_hits<KC>(v, cl.thr, st_slot, SCF_KNN_DEBUG);
           // v is dead: the TMEM load of the next chunk overlaps the drain of this one
           if (cc + 1 < BN / 32) tc::tmem_ld32(t_row + (uint32_t)((cc + 1) * 32), v);
-          drain_hits<KC>(mask, j0 + cc * 32, cl, li_slot, st_slot, p.flags);
+          drain_hits<KC>(mask, j0 + cc * 32, cl, li_slot, st_slot, SCF_KNN_DEBUG);
         }
         tc::tc_fence_before();
         tc::mbar_arrive(tmem_empty + acc);
@@ -744,7 +747,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
                                                                   fail_ids, fail_keys, fix_thr, fail_count);
   rc = scf_check_launch("scf_knn_l2(rerank)");
   if (rc) return rc;
-  if (prm.flags & 16) {
+  if (SCF_KNN_DEBUG & 16) {
     unsigned long long h[8];
     cudaStreamSynchronize(stream);
     cudaMemcpyFromSymbol(h, g_dbg, sizeof(h));

@@ -129,11 +129,28 @@ __global__ void __launch_bounds__(256) membership_kernel(const int64_t* __restri
   edges[2 * e] = g;
   edges[2 * e + 1] = nb;
   weights[e] = w;
+  // per-chunk minimum of the non-zero weights / "has a zero" flag.  A full warp whose 32 consecutive edges lie in
+  // one chunk (all but the warps that straddle a chunk boundary or the tail) reduces first: one atomic per warp
+  // instead of one per edge on the same handful of addresses.
   const int64_t c = g / chunk_size;
-  if (w == 0.f)
+  const unsigned active = __activemask();
+  if (active == SCF_FULL && __match_any_sync(SCF_FULL, c) == SCF_FULL) {
+    float wmin = w > 0.f ? w : CUDART_INF_F;
+    int zero = w == 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wmin = fminf(wmin, __shfl_xor_sync(SCF_FULL, wmin, o));
+      zero |= __shfl_xor_sync(SCF_FULL, zero, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (zero) chunk_has_zero[c] = 1;
+      if (wmin < CUDART_INF_F) atomic_min_pos(chunk_min + c, wmin);
+    }
+  } else if (w == 0.f) {
     chunk_has_zero[c] = 1;
-  else
+  } else {
     atomic_min_pos(chunk_min + c, w);
+  }
 }
 
 __global__ void fill_zero_kernel(float* __restrict__ w, int64_t n, float v) {

@@ -71,8 +71,8 @@ def mark_hvgs_csr(csr: CsrDevice, cell_idx, feat_I, n_counts, n_cells_total, gen
     feat_I_t = feat_I if torch.is_tensor(feat_I) else torch.from_numpy(np.asarray(feat_I, dtype=bool))
     keep_t = keep_mask if torch.is_tensor(keep_mask) else torch.from_numpy(np.asarray(keep_mask, dtype=bool))
     feat_I_t, keep_t = feat_I_t.to(dev), keep_t.to(dev)
-    c_var = torch.full((csr.n_cols,), math.nan, dtype=torch.float64, device=dev)
-    c_var[feat_I_t] = hvg_host.remove_trend_device(st["avg"][feat_I_t], st["sigmas"][feat_I_t], n_bins, lowess_frac)
+    c_var = hvg_host.remove_trend_device(st["avg"], st["sigmas"], n_bins, lowess_frac, select=feat_I_t)
+    c_var = torch.where(feat_I_t, c_var, torch.full_like(c_var, math.nan))
     mask = hvg_host.choose_hvgs_device(st["normed_n"], st["nz_mean"], c_var, feat_I_t & keep_t, top_n, min_cells,
                                        max_cells, min_mean, max_mean)
     out = mask if as_tensor else mask.cpu().numpy()

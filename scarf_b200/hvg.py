@@ -151,56 +151,66 @@ def blacklist_keep_mask(gene_names, n_genes, blacklist=DEFAULT_BLACKLIST):
     return np.ones(n_genes, dtype=bool)
 
 
-def remove_trend_device(avg, sigmas, n_bins=200, lowess_frac=0.1):
-    """:func:`remove_trend` on float64 device vectors (any device); returns a device vector."""
+def remove_trend_device(avg, sigmas, n_bins=200, lowess_frac=0.1, select=None):
+    """:func:`remove_trend` on float64 device vectors (any device); returns a device vector of the same length.
+    ``select`` (bool tensor, optional) restricts the fit to those entries (the feature ``I`` column); the others get
+    0.  Written without boolean indexing so that the only device->host synchronisation is the copy of the <= n_bins
+    binned points that the LOWESS fit needs."""
     import torch
 
-    out = torch.zeros_like(avg)
-    pos = avg > 0
-    la, lb = torch.log(avg[pos]), torch.log(sigmas[pos])
-    if la.numel() == 0:
-        return out
-    lo_hi = torch.stack([la.min(), la.max()]).cpu().numpy()
-    # np.histogram's edges for `bins=n_bins` (linspace over the data range), last edge widened like the reference
-    first, last = (float(lo_hi[0]) - 0.5, float(lo_hi[1]) + 0.5) if lo_hi[0] == lo_hi[1] else (float(lo_hi[0]), float(lo_hi[1]))
-    edges = np.linspace(first, last, n_bins + 1, endpoint=True)
-    edges[-1] += 0.1
-    edges_t = torch.from_numpy(edges).to(la.device)
-    which = torch.bucketize(la, edges_t, right=True) - 1  # edges[i] <= la < edges[i+1]
-    valid = (which >= 0) & (which < n_bins)
+    n = avg.numel()
+    dev = avg.device
+    pos = avg > 0 if select is None else (avg > 0) & select
+    nan = torch.full_like(avg, float("nan"))
+    la = torch.where(pos, torch.log(torch.where(pos, avg, torch.ones_like(avg))), nan)
+    lb = torch.where(pos, torch.log(torch.where(pos, sigmas, torch.ones_like(sigmas))), nan)
+    inf = torch.full_like(avg, float("inf"))
+    first = torch.where(pos, la, inf).min()
+    last = torch.where(pos, la, -inf).max()
+    same = first == last  # np.histogram widens a zero-width range by +-0.5
+    first, last = torch.where(same, first - 0.5, first), torch.where(same, last + 0.5, last)
+    # np.histogram's edges for `bins=n_bins`: linspace(first, last, n_bins + 1) = arange * step + first with the last
+    # edge set to `last` exactly; the reference then widens the last edge by 0.1 (feat_utils.py:25-27)
+    step = (last - first) / n_bins
+    edges = torch.arange(n_bins + 1, dtype=torch.float64, device=dev) * step + first
+    edges[-1] = last + 0.1
+    which = torch.bucketize(torch.where(pos, la, inf), edges, right=True) - 1  # edges[i] <= la < edges[i+1]
+    valid = pos & (which >= 0) & (which < n_bins)
     which = torch.where(valid, which, torch.full_like(which, n_bins))  # invalid -> a bin past the end
-    # min-log(b) gene of every non-empty bin, first one on ties: stable sort by lb, then stable sort by bin
-    i1 = torch.argsort(lb, stable=True)
-    i2 = torch.argsort(which[i1], stable=True)
-    order = i1[i2]
-    w_sorted = which[order]
-    is_first = torch.ones_like(w_sorted, dtype=torch.bool)
-    is_first[1:] = w_sorted[1:] != w_sorted[:-1]
-    firsts = order[is_first & (w_sorted < n_bins)]
-    pts = torch.stack([which[firsts].to(torch.float64), la[firsts], lb[firsts]]).cpu().numpy()
-    fit = _lowess(pts[2], pts[1], lowess_frac, 100)
+    # min-log(b) gene of every non-empty bin, the first one on ties (argmin over the bin's members)
+    binmin = torch.full((n_bins + 1,), float("inf"), dtype=torch.float64, device=dev)
+    binmin.scatter_reduce_(0, which, torch.where(valid, lb, inf), "amin", include_self=True)
+    ids = torch.arange(n, device=dev)
+    cand = torch.where(valid & (lb == binmin[which]), ids, torch.full_like(ids, n))
+    firsts = torch.full((n_bins + 1,), n, dtype=ids.dtype, device=dev)
+    firsts.scatter_reduce_(0, which, cand, "amin", include_self=True)
+    firsts = firsts[:n_bins]
+    safe = firsts.clamp(max=max(n - 1, 0))
+    pts = torch.stack([(firsts < n).to(torch.float64), la[safe], lb[safe]]).cpu().numpy()  # the one synchronisation
+    bins = np.where(pts[0] > 0)[0]
     fit_of_bin = np.full(n_bins + 1, np.nan)
-    fit_of_bin[pts[0].astype(np.int64)] = fit
-    fit_t = torch.from_numpy(fit_of_bin).to(la.device)
+    if bins.size:
+        fit_of_bin[bins] = _lowess(pts[2][bins], pts[1][bins], lowess_frac, 100)
+    fit_t = torch.from_numpy(fit_of_bin).to(dev)
     val = torch.exp(lb - fit_t[which])
-    val = torch.where(valid, val, torch.zeros_like(val))
-    out[pos] = val
-    return out
+    return torch.where(valid, val, torch.zeros_like(val))
 
 
 def choose_hvgs_device(normed_n, nz_mean, c_var, eligible, top_n=500, min_cells=0, max_cells=np.inf,
                        min_mean=-np.inf, max_mean=np.inf, min_var=None, max_var=np.inf):
-    """:func:`choose_hvgs` on device vectors; ``eligible`` = feat_I & blacklist-keep (bool tensor)."""
+    """:func:`choose_hvgs` on device vectors; ``eligible`` = feat_I & blacklist-keep (bool tensor).  No
+    synchronisation: the (top_n+1)-th largest corrected variance is picked with a device-side index."""
     import torch
 
     min_mean = 2.0 ** min_mean if min_mean != -np.inf else min_mean
     max_mean = 2.0 ** max_mean if max_mean != np.inf else max_mean
     idx = (normed_n > min_cells) & (normed_n < max_cells) & (nz_mean > min_mean) & (nz_mean < max_mean) & eligible
+    idx = idx & ~torch.isnan(c_var)
     if top_n is not None:
-        cv = torch.sort(c_var[idx], descending=True).values
-        n_valid = int(cv.numel())
-        if top_n > n_valid:
-            top_n = n_valid - 1
-        thr = cv[top_n]
+        ninf = torch.full_like(c_var, float("-inf"))
+        cv = torch.sort(torch.where(idx, c_var, ninf), descending=True).values
+        n_valid = idx.sum()
+        kk = torch.minimum(torch.full_like(n_valid, int(top_n)), n_valid - 1).clamp(min=0)  # assay.py:1035-1040
+        thr = cv[kk]
         return idx & (c_var > thr)
     return idx & (c_var > 2.0 ** min_var) & (c_var < 2.0 ** max_var)

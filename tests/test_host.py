@@ -78,8 +78,8 @@ def test_hvg_device_functions_match_host(pbmc):
     hv_o, st = P.mark_hvgs(counts, cell_idx, feat_I, gene_names=pbmc["names"], top_n=100, return_stats=True)
     t = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)) for k, v in st.items()}
     fI = torch.from_numpy(feat_I)
-    c_var = torch.full((counts.shape[1],), float("nan"), dtype=torch.float64)
-    c_var[fI] = hvg.remove_trend_device(t["avg"][fI], t["sigmas"][fI])
+    c_var = hvg.remove_trend_device(t["avg"], t["sigmas"], select=fI)
+    c_var = torch.where(fI, c_var, torch.full_like(c_var, float("nan")))
     ref = hvg.remove_trend(st["avg"][feat_I], st["sigmas"][feat_I])
     np.testing.assert_allclose(c_var[fI].numpy(), ref, rtol=1e-12)
     keep = torch.from_numpy(hvg.blacklist_keep_mask(pbmc["names"], counts.shape[1]))
