@@ -49,6 +49,17 @@ int32_t scf_csr_gene_stats(const int64_t* indptr, const int32_t* indices, const 
                            const double* row_div, double sf, unsigned long long* gene_nnz,
                            double* gene_sum, double* gene_sumsq, void* stream);
 
+/* Same statistics, sector-packed reductions: the three accumulators of a gene share one 32-byte sector of the
+ * workspace (double [n_genes][4]) and one reduction instruction carries all three additions of eight stored values,
+ * a third of the L2 reduction requests of scf_csr_gene_stats.  Results are ACCUMULATED into gene_nnz / gene_sum /
+ * gene_sumsq exactly like scf_csr_gene_stats.  workspace: scf_csr_gene_stats_workspace_bytes(n_genes), device. */
+int64_t scf_csr_gene_stats_workspace_bytes(int32_t n_genes);
+int32_t scf_csr_gene_stats_packed(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
+                                  const int64_t* row_ids, int64_t n_sel, int32_t n_genes,
+                                  const double* row_div, double sf, unsigned long long* gene_nnz,
+                                  double* gene_sum, double* gene_sumsq, void* workspace,
+                                  int64_t workspace_bytes, void* stream);
+
 /* ---- K1a: column sums of the normalised HVG matrix -------------------------------------------
  * x = log1p(sf*c/row_sum[r]) (log_transform) or sf*c/row_sum[r]   (scarf/assay.py:54-64,826)
  * accumulates sum x and sum x^2 per selected column as int64 fixed point (<< SCF_COLSTAT_SHIFT):
@@ -159,6 +170,14 @@ int32_t scf_fill_zero_weights(float* weights, int64_t n, float floor_value, void
  * mark_hvgs' trend removal.  All pointers are HOST pointers; out[i] = fitted value at exog[i]. */
 int32_t scf_host_lowess(const double* endog, const double* exog, int64_t n, double frac, int32_t it,
                         double* out);
+
+/* ---- the same fit on the device (one CTA, no host round trip) -------------------------------------
+ * endog / exog / out: DEVICE float64 [n], n <= 512; valid (nullable, uint8 [n]): points with valid[i] == 0 are
+ * left out of the fit (mark_hvgs' empty bins) and get out[i] = NaN.  Same arithmetic, in the same order, as
+ * scf_host_lowess.  If fewer than 2 points are usable or frac * n_usable is outside [2, n_usable] (the host routine's
+ * argument error) every out[i] is NaN. */
+int32_t scf_lowess(const double* endog, const double* exog, const uint8_t* valid, int32_t n, double frac,
+                   int32_t it, double* out, void* stream);
 
 #ifdef __cplusplus
 }

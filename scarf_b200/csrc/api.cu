@@ -26,8 +26,18 @@ extern "C" const char* scf_last_error(void) { return g_err; }
 
 // ---- TMA descriptor helper shared by the tcgen05 kernels ----
 #include "tc_common.cuh"
+static int32_t make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint32_t esize,
+                            uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows);
 int32_t scf_make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld,
                              uint32_t box_cols, uint32_t box_rows) {
+  return make_tmap_2d(out, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, cols, ld, box_cols, box_rows);
+}
+int32_t scf_make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_cols, uint32_t box_rows) {
+  return make_tmap_2d(out, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, rows, cols, ld, box_cols, box_rows);
+}
+static int32_t make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint32_t esize,
+                            uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
   static scf_encode_tiled_fn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -40,10 +50,10 @@ int32_t scf_make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows,
     fn = (scf_encode_tiled_fn)p;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint64_t strides[1] = {ld * esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+  CUresult r = fn(out, dtype, 2, (void*)base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -1,18 +1,28 @@
-// K5, method 1: exact kNN = tcgen05 TF32 candidate generation + exact FP64 re-rank + proven guard band.
+// K5, method 1: exact kNN = tcgen05 FP16 candidate generation + exact FP64 re-rank + proven guard band.
 //
 //   score(i,j) = |b_j|^2 - 2 a_i.b_j  (= d(i,j) - |a_i|^2) is produced by ONE tensor-core contraction: the
 //   operands are augmented along K,   A' = [a, 1, 1, 1, 0..],  B' = [-2b, n_hi, n_mid, n_lo, 0..]  with
-//   |b|^2 = n_hi + n_mid + n_lo split into TF32-exact pieces, so the epilogue has no per-element arithmetic
-//   besides the top-k' filter.  Pad reference rows carry n_hi = 1e30 and never win.
+//   |b|^2 = n_hi + n_mid + n_lo split into FP16-exact pieces, so the epilogue has no per-element arithmetic
+//   besides the top-k' filter.
 //
-//   kernel 1 (knn_prep)    builds A', B' (values pre-rounded to TF32, round-to-nearest), |a|^2, max|b|.
-//   kernel 2 (knn_tc)      one CTA per (128-query tile, reference split): TMA -> smem (128B swizzle) ->
-//                          tcgen05.mma kind::tf32 (M=128, N=256, K=8) -> TMEM (2 x 256 columns, double
-//                          buffered) -> 4 epilogue warps, one query row per thread, keep the k' smallest.
+//   Operands are FP16 (kind::f16, FP32 accumulate), not TF32: both formats keep an 11-bit significand, so the
+//   guard band is the same, but an FP16 instruction covers K = 16 instead of 8 for the same 32 bytes per operand
+//   row.  On B200 one M128 x N128 tcgen05.mma costs ~175 cycles whatever the kind (measured, profiles/), so half
+//   the instructions is half the tensor time, and the reference stream through L2 / shared memory halves too.
+//   FP16's 5-bit exponent is handled by an exact power-of-two scale s (both operands are multiplied by s before
+//   rounding, s^2 max|b|^2 <= 2^15): distances scale by s^2, the guard works in scaled units.
+//
+//   kernel 0 (knn_range)   max |b|^2 over the references, max |a_t| over the queries -> s.
+//   kernel 1 (knn_prep)    builds A', B' (s * value rounded to FP16, round-to-nearest), |a|^2, max|b|, rounding norms.
+//   kernel 2 (knn_tc)      one CTA per SM walks an equal share of the (256-query tile, 128-reference tile) space:
+//                          TMA -> smem (128B swizzle) -> tcgen05.mma kind::f16 (M=128, N=128, K=16) -> TMEM
+//                          (2 x 2 x 128 columns, double buffered) -> 8 epilogue warps, one query row per thread,
+//                          keep the k' smallest.
 //   kernel 3 (knn_rerank)  one warp per query: the oracle's FP64 distance for every candidate, order by
 //                          (float32 distance, index), and the guard: everything the tensor cores rejected is
 //                          provably farther than the k-th kept neighbour, else the row goes on the fail list.
 //   kernel 4 (knn_exact)   FP64 brute force for the fail list (device-side count, no host round trip).
+#include <cuda_fp16.h>
 #include <float.h>
 #include <stdlib.h>
 #include <string.h>
@@ -23,60 +33,109 @@
 namespace {
 
 #ifndef SCF_KNN_DEBUG
-#define SCF_KNN_DEBUG 0  // compile-time developer switches for the epilogue: 4 / 8 = timing experiments, 16 = counters
+#define SCF_KNN_DEBUG 0  // compile-time developer switches: 4 / 8 / 32 / 64 = timing experiments (no drain / read-out only / no read-out / no MMA), 16 = counters
 #endif
 __device__ unsigned long long g_dbg[8];  // SCF_KNN_DEBUG & 16: event counters (developer diagnostics)
 
 constexpr int BM = 128;        // queries per MMA (= TMEM lanes)
 constexpr int QT = 2;          // query tiles per CTA: both reuse every reference tile staged in shared memory
 constexpr int BN = 128;        // references per MMA / accumulator tile (TMEM columns)
-constexpr int KCH = 32;        // float32 per 128-byte swizzle row
+constexpr int KCH = 64;        // FP16 values per 128-byte swizzle row
+constexpr int KSTEP = 16;      // K per tcgen05.mma kind::f16 (32 bytes of every operand row)
 constexpr int A_CHUNK_BYTES = BM * 128;
 constexpr int B_STAGE_BYTES = BN * 128;
 constexpr int NTHREADS = 320;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue
 constexpr int NLISTS = QT * BM;  // one candidate list per query row of the CTA
-constexpr float PAD_NORM = 1e30f;
 
-// error model of the tensor-core score (see DESIGN.md "kNN guard band"), a~ = tf32(a), da = a - a~ (known exactly):
+// error model of the tensor-core score (see DESIGN.md "kNN guard band"), all in scaled units (a := s a, b := s b),
+// a~ = fp16(a), da = a - a~ (known exactly):
 //   |2 a.b - 2 a~.b~| = 2 |da.b + a~.db| <= 2 (|da| |b| + |a| |db|)      with |da| per query, max |b|, max |db|
-//   tf32 x tf32 products are exact in FP32; accumulation of <= 131 terms in any order with a truncating adder
-//   (2^-23 per add, x4 margin) -> 2^-14 (2|a||b| + |b|^2); the |b|^2 split leaves < 2^-28 |b|^2
-__device__ __host__ inline double eps_acc() { return 0x1p-14 + 0x1p-28; }
+//   fp16 x fp16 products are exact in FP32; accumulation of kp terms in any order with a truncating adder
+//   (2^-23 per add, x4 margin) -> 4 kp 2^-23 (2|a||b| + |b|^2); the three-way FP16 split of |b|^2 leaves less than
+//   2^-30 |b|^2 + 2^-24 (the last piece may be subnormal)
+__device__ __host__ inline double eps_acc(int kp) { return 4.0 * kp * 0x1p-23 + 0x1p-30; }
+constexpr double EPS_SPLIT_ABS = 0x1p-24;
 
-__device__ __forceinline__ float to_tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// the power-of-two operand scale: s^2 max|b|^2 <= 2^15 and s max|a_t| <= 2^14 (FP16 holds up to 65504)
+__device__ __forceinline__ float knn_scale(const float* __restrict__ range) {
+  const float bn2 = range[0], amax = range[1];
+  int e = 0;  // s = 2^e
+  if (bn2 > 0.f) {
+    int eb;
+    frexpf(bn2, &eb);  // bn2 < 2^eb
+    e = (15 - eb) >> 1;  // floor: s^2 bn2 < 2^(2e + eb) <= 2^15
+  }
+  if (amax > 0.f) {
+    int ea;
+    frexpf(amax, &ea);  // amax < 2^ea
+    e = min(e, 14 - ea);
+  }
+  e = max(-60, min(e, 14));  // large e only blows tiny data up into the normal FP16 range
+  return ldexpf(1.f, e);
 }
-__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// ---------------------------------------------------------------------------------------------- prep
-// one warp per row; rows [0, nq_pad) of qop and [0, nr_pad) of rop
-__global__ void __launch_bounds__(256) knn_prep_kernel(const float* __restrict__ q, int64_t nq, int64_t nq_pad,
-                                                       const float* __restrict__ ref, int64_t nref, int64_t nr_pad,
-                                                       int dim, int64_t ld, int kp, float* __restrict__ qop,
-                                                       float* __restrict__ rop, double* __restrict__ qnorm2,
-                                                       float* __restrict__ qerr, float* __restrict__ bmax) {
+__global__ void __launch_bounds__(256) knn_range_kernel(const float* __restrict__ q, int64_t nq,
+                                                        const float* __restrict__ ref, int64_t nref, int dim, int64_t ld,
+                                                        float* __restrict__ range) {
   const int lane = threadIdx.x & 31;
   const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
-  float local_bmax = 0.f, local_dbmax = 0.f;  // bmax[0] = max |b|, bmax[1] = max |b - tf32(b)|
+  float bn2 = 0.f, amax = 0.f;
+  for (int64_t r = w0; r < nq + nref; r += nw) {
+    const bool is_q = r < nq;
+    const float* src = is_q ? q + r * ld : ref + (r - nq) * ld;
+    float n2 = 0.f, m = 0.f;
+    for (int t = lane; t < dim; t += 32) {
+      const float x = src[t];
+      n2 = fmaf(x, x, n2);
+      m = fmaxf(m, fabsf(x));
+    }
+    if (is_q) {
+      amax = fmaxf(amax, m);
+    } else {
+      n2 = warp_sum(n2);
+      bn2 = fmaxf(bn2, n2 * 1.001f);  // margin for the float32 summation
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(SCF_FULL, amax, o));
+  if (lane == 0) {
+    // non-negative floats order like their bit patterns; NaN / inf inputs saturate the scale, the FP64 re-rank and
+    // the guard then send such rows to the exact path
+    if (bn2 > 0.f) atomicMax(reinterpret_cast<int*>(range), __float_as_int(fminf(bn2, 3e38f)));
+    if (amax > 0.f) atomicMax(reinterpret_cast<int*>(range + 1), __float_as_int(fminf(amax, 3e38f)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- prep
+// one warp per row; rows [0, nq_pad) of qop and [0, nr_pad) of rop.  Pad rows are all zero: pad queries never keep a
+// candidate (threshold -FLT_MAX), pad references are rejected by index in the epilogue.
+__global__ void __launch_bounds__(256) knn_prep_kernel(const float* __restrict__ q, int64_t nq, int64_t nq_pad,
+                                                       const float* __restrict__ ref, int64_t nref, int64_t nr_pad,
+                                                       int dim, int64_t ld, int kp, __half* __restrict__ qop,
+                                                       __half* __restrict__ rop, double* __restrict__ qnorm2,
+                                                       float* __restrict__ qerr, const float* __restrict__ range,
+                                                       float* __restrict__ bmax) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
+  const float sc = knn_scale(range);
+  float local_bmax = 0.f, local_dbmax = 0.f;  // bmax[0] = max |b|, bmax[1] = max |b - fp16(b)|  (scaled units)
   for (int64_t r = w0; r < nq_pad + nr_pad; r += nw) {
     const bool is_q = r < nq_pad;
     const int64_t row = is_q ? r : r - nq_pad;
     const bool live = is_q ? row < nq : row < nref;
     const float* src = (is_q ? q : ref) + row * ld;
-    float* dst = (is_q ? qop : rop) + row * kp;
+    __half* dst = (is_q ? qop : rop) + row * kp;
     double n2 = 0.0, e2 = 0.0;
     for (int t = lane; t < kp; t += 32) {
       if (t >= dim && t < dim + 3) continue;  // the three augmentation slots are written below
-      float v = 0.f;
+      __half v = __float2half_rn(0.f);
       if (live && t < dim) {
-        const float x = src[t];
-        const float xr = to_tf32_rn(x);
-        const double dx = (double)x - (double)xr;
+        const float x = src[t] * sc;  // exact: sc is a power of two
+        const __half xr = __float2half_rn(x);
+        const double dx = (double)x - (double)__half2float(xr);
         n2 += (double)x * (double)x;
         e2 += dx * dx;
-        v = is_q ? xr : -2.f * xr;
+        v = is_q ? xr : __float2half_rn(-2.f * __half2float(xr));  // exact doubling
       }
       dst[t] = v;
     }
@@ -87,14 +146,12 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const float* __restrict__
       if (is_q) {
         aug = live ? 1.f : 0.f;
       } else if (live) {
-        const float hi = tf32_trunc((float)n2);
-        const float mid = tf32_trunc((float)(n2 - (double)hi));
-        const float lo = tf32_trunc((float)(n2 - (double)hi - (double)mid));
+        const float hi = __half2float(__float2half_rn((float)n2));
+        const float mid = __half2float(__float2half_rn((float)(n2 - (double)hi)));
+        const float lo = __half2float(__float2half_rn((float)(n2 - (double)hi - (double)mid)));
         aug = lane == 0 ? hi : (lane == 1 ? mid : lo);
-      } else {
-        aug = lane == 0 ? PAD_NORM : 0.f;
       }
-      dst[dim + lane] = aug;
+      dst[dim + lane] = __float2half_rn(aug);
     }
     if (lane == 0 && live) {
       if (is_q) {
@@ -108,6 +165,7 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const float* __restrict__
   }
   if (lane == 0 && local_bmax > 0.f) atomicMax(reinterpret_cast<int*>(bmax), __float_as_int(local_bmax));
   if (lane == 0 && local_dbmax > 0.f) atomicMax(reinterpret_cast<int*>(bmax + 1), __float_as_int(local_dbmax));
+  if (blockIdx.x == 0 && threadIdx.x == 0) bmax[2] = sc * sc;  // distances in scaled units = s^2 * distance
 }
 
 // ---------------------------------------------------------------------------------------------- main
@@ -194,7 +252,7 @@ __device__ __forceinline__ uint32_t stage_hits(const uint32_t (&v)[32], float th
 }
 
 template <int KC>
-__device__ __forceinline__ void drain_hits(uint32_t mask, int jbase, CandList<KC>& cl, int* li_slot,
+__device__ __forceinline__ void drain_hits(uint32_t mask, int jbase, int nref, CandList<KC>& cl, int* li_slot,
                                            const float* st_slot, int dbg) {
   const bool cnt = (dbg & 16) && (threadIdx.x & 31) == 0;
   while (__any_sync(SCF_FULL, mask != 0u)) {
@@ -203,7 +261,7 @@ __device__ __forceinline__ void drain_hits(uint32_t mask, int jbase, CandList<KC
       const int c = __ffs(mask) - 1;
       mask &= mask - 1;
       const float sc = st_slot[c * NLISTS];
-      if (sc < cl.thr) {
+      if (sc < cl.thr && jbase + c < nref) {
         if (dbg & 16) atomicAdd(&g_dbg[3], 1ull);
         cl.replace_max(sc, jbase + c, li_slot);
       }
@@ -221,7 +279,10 @@ struct KnnTcParams {
   float* cand_score;    // [nq_pad, nsplit, KC]  (unsorted)
   int* cand_idx;
   float* cand_tau;      // [nq_pad, nsplit]  largest kept score = lower bound of every rejected score
+  int balanced;         // 1: the (query tile, reference tile) space is cut into gridDim.x equal contiguous ranges
+  long long total_work; //    n_q_tiles * n_ref_tiles (balanced mode)
   int nq;               // live query rows (pad rows keep nothing)
+  int nref;             // live reference rows (pad rows are rejected by index)
   int flags;            // developer switches (SCF_KNN_FLAGS): 2 = back off in waits, 4/8 = timing experiments, 16 = counters
   // collect pass (repair of guard failures): query row r of this launch is failed row r of the fail list
   const int* fail_count;   // device count of failed rows (rows >= min(count, FIXTC_ROWS) do nothing)
@@ -252,7 +313,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   float* st = reinterpret_cast<float*>(li + (size_t)KC * NLISTS);           // staged chunk values [32][NLISTS]
   uint64_t* bars = reinterpret_cast<uint64_t*>(st + (size_t)32 * NLISTS);
   uint64_t* a_full = bars;
-  uint64_t* full = bars + 1;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* full = bars + 2;
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -260,14 +322,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t backoff = (p.flags & 2) ? 32u : 0u;
-  const int q0 = blockIdx.x * (QT * BM);
-  const int split = blockIdx.y;
-  const int tile_begin = split * p.tiles_per_split;
-  const int tile_end = min(tile_begin + p.tiles_per_split, p.n_ref_tiles);
-  const int ntiles = max(tile_end - tile_begin, 0);
+  // Work of this CTA: a contiguous range [w0, w1) of the linearised (query tile, reference tile) space, walked as
+  // segments that stay inside one query tile.  Legacy grid (blockIdx.x = query tile, blockIdx.y = reference split):
+  // exactly one segment.  Balanced grid: every CTA gets total_work / gridDim.x tile steps, so all SMs finish
+  // together whatever the number of query tiles; a query tile cut by a range boundary keeps one candidate list per
+  // part (slot = this CTA's index minus the index of the CTA that holds the tile's first step).
+  const int T = p.n_ref_tiles;
+  long long w0, w1;
+  if (p.balanced) {
+    w0 = (long long)blockIdx.x * p.total_work / gridDim.x;
+    w1 = (long long)(blockIdx.x + 1) * p.total_work / gridDim.x;
+  } else {
+    const int tile_begin = (int)blockIdx.y * p.tiles_per_split;
+    const int tile_end = min(tile_begin + p.tiles_per_split, T);
+    w0 = (long long)blockIdx.x * T + tile_begin;
+    w1 = w0 + max(tile_end - tile_begin, 0);
+  }
+  auto split_of = [&](int q) -> int {
+    if (!p.balanced) return (int)blockIdx.y;
+    const long long target = (long long)q * T;  // first step of the tile; find c with b(c) <= target < b(c + 1)
+    long long c = target * gridDim.x / p.total_work;
+    while (c + 1 < (long long)gridDim.x && (c + 1) * p.total_work / gridDim.x <= target) ++c;
+    while (c > 0 && c * p.total_work / gridDim.x > target) --c;
+    return (int)blockIdx.x - (int)c;
+  };
 
   if (threadIdx.x == 0) {
     tc::mbar_init(a_full, 1);
+    tc::mbar_init(a_empty, 1);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(full + s, 1);
       tc::mbar_init(empty + s, 1);
@@ -291,126 +373,157 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      tc::mbar_expect_tx(a_full, (uint32_t)(QT * p.kchunks * A_CHUNK_BYTES));
-      for (int t = 0; t < QT; ++t)
-        for (int c = 0; c < p.kchunks; ++c)
-          tc::tma_load_2d(sA + (size_t)(t * p.kchunks + c) * A_CHUNK_BYTES, &tmap_q, a_full, c * KCH, q0 + t * BM);
-      int it = 0;
-      for (int t = tile_begin; t < tile_end; ++t)
-        for (int c = 0; c < p.kchunks; ++c, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          tc::mbar_wait(empty + s, ph ^ 1u, backoff);
-          tc::mbar_expect_tx(full + s, B_STAGE_BYTES);
-          tc::tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmap_r, full + s, c * KCH, t * BN);
-        }
+      int it = 0, seg = 0;
+      for (long long cur = w0; cur < w1; ++seg) {
+        const int q = (int)(cur / T), t0 = (int)(cur % T);
+        const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
+        cur += t1 - t0;
+        if (seg > 0) tc::mbar_wait(a_empty, (uint32_t)(seg - 1) & 1u, backoff);  // MMAs of the last segment done with sA
+        tc::mbar_expect_tx(a_full, (uint32_t)(QT * p.kchunks * A_CHUNK_BYTES));
+        for (int t = 0; t < QT; ++t)
+          for (int c = 0; c < p.kchunks; ++c)
+            tc::tma_load_2d(sA + (size_t)(t * p.kchunks + c) * A_CHUNK_BYTES, &tmap_q, a_full, c * KCH,
+                            q * (QT * BM) + t * BM);
+        for (int t = t0; t < t1; ++t)
+          for (int c = 0; c < p.kchunks; ++c, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            tc::mbar_wait(empty + s, ph ^ 1u, backoff);
+            if (SCF_KNN_DEBUG & 128) {  // timing experiment: no reference traffic, the MMAs run on stale tiles
+              tc::mbar_arrive(full + s);
+              continue;
+            }
+            tc::mbar_expect_tx(full + s, B_STAGE_BYTES);
+            tc::tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmap_r, full + s, c * KCH, t * BN);
+          }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc_tf32(BM, BN, false, false);
-      tc::mbar_wait(a_full, 0);
-      tc::tc_fence_after();
-      int it = 0;
-      for (int lt = 0; lt < ntiles; ++lt) {
-        const int acc = lt & 1;
-        const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
-        tc::mbar_wait(tmem_empty + acc, acc_ph ^ 1u, backoff);
+      constexpr uint32_t idesc = tc::umma_idesc_f16(BM, BN, false, false);
+      int it = 0, lt = 0, seg = 0;
+      for (long long cur = w0; cur < w1; ++seg) {
+        const int t0 = (int)(cur % T);
+        const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
+        cur += t1 - t0;
+        tc::mbar_wait(a_full, (uint32_t)seg & 1u);
         tc::tc_fence_after();
-        for (int c = 0; c < p.kchunks; ++c, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          tc::mbar_wait(full + s, ph, backoff);
+        for (int t = t0; t < t1; ++t, ++lt) {
+          const int acc = lt & 1;
+          const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
+          tc::mbar_wait(tmem_empty + acc, acc_ph ^ 1u, backoff);
           tc::tc_fence_after();
-          const uint64_t db = tc::umma_desc_k_sw128(sB + (size_t)s * B_STAGE_BYTES);
-          const int nk = c + 1 == p.kchunks ? p.ksteps_last : KCH / 8;
+          for (int c = 0; c < p.kchunks; ++c, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            tc::mbar_wait(full + s, ph, backoff);
+            tc::tc_fence_after();
+            const uint64_t db = tc::umma_desc_k_sw128(sB + (size_t)s * B_STAGE_BYTES);
+            const int nk = c + 1 == p.kchunks ? p.ksteps_last : KCH / KSTEP;
 #pragma unroll
-          for (int t = 0; t < QT; ++t) {
-            const uint64_t da = tc::umma_desc_k_sw128(sA + (size_t)(t * p.kchunks + c) * A_CHUNK_BYTES);
-            const uint32_t d_tmem = tmem_base + (uint32_t)((acc * QT + t) * BN);
+            for (int tq = 0; tq < QT; ++tq) {
+              const uint64_t da = tc::umma_desc_k_sw128(sA + (size_t)(tq * p.kchunks + c) * A_CHUNK_BYTES);
+              const uint32_t d_tmem = tmem_base + (uint32_t)((acc * QT + tq) * BN);
 #pragma unroll
-            for (int kk = 0; kk < KCH / 8; ++kk)  // K = 8 tf32 = 32 bytes per instruction: +2 in 16-byte units
-              if (kk < nk) tc::umma_tf32(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (c | kk) != 0);
+              for (int kk = 0; kk < KCH / KSTEP; ++kk)  // K = 16 fp16 = 32 bytes per instruction: +2 in 16-byte units
+                if (kk < nk && !(SCF_KNN_DEBUG & 64))
+                  tc::umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (c | kk) != 0);
+            }
+            tc::umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
           }
-          tc::umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
+          tc::umma_commit(tmem_full + acc);  // both accumulators of this reference tile complete
         }
-        tc::umma_commit(tmem_full + acc);  // both accumulators of this reference tile complete
+        tc::umma_commit(a_empty);  // the query operand may be replaced once every MMA of the segment has run
       }
     }
   } else {
-    // ===================== epilogue: one query row per thread, top-k' of the whole reference range ===========
+    // ===================== epilogue: one query row per thread, top-k' of the segment's reference range ===========
     const int quarter = warp & 3;      // TMEM lane quarter this warp may read
     const int qt = (warp - 2) >> 2;    // which of the CTA's query tiles
     const int row = quarter * 32 + lane;
     int* li_slot = li + qt * BM + row;
     float* st_slot = st + qt * BM + row;
-    if constexpr (COLLECT) {
-      // fixed per-row threshold, append-only: every reference whose score is below it goes on the row's list
-      const int slot = q0 + qt * BM + row;
-      const float thr = slot < n_fix ? p.fix_thr[slot] : -FLT_MAX;
-      for (int lt = 0; lt < ntiles; ++lt) {
-        const int acc = lt & 1;
-        const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
-        tc::mbar_wait(tmem_full + acc, acc_ph);
-        tc::tc_fence_after();
-        const int j0 = (tile_begin + lt) * BN;
-        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
+    int lt = 0;
+    for (long long cur = w0; cur < w1;) {
+      const int q = (int)(cur / T), t0 = (int)(cur % T);
+      const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
+      cur += t1 - t0;
+      const int q0 = q * (QT * BM);
+      if constexpr (COLLECT) {
+        // fixed per-row threshold, append-only: every reference whose score is below it goes on the row's list
+        const int slot = q0 + qt * BM + row;
+        const float thr = slot < n_fix ? p.fix_thr[slot] : -FLT_MAX;
+        for (int t = t0; t < t1; ++t, ++lt) {
+          const int acc = lt & 1;
+          const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
+          tc::mbar_wait(tmem_full + acc, acc_ph);
+          tc::tc_fence_after();
+          const int j0 = t * BN;
+          const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          uint32_t v[32];
-          tc::tmem_ld32(t_row + (uint32_t)(cc * 32), v);
-          tc::tmem_ld_wait();
-          float g[4];
+          for (int cc = 0; cc < BN / 32; ++cc) {
+            uint32_t v[32];
+            tc::tmem_ld32(t_row + (uint32_t)(cc * 32), v);
+            tc::tmem_ld_wait();
+            float g[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) g[i] = min8(v + 8 * i);
-          const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
-          if (!__any_sync(SCF_FULL, m < thr)) continue;
-          if (m < thr) {
+            for (int i = 0; i < 4; ++i) g[i] = min8(v + 8 * i);
+            const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
+            if (!__any_sync(SCF_FULL, m < thr)) continue;
+            if (m < thr) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (__uint_as_float(v[c]) < thr) {
-                const int pos = atomicAdd(p.fix_cnt + slot, 1);
-                if (pos < FIXTC_CAP) p.fix_list[(size_t)slot * FIXTC_CAP + pos] = j0 + cc * 32 + c;
-              }
+              for (int c = 0; c < 32; ++c)
+                if (__uint_as_float(v[c]) < thr && j0 + cc * 32 + c < p.nref) {
+                  const int pos = atomicAdd(p.fix_cnt + slot, 1);
+                  if (pos < FIXTC_CAP) p.fix_list[(size_t)slot * FIXTC_CAP + pos] = j0 + cc * 32 + c;
+                }
+            }
           }
+          tc::tc_fence_before();
+          tc::mbar_arrive(tmem_empty + acc);
         }
-        tc::tc_fence_before();
-        tc::mbar_arrive(tmem_empty + acc);
-      }
-    } else {
-    CandList<KC> cl;
-      cl.init();
-      if (q0 + qt * BM + row >= p.nq) cl.thr = -FLT_MAX;  // pad row: never a candidate
-  #pragma unroll
-      for (int e = 0; e < KC; ++e) li_slot[e * NLISTS] = -1;
-      for (int lt = 0; lt < ntiles; ++lt) {
-        const int acc = lt & 1;
-        const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
-        tc::mbar_wait(tmem_full + acc, acc_ph);
-        tc::tc_fence_after();
-        const int j0 = (tile_begin + lt) * BN;
-        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
-        uint32_t v[32];
-        tc::tmem_ld32(t_row, v);
-  #pragma unroll
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          tc::tmem_ld_wait();
-          const uint32_t mask = stage_hits<KC>(v, cl.thr, st_slot, SCF_KNN_DEBUG);
-          // v is dead: the TMEM load of the next chunk overlaps the drain of this one
-          if (cc + 1 < BN / 32) tc::tmem_ld32(t_row + (uint32_t)((cc + 1) * 32), v);
-          drain_hits<KC>(mask, j0 + cc * 32, cl, li_slot, st_slot, SCF_KNN_DEBUG);
+      } else {
+        const int split = split_of(q);
+        CandList<KC> cl;
+        cl.init();
+        if (q0 + qt * BM + row >= p.nq) cl.thr = -FLT_MAX;  // pad row: never a candidate
+#pragma unroll
+        for (int e = 0; e < KC; ++e) li_slot[e * NLISTS] = -1;
+        for (int t = t0; t < t1; ++t, ++lt) {
+          const int acc = lt & 1;
+          const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
+          tc::mbar_wait(tmem_full + acc, acc_ph);
+          tc::tc_fence_after();
+          const int j0 = t * BN;
+          const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
+          uint32_t v[32];
+          if (SCF_KNN_DEBUG & 32) {  // timing experiment: no accumulator read-out at all
+            tc::tc_fence_before();
+            tc::mbar_arrive(tmem_empty + acc);
+            continue;
+          }
+          tc::tmem_ld32(t_row, v);
+#pragma unroll
+          for (int cc = 0; cc < BN / 32; ++cc) {
+            tc::tmem_ld_wait();
+            const uint32_t mask = stage_hits<KC>(v, cl.thr, st_slot, SCF_KNN_DEBUG);
+            // v is dead: the TMEM load of the next chunk overlaps the drain of this one
+            if (cc + 1 < BN / 32) tc::tmem_ld32(t_row + (uint32_t)((cc + 1) * 32), v);
+            drain_hits<KC>(mask, j0 + cc * 32, p.nref, cl, li_slot, st_slot, SCF_KNN_DEBUG);
+          }
+          tc::tc_fence_before();
+          tc::mbar_arrive(tmem_empty + acc);
         }
-        tc::tc_fence_before();
-        tc::mbar_arrive(tmem_empty + acc);
+        // candidates out: [query, split, KC]
+        const size_t sub = (size_t)(q0 + qt * BM + row) * p.nsplit + split;
+#pragma unroll
+        for (int e = 0; e < KC; ++e) {
+          p.cand_score[sub * KC + e] = cl.r[e];
+          p.cand_idx[sub * KC + e] = li_slot[e * NLISTS];
+        }
+        p.cand_tau[sub] = cl.thr;
       }
-      // candidates out: [query, split, KC]
-      const size_t sub = (size_t)(q0 + qt * BM + row) * p.nsplit + split;
-  #pragma unroll
-      for (int e = 0; e < KC; ++e) {
-        p.cand_score[sub * KC + e] = cl.r[e];
-        p.cand_idx[sub * KC + e] = li_slot[e * NLISTS];
-      }
-      p.cand_tau[sub] = cl.thr;
     }
   }
   tc::tc_fence_before();
@@ -426,7 +539,7 @@ constexpr int MAXU = 8;  // candidates per lane: nsplit * kc <= 256
 
 __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict__ q, int64_t nq,
                                                          const float* __restrict__ ref, int64_t nref, int dim,
-                                                         int64_t ld, int k, int64_t self_offset, int kc, int nsplit,
+                                                         int64_t ld, int k, int64_t self_offset, int kc, int nsplit, int kp,
                                                          const float* __restrict__ cand_score,
                                                          const int* __restrict__ cand_idx,
                                                          const float* __restrict__ cand_tau,
@@ -492,11 +605,13 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   }
   if (lane == 0) {
     bool ok = enough;
-    const double an2 = qnorm2[qi], an = sqrt(an2), bm = (double)bmax[0], dbm = (double)bmax[1];
-    const double eps = 2.0 * ((double)qerr[qi] * bm + an * dbm) * (1.0 + 1e-6) + eps_acc() * (2.0 * an * bm + bm * bm);
+    // scaled units: the operands were multiplied by s, so scores / norms / eps are s^2 times the distance scale
+    const double an2 = qnorm2[qi], an = sqrt(an2), bm = (double)bmax[0], dbm = (double)bmax[1], s2 = (double)bmax[2];
+    const double eps = 2.0 * ((double)qerr[qi] * bm + an * dbm) * (1.0 + 1e-6) +
+                       eps_acc(kp) * (2.0 * an * bm + bm * bm) + EPS_SPLIT_ABS;
     const float dk = __uint_as_float((unsigned)(last >> 32));
     if (ok && tau < 1e29f) {  // lists were full: something was rejected, prove it is farther than the k-th kept
-      const double lower = ((double)tau - eps + an2) * (1.0 - 1e-12);  // bound on any rejected exact distance
+      const double lower = ((double)tau - eps + an2) * (1.0 - 1e-12) / s2;  // bound on any rejected exact distance
       ok = lower > 0.0 && dk < __double2float_rd(lower);  // strict: a tie would be decided by the index
     }
     if (!ok) {
@@ -507,7 +622,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
       fail_ids[slot] = qi;
       fail_keys[slot] = enough ? last : ~0ull;
       if (slot < FIXTC_ROWS) {
-        const double t = (double)dk * (1.0 + 0x1p-22) - an2 + eps;
+        const double t = (double)dk * s2 * (1.0 + 0x1p-22) - an2 + eps;
         fix_thr[slot] = enough ? __double2float_ru(t + fabs(t) * 1e-9) : FLT_MAX;
       }
     }
@@ -515,14 +630,14 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
 }
 
 // rows of the augmented query operand of the failed queries, compacted for the collect pass
-__global__ void __launch_bounds__(256) knn_fix_gather_kernel(const float* __restrict__ qop, int kp,
+__global__ void __launch_bounds__(256) knn_fix_gather_kernel(const __half* __restrict__ qop, int kp,
                                                              const int64_t* __restrict__ fail_ids,
                                                              const int* __restrict__ fail_count,
-                                                             float* __restrict__ qfix) {
+                                                             __half* __restrict__ qfix) {
   const int n = min(*fail_count, FIXTC_ROWS);
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += gridDim.x * 8) {
-    const float* src = qop + fail_ids[r] * kp;
+    const __half* src = qop + fail_ids[r] * kp;
     for (int t = lane; t < kp; t += 32) qfix[(size_t)r * kp + t] = src[t];
   }
 }
@@ -607,7 +722,8 @@ int pick_kc(int k) {
 }
 
 struct Plan {
-  int kp, kchunks, kc, stages, nsplit, tiles_per_split, n_ref_tiles;
+  int kp, kchunks, kc, stages, nsplit, tiles_per_split, n_ref_tiles, grid;
+  long long total_work;
   int64_t nq_pad, nr_pad;
   size_t smem;
   // workspace offsets (bytes)
@@ -619,22 +735,29 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.kc = pick_kc(k);
   pl.kp = (dim + 3 + KCH - 1) / KCH * KCH;
   pl.kchunks = pl.kp / KCH;
-  if (pl.kc == 0 || pl.kchunks > 4) return false;  // k > 24 or dim > 125: method 0 handles those
+  if (pl.kc == 0 || pl.kchunks > 4) return false;  // k > 24 or dim > 253: method 0 handles those
   pl.nq_pad = (nq + QT * BM - 1) / (QT * BM) * (QT * BM);
   pl.nr_pad = (nref + BN - 1) / BN * BN;
   pl.n_ref_tiles = (int)(pl.nr_pad / BN);
-  const int64_t ctas = pl.nq_pad / (QT * BM);
-  // One candidate list per query over the WHOLE reference range keeps the number of list updates at
-  // k' ln(N/k'); the references are split across CTAs only when there are too few query tiles to fill the GPU.
-  int s = 1;
-  if (ctas < SCF_NUM_SMS) s = (int)std::min<int64_t>((SCF_NUM_SMS + ctas - 1) / ctas, 8);
-  s = std::max(1, std::min(s, pl.n_ref_tiles / 8));
-  while (s > 1 && s * pl.kc > 32 * MAXU) --s;
-  pl.tiles_per_split = (pl.n_ref_tiles + s - 1) / s;
-  pl.nsplit = (pl.n_ref_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split;
+  const int64_t q_tiles = pl.nq_pad / (QT * BM);
+  // Balanced schedule: the q_tiles x n_ref_tiles tile steps are cut into `grid` equal contiguous ranges (one CTA per
+  // SM, at least 8 steps each).  A query tile spans at most nsplit = ceil(T / L) + 1 ranges (L = steps per range) and
+  // keeps one candidate list per range; with at least as many query tiles as SMs that is 2.  One list over (nearly)
+  // the whole reference range keeps the number of list updates at k' ln(N/k').
+  const long long work = (long long)q_tiles * pl.n_ref_tiles;
+  long long grid = std::max<long long>(1, std::min<long long>(SCF_NUM_SMS, work / 8));
+  for (;;) {
+    const long long L = work / grid;
+    pl.nsplit = (int)((pl.n_ref_tiles + L - 1) / L) + 1;
+    if (pl.nsplit * pl.kc <= 32 * MAXU || grid == 1) break;
+    --grid;
+  }
+  pl.grid = (int)grid;
+  pl.total_work = work;
+  pl.tiles_per_split = pl.n_ref_tiles;
   auto smem_for = [&](int stages) {
     return (size_t)QT * pl.kchunks * A_CHUNK_BYTES + (size_t)stages * B_STAGE_BYTES + (size_t)pl.kc * NLISTS * 4 +
-           (size_t)32 * NLISTS * 4 + (size_t)(1 + 2 * stages + 4) * 8 + 64;
+           (size_t)32 * NLISTS * 4 + (size_t)(2 + 2 * stages + 4) * 8 + 64;
   };
   pl.stages = 6;
   while (pl.stages > 2 && smem_for(pl.stages) + 1024 > 227 * 1024) --pl.stages;
@@ -642,8 +765,8 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   if (pl.smem > 227 * 1024) return false;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t o = 0;
-  pl.off_qop = o, o = al(o + (size_t)pl.nq_pad * pl.kp * 4);
-  pl.off_rop = o, o = al(o + (size_t)pl.nr_pad * pl.kp * 4);
+  pl.off_qop = o, o = al(o + (size_t)pl.nq_pad * pl.kp * 2);
+  pl.off_rop = o, o = al(o + (size_t)pl.nr_pad * pl.kp * 2);
   pl.off_qn = o, o = al(o + (size_t)pl.nq_pad * 8);
   pl.off_qe = o, o = al(o + (size_t)pl.nq_pad * 4);
   pl.off_cs = o, o = al(o + (size_t)pl.nq_pad * pl.nsplit * pl.kc * 4);
@@ -653,7 +776,7 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.off_fkey = o, o = al(o + (size_t)nq * 8);
   pl.off_misc = o, o = al(o + 256);
   pl.off_fix = o, o = al(o + knn_exact_fix_scratch_bytes(nq, k));
-  pl.off_qfix = o, o = al(o + (size_t)FIXTC_ROWS * pl.kp * 4);
+  pl.off_qfix = o, o = al(o + (size_t)FIXTC_ROWS * pl.kp * 2);
   pl.off_fthr = o, o = al(o + (size_t)FIXTC_ROWS * 4);
   pl.off_fcnt = o, o = al(o + (size_t)FIXTC_ROWS * 4);
   pl.off_flist = o, o = al(o + (size_t)FIXTC_ROWS * FIXTC_CAP * 4);
@@ -689,8 +812,8 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     return 1;
   }
   unsigned char* ws = (unsigned char*)workspace;
-  float* qop = (float*)(ws + pl.off_qop);
-  float* rop = (float*)(ws + pl.off_rop);
+  __half* qop = (__half*)(ws + pl.off_qop);
+  __half* rop = (__half*)(ws + pl.off_rop);
   double* qn = (double*)(ws + pl.off_qn);
   float* qe = (float*)(ws + pl.off_qe);
   float* cs = (float*)(ws + pl.off_cs);
@@ -701,7 +824,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   int* fail_count = (int*)(ws + pl.off_misc);
   float* bmax = (float*)(ws + pl.off_misc + 64);
   int* rest_count = (int*)(ws + pl.off_misc + 128);
-  float* qfix = (float*)(ws + pl.off_qfix);
+  __half* qfix = (__half*)(ws + pl.off_qfix);
   float* fix_thr = (float*)(ws + pl.off_fthr);
   int* fix_cnt = (int*)(ws + pl.off_fcnt);
   int* fix_list = (int*)(ws + pl.off_flist);
@@ -713,20 +836,32 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
+  float* range = bmax + 4;  // [0] max |b|^2 of the references, [1] max |a_t| of the queries (zeroed with the misc block)
+  knn_range_kernel<<<4 * SCF_NUM_SMS, 256, 0, stream>>>(q, nq, ref, nref, dim, ld, range);
+  int32_t rc = scf_check_launch("scf_knn_l2(range)");
+  if (rc) return rc;
   knn_prep_kernel<<<4 * SCF_NUM_SMS, 256, 0, stream>>>(q, nq, pl.nq_pad, ref, nref, pl.nr_pad, dim, ld, pl.kp, qop, rop,
-                                                       qn, qe, bmax);
-  int32_t rc = scf_check_launch("scf_knn_l2(prep)");
+                                                       qn, qe, range, bmax);
+  rc = scf_check_launch("scf_knn_l2(prep)");
   if (rc) return rc;
   CUtensorMap tq, tr;
-  rc = scf_make_tmap_2d_f32(&tq, qop, (uint64_t)pl.nq_pad, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BM);
+  rc = scf_make_tmap_2d_f16(&tq, qop, (uint64_t)pl.nq_pad, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BM);
   if (rc) return rc;
-  rc = scf_make_tmap_2d_f32(&tr, rop, (uint64_t)pl.nr_pad, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BN);
+  rc = scf_make_tmap_2d_f16(&tr, rop, (uint64_t)pl.nr_pad, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BN);
   if (rc) return rc;
   KnnTcParams prm;
   prm.kchunks = pl.kchunks, prm.stages = pl.stages, prm.n_ref_tiles = pl.n_ref_tiles;
-  prm.nq = (int)nq;
-  prm.ksteps_last = ((dim + 3 + 7) / 8) - (pl.kchunks - 1) * (KCH / 8);
+  prm.nq = (int)nq, prm.nref = (int)nref;
+  prm.ksteps_last = ((dim + 3 + KSTEP - 1) / KSTEP) - (pl.kchunks - 1) * (KCH / KSTEP);
   prm.tiles_per_split = pl.tiles_per_split, prm.nsplit = pl.nsplit, prm.cand_score = cs, prm.cand_idx = ci, prm.cand_tau = ctau;
+  prm.balanced = 1, prm.total_work = pl.total_work;
+  // list slots that no range fills (a query tile that is not cut uses one of its nsplit slots): ids -1, tau "nothing rejected"
+  e = cudaMemsetAsync(ci, 0xFF, (size_t)pl.nq_pad * pl.nsplit * pl.kc * 4, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctau, 0x7F, (size_t)pl.nq_pad * pl.nsplit * 4, stream);
+  if (e != cudaSuccess) {
+    scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
+    return -(int32_t)e;
+  }
   {
     const char* f = getenv("SCF_KNN_FLAGS");
     prm.flags = f ? atoi(f) : 2;
@@ -738,12 +873,12 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
-  dim3 grid((unsigned)(pl.nq_pad / (QT * BM)), (unsigned)pl.nsplit);
-  kern<<<grid, NTHREADS, pl.smem, stream>>>(tq, tr, prm);
+  kern<<<dim3((unsigned)pl.grid), NTHREADS, pl.smem, stream>>>(tq, tr, prm);
   rc = scf_check_launch("scf_knn_l2(tcgen05)");
   if (rc) return rc;
+  if (SCF_KNN_DEBUG & (8 | 32 | 64 | 128)) return 0;  // timing experiments: candidates are meaningless, stop here
   knn_rerank_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(q, nq, ref, nref, dim, ld, k, self_offset, pl.kc,
-                                                                  pl.nsplit, cs, ci, ctau, qn, qe, bmax, out_idx, out_dist,
+                                                                  pl.nsplit, pl.kp, cs, ci, ctau, qn, qe, bmax, out_idx, out_dist,
                                                                   fail_ids, fail_keys, fix_thr, fail_count);
   rc = scf_check_launch("scf_knn_l2(rerank)");
   if (rc) return rc;
@@ -762,10 +897,11 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   rc = scf_check_launch("scf_knn_l2(fix,gather)");
   if (rc) return rc;
   CUtensorMap tf;
-  rc = scf_make_tmap_2d_f32(&tf, qfix, (uint64_t)FIXTC_ROWS, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BM);
+  rc = scf_make_tmap_2d_f16(&tf, qfix, (uint64_t)FIXTC_ROWS, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BM);
   if (rc) return rc;
   KnnTcParams fp = prm;
   fp.nq = FIXTC_ROWS;
+  fp.balanced = 0, fp.total_work = 0;  // collect pass: static (query tile, reference split) grid
   fp.nsplit = std::max(1, std::min(FIXTC_NSPLIT, pl.n_ref_tiles));
   fp.tiles_per_split = (pl.n_ref_tiles + fp.nsplit - 1) / fp.nsplit;
   fp.nsplit = (pl.n_ref_tiles + fp.tiles_per_split - 1) / fp.tiles_per_split;

@@ -137,15 +137,24 @@ def _finish_eig(w, v, dims):
 
 def _cheb_filter(cov, x, degree, cut, top):
     """Scaled Chebyshev filter p(C) x (Zhou & Saad): damps the spectrum in [0, cut] (covariances are PSD), keeps the
-    component at ``top`` near unit size, amplifies everything above ``cut`` like T_degree."""
-    e, c = 0.5 * cut, 0.5 * cut
-    sigma = e / (top - c)
-    sigma1 = sigma
-    y = (cov @ x - c * x) * (sigma1 / e)
-    for _ in range(1, degree):
-        sigma2 = 1.0 / (2.0 / sigma1 - sigma)
-        y_new = (cov @ y - c * y) * (2.0 * sigma2 / e) - (sigma * sigma2) * x
-        x, y, sigma = y, y_new, sigma2
+    component at ``top`` near unit size, amplifies everything above ``cut`` like T_degree.  ``cut`` / ``top`` may be
+    Python floats or 0-dim device tensors: the coefficients of the three-term recurrence are evaluated on the device
+    in closed form (sigma_j = T_{j-1}(t) / T_j(t), t = (top - c) / e), so the filter never synchronises."""
+    dev, dt = cov.device, cov.dtype
+    cut = torch.as_tensor(cut, dtype=dt, device=dev)
+    top = torch.as_tensor(top, dtype=dt, device=dev)
+    e = 0.5 * cut  # centre c == half width e: the damped interval is [0, cut]
+    t = (top - e) / e
+    r = 1.0 / (t + torch.sqrt(t * t - 1.0))  # exp(-acosh t)
+    j = torch.arange(1, degree + 1, dtype=dt, device=dev)
+    sig = r * (1.0 + r ** (2.0 * (j - 1.0))) / (1.0 + r ** (2.0 * j))  # sigma_1 .. sigma_degree
+    a = 2.0 * sig[1:] / e          # step j: y_{j+1} = a_j (C - c) y_j - d_j y_{j-1}
+    d = sig[:-1] * sig[1:]
+    cs = cov - torch.diag_embed(e.expand(cov.shape[0]))
+    y = (cs @ x) * (sig[0] / e)
+    for i in range(degree - 1):
+        y_new = (cs @ y).mul_(a[i]).addcmul_(x, d[i], value=-1.0)
+        x, y = y, y_new
     return y
 
 
@@ -155,18 +164,32 @@ def _orthonormalise(y):
     return torch.linalg.qr(y)[0]
 
 
-def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
+def _cheb_growth(x):
+    """|T_m(x)|^(1/m) for large m: x + sqrt(x^2 - 1) (x >= 1)."""
+    return x + math.sqrt(max(x * x - 1.0, 0.0))
+
+
+def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
     """K3: top-``dims`` eigenpairs of the symmetric PSD float64 matrix ``cov`` (replicated on every rank; the inputs
     are bit-identical after the integer all-reduce and the start block is seeded, so every rank gets the same
     loadings).
 
     Only ``dims`` << H pairs are needed, so instead of a full tridiagonalisation (cuSOLVER syevd: ~28 ms at H = 2000
     on B200 -- two thousand dependent BLAS-2 panels) this runs Chebyshev-filtered subspace iteration on a
-    ``b = 2*dims + 64`` wide block: a polynomial of C (GEMMs) that damps everything below the block's smallest Ritz
-    value, an orthonormalisation, and a Rayleigh-Ritz step.  It stops when every kept pair has a residual
-    ``|C v - lambda v| <= tol * lambda_max`` (angle to the exact eigenvector <= residual / eigengap).  When the
-    measured residual reduction says the remaining budget cannot reach ``tol`` (no usable gap after the block), or
-    for small matrices, the full ``eigh`` runs instead -- same answer, more time."""
+    ``b = 2*dims + 64`` wide block: a polynomial of C (GEMMs) that damps the spectrum below the block, a Householder
+    QR, and a Rayleigh-Ritz step per round.  It stops when every kept pair has a residual
+    ``|C v - lambda v| <= tol * lambda_max`` (angle to the exact eigenvector <= residual * lambda_max / eigengap:
+    1e-8 keeps the angle below 1e-5 rad for relative gaps down to 1e-3; the Gram matrix itself carries a 2e-5
+    relative error from the 3xTF32 tensor-core accumulation).
+
+    Filter degree.  The wanted spectrum is wide (lambda_1 / lambda_dims ~ 50), and T_m grows like rho^m faster at
+    lambda_1 than at lambda_dims (rho ~ 60 per degree here).  From a random start every column mixes all
+    eigenvectors, so the weak directions survive only down to eps * rho^m: the first filter keeps m = ``degree``.
+    After a Rayleigh-Ritz rotation column i is its own Ritz vector with eps-sized leakage along the strong ones; the
+    filter blows that leakage up by rho^m, and the Householder QR still resolves the weak direction to
+    eps * (eps * rho^m).  Each later round therefore takes the largest m with rho^m <= 1e20 (rho from the current
+    Ritz values): the iteration cannot bury the weak pairs, whatever the spectrum.  Small matrices, and the (never
+    observed) case of max_rounds without convergence, take the full ``eigh``."""
     h = cov.shape[0]
     b = 2 * dims + 64
     if h < 4 * b:
@@ -175,40 +198,36 @@ def eig_topk(cov, dims, tol=1e-9, degree=6, max_rounds=6, stats=None):
     g = torch.Generator(device=cov.device)
     g.manual_seed(4466)
     q = torch.randn((h, b), dtype=torch.float64, device=cov.device, generator=g)
-    # first filter without a Rayleigh-Ritz step: cut at the mean eigenvalue (the wanted ones lie above it),
-    # upper bound from the 1-norm
-    bounds = torch.stack([torch.diagonal(cov).sum() / h, cov.abs().sum(dim=0).max()]).tolist()
-    q = _orthonormalise(_cheb_filter(cov, q, degree, float(bounds[0]), float(bounds[1])))
-    rounds, prev_res, prev_deg = 1, None, 0
-    while True:
+    # first filter without a Rayleigh-Ritz step: cut at the mean eigenvalue (the wanted ones lie above it), upper
+    # bound from the 1-norm; both stay on the device
+    trace = torch.diagonal(cov).sum()
+    q = _orthonormalise(_cheb_filter(cov, q, degree, trace / h, cov.abs().sum(dim=0).max()))
+    for rounds in range(1, max_rounds + 1):
         aq = cov @ q
         t = q.T @ aq
         w, s = torch.linalg.eigh(0.5 * (t + t.T))
         top, wt = s[:, -dims:], w[-dims:]
         v = q @ top
         res_t = (aq @ top - v * wt).norm(dim=0).max() / w[-1]
-        res, th_min, th_max = (float(x) for x in torch.stack([res_t, w[0], w[-1]]).tolist())
+        # the one synchronisation of the round: residual + the Ritz values that fix the next filter
+        res, th_min, th_max, th_dims, bulk = torch.stack([res_t, w[0], w[-1], wt[0], (trace - w.sum()) / (h - b)]).tolist()
         if stats is not None:
             stats["eig_rounds"], stats["eig_residual"] = rounds, res
         if res <= tol:
             return _finish_eig(wt, v, dims)
-        # From a random start a column mixes all eigenvectors and a high degree would bury the weak ones under the
-        # rounding noise of the strong ones (T_m grows like 70^m between them); once the block is rotated to Ritz
-        # vectors each column is dominated by its own eigenvector and the degree can double.  A Rayleigh-Ritz
-        # rotation precedes EVERY further filter application for the same reason.
-        m = 2 * degree
-        if prev_res is not None:  # measured reduction per degree of the last round -> rounds still needed
-            seen = math.log(max(prev_res / res, 1.0 + 1e-12)) / prev_deg
-            if math.log(res / tol) / seen > 2.0 * m * (max_rounds - rounds):
-                break
-        if rounds >= max_rounds:
+        if rounds == max_rounds or not (th_dims > 0.0 and th_max > th_dims):
             break
-        q = _orthonormalise(_cheb_filter(cov, q @ s, m, th_min, th_max))
-        rounds += 1
-        prev_res, prev_deg = res, m
+        # damped interval [0, cut]: the block's smallest Ritz value, or the mean of the spectrum outside the block
+        # when that is larger (it never exceeds lambda_{b+1}); kept clear of the wanted Ritz values
+        cut = max(th_min, min(bulk, 0.5 * (th_min + th_dims)))
+        cut = min(max(cut, 1e-3 * th_dims), 0.9 * th_dims)
+        e = 0.5 * cut
+        rho = _cheb_growth((th_max - e) / e) / _cheb_growth((th_dims - e) / e)
+        m = int(max(2, min(32, math.floor(math.log(1e20) / math.log(max(rho, 1.0 + 1e-9))))))
+        q = _orthonormalise(_cheb_filter(cov, q @ s, m, cut, th_max))
     w, v = torch.linalg.eigh(cov)
     if stats is not None:
-        stats["eig_rounds"] = -1 - rounds
+        stats["eig_rounds"] = -1 - stats.get("eig_rounds", 0)
     return _finish_eig(w, v, dims)
 
 

@@ -154,8 +154,8 @@ def blacklist_keep_mask(gene_names, n_genes, blacklist=DEFAULT_BLACKLIST):
 def remove_trend_device(avg, sigmas, n_bins=200, lowess_frac=0.1, select=None):
     """:func:`remove_trend` on float64 device vectors (any device); returns a device vector of the same length.
     ``select`` (bool tensor, optional) restricts the fit to those entries (the feature ``I`` column); the others get
-    0.  Written without boolean indexing so that the only device->host synchronisation is the copy of the <= n_bins
-    binned points that the LOWESS fit needs."""
+    0.  Written without boolean indexing: on a GPU nothing synchronises (the <= n_bins binned points are fitted by
+    the one-CTA device LOWESS, ``scf_lowess``); CPU tensors use the native host routine."""
     import torch
 
     n = avg.numel()
@@ -186,6 +186,14 @@ def remove_trend_device(avg, sigmas, n_bins=200, lowess_frac=0.1, select=None):
     firsts.scatter_reduce_(0, which, cand, "amin", include_self=True)
     firsts = firsts[:n_bins]
     safe = firsts.clamp(max=max(n - 1, 0))
+    if avg.is_cuda and n_bins <= 512:  # device LOWESS (one CTA): the whole trend removal stays asynchronous
+        from . import ops
+
+        occupied = firsts < n
+        fit_t = ops.lowess(lb[safe].contiguous(), la[safe].contiguous(), occupied.to(torch.uint8), lowess_frac, 100)
+        fit_t = torch.cat([fit_t, torch.full((1,), float("nan"), dtype=torch.float64, device=dev)])
+        val = torch.exp(lb - fit_t[which])
+        return torch.where(valid, val, torch.zeros_like(val))
     pts = torch.stack([(firsts < n).to(torch.float64), la[safe], lb[safe]]).cpu().numpy()  # the one synchronisation
     bins = np.where(pts[0] > 0)[0]
     fit_of_bin = np.full(n_bins + 1, np.nan)

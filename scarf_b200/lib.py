@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libscarf_b200.so")
+LIB_PATH = os.environ.get("SCARF_B200_LIB") or os.path.join(_HERE, "csrc", "libscarf_b200.so")  # env: developer builds
 
 _p, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 
@@ -19,6 +19,8 @@ SIGNATURES = {
     "scf_last_error": (ctypes.c_char_p, []),
     "scf_csr_row_sums": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "scf_csr_gene_stats": (_i32, [_p, _p, _p, _p, _i64, _i32, _p, _f64, _p, _p, _p, _p]),
+    "scf_csr_gene_stats_workspace_bytes": (_i64, [_i32]),
+    "scf_csr_gene_stats_packed": (_i32, [_p, _p, _p, _p, _i64, _i32, _p, _f64, _p, _p, _p, _p, _i64, _p]),
     "scf_csr_hvg_colstats": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _f64, _i32, _i32, _i32, _p, _p, _p]),
     "scf_csr_norm_scale": (_i32, [_p, _p, _p, _p, _i64, _p, _i32, _p, _f64, _i32, _p, _p, _p, _p, _p, _i64, _p]),
     "scf_csr_hvg_compact": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _f64, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p]),
@@ -34,6 +36,7 @@ SIGNATURES = {
     "scf_membership_coo": (_i32, [_p, _p, _p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p]),
     "scf_fill_zero_weights": (_i32, [_p, _i64, _f32, _p]),
     "scf_host_lowess": (_i32, [_p, _p, _i64, _f64, _i32, _p]),
+    "scf_lowess": (_i32, [_p, _p, _p, _i32, _f64, _i32, _p, _p]),
 }
 
 COLSTAT_SHIFT = 34

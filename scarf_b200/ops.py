@@ -83,7 +83,8 @@ def csr_row_sums(csr: CsrDevice, row_ids=None, col_map=None):
     return s, c
 
 
-def csr_gene_stats(csr: CsrDevice, row_ids=None, row_div=None, sf=1000.0, out=None, with_moments=True):
+def csr_gene_stats(csr: CsrDevice, row_ids=None, row_div=None, sf=1000.0, out=None, with_moments=True,
+                   packed=True):
     """Per-gene (nnz uint64-in-int64, sum f64, sumsq f64) of sf*c/row_div over the selected rows; accumulates into out."""
     _chk(row_ids, torch.int64, "row_ids"), _chk(row_div, torch.float64, "row_div")
     n = csr.n_rows if row_ids is None else int(row_ids.numel())
@@ -93,9 +94,25 @@ def csr_gene_stats(csr: CsrDevice, row_ids=None, row_div=None, sf=1000.0, out=No
         sq = torch.zeros(csr.n_cols, dtype=torch.float64, device=csr.device) if with_moments else None
     else:
         nnz, sm, sq = out
-    lib.call("scf_csr_gene_stats", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
-             csr.n_cols, _ptr(row_div), float(sf), _ptr(nnz), _ptr(sm), _ptr(sq), _stream())
+    if packed:
+        ws_bytes = int(lib.raw("scf_csr_gene_stats_workspace_bytes")(csr.n_cols))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=csr.device)
+        lib.call("scf_csr_gene_stats_packed", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
+                 csr.n_cols, _ptr(row_div), float(sf), _ptr(nnz), _ptr(sm), _ptr(sq), ws.data_ptr(), ws_bytes,
+                 _stream(), launches=2)
+    else:
+        lib.call("scf_csr_gene_stats", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
+                 csr.n_cols, _ptr(row_div), float(sf), _ptr(nnz), _ptr(sm), _ptr(sq), _stream())
     return nnz, sm, sq
+
+
+def lowess(endog, exog, valid=None, frac=0.1, it=100):
+    """Robust LOWESS fit at every usable point, on the device (float64 vectors of <= 512 points; NaN elsewhere)."""
+    _chk(endog, torch.float64, "endog"), _chk(exog, torch.float64, "exog"), _chk(valid, torch.uint8, "valid")
+    out = torch.empty_like(endog)
+    lib.call("scf_lowess", _ptr(endog), _ptr(exog), _ptr(valid), int(endog.numel()), float(frac), int(it), _ptr(out),
+             _stream())
+    return out
 
 
 # ------------------------------------------------------------------------------------------ K1

@@ -413,3 +413,73 @@ def test_run_mapping_pbmc_golden(gpu, pbmc):
     assert np.array_equal(idx[:, 0], np.arange(808))
     sc = P.mapping_score(idx, m.distances.cpu().numpy().astype(np.float64), 808, per_k=False)
     assert (np.abs(sc - pbmc["mapping_scores"]) < 1e-2).mean() > 0.98
+
+
+def test_device_lowess_equals_host(gpu):
+    """scf_lowess (one CTA, no host round trip) against the native host routine and the oracle restatement: ties,
+    an outlier, unsorted input, masked-out points."""
+    from oracle.lowess import lowess as lowess_o
+    from scarf_b200.hvg import _lowess
+
+    torch, ops = gpu["torch"], gpu["ops"]
+    rng = np.random.default_rng(5)
+    x = np.sort(rng.normal(size=60))
+    x[10] = x[9]
+    x[30:33] = x[30]
+    y = np.sin(x) + 0.1 * rng.normal(size=60)
+    y[20] += 3.0
+    d = ops.lowess(torch.from_numpy(y).cuda(), torch.from_numpy(x).cuda(), None, 0.2, 100).cpu().numpy()
+    np.testing.assert_allclose(d, _lowess(y, x, 0.2, 100), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(d, lowess_o(y, x, frac=0.2, it=100), rtol=1e-9, atol=1e-12)
+    x2 = rng.gamma(2.0, 1.0, size=200)
+    y2 = np.log1p(x2) + 0.05 * rng.normal(size=200)
+    valid = rng.random(200) > 0.15
+    d2 = ops.lowess(torch.from_numpy(y2).cuda(), torch.from_numpy(x2).cuda(),
+                    torch.from_numpy(valid.astype(np.uint8)).cuda(), 0.1, 100).cpu().numpy()
+    assert np.isnan(d2[~valid]).all()
+    np.testing.assert_allclose(d2[valid], _lowess(y2[valid], x2[valid], 0.1, 100), rtol=1e-12, atol=1e-13)
+    # too few points for the window: the host routine raises, the device routine answers NaN
+    d3 = ops.lowess(torch.from_numpy(y2[:8]).cuda(), torch.from_numpy(x2[:8]).cuda(), None, 0.1, 100).cpu().numpy()
+    assert np.isnan(d3).all()
+
+
+def test_gene_stats_packed_equals_plain(gpu, synth_small):
+    """Sector-packed reductions (scf_csr_gene_stats_packed) against the per-array kernel and the oracle."""
+    from oracle import pipeline as P
+
+    torch, graph, ops = gpu["torch"], gpu["graph"], gpu["ops"]
+    csr = _dev(gpu, synth_small)
+    n_counts, _ = graph.cell_totals(csr)
+    rows = torch.arange(3, 2900, 2, device="cuda")
+    div = n_counts[rows].contiguous()
+    a = ops.csr_gene_stats(csr, rows, div, 1000.0, packed=False)
+    b = ops.csr_gene_stats(csr, rows, div, 1000.0, packed=True)
+    assert torch.equal(a[0], b[0])
+    np.testing.assert_allclose(b[1].cpu().numpy(), a[1].cpu().numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(b[2].cpu().numpy(), a[2].cpu().numpy(), rtol=1e-12, atol=1e-12)
+    nn = ops.csr_gene_stats(csr, None, None, with_moments=False, packed=True)[0]
+    assert np.array_equal(nn.cpu().numpy(), P.gene_ncells(synth_small))
+
+
+def test_eig_topk_on_device(gpu):
+    """Chebyshev-filtered subspace iteration against the full eigh on a covariance with a wide wanted spectrum and a
+    dense noise bulk (the shape that makes a fixed high-degree filter bury the weak pairs)."""
+    torch, graph = gpu["torch"], gpu["graph"]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, h, nf = 20000, 1500, 40
+    z = torch.randn((n, h), device="cuda", dtype=torch.float64, generator=g)
+    f = torch.randn((n, nf), device="cuda", dtype=torch.float64, generator=g)
+    w = torch.randn((nf, h), device="cuda", dtype=torch.float64, generator=g)
+    w = w * (torch.rand((nf, h), device="cuda", dtype=torch.float64, generator=g) < 0.1)
+    z = z + f @ (w * (2.5 * 0.9 ** torch.arange(nf, device="cuda"))[:, None])
+    z = (z - z.mean(0)) / z.std(0)
+    cov = (z.T @ z) / (n - 1)
+    wf, vf = torch.linalg.eigh(cov)
+    for dims in (10, 30):
+        st = {}
+        ev, load = graph.eig_topk(cov, dims, stats=st)
+        assert st["eig_rounds"] > 0, st  # converged without the full-eigh fallback
+        np.testing.assert_allclose(ev.cpu().numpy(), torch.flip(wf[-dims:], [0]).cpu().numpy(), rtol=1e-10)
+        ref = graph.sign_rule(torch.flip(vf[:, -dims:], [1]).T.contiguous()).T
+        cosang = (ref * load).sum(0).abs().clamp(max=1.0)
+        assert float(torch.acos(cosang).max()) < 1e-5
