@@ -876,7 +876,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   kern<<<dim3((unsigned)pl.grid), NTHREADS, pl.smem, stream>>>(tq, tr, prm);
   rc = scf_check_launch("scf_knn_l2(tcgen05)");
   if (rc) return rc;
-  if (SCF_KNN_DEBUG & (8 | 32 | 64 | 128)) return 0;  // timing experiments: candidates are meaningless, stop here
+  if (SCF_KNN_DEBUG & (4 | 8 | 32 | 64 | 128)) return 0;  // timing experiments: candidates are meaningless, stop here
   knn_rerank_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(q, nq, ref, nref, dim, ld, k, self_offset, pl.kc,
                                                                   pl.nsplit, pl.kp, cs, ci, ctau, qn, qe, bmax, out_idx, out_dist,
                                                                   fail_ids, fail_keys, fix_thr, fail_count);

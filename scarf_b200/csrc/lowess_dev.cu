@@ -8,12 +8,12 @@
 namespace {
 
 constexpr int kMaxN = 512;
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024;
 
 __global__ void __launch_bounds__(kThreads) lowess_kernel(const double* __restrict__ endog,
                                                           const double* __restrict__ exog,
                                                           const uint8_t* __restrict__ valid, int n_in, double frac, int it,
-                                                          double* __restrict__ out) {
+                                                          int cache_tri, double* __restrict__ out) {
   __shared__ double x[kMaxN], y[kMaxN], fit[kMaxN], rw[kMaxN], r[kMaxN];
   __shared__ int src[kMaxN], lefts[kMaxN], first[kMaxN];
   __shared__ int s_n;
@@ -60,42 +60,91 @@ __global__ void __launch_bounds__(kThreads) lowess_kernel(const double* __restri
     }
   }
   __syncthreads();
+  // tricube weights do not change between the robustness passes: kept in shared memory when n * k values fit
+  // (always for the 200 x 20 problem of mark_hvgs), recomputed otherwise.  wn = this pass's normalised weights.
+  extern __shared__ double dyn[];
+  const bool cached = cache_tri != 0;
+  double* tri = dyn;                        // [n][k]
+  double* wn_all = dyn + (size_t)n * k;     // [n][k]
+  auto tricube = [&](int i, int left, int j) {
+    const double xi = x[i];
+    const double radius = fmax(__dsub_rn(xi, x[left]), __dsub_rn(x[left + k - 1], xi));
+    const double d = __ddiv_rn(fabs(__dsub_rn(x[left + j], xi)), radius);
+    double t = __dsub_rn(1.0, __dmul_rn(__dmul_rn(d, d), d));
+    t = __dmul_rn(__dmul_rn(t, t), t);
+    return isfinite(t) ? t : 0.0;
+  };
+  if (cached) {
+    for (int e = tid; e < n * k; e += kThreads) {
+      const int i = e / k, j = e - i * k;
+      tri[e] = tricube(i, lefts[i], j);
+    }
+    __syncthreads();
+  }
+  // Four lanes per point: the divisions (the expensive part) of a window are spread over the quad, every sum runs on
+  // the quad's first lane in the host routine's order, so the fit is bit-identical to the one-thread form.
+  const int quad = tid & 3;
+  const unsigned qmask = 0xFu << ((tid & 31) & ~3);
   for (int pass = 0; pass <= it; ++pass) {
-    for (int i = tid; i < n; i += kThreads) {
-      if (first[i] != i) continue;
+    for (int i0 = 0; i0 < n; i0 += kThreads / 4) {
+      const int i = i0 + (tid >> 2);
+      const bool live = i < n && first[i] == i;  // uniform inside a quad
+      if (!live) continue;
       const int left = lefts[i];
       const double xi = x[i];
-      const double radius = fmax(__dsub_rn(xi, x[left]), __dsub_rn(x[left + k - 1], xi));
-      auto weight = [&](int j) {  // tricube(|x_j - x_i| / radius) * robustness weight, un-normalised
-        const double d = __ddiv_rn(fabs(__dsub_rn(x[left + j], xi)), radius);
-        double t = __dsub_rn(1.0, __dmul_rn(__dmul_rn(d, d), d));
-        t = __dmul_rn(__dmul_rn(t, t), t);
-        if (!isfinite(t)) t = 0.0;
-        return __dmul_rn(t, rw[left + j]);
+      auto weight = [&](int j) {  // tricube * robustness weight, un-normalised
+        return __dmul_rn(cached ? tri[(size_t)i * k + j] : tricube(i, left, j), rw[left + j]);
       };
+      double* wn = wn_all + (size_t)i * k;  // per-point scratch (only when cached)
       double sw = 0.0;
-      for (int j = 0; j < k; ++j) sw = __dadd_rn(sw, weight(j));
-      double f;
-      if (!(sw > 0.0)) {
-        f = y[i];
-      } else {
-        double xm = 0.0;
-        for (int j = 0; j < k; ++j) xm = __dadd_rn(xm, __dmul_rn(__ddiv_rn(weight(j), sw), x[left + j]));
-        double sq = 0.0;
-        for (int j = 0; j < k; ++j) {
-          const double dx = __dsub_rn(x[left + j], xm);
-          sq = __dadd_rn(sq, __dmul_rn(__dmul_rn(__ddiv_rn(weight(j), sw), dx), dx));
+      if (cached) {
+        for (int j = quad; j < k; j += 4) wn[j] = weight(j);
+        __syncwarp(qmask);
+        if (quad == 0)
+          for (int j = 0; j < k; ++j) sw = __dadd_rn(sw, wn[j]);
+      } else if (quad == 0) {
+        for (int j = 0; j < k; ++j) sw = __dadd_rn(sw, weight(j));
+      }
+      sw = __shfl_sync(qmask, sw, (tid & 31) & ~3);
+      double f = y[i];
+      if (sw > 0.0) {
+        if (cached) {
+          for (int j = quad; j < k; j += 4) wn[j] = __ddiv_rn(wn[j], sw);
+          __syncwarp(qmask);
         }
-        f = 0.0;
-        for (int j = 0; j < k; ++j) {
-          const double w = __ddiv_rn(weight(j), sw);
+        auto w_of = [&](int j) { return cached ? wn[j] : __ddiv_rn(weight(j), sw); };
+        double xm = 0.0, sq = 0.0;
+        if (quad == 0) {
+          for (int j = 0; j < k; ++j) xm = __dadd_rn(xm, __dmul_rn(w_of(j), x[left + j]));
+          for (int j = 0; j < k; ++j) {
+            const double dx = __dsub_rn(x[left + j], xm);
+            sq = __dadd_rn(sq, __dmul_rn(__dmul_rn(w_of(j), dx), dx));
+          }
+        }
+        xm = __shfl_sync(qmask, xm, (tid & 31) & ~3);
+        sq = __shfl_sync(qmask, sq, (tid & 31) & ~3);
+        const double xd = __dsub_rn(xi, xm);
+        auto term = [&](int j) {
+          const double w = w_of(j);
           const double p =
-              sq > 1e-12 ? __dmul_rn(w, __dadd_rn(1.0, __ddiv_rn(__dmul_rn(__dsub_rn(xi, xm), __dsub_rn(x[left + j], xm)), sq)))
-                         : w;
-          f = __dadd_rn(f, __dmul_rn(p, y[left + j]));
+              sq > 1e-12 ? __dmul_rn(w, __dadd_rn(1.0, __ddiv_rn(__dmul_rn(xd, __dsub_rn(x[left + j], xm)), sq))) : w;
+          return __dmul_rn(p, y[left + j]);
+        };
+        if (cached) {
+          // lane q is the only reader of wn[j], j = q mod 4, from here on (the first lane's sums above are complete:
+          // the shuffles synchronised the quad), so each lane replaces its weights by its terms in place
+          for (int j = quad; j < k; j += 4) wn[j] = term(j);
+          __syncwarp(qmask);
+          f = 0.0;
+          if (quad == 0)
+            for (int j = 0; j < k; ++j) f = __dadd_rn(f, wn[j]);
+        } else {
+          f = 0.0;
+          if (quad == 0)
+            for (int j = 0; j < k; ++j) f = __dadd_rn(f, term(j));
         }
       }
-      fit[i] = f;
+      if (quad == 0) fit[i] = f;
     }
     __syncthreads();
     for (int i = tid; i < n; i += kThreads) {
@@ -132,6 +181,18 @@ extern "C" int32_t scf_lowess(const double* endog, const double* exog, const uin
                               int32_t it, double* out, void* stream) {
   SCF_ARG(endog && exog && out, "null pointer");
   SCF_ARG(n >= 1 && n <= kMaxN && it >= 0, "n must be within [1, 512]");
-  lowess_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(endog, exog, valid, n, frac, it, out);
+  // shared-memory cache of the tricube and normalised weights: 2 * n * k doubles with k <= frac * n + 1
+  const int64_t kmax = (int64_t)(frac * (double)n + 1e-10) + 1;
+  size_t dyn = (size_t)2 * n * (kmax > 0 ? kmax : 1) * sizeof(double);
+  int cache = 1;
+  if (dyn > 160 * 1024) dyn = 0, cache = 0;
+  if (dyn > 20 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(lowess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) {
+      scf_set_error("scf_lowess: %s", cudaGetErrorString(e));
+      return -(int32_t)e;
+    }
+  }
+  lowess_kernel<<<1, kThreads, dyn, (cudaStream_t)stream>>>(endog, exog, valid, n, frac, it, cache, out);
   return scf_check_launch("scf_lowess");
 }
