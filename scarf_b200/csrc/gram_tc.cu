@@ -116,8 +116,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_tc_kernel(const __grid_const
   constexpr int STAGES_PER_SLAB = (SCF_GRAM_SLAB + C::KR - 1) / C::KR;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer =====================  (whole warp, one elected lane issues)
+    {
+      const bool leader = tc::elect_one();
       int it = 0;
       for (int i = 0; i < my_slabs; ++i) {
         const int64_t r0 = (int64_t)(split + i * nsplit) * SCF_GRAM_SLAB;
@@ -126,26 +127,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_tc_kernel(const __grid_const
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           tc::mbar_wait(empty + s, ph ^ 1u, 32);
           unsigned char* base = stages + (size_t)s * C::STAGE_BYTES;
-          tc::mbar_expect_tx(full + s, C::STAGE_BYTES);
           const int row = (int)(r0 + (int64_t)st * C::KR);
-          // one request = 4 feature blocks (128 features) x KR cells; B (256 features) takes two
-          tma_load_3d(base, &tmap_hi, full + s, 0, row, mi * 4);
-          tma_load_3d(base + C::A_BYTES, &tmap_hi, full + s, 0, row, nj * 8);
-          tma_load_3d(base + 2 * C::A_BYTES, &tmap_hi, full + s, 0, row, nj * 8 + 4);
-          if (MODE == 3) {
-            unsigned char* lo = base + C::A_BYTES + C::B_BYTES;
-            tma_load_3d(lo, &tmap_lo, full + s, 0, row, mi * 4);
-            tma_load_3d(lo + C::A_BYTES, &tmap_lo, full + s, 0, row, nj * 8);
-            tma_load_3d(lo + 2 * C::A_BYTES, &tmap_lo, full + s, 0, row, nj * 8 + 4);
+          if (leader) {
+            tc::mbar_expect_tx(full + s, C::STAGE_BYTES);
+            // one request = 4 feature blocks (128 features) x KR cells; B (256 features) takes two
+            tma_load_3d(base, &tmap_hi, full + s, 0, row, mi * 4);
+            tma_load_3d(base + C::A_BYTES, &tmap_hi, full + s, 0, row, nj * 8);
+            tma_load_3d(base + 2 * C::A_BYTES, &tmap_hi, full + s, 0, row, nj * 8 + 4);
+            if (MODE == 3) {
+              unsigned char* lo = base + C::A_BYTES + C::B_BYTES;
+              tma_load_3d(lo, &tmap_lo, full + s, 0, row, mi * 4);
+              tma_load_3d(lo + C::A_BYTES, &tmap_lo, full + s, 0, row, nj * 8);
+              tma_load_3d(lo + 2 * C::A_BYTES, &tmap_lo, full + s, 0, row, nj * 8 + 4);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp, warp-uniform values, one elected lane issues: descriptors stay in uniform registers (issuing from an
+    // `if (lane == 0)` region costs a vector->uniform waterfall per instruction, see knn_tc.cu)
+    {
       constexpr uint32_t idesc = tc::umma_idesc_tf32(GM, GN, true, true);
       constexpr uint32_t LBO = C::KR * 128;  // bytes between 32-feature blocks
+      const bool leader = tc::elect_one();
+      const uint32_t stages_u = tc::smem_u32(stages);
       int it = 0;
       for (int i = 0; i < my_slabs; ++i) {
         const int acc = i & 1;
@@ -158,28 +166,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_tc_kernel(const __grid_const
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           tc::mbar_wait(full + s, ph);
           tc::tc_fence_after();
-          unsigned char* base = stages + (size_t)s * C::STAGE_BYTES;
-          const uint64_t da = tc::umma_desc_mn_sw128_32b(base, LBO, 512);
-          const uint64_t db = tc::umma_desc_mn_sw128_32b(base + C::A_BYTES, LBO, 512);
+          const uint32_t base = stages_u + (uint32_t)s * C::STAGE_BYTES;
+          const uint64_t da = tc::umma_desc_mn_sw128_32b_u32(base, LBO, 512);
+          const uint64_t db = tc::umma_desc_mn_sw128_32b_u32(base + C::A_BYTES, LBO, 512);
+          const uint64_t dal = tc::umma_desc_mn_sw128_32b_u32(base + C::A_BYTES + C::B_BYTES, LBO, 512);
+          const uint64_t dbl = tc::umma_desc_mn_sw128_32b_u32(base + 2 * C::A_BYTES + C::B_BYTES, LBO, 512);
           // cells of this stage that still belong to the slab (SCF_GRAM_SLAB is a multiple of 8)
           const int rows_left = SCF_GRAM_SLAB - st * C::KR;
           const int nk = (rows_left < C::KR ? rows_left : C::KR) / 8;
 #pragma unroll
           for (int kk = 0; kk < C::KR / 8; ++kk) {
-            if (kk < nk) {
+            if (kk < nk && leader) {
               const uint64_t adv = (uint64_t)(kk * (1024 >> 4));  // 8 cells = two 512-B atoms per K step
               tc::umma_tf32(d_tmem, da + adv, db + adv, idesc, (st | kk) != 0);
               if (MODE == 3) {
-                const uint64_t dal = tc::umma_desc_mn_sw128_32b(base + C::A_BYTES + C::B_BYTES, LBO, 512);
-                const uint64_t dbl = tc::umma_desc_mn_sw128_32b(base + 2 * C::A_BYTES + C::B_BYTES, LBO, 512);
                 tc::umma_tf32(d_tmem, da + adv, dbl + adv, idesc, 1u);
                 tc::umma_tf32(d_tmem, dal + adv, db + adv, idesc, 1u);
               }
             }
           }
-          tc::umma_commit(empty + s);
+          if (leader) tc::umma_commit(empty + s);
+          __syncwarp();
         }
-        tc::umma_commit(tmem_full + acc);
+        if (leader) tc::umma_commit(tmem_full + acc);
+        __syncwarp();
       }
     }
   } else {

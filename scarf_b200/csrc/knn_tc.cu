@@ -371,37 +371,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer =====================  (whole warp, one elected lane issues)
+    {
+      const bool leader = tc::elect_one();
       int it = 0, seg = 0;
       for (long long cur = w0; cur < w1; ++seg) {
         const int q = (int)(cur / T), t0 = (int)(cur % T);
         const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
         cur += t1 - t0;
         if (seg > 0) tc::mbar_wait(a_empty, (uint32_t)(seg - 1) & 1u, backoff);  // MMAs of the last segment done with sA
-        tc::mbar_expect_tx(a_full, (uint32_t)(QT * p.kchunks * A_CHUNK_BYTES));
-        for (int t = 0; t < QT; ++t)
-          for (int c = 0; c < p.kchunks; ++c)
-            tc::tma_load_2d(sA + (size_t)(t * p.kchunks + c) * A_CHUNK_BYTES, &tmap_q, a_full, c * KCH,
-                            q * (QT * BM) + t * BM);
+        if (leader) {
+          tc::mbar_expect_tx(a_full, (uint32_t)(QT * p.kchunks * A_CHUNK_BYTES));
+          for (int t = 0; t < QT; ++t)
+            for (int c = 0; c < p.kchunks; ++c)
+              tc::tma_load_2d(sA + (size_t)(t * p.kchunks + c) * A_CHUNK_BYTES, &tmap_q, a_full, c * KCH,
+                              q * (QT * BM) + t * BM);
+        }
+        __syncwarp();
         for (int t = t0; t < t1; ++t)
           for (int c = 0; c < p.kchunks; ++c, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             tc::mbar_wait(empty + s, ph ^ 1u, backoff);
-            if (SCF_KNN_DEBUG & 128) {  // timing experiment: no reference traffic, the MMAs run on stale tiles
-              tc::mbar_arrive(full + s);
-              continue;
+            if (leader) {
+              if (SCF_KNN_DEBUG & 128) {  // timing experiment: no reference traffic, the MMAs run on stale tiles
+                tc::mbar_arrive(full + s);
+              } else {
+                tc::mbar_expect_tx(full + s, B_STAGE_BYTES);
+                tc::tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmap_r, full + s, c * KCH, t * BN);
+              }
             }
-            tc::mbar_expect_tx(full + s, B_STAGE_BYTES);
-            tc::tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmap_r, full + s, c * KCH, t * BN);
+            __syncwarp();
           }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop with identical (warp-uniform) values and one elected lane issues the tensor
+    // instructions: descriptors then live in uniform registers.  Issuing from inside an `if (lane == 0)` region makes
+    // the compiler move every descriptor from vector to uniform registers through a waterfall loop per MMA (~110
+    // idle cycles between 64-cycle instructions, measured).
+    {
       constexpr uint32_t idesc = tc::umma_idesc_f16(BM, BN, false, false);
+      const bool leader = tc::elect_one();
+      const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
       int it = 0, lt = 0, seg = 0;
       for (long long cur = w0; cur < w1; ++seg) {
         const int t0 = (int)(cur % T);
@@ -419,22 +432,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             tc::mbar_wait(full + s, ph, backoff);
             tc::tc_fence_after();
-            const uint64_t db = tc::umma_desc_k_sw128(sB + (size_t)s * B_STAGE_BYTES);
+            const uint64_t db = tc::umma_desc_k_sw128_u32(sB_u + (uint32_t)s * B_STAGE_BYTES);
             const int nk = c + 1 == p.kchunks ? p.ksteps_last : KCH / KSTEP;
 #pragma unroll
             for (int tq = 0; tq < QT; ++tq) {
-              const uint64_t da = tc::umma_desc_k_sw128(sA + (size_t)(tq * p.kchunks + c) * A_CHUNK_BYTES);
+              const uint64_t da = tc::umma_desc_k_sw128_u32(sA_u + (uint32_t)(tq * p.kchunks + c) * A_CHUNK_BYTES);
               const uint32_t d_tmem = tmem_base + (uint32_t)((acc * QT + tq) * BN);
 #pragma unroll
               for (int kk = 0; kk < KCH / KSTEP; ++kk)  // K = 16 fp16 = 32 bytes per instruction: +2 in 16-byte units
-                if (kk < nk && !(SCF_KNN_DEBUG & 64))
+                if (kk < nk && !(SCF_KNN_DEBUG & 64) && leader)
                   tc::umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (c | kk) != 0);
             }
-            tc::umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
+            if (leader) tc::umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
+            __syncwarp();
           }
-          tc::umma_commit(tmem_full + acc);  // both accumulators of this reference tile complete
+          if (leader) tc::umma_commit(tmem_full + acc);  // both accumulators of this reference tile complete
+          __syncwarp();
         }
-        tc::umma_commit(a_empty);  // the query operand may be replaced once every MMA of the segment has run
+        if (leader) tc::umma_commit(a_empty);  // the query operand may be replaced once every MMA of the segment has run
+        __syncwarp();
       }
     }
   } else {

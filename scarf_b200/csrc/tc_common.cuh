@@ -98,6 +98,15 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(const void* smem_tile) {
   d |= (uint64_t)2 << 61;                                 // layout type SWIZZLE_128B          [61,64)
   return d;
 }
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_u32(uint32_t smem_addr) {  // same, from a shared-window address
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // MN-major operand of 32-bit (tf32) elements: the MN index is contiguous in memory.  The only layout the tensor
 // core accepts here is SWIZZLE_128B_BASE32B (layout type 1): rows of 128 B hold 32 consecutive MN positions of
 // one k, the 32-byte chunks of a row are XORed with (row % 4), 4 consecutive k form a 512-B atom
@@ -111,6 +120,16 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(const void* smem_tile
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b_u32(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                                uint32_t sbo_bytes) {  // same, from a shared-window address
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 // Instruction descriptor for kind::tf32, FP32 accumulate, dense.
