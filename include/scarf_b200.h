@@ -49,16 +49,17 @@ int32_t scf_csr_gene_stats(const int64_t* indptr, const int32_t* indices, const 
                            const double* row_div, double sf, unsigned long long* gene_nnz,
                            double* gene_sum, double* gene_sumsq, void* stream);
 
-/* Same statistics, sector-packed reductions: the three accumulators of a gene share one 32-byte sector of the
- * workspace (double [n_genes][4]) and one reduction instruction carries all three additions of eight stored values,
- * a third of the L2 reduction requests of scf_csr_gene_stats.  Results are ACCUMULATED into gene_nnz / gene_sum /
- * gene_sumsq exactly like scf_csr_gene_stats.  workspace: scf_csr_gene_stats_workspace_bytes(n_genes), device. */
-int64_t scf_csr_gene_stats_workspace_bytes(int32_t n_genes);
-int32_t scf_csr_gene_stats_packed(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
-                                  const int64_t* row_ids, int64_t n_sel, int32_t n_genes,
-                                  const double* row_div, double sf, unsigned long long* gene_nnz,
-                                  double* gene_sum, double* gene_sumsq, void* workspace,
-                                  int64_t workspace_bytes, void* stream);
+/* Same statistics without a reduction per stored value: a CTA owns (block of rows) x (window of 4096 genes), adds
+ * the rows one after the other into shared-memory accumulators with plain read-modify-writes (a gene occurs once per
+ * row) and flushes one reduction per gene.  Needs ascending column ids inside every row (the CSR contract of this
+ * library).  Results are ACCUMULATED into gene_nnz / gene_sum / gene_sumsq exactly like scf_csr_gene_stats
+ * (gene_sum == NULL: nnz only).  workspace (device): scf_csr_gene_stats_workspace_bytes(n_sel, n_genes). */
+int64_t scf_csr_gene_stats_workspace_bytes(int64_t n_sel, int32_t n_genes);
+int32_t scf_csr_gene_stats_windowed(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
+                                    const int64_t* row_ids, int64_t n_sel, int32_t n_genes,
+                                    const double* row_div, double sf, unsigned long long* gene_nnz,
+                                    double* gene_sum, double* gene_sumsq, void* workspace,
+                                    int64_t workspace_bytes, void* stream);
 
 /* ---- K1a: column sums of the normalised HVG matrix -------------------------------------------
  * x = log1p(sf*c/row_sum[r]) (log_transform) or sf*c/row_sum[r]   (scarf/assay.py:54-64,826)

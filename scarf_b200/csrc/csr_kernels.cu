@@ -90,69 +90,6 @@ __global__ void __launch_bounds__(kThreads) gene_stats_kernel(const int64_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// K0b, sector-packed variant.  The three per-gene accumulators live side by side in one 32-byte sector
-// (double acc[g][4] = {nnz, sum, sumsq, -}), and the lanes are regrouped so that ONE red.f64 instruction carries
-// the three additions of eight stored values: lane l serves value (l >> 2) of the current group of eight, field
-// (l & 3).  The SM's reduction path is paid per request (sector), not per lane, so this issues a third of the
-// requests of gene_stats_kernel for the same arithmetic.  nnz is accumulated as a double (exact below 2^53).
-__global__ void __launch_bounds__(kThreads) gene_stats4_kernel(const int64_t* __restrict__ indptr,
-                                                               const int32_t* __restrict__ indices,
-                                                               const uint32_t* __restrict__ data,
-                                                               const int64_t* __restrict__ row_ids, int64_t n_sel,
-                                                               const double* __restrict__ row_div, double sf,
-                                                               double* __restrict__ acc4) {
-  const int lane = threadIdx.x & 31;
-  const int field = lane & 3, sub = lane >> 2;
-  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
-  for (int64_t r = warp0; r < n_sel; r += nwarps) {
-    const int64_t row = row_of(row_ids, r);
-    const int64_t s = indptr[row], e = indptr[row + 1];
-    const double dv = row_div ? row_div[r] : 1.0;
-    const bool norm = row_div != nullptr;
-    for (int64_t p = s + lane; p - lane < e; p += 128) {
-      int32_t g[4];
-      uint32_t c[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t pp = p + 32 * u;
-        const bool ok = pp < e;
-        g[u] = ok ? ld_stream(indices + pp) : -1;
-        c[u] = ok ? ld_stream(data + pp) : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (p - lane + 32 * u >= e) break;  // warp-uniform
-        // norm_lib_size: sf * counts / scalar  (scarf/assay.py:51), evaluated left to right in float64
-        const double v = norm ? __ddiv_rn(sf * (double)c[u], dv) : (double)c[u];
-        const int gg = c[u] != 0u ? g[u] : -1;  // explicit zeros carry no statistics
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int srcl = 8 * q + sub;
-          const int ge = __shfl_sync(SCF_FULL, gg, srcl);
-          const double ve = __shfl_sync(SCF_FULL, v, srcl);
-          if (ge >= 0 && field < 3) {
-            const double add = field == 0 ? 1.0 : (field == 1 ? ve : ve * ve);
-            atomicAdd(acc4 + (int64_t)ge * 4 + field, add);
-          }
-        }
-      }
-    }
-  }
-}
-
-// acc4 -> the separate vectors of the C-ABI (accumulating, like gene_stats_kernel)
-__global__ void gene_stats4_unpack_kernel(const double* __restrict__ acc4, int n_genes,
-                                          unsigned long long* __restrict__ gene_nnz, double* __restrict__ gene_sum,
-                                          double* __restrict__ gene_sumsq) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_genes) return;
-  gene_nnz[g] += (unsigned long long)__double2ll_rn(acc4[(int64_t)g * 4]);
-  if (gene_sum) gene_sum[g] += acc4[(int64_t)g * 4 + 1];
-  if (gene_sumsq) gene_sumsq[g] += acc4[(int64_t)g * 4 + 2];
-}
-
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double norm_value(uint32_t c, double s, double sf, bool log_transform) {
   const double v = __ddiv_rn(sf * (double)c, s);
   return log_transform ? log1p(v) : v;
@@ -400,32 +337,6 @@ extern "C" int32_t scf_csr_gene_stats(const int64_t* indptr, const int32_t* indi
   gene_stats_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, row_ids, n_sel, row_div, sf,
                                                                   gene_nnz, gene_sum, gene_sumsq);
   return scf_check_launch("scf_csr_gene_stats");
-}
-
-extern "C" int64_t scf_csr_gene_stats_workspace_bytes(int32_t n_genes) { return (int64_t)n_genes * 4 * 8; }
-
-extern "C" int32_t scf_csr_gene_stats_packed(const int64_t* indptr, const int32_t* indices, const uint32_t* data,
-                                             const int64_t* row_ids, int64_t n_sel, int32_t n_genes,
-                                             const double* row_div, double sf, unsigned long long* gene_nnz,
-                                             double* gene_sum, double* gene_sumsq, void* workspace,
-                                             int64_t workspace_bytes, void* stream) {
-  SCF_ARG(indptr && indices && data && gene_nnz && workspace, "null pointer");
-  SCF_ARG(n_sel >= 0 && n_genes > 0, "bad sizes");
-  SCF_ARG(workspace_bytes >= scf_csr_gene_stats_workspace_bytes(n_genes), "workspace too small");
-  if (n_sel == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)n_genes * 32, st);
-  if (e != cudaSuccess) {
-    scf_set_error("scf_csr_gene_stats_packed: %s", cudaGetErrorString(e));
-    return -(int32_t)e;
-  }
-  const int grid = grid_for((const void*)gene_stats4_kernel, kThreads, 0);
-  gene_stats4_kernel<<<grid, kThreads, 0, st>>>(indptr, indices, data, row_ids, n_sel, row_div, sf, (double*)workspace);
-  int32_t rc = scf_check_launch("scf_csr_gene_stats_packed");
-  if (rc) return rc;
-  gene_stats4_unpack_kernel<<<(n_genes + 255) / 256, 256, 0, st>>>((const double*)workspace, n_genes, gene_nnz, gene_sum,
-                                                                  gene_sumsq);
-  return scf_check_launch("scf_csr_gene_stats_packed(unpack)");
 }
 
 extern "C" int32_t scf_csr_hvg_colstats(const int64_t* indptr, const int32_t* indices, const uint32_t* data,

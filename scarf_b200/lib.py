@@ -19,8 +19,8 @@ SIGNATURES = {
     "scf_last_error": (ctypes.c_char_p, []),
     "scf_csr_row_sums": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "scf_csr_gene_stats": (_i32, [_p, _p, _p, _p, _i64, _i32, _p, _f64, _p, _p, _p, _p]),
-    "scf_csr_gene_stats_workspace_bytes": (_i64, [_i32]),
-    "scf_csr_gene_stats_packed": (_i32, [_p, _p, _p, _p, _i64, _i32, _p, _f64, _p, _p, _p, _p, _i64, _p]),
+    "scf_csr_gene_stats_workspace_bytes": (_i64, [_i64, _i32]),
+    "scf_csr_gene_stats_windowed": (_i32, [_p, _p, _p, _p, _i64, _i32, _p, _f64, _p, _p, _p, _p, _i64, _p]),
     "scf_csr_hvg_colstats": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _f64, _i32, _i32, _i32, _p, _p, _p]),
     "scf_csr_norm_scale": (_i32, [_p, _p, _p, _p, _i64, _p, _i32, _p, _f64, _i32, _p, _p, _p, _p, _p, _i64, _p]),
     "scf_csr_hvg_compact": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _f64, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p]),

@@ -84,7 +84,7 @@ def csr_row_sums(csr: CsrDevice, row_ids=None, col_map=None):
 
 
 def csr_gene_stats(csr: CsrDevice, row_ids=None, row_div=None, sf=1000.0, out=None, with_moments=True,
-                   packed=True):
+                   windowed=True):
     """Per-gene (nnz uint64-in-int64, sum f64, sumsq f64) of sf*c/row_div over the selected rows; accumulates into out."""
     _chk(row_ids, torch.int64, "row_ids"), _chk(row_div, torch.float64, "row_div")
     n = csr.n_rows if row_ids is None else int(row_ids.numel())
@@ -94,10 +94,10 @@ def csr_gene_stats(csr: CsrDevice, row_ids=None, row_div=None, sf=1000.0, out=No
         sq = torch.zeros(csr.n_cols, dtype=torch.float64, device=csr.device) if with_moments else None
     else:
         nnz, sm, sq = out
-    if packed:
-        ws_bytes = int(lib.raw("scf_csr_gene_stats_workspace_bytes")(csr.n_cols))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=csr.device)
-        lib.call("scf_csr_gene_stats_packed", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
+    if windowed:
+        ws_bytes = int(lib.raw("scf_csr_gene_stats_workspace_bytes")(n, csr.n_cols))
+        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=csr.device)
+        lib.call("scf_csr_gene_stats_windowed", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(row_ids), n,
                  csr.n_cols, _ptr(row_div), float(sf), _ptr(nnz), _ptr(sm), _ptr(sq), ws.data_ptr(), ws_bytes,
                  _stream(), launches=2)
     else:

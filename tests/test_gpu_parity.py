@@ -443,8 +443,8 @@ def test_device_lowess_equals_host(gpu):
     assert np.isnan(d3).all()
 
 
-def test_gene_stats_packed_equals_plain(gpu, synth_small):
-    """Sector-packed reductions (scf_csr_gene_stats_packed) against the per-array kernel and the oracle."""
+def test_gene_stats_windowed_equals_plain(gpu, synth_small):
+    """Windowed shared-memory accumulation (scf_csr_gene_stats_windowed) against the per-array kernel and the oracle."""
     from oracle import pipeline as P
 
     torch, graph, ops = gpu["torch"], gpu["graph"], gpu["ops"]
@@ -452,12 +452,12 @@ def test_gene_stats_packed_equals_plain(gpu, synth_small):
     n_counts, _ = graph.cell_totals(csr)
     rows = torch.arange(3, 2900, 2, device="cuda")
     div = n_counts[rows].contiguous()
-    a = ops.csr_gene_stats(csr, rows, div, 1000.0, packed=False)
-    b = ops.csr_gene_stats(csr, rows, div, 1000.0, packed=True)
+    a = ops.csr_gene_stats(csr, rows, div, 1000.0, windowed=False)
+    b = ops.csr_gene_stats(csr, rows, div, 1000.0, windowed=True)
     assert torch.equal(a[0], b[0])
     np.testing.assert_allclose(b[1].cpu().numpy(), a[1].cpu().numpy(), rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(b[2].cpu().numpy(), a[2].cpu().numpy(), rtol=1e-12, atol=1e-12)
-    nn = ops.csr_gene_stats(csr, None, None, with_moments=False, packed=True)[0]
+    nn = ops.csr_gene_stats(csr, None, None, with_moments=False, windowed=True)[0]
     assert np.array_equal(nn.cpu().numpy(), P.gene_ncells(synth_small))
 
 

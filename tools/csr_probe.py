@@ -42,10 +42,10 @@ def timed(name, fn, bytes_, reps=5):
 
 timed("row_sums (all genes)", lambda: ops.csr_row_sums(csr), csr_bytes + 12 * n)
 row_sum, row_nnz = timed("row_sums (HVG subset)", lambda: ops.csr_row_sums(csr, None, col_map), csr_bytes + 12 * n)
-timed("gene_stats plain (3 RED/value)", lambda: ops.csr_gene_stats(csr, None, n_counts, 1000.0, packed=False), csr_bytes + 8 * n)
-timed("gene_stats packed (sector RED)", lambda: ops.csr_gene_stats(csr, None, n_counts, 1000.0, packed=True), csr_bytes + 8 * n)
-timed("gene_ncells plain", lambda: ops.csr_gene_stats(csr, None, None, with_moments=False, packed=False), csr_bytes)
-timed("gene_ncells packed", lambda: ops.csr_gene_stats(csr, None, None, with_moments=False, packed=True), csr_bytes)
+timed("gene_stats plain (3 RED/value)", lambda: ops.csr_gene_stats(csr, None, n_counts, 1000.0, windowed=False), csr_bytes + 8 * n)
+timed("gene_stats windowed (smem RMW)", lambda: ops.csr_gene_stats(csr, None, n_counts, 1000.0, windowed=True), csr_bytes + 8 * n)
+timed("gene_ncells plain", lambda: ops.csr_gene_stats(csr, None, None, with_moments=False, windowed=False), csr_bytes)
+timed("gene_ncells windowed", lambda: ops.csr_gene_stats(csr, None, None, with_moments=False, windowed=True), csr_bytes)
 comp = timed("hvg_compact", lambda: ops.csr_hvg_compact(csr, None, col_map, 2000, row_sum, row_nnz), csr_bytes + 8 * n)
 row_off, cols, xs, sx, sxx = comp
 hnnz = int(cols.numel())
