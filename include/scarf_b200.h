@@ -125,6 +125,15 @@ int32_t scf_gram_symmetrize(int64_t* g_fx, int32_t n_cols, int64_t ldg, void* st
 int32_t scf_project(const float* z, int64_t ldz, int64_t n_rows, int32_t n_cols, const float* v,
                     int64_t ldv, int32_t dims, float* y, int64_t ldy, void* stream);
 
+/* Same product on the tensor cores (3xTF32, FP32 accumulate): needs the second plane z_lo = Z - tf32_trunc(Z) that
+ * scf_csr_norm_scale / scf_hvg_dense_scale write for the Gram kernel (same shape / stride as z), ldz % 32 == 0,
+ * dims <= 128, 16-byte aligned z / z_lo / y / workspace.  Relative error of an entry <= ~2e-5 (truncating tensor-core
+ * accumulation over four interleaved chains).  workspace (device): scf_project_tc_workspace_bytes(ldz, dims). */
+int64_t scf_project_tc_workspace_bytes(int64_t ldz, int32_t dims);
+int32_t scf_project_tc(const float* z, const float* z_lo, int64_t ldz, int64_t n_rows, int32_t n_cols,
+                       const float* v, int64_t ldv, int32_t dims, float* y, int64_t ldy, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
 /* ---- K5: exact k nearest neighbours, squared L2 --------------------------------------------------
  * Replaces hnswlib Index(space='l2').knn_query + fix_knn_query (scarf/ann.py:14-52,194-205):
  *   d(a,b) = (float) sum_t ((double)a_t - (double)b_t)^2   (t ascending), order by (d, index),

@@ -308,7 +308,6 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
         g_fx = ops.gram_accumulate(z, n_local, n_feat, mode=gram_mode, z_lo=z_lo)
         comm.allreduce_sum_(g_fx)
         ops.gram_symmetrize(g_fx, n_feat)
-        del z_lo
         mark("gram")
         cov = g_fx[:n_feat, :n_feat].to(torch.float64) * (2.0 ** -lib.GRAM_SHIFT / max(n_total - 1, 1))
         evals, load = eig_topk(cov, dims)
@@ -320,8 +319,8 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
     v32[:, :dims] = load.to(torch.float32)
 
     # ---- embedding (K4) + exchange (collective 3) ----
-    y = ops.project(z, n_local, n_feat, v32, dims)
-    del z
+    y = ops.project(z, n_local, n_feat, v32, dims, z_lo=z_lo)  # tensor cores when the 3xTF32 plane exists
+    del z, z_lo
     y_all = comm.allgather_rows(y, counts)
     mark("project")
 
@@ -419,13 +418,14 @@ def run_mapping_csr(target: CsrDevice, target_cell_idx, t_col_of_feature, ref_mu
             sigma_d = clean_array(torch.sqrt(var), 1.0)
     ldz = round_up(n_feat, 128)
     z = torch.empty((max(n_local, 1), ldz), dtype=torch.float32, device=dev)
+    z_lo = torch.empty_like(z)  # second 3xTF32 plane: the projection runs on the tensor cores
     ops.csr_norm_scale(target, target_cell_idx, col_map, n_feat, row_sum, z, SF, log_transform, mu_d, sigma_d,
-                       missing_fill=missing_fill)
+                       missing_fill=missing_fill, z_lo=z_lo)
     ldv = round_up(dims, 4)
     v32 = torch.zeros((n_feat, ldv), dtype=torch.float32, device=dev)
     v32[:, :dims] = ref_loadings[:, :dims].to(torch.float32)
-    y = ops.project(z, n_local, n_feat, v32, dims, ldy=int(ref_embedding_all.stride(0)))
-    del z
+    y = ops.project(z, n_local, n_feat, v32, dims, ldy=int(ref_embedding_all.stride(0)), z_lo=z_lo)
+    del z, z_lo
     save_k = min(save_k, int(ref_embedding_all.shape[0]))
     idx, dist = ops.knn_l2(y, ref_embedding_all, dims, save_k, self_offset=-1, method=1)
     return MappingResult(idx, dist, y, mu_d, sigma_d)

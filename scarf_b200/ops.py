@@ -190,12 +190,21 @@ def gram_symmetrize(g_fx, n_cols):
     return g_fx
 
 
-def project(z, n_rows, n_cols, v, dims, y=None, ldy=None):
-    """y[:n_rows, :dims] = z[:n_rows, :n_cols] @ v[:n_cols, :dims]; pad columns of y are zeroed."""
+def project(z, n_rows, n_cols, v, dims, y=None, ldy=None, z_lo=None):
+    """y[:n_rows, :dims] = z[:n_rows, :n_cols] @ v[:n_cols, :dims]; pad columns of y are zeroed.  With the second plane
+    ``z_lo`` (= z - tf32_trunc(z), the 3xTF32 Gram operand) the product runs on the tensor cores."""
     assert z.dtype == torch.float32 and v.dtype == torch.float32 and v.stride(1) == 1
     if y is None:
         ldy = ldy or round_up(dims, 32)
         y = torch.empty((n_rows, ldy), dtype=torch.float32, device=z.device)
+    if z_lo is not None and dims <= 128 and z.stride(0) % 32 == 0 and y.stride(0) % 4 == 0:
+        assert z_lo.dtype == torch.float32 and z_lo.stride() == z.stride()
+        ws_bytes = int(lib.raw("scf_project_tc_workspace_bytes")(int(z.stride(0)), int(dims)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+        lib.call("scf_project_tc", z.data_ptr(), z_lo.data_ptr(), int(z.stride(0)), int(n_rows), int(n_cols),
+                 v.data_ptr(), int(v.stride(0)), int(dims), y.data_ptr(), int(y.stride(0)), ws.data_ptr(), ws_bytes,
+                 _stream(), launches=2)
+        return y
     lib.call("scf_project", z.data_ptr(), int(z.stride(0)), int(n_rows), int(n_cols), v.data_ptr(), int(v.stride(0)),
              int(dims), y.data_ptr(), int(y.stride(0)), _stream())
     return y

@@ -483,3 +483,23 @@ def test_eig_topk_on_device(gpu):
         ref = graph.sign_rule(torch.flip(vf[:, -dims:], [1]).T.contiguous()).T
         cosang = (ref * load).sum(0).abs().clamp(max=1.0)
         assert float(torch.acos(cosang).max()) < 1e-5
+
+
+@pytest.mark.parametrize("n,h,dims", [(3000, 2000, 50), (1000, 500, 100), (130, 70, 3), (4096, 1999, 125)])
+def test_project_tensor_core_equals_fp64(gpu, n, h, dims):
+    """scf_project_tc (3xTF32 tcgen05) against the float64 product and the FP32 SIMT kernel on z-score-like data."""
+    torch, ops = gpu["torch"], gpu["ops"]
+    g = torch.Generator(device="cuda").manual_seed(n + dims)
+    ldz = ops.round_up(h, 128)
+    z = torch.zeros((n, ldz), device="cuda")
+    z[:, :h] = torch.randn((n, h), device="cuda", generator=g) * (torch.rand((n, h), device="cuda", generator=g) < 0.3) * 3.0 - 0.4
+    z_lo = z - (z.view(torch.int32) & -8192).view(torch.float32)
+    v = torch.zeros((h, ops.round_up(dims, 4)), device="cuda")
+    v[:, :dims] = torch.linalg.qr(torch.randn((h, dims), device="cuda", generator=g))[0]
+    ref = z[:, :h].double() @ v[:, :dims].double()
+    y_tc = ops.project(z, n, h, v, dims, z_lo=z_lo)
+    y_simt = ops.project(z, n, h, v, dims)
+    assert y_tc.shape == y_simt.shape and torch.all(y_tc[:, dims:] == 0)
+    scale = float(ref.abs().max())
+    assert float((y_simt[:, :dims].double() - ref).abs().max()) < 1e-5 * scale
+    assert float((y_tc[:, :dims].double() - ref).abs().max()) < 3e-5 * scale

@@ -61,7 +61,11 @@ timed("hvg_dense_scale (Z only)", lambda: ops.hvg_dense_scale(row_off, cols, xs,
 timed("csr_norm_scale (Z + Z_lo)", lambda: ops.csr_norm_scale(csr, None, col_map, 2000, row_sum, z, mu=mu, sigma=sigma, z_lo=z_lo),
       csr_bytes + 2 * 4.0 * 2048 * n)
 v32 = torch.randn((2000, 52), dtype=torch.float32, device=dev)
-timed("project D=50", lambda: ops.project(z, n, 2000, v32, 50), 4.0 * 2048 * n + 4 * 64 * n)
+timed("project D=50 (FP32 SIMT)", lambda: ops.project(z, n, 2000, v32, 50), 4.0 * 2048 * n + 4 * 64 * n)
+timed("project D=50 (3xTF32 tcgen05)", lambda: ops.project(z, n, 2000, v32, 50, z_lo=z_lo), 2 * 4.0 * 2048 * n + 4 * 64 * n)
+v100 = torch.randn((2000, 100), dtype=torch.float32, device=dev)
+timed("project D=100 (FP32 SIMT)", lambda: ops.project(z, n, 2000, v100, 100), 4.0 * 2048 * n + 4 * 128 * n)
+timed("project D=100 (3xTF32 tcgen05)", lambda: ops.project(z, n, 2000, v100, 100, z_lo=z_lo), 2 * 4.0 * 2048 * n + 4 * 128 * n)
 st = {}
 cov = torch.randn((2000, 2000), dtype=torch.float64, device=dev)
 timed("mark_hvgs_csr (whole)", lambda: graph.mark_hvgs_csr(csr, None, feat_I, n_counts, n, top_n=2000, as_tensor=True,
