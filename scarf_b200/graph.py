@@ -210,13 +210,25 @@ def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
         v = q @ top
         res_t = (aq @ top - v * wt).norm(dim=0).max() / w[-1]
         # the one synchronisation of the round: residual + the Ritz values that fix the next filter
-        res, th_min, th_max, th_dims, bulk = torch.stack([res_t, w[0], w[-1], wt[0], (trace - w.sum()) / (h - b)]).tolist()
+        width = int(q.shape[1])
+        keep = min(width, dims + 32)
+        res, th_min, th_max, th_dims, bulk, th_keep, bulk_keep = torch.stack(
+            [res_t, w[0], w[-1], wt[0], (trace - w.sum()) / (h - width), w[-keep],
+             (trace - w[-keep:].sum()) / (h - keep)]).tolist()
         if stats is not None:
             stats["eig_rounds"], stats["eig_residual"] = rounds, res
         if res <= tol:
             return _finish_eig(wt, v, dims)
         if rounds == max_rounds or not (th_dims > 0.0 and th_max > th_dims):
             break
+        # The wide start block is only needed to catch the wanted directions: once the block is rotated to Ritz
+        # vectors, and if the spectrum has a gap below the wanted pairs (theta_{dims+32} < 0.8 theta_dims), the later
+        # rounds keep the top dims + 32 Ritz vectors only.  The damped interval then ends at the smallest KEPT Ritz
+        # value, closer to lambda_dims: faster convergence for half the GEMM / QR / eigh work.  Without such a gap
+        # (wanted pairs inside a dense bulk) the full block stays.
+        if keep < width and th_keep < 0.8 * th_dims:
+            s = s[:, -keep:]
+            th_min, bulk = th_keep, bulk_keep
         # damped interval [0, cut]: the block's smallest Ritz value, or the mean of the spectrum outside the block
         # when that is larger (it never exceeds lambda_{b+1}); kept clear of the wanted Ritz values
         cut = max(th_min, min(bulk, 0.5 * (th_min + th_dims)))
