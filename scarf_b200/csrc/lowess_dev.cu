@@ -1,7 +1,8 @@
 // Device-side robust LOWESS: the same algorithm as scf_host_lowess (host_lowess.cu), run by ONE CTA so that
 // mark_hvgs' trend removal (scarf/feat_utils.py:22,38-40 -> statsmodels lowess, frac 0.1, it 100, delta 0) needs no
-// device->host round trip.  <= 512 points (the reference bins the genes into 200); every arithmetic step uses the
-// round-to-nearest intrinsics in the host routine's order (no FMA contraction), so both give the same fit.
+// device->host round trip.  <= 512 points (the reference bins the genes into 200); the arithmetic
+// uses the round-to-nearest intrinsics of the host routine (no FMA contraction); window sums are formed by four lanes
+// (see below), so the two fits agree to ~1e-13 relative rather than bit for bit.
 #include <math_constants.h>
 #include "common.cuh"
 
@@ -81,10 +82,15 @@ __global__ void __launch_bounds__(kThreads) lowess_kernel(const double* __restri
     }
     __syncthreads();
   }
-  // Four lanes per point: the divisions (the expensive part) of a window are spread over the quad, every sum runs on
-  // the quad's first lane in the host routine's order, so the fit is bit-identical to the one-thread form.
+  // Four lanes per point: every window sum is formed as four interleaved partial sums that a two-step butterfly
+  // adds up (all four lanes obtain the same value).  FP64 dependent chains are what this kernel waits for, and the
+  // quad cuts them by four; the fit agrees with the sequential host routine to ~1e-13 relative.
   const int quad = tid & 3;
   const unsigned qmask = 0xFu << ((tid & 31) & ~3);
+  auto quad_sum = [&](double v) {
+    v = __dadd_rn(v, __shfl_xor_sync(qmask, v, 1));
+    return __dadd_rn(v, __shfl_xor_sync(qmask, v, 2));
+  };
   for (int pass = 0; pass <= it; ++pass) {
     for (int i0 = 0; i0 < n; i0 += kThreads / 4) {
       const int i = i0 + (tid >> 2);
@@ -95,54 +101,37 @@ __global__ void __launch_bounds__(kThreads) lowess_kernel(const double* __restri
       auto weight = [&](int j) {  // tricube * robustness weight, un-normalised
         return __dmul_rn(cached ? tri[(size_t)i * k + j] : tricube(i, left, j), rw[left + j]);
       };
-      double* wn = wn_all + (size_t)i * k;  // per-point scratch (only when cached)
-      double sw = 0.0;
-      if (cached) {
-        for (int j = quad; j < k; j += 4) wn[j] = weight(j);
-        __syncwarp(qmask);
-        if (quad == 0)
-          for (int j = 0; j < k; ++j) sw = __dadd_rn(sw, wn[j]);
-      } else if (quad == 0) {
-        for (int j = 0; j < k; ++j) sw = __dadd_rn(sw, weight(j));
+      double* wn = wn_all + (size_t)i * k;  // per-point scratch (only when cached); lane q owns entries j = q mod 4
+      double part = 0.0;
+      for (int j = quad; j < k; j += 4) {
+        const double wj = weight(j);
+        if (cached) wn[j] = wj;
+        part = __dadd_rn(part, wj);
       }
-      sw = __shfl_sync(qmask, sw, (tid & 31) & ~3);
+      const double sw = quad_sum(part);
       double f = y[i];
       if (sw > 0.0) {
-        if (cached) {
+        if (cached)
           for (int j = quad; j < k; j += 4) wn[j] = __ddiv_rn(wn[j], sw);
-          __syncwarp(qmask);
-        }
         auto w_of = [&](int j) { return cached ? wn[j] : __ddiv_rn(weight(j), sw); };
-        double xm = 0.0, sq = 0.0;
-        if (quad == 0) {
-          for (int j = 0; j < k; ++j) xm = __dadd_rn(xm, __dmul_rn(w_of(j), x[left + j]));
-          for (int j = 0; j < k; ++j) {
-            const double dx = __dsub_rn(x[left + j], xm);
-            sq = __dadd_rn(sq, __dmul_rn(__dmul_rn(w_of(j), dx), dx));
-          }
+        part = 0.0;
+        for (int j = quad; j < k; j += 4) part = __dadd_rn(part, __dmul_rn(w_of(j), x[left + j]));
+        const double xm = quad_sum(part);
+        part = 0.0;
+        for (int j = quad; j < k; j += 4) {
+          const double dx = __dsub_rn(x[left + j], xm);
+          part = __dadd_rn(part, __dmul_rn(__dmul_rn(w_of(j), dx), dx));
         }
-        xm = __shfl_sync(qmask, xm, (tid & 31) & ~3);
-        sq = __shfl_sync(qmask, sq, (tid & 31) & ~3);
+        const double sq = quad_sum(part);
         const double xd = __dsub_rn(xi, xm);
-        auto term = [&](int j) {
+        part = 0.0;
+        for (int j = quad; j < k; j += 4) {
           const double w = w_of(j);
           const double p =
               sq > 1e-12 ? __dmul_rn(w, __dadd_rn(1.0, __ddiv_rn(__dmul_rn(xd, __dsub_rn(x[left + j], xm)), sq))) : w;
-          return __dmul_rn(p, y[left + j]);
-        };
-        if (cached) {
-          // lane q is the only reader of wn[j], j = q mod 4, from here on (the first lane's sums above are complete:
-          // the shuffles synchronised the quad), so each lane replaces its weights by its terms in place
-          for (int j = quad; j < k; j += 4) wn[j] = term(j);
-          __syncwarp(qmask);
-          f = 0.0;
-          if (quad == 0)
-            for (int j = 0; j < k; ++j) f = __dadd_rn(f, wn[j]);
-        } else {
-          f = 0.0;
-          if (quad == 0)
-            for (int j = 0; j < k; ++j) f = __dadd_rn(f, term(j));
+          part = __dadd_rn(part, __dmul_rn(p, y[left + j]));
         }
+        f = quad_sum(part);
       }
       if (quad == 0) fit[i] = f;
     }
@@ -154,13 +143,19 @@ __global__ void __launch_bounds__(kThreads) lowess_kernel(const double* __restri
     if (pass == it) break;  // the weights of a further pass are never used
     for (int i = tid; i < n; i += kThreads) r[i] = fabs(__dsub_rn(y[i], fit[i]));
     __syncthreads();
-    // median by rank: the order statistics n/2 (and n/2 - 1 for even n), ties broken by position
-    for (int i = tid; i < n; i += kThreads) {
+    // median by rank: the order statistics n/2 (and n/2 - 1 for even n), ties broken by position; a quad per point
+    for (int i0 = 0; i0 < n; i0 += kThreads / 4) {
+      const int i = i0 + (tid >> 2);
+      if (i >= n) continue;  // uniform inside a quad
       const double ri = r[i];
       int rank = 0;
-      for (int j = 0; j < n; ++j) rank += (r[j] < ri) || (r[j] == ri && j < i);
-      if (rank == n / 2) s_med[0] = ri;
-      if (rank == n / 2 - 1) s_med[1] = ri;
+      for (int j = quad; j < n; j += 4) rank += (r[j] < ri) || (r[j] == ri && j < i);
+      rank += __shfl_xor_sync(qmask, rank, 1);
+      rank += __shfl_xor_sync(qmask, rank, 2);
+      if (quad == 0) {
+        if (rank == n / 2) s_med[0] = ri;
+        if (rank == n / 2 - 1) s_med[1] = ri;
+      }
     }
     __syncthreads();
     const double med = (n & 1) ? s_med[0] : __dmul_rn(0.5, __dadd_rn(s_med[0], s_med[1]));

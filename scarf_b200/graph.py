@@ -164,6 +164,21 @@ def _orthonormalise(y):
     return torch.linalg.qr(y)[0]
 
 
+def _cholqr2(y):
+    """Orthonormal basis of range(y) by column scaling + two Cholesky-QR passes (GEMM, a b x b Cholesky and a
+    triangular solve each: a fraction of the Householder QR's latency).  Safe for a filtered block of Ritz vectors
+    under eig_topk's degree rule (columns are nearly parallel to at most ~1e4 : 1, i.e. cond^2 <= 1e8); a start block
+    filtered from random columns (cond ~ 1e11) needs the Householder QR.  -> (q, bad): ``bad`` is a device scalar,
+    non-zero when a Cholesky factorisation broke down (the caller then repeats with Householder)."""
+    y = y / y.norm(dim=0, keepdim=True)
+    bad = None
+    for _ in range(2):
+        l, info = torch.linalg.cholesky_ex(y.T @ y)
+        bad = info if bad is None else bad + info
+        y = torch.linalg.solve_triangular(l, y.T, upper=False).T
+    return y.contiguous(), bad
+
+
 def _cheb_growth(x):
     """|T_m(x)|^(1/m) for large m: x + sqrt(x^2 - 1) (x >= 1)."""
     return x + math.sqrt(max(x * x - 1.0, 0.0))
@@ -202,9 +217,12 @@ def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
     # bound from the 1-norm; both stay on the device
     trace = torch.diagonal(cov).sum()
     q = _orthonormalise(_cheb_filter(cov, q, degree, trace / h, cov.abs().sum(dim=0).max()))
-    for rounds in range(1, max_rounds + 1):
+    y_prev, chol_bad = None, torch.zeros((), dtype=torch.int32, device=cov.device)
+    rounds = 0
+    while rounds < max_rounds:
+        rounds += 1
         aq = cov @ q
-        t = q.T @ aq
+        t = torch.nan_to_num(q.T @ aq)  # a broken-down Cholesky-QR must reach the check below, not make eigh throw
         w, s = torch.linalg.eigh(0.5 * (t + t.T))
         top, wt = s[:, -dims:], w[-dims:]
         v = q @ top
@@ -212,9 +230,13 @@ def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
         # the one synchronisation of the round: residual + the Ritz values that fix the next filter
         width = int(q.shape[1])
         keep = min(width, dims + 32)
-        res, th_min, th_max, th_dims, bulk, th_keep, bulk_keep = torch.stack(
+        res, th_min, th_max, th_dims, bulk, th_keep, bulk_keep, bad = torch.stack(
             [res_t, w[0], w[-1], wt[0], (trace - w.sum()) / (h - width), w[-keep],
-             (trace - w[-keep:].sum()) / (h - keep)]).tolist()
+             (trace - w[-keep:].sum()) / (h - keep), chol_bad.to(torch.float64)]).tolist()
+        if bad != 0.0 or res != res:  # the Cholesky-QR of this round's basis broke down: Householder, same round again
+            q, chol_bad = _orthonormalise(y_prev), torch.zeros_like(chol_bad)
+            rounds -= 1
+            continue
         if stats is not None:
             stats["eig_rounds"], stats["eig_residual"] = rounds, res
         if res <= tol:
@@ -236,7 +258,8 @@ def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
         e = 0.5 * cut
         rho = _cheb_growth((th_max - e) / e) / _cheb_growth((th_dims - e) / e)
         m = int(max(2, min(32, math.floor(math.log(1e20) / math.log(max(rho, 1.0 + 1e-9))))))
-        q = _orthonormalise(_cheb_filter(cov, q @ s, m, cut, th_max))
+        y_prev = _cheb_filter(cov, q @ s, m, cut, th_max)
+        q, chol_bad = _cholqr2(y_prev)
     w, v = torch.linalg.eigh(cov)
     if stats is not None:
         stats["eig_rounds"] = -1 - stats.get("eig_rounds", 0)

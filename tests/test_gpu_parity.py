@@ -429,7 +429,7 @@ def test_device_lowess_equals_host(gpu):
     y = np.sin(x) + 0.1 * rng.normal(size=60)
     y[20] += 3.0
     d = ops.lowess(torch.from_numpy(y).cuda(), torch.from_numpy(x).cuda(), None, 0.2, 100).cpu().numpy()
-    np.testing.assert_allclose(d, _lowess(y, x, 0.2, 100), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(d, _lowess(y, x, 0.2, 100), rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(d, lowess_o(y, x, frac=0.2, it=100), rtol=1e-9, atol=1e-12)
     x2 = rng.gamma(2.0, 1.0, size=200)
     y2 = np.log1p(x2) + 0.05 * rng.normal(size=200)
@@ -437,7 +437,7 @@ def test_device_lowess_equals_host(gpu):
     d2 = ops.lowess(torch.from_numpy(y2).cuda(), torch.from_numpy(x2).cuda(),
                     torch.from_numpy(valid.astype(np.uint8)).cuda(), 0.1, 100).cpu().numpy()
     assert np.isnan(d2[~valid]).all()
-    np.testing.assert_allclose(d2[valid], _lowess(y2[valid], x2[valid], 0.1, 100), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(d2[valid], _lowess(y2[valid], x2[valid], 0.1, 100), rtol=1e-11, atol=1e-12)
     # too few points for the window: the host routine raises, the device routine answers NaN
     d3 = ops.lowess(torch.from_numpy(y2[:8]).cuda(), torch.from_numpy(x2[:8]).cuda(), None, 0.1, 100).cpu().numpy()
     assert np.isnan(d3).all()
