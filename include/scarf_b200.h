@@ -134,6 +134,16 @@ int32_t scf_project_tc(const float* z, const float* z_lo, int64_t ldz, int64_t n
                        const float* v, int64_t ldv, int32_t dims, float* y, int64_t ldy, void* workspace,
                        int64_t workspace_bytes, void* stream);
 
+/* ---- K3 helper: all eigenpairs of a small symmetric positive semi-definite matrix -------------------
+ * The Rayleigh-Ritz matrices of the PCA eigensolve (scarf_b200/graph.py: eig_topk, which replaces the SVD updates of
+ * IncrementalPCA.partial_fit, scarf/ann.py:207-256).  One CTA, one-sided Jacobi with the matrix in shared memory,
+ * n <= scf_sym_eig_max_n() (168; worthwhile for n <~ 100).  a: n x n float64, row stride lda (symmetrised on load);
+ * evals[n] ascending; evecs n x n row-major (row stride ldv), column k = eigenvector of evals[k]; info (device int32,
+ * nullable): sweeps used, or -1 if the iteration did not converge. */
+int32_t scf_sym_eig_max_n(void);
+int32_t scf_sym_eig_jacobi(const double* a, int32_t n, int64_t lda, double* evals, double* evecs, int64_t ldv,
+                           int32_t* info, void* stream);
+
 /* ---- K5: exact k nearest neighbours, squared L2 --------------------------------------------------
  * Replaces hnswlib Index(space='l2').knn_query + fix_knn_query (scarf/ann.py:14-52,194-205):
  *   d(a,b) = (float) sum_t ((double)a_t - (double)b_t)^2   (t ascending), order by (d, index),

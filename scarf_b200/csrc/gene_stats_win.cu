@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(GS_THREADS, 2) gene_stats_win_kernel(
       if (r < r_end) {
         base = __ldg(seg + r * (nwin + 1) + w);
         cnt = (int)(__ldg(seg + r * (nwin + 1) + w + 1) - base);
-        if (norm) d = __ldg(row_div + r);
+        // norm_lib_size = sf * counts / scalar (scarf/assay.py:51): one division per ROW (sf / scalar) and a multiply
+        // per stored value; differs from the per-value division by at most one unit in the last place
+        if (norm) d = __ddiv_rn(sf, __ldg(row_div + r));
       }
       s_base[buf][tid] = base, s_cnt[buf][tid] = cnt, s_dv[buf][tid] = d;
     }
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(GS_THREADS, 2) gene_stats_win_kernel(
       }
     }
     fetch_meta(rb + GS_BATCH, buf ^ 1);  // visible after the first row barrier below
-    // ---- values: norm_lib_size = sf * counts / scalar (scarf/assay.py:51), left to right in float64 ----
+    // ---- values: counts * (sf / scalar) ----
     double v[GS_BATCH][GS_PER_LANE];
     if (moments) {
 #pragma unroll
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(GS_THREADS, 2) gene_stats_win_kernel(
 #pragma unroll
         for (int u = 0; u < GS_PER_LANE; ++u)
           if (c[k][u] != 0u)  // whole warps hold no entry in their second slot: they skip the division
-            v[k][u] = norm ? __ddiv_rn(sf * (double)c[k][u], s_dv[buf][k]) : (double)c[k][u];
+            v[k][u] = norm ? (double)c[k][u] * s_dv[buf][k] : (double)c[k][u];
           else
             v[k][u] = 0.0;
     }
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(GS_THREADS, 2) gene_stats_win_kernel(
             const int j = ld_stream(indices + base + e) - g0;
             s_n[j] += 1u;
             if (moments) {
-              const double vv = norm ? __ddiv_rn(sf * (double)cc, d) : (double)cc;
+              const double vv = norm ? (double)cc * d : (double)cc;
               double2 m = s_mom[j];
               m.x += vv;
               m.y += vv * vv;

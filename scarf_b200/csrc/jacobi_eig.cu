@@ -1,0 +1,140 @@
+// Small symmetric eigensolver for the later Rayleigh-Ritz steps of the PCA eigensolve (graph.eig_topk): all eigenpairs
+// of a symmetric positive semi-definite n x n matrix in ONE CTA with the matrix resident in shared memory.
+//
+// cuSOLVER's syevd spends ~1.5 ms on an 82 x 82 matrix (a few hundred dependent tiny kernels: tridiagonalisation, 81
+// reflector applications for the back-transformation).  The Ritz matrices of the second and later rounds are small
+// (dims + 32 columns), well conditioned and nearly diagonal (the basis is a filtered set of Ritz vectors), which is
+// the case one-sided (Hestenes) Jacobi is made for: the columns of W = T are rotated pairwise until they are mutually
+// orthogonal, then W = V * Lambda, i.e. the column norms are the eigenvalues and the normalised columns the
+// eigenvectors.  n/2 disjoint column pairs are rotated at once (round-robin ordering, n - 1 steps per sweep, eight
+// threads per pair); convergence is quadratic once the columns are nearly orthogonal (2-3 sweeps here).  A sweep moves
+// the whole matrix through shared memory n - 1 times (3 n^3 * 8 bytes), so the kernel pays off for n <~ 100 only:
+// scarf_b200.ops.sym_eig_small keeps the library eigh for the wide first-round block.  Deterministic: every rank
+// computes bit-identical pairs from bit-identical input.
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int JE_THREADS = 1024;
+constexpr int JE_TPP = 8;      // threads per column pair
+constexpr int JE_MAXN = 168;   // 168 * 168 * 8 B = 226 KB of shared memory
+constexpr int JE_MAX_SWEEPS = 40;
+
+// sum over the eight lanes of a pair; only the lanes of that group take part (a warp can hold idle groups)
+__device__ __forceinline__ double group_sum8(double v, unsigned mask) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double* __restrict__ a, int n, int64_t lda,
+                                                                   double* __restrict__ evals,
+                                                                   double* __restrict__ evecs, int64_t ldv,
+                                                                   int* __restrict__ info) {
+  extern __shared__ __align__(16) double w[];  // column major, n rows x ne columns (ne = n rounded up to even)
+  __shared__ int s_rotated;
+  __shared__ double s_norm[JE_MAXN + 1];
+  __shared__ int s_rank[JE_MAXN + 1];
+  const int tid = threadIdx.x;
+  const int ne = n + (n & 1);
+  for (int e = tid; e < n * ne; e += JE_THREADS) {
+    const int col = e / n, row = e - col * n;
+    // symmetrised read: the caller's matrix is symmetric up to rounding
+    w[e] = col < n ? 0.5 * (a[(int64_t)row * lda + col] + a[(int64_t)col * lda + row]) : 0.0;
+  }
+  if (tid == 0) s_rotated = 0;
+  __syncthreads();
+  const int pair = tid / JE_TPP, sub = tid % JE_TPP;
+  const int npairs = ne / 2;
+  const bool active = pair < npairs;
+  const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+  int sweeps = 0;
+  for (; sweeps < JE_MAX_SWEEPS; ++sweeps) {
+    for (int step = 0; step < ne - 1; ++step) {
+      if (active) {
+        // round-robin tournament: column ne-1 stays, the others rotate
+        int ci, cj;
+        if (pair == 0) {
+          ci = ne - 1, cj = step;
+        } else {
+          ci = (step + pair) % (ne - 1);
+          cj = (step - pair + (ne - 1)) % (ne - 1);
+        }
+        double* wi = w + (size_t)ci * n;
+        double* wj = w + (size_t)cj * n;
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll 4
+        for (int r = sub; r < n; r += JE_TPP) {
+          const double x = wi[r], y = wj[r];
+          alpha = fma(x, x, alpha);
+          beta = fma(y, y, beta);
+          gamma = fma(x, y, gamma);
+        }
+        alpha = group_sum8(alpha, gmask), beta = group_sum8(beta, gmask), gamma = group_sum8(gamma, gmask);
+        const double lim = 1e-15 * sqrt(alpha * beta);
+        if (fabs(gamma) > lim && alpha > 0.0 && beta > 0.0) {  // uniform inside the group of eight
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = rsqrt(1.0 + t * t), s = c * t;
+#pragma unroll 4
+          for (int r = sub; r < n; r += JE_TPP) {  // the columns are re-read: a 1024-thread CTA has 64 registers a thread
+            const double x = wi[r], y = wj[r];
+            wi[r] = c * x - s * y;
+            wj[r] = s * x + c * y;
+          }
+          if (sub == 0 && fabs(gamma) > 1e-13 * sqrt(alpha * beta)) s_rotated = 1;  // benign race: any writer wins
+        }
+      }
+      __syncthreads();
+    }
+    const int again = s_rotated;
+    __syncthreads();
+    if (tid == 0) s_rotated = 0;
+    __syncthreads();
+    if (!again) {
+      ++sweeps;
+      break;
+    }
+  }
+  // eigenvalues = column norms; ascending order by rank (ties by column index)
+  for (int c = tid; c < n; c += JE_THREADS) {
+    double s2 = 0.0;
+    for (int r = 0; r < n; ++r) s2 = fma(w[(size_t)c * n + r], w[(size_t)c * n + r], s2);
+    s_norm[c] = sqrt(s2);
+  }
+  __syncthreads();
+  for (int c = tid; c < n; c += JE_THREADS) {
+    int rank = 0;
+    const double mine = s_norm[c];
+    for (int o = 0; o < n; ++o) rank += (s_norm[o] < mine) || (s_norm[o] == mine && o < c);
+    s_rank[c] = rank;
+    evals[rank] = mine;
+  }
+  __syncthreads();
+  for (int e = tid; e < n * n; e += JE_THREADS) {
+    const int c = e / n, r = e - c * n;
+    const double nv = s_norm[c];
+    // a zero column can only come from an exactly singular matrix: its direction is undefined, emit a unit vector
+    evecs[(int64_t)r * ldv + s_rank[c]] = nv > 0.0 ? w[e] / nv : (r == c ? 1.0 : 0.0);
+  }
+  if (tid == 0 && info) *info = sweeps < JE_MAX_SWEEPS ? sweeps : -1;
+}
+
+}  // namespace
+
+extern "C" int32_t scf_sym_eig_max_n(void) { return JE_MAXN; }
+
+extern "C" int32_t scf_sym_eig_jacobi(const double* a, int32_t n, int64_t lda, double* evals, double* evecs, int64_t ldv,
+                                      int32_t* info, void* stream) {
+  SCF_ARG(a && evals && evecs, "null pointer");
+  SCF_ARG(n >= 1 && n <= JE_MAXN && lda >= n && ldv >= n, "n must be within [1, 168]");
+  const size_t smem = (size_t)n * (n + (n & 1)) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    scf_set_error("scf_sym_eig_jacobi: %s", cudaGetErrorString(e));
+    return -(int32_t)e;
+  }
+  jacobi_eig_kernel<<<1, JE_THREADS, smem, (cudaStream_t)stream>>>(a, n, lda, evals, evecs, ldv, info);
+  return scf_check_launch("scf_sym_eig_jacobi");
+}

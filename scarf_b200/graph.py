@@ -223,7 +223,7 @@ def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
         rounds += 1
         aq = cov @ q
         t = torch.nan_to_num(q.T @ aq)  # a broken-down Cholesky-QR must reach the check below, not make eigh throw
-        w, s = torch.linalg.eigh(0.5 * (t + t.T))
+        w, s = ops.sym_eig_small(t)  # one-CTA Jacobi for the shrunk blocks of the later rounds, library eigh else
         top, wt = s[:, -dims:], w[-dims:]
         v = q @ top
         res_t = (aq @ top - v * wt).norm(dim=0).max() / w[-1]

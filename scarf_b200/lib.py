@@ -30,6 +30,8 @@ SIGNATURES = {
     "scf_project": (_i32, [_p, _i64, _i64, _i32, _p, _i64, _i32, _p, _i64, _p]),
     "scf_project_tc_workspace_bytes": (_i64, [_i64, _i32]),
     "scf_project_tc": (_i32, [_p, _p, _i64, _i64, _i32, _p, _i64, _i32, _p, _i64, _p, _i64, _p]),
+    "scf_sym_eig_max_n": (_i32, []),
+    "scf_sym_eig_jacobi": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p]),
     "scf_knn_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32]),
     "scf_knn_fail_count_offset": (_i64, [_i64, _i64, _i32, _i32, _i32]),
     "scf_knn_l2": (_i32, [_p, _i64, _p, _i64, _i32, _i64, _i32, _i64, _p, _p, _i32, _p, _i64, _p]),

@@ -210,6 +210,24 @@ def project(z, n_rows, n_cols, v, dims, y=None, ldy=None, z_lo=None):
     return y
 
 
+JACOBI_MAX_N = 96  # beyond this the one-CTA Jacobi kernel loses to the library eigh (3 n^3 * 8 B through smem per sweep)
+
+
+def sym_eig_small(a, info=None, max_n=JACOBI_MAX_N):
+    """(eigenvalues ascending, eigenvectors as columns) of a small symmetric PSD float64 matrix on the device: the
+    one-CTA Jacobi kernel for n <= ``max_n``, ``torch.linalg.eigh`` otherwise (and for CPU tensors)."""
+    n = int(a.shape[0])
+    if not a.is_cuda or n > min(max_n, int(lib.raw("scf_sym_eig_max_n")())):
+        return torch.linalg.eigh(0.5 * (a + a.T))
+    _chk(a, torch.float64, "a")
+    a = a.contiguous()
+    w = torch.empty(n, dtype=torch.float64, device=a.device)
+    v = torch.empty((n, n), dtype=torch.float64, device=a.device)
+    lib.call("scf_sym_eig_jacobi", _ptr(a), n, int(a.stride(0)), _ptr(w), _ptr(v), int(v.stride(0)),
+             _ptr(info), _stream())
+    return w, v
+
+
 # ------------------------------------------------------------------------------------------ K5
 def knn_l2(q, ref, dim, k, self_offset=-1, method=0, stats=None):
     """Exact kNN (squared L2).  q, ref: float32 [n, ld] sharing the row stride.  -> (int64 idx, float32 dist).

@@ -503,3 +503,45 @@ def test_project_tensor_core_equals_fp64(gpu, n, h, dims):
     scale = float(ref.abs().max())
     assert float((y_simt[:, :dims].double() - ref).abs().max()) < 1e-5 * scale
     assert float((y_tc[:, :dims].double() - ref).abs().max()) < 3e-5 * scale
+
+
+def test_knn_full_size_c2_properties(gpu):
+    """BASELINE.json C2 size (100k x 50, k = 11): the tensor-core path against the FP64 brute force on every row, plus
+    the size-independent properties of the result (ascending distances, no self hit, ids in range, ties by index)."""
+    torch, ops = gpu["torch"], gpu["ops"]
+    n, dim, k = 100_000, 50, 11
+    g = torch.Generator(device="cuda").manual_seed(2)
+    scale = torch.sqrt(66.0 * 0.93 ** torch.arange(dim, device="cuda", dtype=torch.float32) + 1.4)
+    y = torch.zeros((n, 64), device="cuda")
+    y[:, :dim] = torch.randn((n, dim), generator=g, device="cuda") * scale
+    y[5000:5040] = y[4000:4040]  # exact duplicates: distance 0, order decided by the index
+    idx, dist = ops.knn_l2(y, y, dim, k, self_offset=0, method=1)
+    rows = torch.arange(n, device="cuda")[:, None]
+    assert bool((idx != rows).all()) and bool((idx >= 0).all()) and bool((idx < n).all())
+    assert bool((dist[:, 1:] >= dist[:, :-1]).all())
+    tie = dist[:, 1:] == dist[:, :-1]
+    assert bool((idx[:, 1:][tie] > idx[:, :-1][tie]).all())
+    assert bool((dist[5000:5040, 0] == 0).all()) and bool((idx[5000:5040, 0] == rows[4000:4040, 0]).all())
+    idx0, dist0 = ops.knn_l2(y, y, dim, k, self_offset=0, method=0)
+    assert torch.equal(idx, idx0) and torch.equal(dist, dist0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 82, 96, 133, 164, 168])
+def test_sym_eig_jacobi_equals_eigh(gpu, n):
+    """One-CTA Jacobi eigensolver (Rayleigh-Ritz matrices of eig_topk) against torch.linalg.eigh: a dense PSD matrix
+    with a wide spectrum and a nearly diagonal one (the shape of the later rounds), incl. a repeated eigenvalue."""
+    torch, ops = gpu["torch"], gpu["ops"]
+    g = torch.Generator(device="cuda").manual_seed(100 + n)
+    q = torch.linalg.qr(torch.randn((n, n), device="cuda", dtype=torch.float64, generator=g))[0]
+    lam = torch.sort(torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 60.0 + 0.2).values
+    if n > 4:
+        lam[3] = lam[2]
+    for a in (q @ torch.diag(lam) @ q.T, torch.diag(lam) + 1e-6 * (q + q.T)):
+        a = 0.5 * (a + a.T)
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        w, v = ops.sym_eig_small(a, info, max_n=168)
+        we, _ = torch.linalg.eigh(a)
+        assert int(info.item()) > 0
+        np.testing.assert_allclose(w.cpu().numpy(), we.cpu().numpy(), rtol=1e-12, atol=1e-12)
+        assert float((v.T @ v - torch.eye(n, device="cuda", dtype=torch.float64)).abs().max()) < 1e-12
+        assert float((a @ v - v * w).abs().max()) < 1e-11 * float(we[-1])
