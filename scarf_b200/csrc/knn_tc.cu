@@ -291,7 +291,7 @@ struct KnnTcParams {
   int* fix_list;           // [FIXTC_ROWS][FIXTC_CAP] reference ids
 };
 
-constexpr int FIXTC_ROWS = 8192;  // failed rows repaired by the tensor-core collect pass (the rest: FP64 scan)
+constexpr int FIXTC_ROWS = 32768;  // failed rows repaired by the tensor-core collect pass (the rest: FP64 scan); ~1 % of the rows fail on the C3 embedding
 constexpr int FIXTC_CAP = 64;     // collected references per failed row
 constexpr int FIXTC_NSPLIT = 16;  // reference ranges per query tile in the collect pass
 
