@@ -11,7 +11,11 @@ n_counts, _ = graph.cell_totals(csr)
 feat_I = graph.gene_ncells(csr) > 20
 hv = graph.mark_hvgs_csr(csr, None, feat_I, n_counts, n, top_n=2000, as_tensor=True,
                          keep_mask=torch.ones(30_000, dtype=torch.bool, device=dev))
+_orig = graph.eig_topk
+_st = {}
+graph.eig_topk = lambda cov, dims, **kw: _orig(cov, dims, stats=_st)
 res = graph.make_graph_csr(csr, None, hv, dims=100, k=21, gram_mode=3, knn_method=1)
+print("eig stats", _st)
 del csr
 y = res.embedding_all
 print("evals", [round(float(x), 3) for x in res.eigenvalues[[0, 1, 10, 30, 50, 60, 70, 80, 99]]])
