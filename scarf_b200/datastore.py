@@ -428,6 +428,46 @@ class DataStore:
         self._set_latest(normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc)
         return ann_obj if return_ann_object else None
 
+    def save_normalized_data(self, from_assay: Optional[str] = None, cell_key: str = "I", feat_key: str = "hvgs",
+                             batch_size: int = 1000, log_transform: bool = True, renormalize_subset: bool = True):
+        """Assay.save_normalized_data (scarf/assay.py:400-478 -> writers.dask_to_zarr :915-935): materialises the
+        normalised feature matrix ``x = log1p(sf * c / scalar)`` as ``<assay>/normed__<ck>__<fk>/data`` (f8, shape
+        (N, H), chunks (batch, H)).  ``make_graph`` never needs it here (Z stays in HBM), but the reference's other
+        readers of that array (CORAL, ``integrate_assays``, ``metric_silhouette``) do, so the drop-in store can hold it:
+        the values come from the same fused normalise kernel, one row batch at a time.  Returns the array's location."""
+        if from_assay is None:
+            from_assay = self._defaultAssay
+        assay = self._get_assay(from_assay)
+        zw = self.zw
+        cell_idx = self.cells.active_index(cell_key)
+        feat_col = cell_key + "__" + feat_key if feat_key != "I" else "I"
+        feat_mask = assay.feats.fetch_all(feat_col)
+        if feat_mask.dtype != bool:
+            raise ValueError(f"ERROR: {feat_col} is not of boolean type. Cannot perform fetch operation")
+        feat_idx = np.where(feat_mask)[0]
+        n_feat = int(feat_idx.size)
+        normed_loc = f"{from_assay}/normed__{cell_key}__{feat_key}"
+        if normed_loc not in zw:
+            zw.create_group(normed_loc)
+        dev = self.device
+        cmap = np.full(assay.csr.n_cols, -1, dtype=np.int32)
+        cmap[feat_idx] = np.arange(n_feat, dtype=np.int32)
+        col_map = torch.from_numpy(cmap).to(dev)
+        cells_t = torch.from_numpy(cell_idx).to(dev)
+        if renormalize_subset:
+            row_sum, _ = ops.csr_row_sums(assay.csr, cells_t, col_map)  # assay.py:814-823
+        else:
+            row_sum = torch.from_numpy(assay.nCounts).to(dev)[cells_t].contiguous()
+        out = zw[normed_loc].create_dataset("data", (int(cell_idx.size), n_feat), "f8", (batch_size, n_feat))
+        ldz = ops.round_up(n_feat, 4)
+        buf = torch.empty((batch_size, ldz), dtype=torch.float32, device=dev)
+        for lo in range(0, int(cell_idx.size), batch_size):
+            hi = min(lo + batch_size, int(cell_idx.size))
+            ops.csr_norm_scale(assay.csr, cells_t[lo:hi].contiguous(), col_map, n_feat, row_sum[lo:hi].contiguous(), buf,
+                               graph.SF, log_transform)
+            out[lo:hi] = buf[: hi - lo, :n_feat].cpu().numpy().astype(np.float64)
+        return f"{normed_loc}/data"
+
     def _set_latest(self, normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc):
         zw = self.zw  # graph_datastore.py:1003-1008
         zw[normed_loc].attrs["latest_reduction"] = reduction_loc

@@ -108,6 +108,13 @@ def test_datastore_chain_layout_and_cache(tmp_path, pbmc):
     assert np.abs(weights - w_o).max() < 1e-5
     g = ds.load_graph()
     assert sp.issparse(g) and g.shape == (808, 808) and (g - sp.triu(g)).nnz == 0
+    # Assay.save_normalized_data: the materialised normalised matrix (row a5) against the oracle, 1e-5 relative
+    loc = ds.save_normalized_data(feat_key="hvgs")
+    arr = z[loc.rsplit("/", 1)[0]]["data"]
+    data = arr[:]
+    x_o = P.normed_hvg(counts, pbmc["cell_idx"], np.where(hv)[0])
+    assert loc == f"{base}/data" and data.shape == x_o.shape and arr.chunks == (1000, 100) and arr.dtype.str == "<f8"
+    np.testing.assert_allclose(data, x_o, rtol=1e-5, atol=1e-7)
     g5 = ds.load_graph(symmetric=False, use_k=5)
     assert g5.nnz == 808 * 5
     # second call: cache hit (nothing rewritten), cached k is picked up when k is not given
