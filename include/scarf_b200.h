@@ -49,7 +49,7 @@ int32_t scf_csr_gene_stats(const int64_t* indptr, const int32_t* indices, const 
                            const double* row_div, double sf, unsigned long long* gene_nnz,
                            double* gene_sum, double* gene_sumsq, void* stream);
 
-/* Same statistics without a reduction per stored value: a CTA owns (block of rows) x (window of 4096 genes), adds
+/* Same statistics without a reduction per stored value: a CTA owns (block of rows) x (window of 1024 genes), adds
  * the rows one after the other into shared-memory accumulators with plain read-modify-writes (a gene occurs once per
  * row) and flushes one reduction per gene.  Needs ascending column ids inside every row (the CSR contract of this
  * library).  Results are ACCUMULATED into gene_nnz / gene_sum / gene_sumsq exactly like scf_csr_gene_stats

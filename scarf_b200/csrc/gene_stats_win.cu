@@ -6,23 +6,24 @@
 // memory accumulators with plain read-modify-writes (no atomics: distinct addresses), rows follow each other
 // separated by a CTA barrier.  Shared memory holds a window of GS_W genes (nnz u32, sum f64, sumsq f64 = 20 B per
 // gene), so the gene axis is cut into windows and a CTA owns (block of rows) x (window); rows are sorted by gene, the
-// window's entries of a row are one contiguous range whose bounds a small search kernel writes first.  Two CTAs share
-// an SM: while one waits for its next batch of rows to arrive from HBM the other one accumulates.
+// window's entries of a row are one contiguous range whose bounds a small search kernel writes first.  Several small
+// CTAs share an SM (default: 1024-gene windows, 128 threads, eight CTAs): while some wait for their next batch of rows
+// to arrive from HBM or at their row barrier, the others accumulate.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
 
-constexpr int GS_W = 4096;       // genes per window: 80 KB of accumulators
-constexpr int GS_THREADS = 256;  // few warps: the per-row bookkeeping is paid per warp
-constexpr int GS_PER_LANE = 2;   // entries per thread and row held in registers (the rest of a long row: direct loads)
-constexpr int GS_BATCH = 8;      // rows whose entries are in flight together
+// Tunables (template parameters of the kernel): GS_W genes per window (20 B of accumulators each), GS_THREADS per CTA
+// (few warps: the per-row bookkeeping is paid per warp), GS_PER_LANE entries per thread and row held in registers (the
+// rest of a long row: direct loads), GS_BATCH rows whose entries are in flight together, GS_MINB CTAs per SM.
 
 __device__ __forceinline__ int64_t row_of(const int64_t* row_ids, int64_t r) { return row_ids ? row_ids[r] : r; }
 
 // seg[r][w] = first position of row r (absolute, in indices / data) whose gene id is >= w * GS_W; seg[r][nwin] = row end
 __global__ void gene_window_bounds_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                           const int64_t* __restrict__ row_ids, int64_t n_sel, int nwin,
-                                          int64_t* __restrict__ seg) {
+                                          int GS_W, int64_t* __restrict__ seg) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_sel * (nwin + 1)) return;
   const int64_t r = t / (nwin + 1);
@@ -40,7 +41,8 @@ __global__ void gene_window_bounds_kernel(const int64_t* __restrict__ indptr, co
   seg[t] = lo;
 }
 
-__global__ void __launch_bounds__(GS_THREADS, 2) gene_stats_win_kernel(
+template <int GS_W, int GS_THREADS, int GS_PER_LANE, int GS_BATCH, int GS_MINB>
+__global__ void __launch_bounds__(GS_THREADS, GS_MINB) gene_stats_win_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const uint32_t* __restrict__ data,
     const int64_t* __restrict__ row_ids, int64_t n_sel, const double* __restrict__ row_div, double sf,
     const int64_t* __restrict__ seg, int nwin, int n_genes, int64_t rows_per_block,
@@ -164,10 +166,33 @@ __global__ void __launch_bounds__(GS_THREADS, 2) gene_stats_win_kernel(
   }
 }
 
+struct GsVariant {
+  int w, threads, minb, batch;
+  void (*kernel)(const int64_t*, const int32_t*, const uint32_t*, const int64_t*, int64_t, const double*, double,
+                 const int64_t*, int, int, int64_t, unsigned long long*, double*, double*);
+};
+// measured on a 100k-cell shard (B200): 1.52 ms / 1.67 ms / 1.84 ms; wider batches, narrower windows and more entries
+// per lane were all slower (2.1 - 3.0 ms)
+const GsVariant kVariants[] = {
+    {1024, 128, 8, 8, gene_stats_win_kernel<1024, 128, 1, 8, 8>},
+    {2048, 128, 5, 8, gene_stats_win_kernel<2048, 128, 2, 8, 5>},
+    {4096, 256, 2, 8, gene_stats_win_kernel<4096, 256, 2, 8, 2>},
+};
+constexpr int kDefaultVariant = 0;
+const GsVariant& gs_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SCF_GS_VARIANT");  // developer switch (tools/csr_probe.py sweeps it)
+    v = e ? atoi(e) : kDefaultVariant;
+    if (v < 0 || v >= (int)(sizeof(kVariants) / sizeof(kVariants[0]))) v = kDefaultVariant;
+  }
+  return kVariants[v];
+}
+
 }  // namespace
 
 extern "C" int64_t scf_csr_gene_stats_workspace_bytes(int64_t n_sel, int32_t n_genes) {
-  const int64_t nwin = (n_genes + GS_W - 1) / GS_W;
+  const int64_t nwin = (n_genes + 1024 - 1) / 1024;  // the narrowest window any variant uses
   return n_sel * (nwin + 1) * 8;
 }
 
@@ -182,25 +207,27 @@ extern "C" int32_t scf_csr_gene_stats_windowed(const int64_t* indptr, const int3
   SCF_ARG(workspace_bytes >= scf_csr_gene_stats_workspace_bytes(n_sel, n_genes), "workspace too small");
   if (n_sel == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nwin = (n_genes + GS_W - 1) / GS_W;
+  const GsVariant& var = gs_variant();
+  const int nwin = (n_genes + var.w - 1) / var.w;
   int64_t* seg = (int64_t*)workspace;
   const int64_t nseg = n_sel * (nwin + 1);
-  gene_window_bounds_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(indptr, indices, row_ids, n_sel, nwin, seg);
+  gene_window_bounds_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(indptr, indices, row_ids, n_sel, nwin, var.w,
+                                                                          seg);
   int32_t rc = scf_check_launch("scf_csr_gene_stats_windowed(bounds)");
   if (rc) return rc;
-  const size_t smem = (size_t)GS_W * (8 + 8 + 4);
-  cudaError_t e = cudaFuncSetAttribute(gene_stats_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)var.w * (8 + 8 + 4);
+  cudaError_t e = cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     scf_set_error("scf_csr_gene_stats_windowed: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
-  // (row blocks) x (windows) CTAs, two per SM: about 2 * 148 CTAs in flight, a few waves of them for balance
-  int64_t blocks = (int64_t)(2 * SCF_NUM_SMS * 4 + nwin - 1) / nwin;
+  // (row blocks) x (windows) CTAs, minb per SM: a few waves of them for balance
+  int64_t blocks = (int64_t)(var.minb * SCF_NUM_SMS * 4 + nwin - 1) / nwin;
   int64_t rows_per_block = (n_sel + blocks - 1) / blocks;
-  rows_per_block = (rows_per_block + GS_BATCH - 1) / GS_BATCH * GS_BATCH;
-  if (rows_per_block < GS_BATCH) rows_per_block = GS_BATCH;
+  rows_per_block = (rows_per_block + var.batch - 1) / var.batch * var.batch;
+  if (rows_per_block < var.batch) rows_per_block = var.batch;
   blocks = (n_sel + rows_per_block - 1) / rows_per_block;
-  gene_stats_win_kernel<<<dim3((unsigned)blocks, (unsigned)nwin), GS_THREADS, smem, st>>>(
+  var.kernel<<<dim3((unsigned)blocks, (unsigned)nwin), var.threads, smem, st>>>(
       indptr, indices, data, row_ids, n_sel, row_div, sf, seg, nwin, n_genes, rows_per_block, gene_nnz, gene_sum,
       gene_sumsq);
   return scf_check_launch("scf_csr_gene_stats_windowed");
