@@ -452,16 +452,21 @@ def smoothen_dists(indices, distances, lc=1.0, bw=1.5, chunk_size=1000, vectoris
 # whole path
 # ----------------------------------------------------------------------------------------------
 def make_graph(counts, cell_idx, hvg_mask, dims=11, k=11, lc=1.0, bw=1.5, batch_size=1000, pca="ipca",
-               return_all=False, knn_threads=0):
+               return_all=False, knn_threads=0, use_for_pca=None):
     """Restated ``make_graph(feat_key='hvgs')`` on CSR counts: normalise -> mu/sigma -> PCA -> exact
-    kNN (self excluded) -> edge weights.  ``pca``: 'ipca' (reference's estimator) or 'exact'."""
+    kNN (self excluded) -> edge weights.  ``pca``: 'ipca' (reference's estimator) or 'exact'.
+    ``use_for_pca``: bool mask over the selected cells (``pca_cell_key``, scarf/ann.py:215-228): the PCA is fitted
+    on those rows of the z-scaled matrix only (exact route), every cell is projected."""
     feat_idx = np.where(hvg_mask)[0]
     x = normed_hvg(counts, cell_idx, feat_idx)
     mu, sigma = mu_sigma(x)
     k = min(k, x.shape[0] - 1)  # scarf/ann.py:85-86
     dims = clamp_dims(dims, x.shape[0], batch_size)
     z = (x - mu) / sigma
-    if pca == "ipca":
+    if use_for_pca is not None:
+        dims = clamp_dims(dims, int(np.sum(use_for_pca)), batch_size)
+        loadings, _ = exact_pca_loadings(z[np.asarray(use_for_pca, dtype=bool)], dims)
+    elif pca == "ipca":
         loadings = ipca_loadings(x, mu, sigma, dims, batch_size)
     else:
         loadings, _ = exact_pca_loadings(z, dims)

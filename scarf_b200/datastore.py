@@ -377,8 +377,6 @@ class DataStore:
             ann_metric, ann_efc, ann_ef, ann_m, rand_state, k, n_centroids, local_connectivity, bandwidth)
         if ann_metric != "l2":
             raise NotImplementedError("scarf_b200.make_graph implements ann_metric='l2' only")
-        if pca_cell_key != cell_key:
-            raise NotImplementedError("fitting the PCA on a different cell subset (`pca_cell_key`) is not implemented")
         zw = self.zw
         normed_loc = f"{from_assay}/normed__{cell_key}__{feat_key}"
         reduction_loc = f"{normed_loc}/reduction__{reduction_method}__{dims}__{pca_cell_key}"
@@ -415,10 +413,17 @@ class DataStore:
 
         cells_t = torch.from_numpy(cell_idx).to(self.device)
         n_counts = torch.from_numpy(assay.nCounts).to(self.device)
+        pca_rows = None
+        if pca_cell_key != cell_key:  # use_for_pca = cells.fetch(pca_cell_key, key=cell_key)  (graph_datastore.py:764)
+            use_for_pca = self.cells.fetch_all(pca_cell_key)[cell_idx]
+            if use_for_pca.dtype != bool:
+                raise ValueError(f"ERROR: `pca_use_cell_key` {pca_cell_key} is not of boolean type")
+            if not use_for_pca.all():
+                pca_rows = torch.from_numpy(np.where(use_for_pca)[0]).to(self.device)
         res = graph.make_graph_csr(assay.csr, cells_t, feat_mask, dims=dims, k=k, lc=local_connectivity,
                                    bw=bandwidth, batch_size=batch_size, log_transform=log_transform,
                                    renormalize_subset=renormalize_subset, n_counts=n_counts, comm=self.comm,
-                                   gram_mode=3, knn_method=1)
+                                   gram_mode=3, knn_method=1, pca_rows=pca_rows)
         centers, labels = graph.fit_kmeans(res.embedding_all, res.dims, max(n_centroids, 2), rand_state)
         ann_obj = AnnStream(res, res.k, _KMeans(centers.cpu().numpy().astype(np.float64)),
                             labels.cpu().numpy().astype(np.float64))

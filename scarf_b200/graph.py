@@ -292,13 +292,18 @@ def normalise_stats(csr, cell_idx, col_map, n_feat, comm, log_transform=True, re
 
 def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, bw=1.5, batch_size=1000,
                    log_transform=True, renormalize_subset=True, n_counts=None, comm: Comm | None = None,
-                   gram_mode=0, knn_method=0, loadings=None, mu=None, sigma=None, timers=None) -> GraphResult:
+                   gram_mode=0, knn_method=0, loadings=None, mu=None, sigma=None, timers=None,
+                   pca_rows=None) -> GraphResult:
     """normalise -> mu/sigma -> Z -> Gram -> eig -> project -> exact kNN -> edge weights for this rank's rows.
 
     ``timers``: optional list; (stage name, torch.cuda.Event) pairs are appended at every stage boundary.
     ``cell_idx``: int64 device tensor of the local CSR rows to use (None = all).  ``feat_mask``: bool over all
     genes (numpy), e.g. from :func:`mark_hvgs_csr`.  With ``comm.world > 1`` every rank passes its own shard and
     receives its own rows of the global graph; neighbour ids are global selected-row ids.
+    ``pca_rows``: optional int64 device tensor of positions among this rank's selected rows; the PCA is then fitted on
+    those cells only (``pca_cell_key``, scarf/datastore/graph_datastore.py:764 -> AnnStream._fit_pca ``use_for_pca``,
+    scarf/ann.py:215-228) -- z-scaling still uses the mu / sigma of all selected cells, the covariance is centred on
+    the subset's own mean like the PCA estimator does -- while every selected cell is projected and searched.
     """
     comm = comm or Comm()
     dev = csr.device
@@ -340,11 +345,27 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
 
     # ---- PCA: Gram (K2, collective 2b) + eigensolve (K3) ----
     if loadings is None:
-        g_fx = ops.gram_accumulate(z, n_local, n_feat, mode=gram_mode, z_lo=z_lo)
+        if pca_rows is None:
+            g_fx = ops.gram_accumulate(z, n_local, n_feat, mode=gram_mode, z_lo=z_lo)
+            n_pca, col_mean = n_total, None
+        else:  # PCA on a subset of the cells: Gram of the gathered rows, centred on their own mean
+            zs = z.index_select(0, pca_rows)
+            zs_lo = z_lo.index_select(0, pca_rows) if z_lo is not None else None
+            g_fx = ops.gram_accumulate(zs, int(pca_rows.numel()), n_feat, mode=gram_mode, z_lo=zs_lo)
+            moments = torch.cat([zs[:, :n_feat].sum(dim=0, dtype=torch.float64),
+                                 torch.tensor([float(pca_rows.numel())], dtype=torch.float64, device=dev)])
+            comm.allreduce_sum_(moments)
+            n_pca = int(round(float(moments[-1].item())))
+            col_mean = moments[:-1] / max(n_pca, 1)
+            dims = clamp_dims(dims, n_pca, batch_size)
+            del zs, zs_lo
         comm.allreduce_sum_(g_fx)
         ops.gram_symmetrize(g_fx, n_feat)
         mark("gram")
-        cov = g_fx[:n_feat, :n_feat].to(torch.float64) * (2.0 ** -lib.GRAM_SHIFT / max(n_total - 1, 1))
+        cov = g_fx[:n_feat, :n_feat].to(torch.float64) * 2.0 ** -lib.GRAM_SHIFT
+        if col_mean is not None:
+            cov = cov - float(n_pca) * torch.outer(col_mean, col_mean)
+        cov = cov / max(n_pca - 1, 1)
         evals, load = eig_topk(cov, dims)
         mark("eig")
     else:

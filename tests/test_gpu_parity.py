@@ -545,3 +545,32 @@ def test_sym_eig_jacobi_equals_eigh(gpu, n):
         np.testing.assert_allclose(w.cpu().numpy(), we.cpu().numpy(), rtol=1e-12, atol=1e-12)
         assert float((v.T @ v - torch.eye(n, device="cuda", dtype=torch.float64)).abs().max()) < 1e-12
         assert float((a @ v - v * w).abs().max()) < 1e-11 * float(we[-1])
+
+
+def test_pca_on_a_cell_subset(gpu, chain, synth_small):
+    """``pca_cell_key`` (scarf/ann.py:215-228): the PCA is fitted on a subset of the selected cells (z-scaled with the
+    mu / sigma of all of them), every cell is projected and searched.  Against the oracle's exact route."""
+    from oracle import pipeline as P
+
+    torch, graph = gpu["torch"], gpu["graph"]
+    cell_idx, hv = chain["cell_idx"], chain["hv"]
+    rng = np.random.default_rng(3)
+    use = rng.random(cell_idx.size) < 0.6
+    res = graph.make_graph_csr(chain["csr"], torch.from_numpy(cell_idx).cuda(), hv, dims=15, k=11, gram_mode=3,
+                               knn_method=1, pca_rows=torch.from_numpy(np.where(use)[0]).cuda())
+    o = P.make_graph(synth_small, cell_idx, hv, dims=15, k=11, pca="exact", return_all=True, use_for_pca=use)
+    l0, l1 = o["loadings"], res.loadings.cpu().numpy()
+    assert l0.shape == l1.shape
+    ang = np.arccos(np.clip(np.abs(np.sum(l0 * l1, axis=0)), 0, 1))
+    assert np.all(ang < 1e-4), ang.max()
+    y = res.embedding.cpu().numpy()[:, : res.dims]
+    assert np.abs(y - o["embedding"]).max() < 1e-3
+    idx_o, dist_o = P.exact_knn(y, y, res.k, self_offset=0)
+    assert np.array_equal(res.indices.cpu().numpy().astype(np.uint64), idx_o)
+    assert np.array_equal(res.distances.cpu().numpy(), dist_o)
+    # all cells in the subset == no subset
+    full = graph.make_graph_csr(chain["csr"], torch.from_numpy(cell_idx).cuda(), hv, dims=15, k=11, gram_mode=3,
+                                knn_method=1, pca_rows=torch.arange(cell_idx.size, device="cuda"))
+    base = graph.make_graph_csr(chain["csr"], torch.from_numpy(cell_idx).cuda(), hv, dims=15, k=11, gram_mode=3,
+                                knn_method=1)
+    assert np.abs(full.embedding.cpu().numpy() - base.embedding.cpu().numpy()).max() < 1e-3
