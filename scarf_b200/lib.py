@@ -72,7 +72,9 @@ def version() -> int:
 
 
 LAUNCHES = {"n": 0}  # kernel launches issued through the C-ABI (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"scf_knn_l2": 1}
+# kernels one call launches (method 1 of scf_knn_l2: range, prep, tensor kernel, re-rank, gather, collect, finish,
+# threshold scan, select, FP64 tile kernel; memsets are not counted)
+_LAUNCHES_PER_CALL = {"scf_knn_l2": 10, "scf_gram_symmetrize": 1}
 
 
 def call(name: str, *args, launches=None):

@@ -574,3 +574,27 @@ def test_pca_on_a_cell_subset(gpu, chain, synth_small):
     base = graph.make_graph_csr(chain["csr"], torch.from_numpy(cell_idx).cuda(), hv, dims=15, k=11, gram_mode=3,
                                 knn_method=1)
     assert np.abs(full.embedding.cpu().numpy() - base.embedding.cpu().numpy()).max() < 1e-3
+
+
+@pytest.mark.parametrize("scale,outlier,dim,k", [(1e4, False, 40, 11), (1e-4, False, 40, 11), (1.0, True, 30, 11),
+                                                  (3.0, False, 200, 5), (1.0, False, 253, 3), (1e-30, False, 16, 7)])
+def test_knn_fp16_scale_handling(gpu, scale, outlier, dim, k):
+    """The tensor-core path rounds s * value to FP16 with an exact power-of-two s chosen from the data: very large,
+    very small and mixed magnitudes (one far outlier dominates the scale, so the other rows lose operand precision and
+    lean on the guard + repair) must still give the oracle's answer bit for bit; dims up to 253 stay on tensor cores."""
+    from oracle import pipeline as P
+
+    torch, ops = gpu["torch"], gpu["ops"]
+    rng = np.random.default_rng(dim + k)
+    n = 3000
+    y = (rng.normal(size=(n, dim)) * rng.uniform(0.3, 4.0, size=dim) * scale).astype(np.float32)
+    if outlier:
+        y[17] *= 3000.0
+        y[1900] = y[17] * 1.0001
+    ld = ops.round_up(dim, 32)
+    yp = torch.zeros((n, ld), dtype=torch.float32, device="cuda")
+    yp[:, :dim] = torch.from_numpy(y).cuda()
+    idx, dist = ops.knn_l2(yp, yp, dim, k, self_offset=0, method=1)
+    idx_o, dist_o = P.exact_knn(y, y, k, self_offset=0)
+    assert np.array_equal(idx.cpu().numpy().astype(np.uint64), idx_o)
+    assert np.array_equal(dist.cpu().numpy(), dist_o)
