@@ -149,9 +149,11 @@ int32_t scf_sym_eig_jacobi(const double* a, int32_t n, int64_t lda, double* eval
  *   d(a,b) = (float) sum_t ((double)a_t - (double)b_t)^2   (t ascending), order by (d, index),
  *   query i is reference i + self_offset and is excluded when self_offset >= 0 (-1: keep all).
  * q: nq x ld float32, ref: nref x ld float32 (row stride ld >= dim).  out_idx int64 [nq,k],
- * out_dist float32 [nq,k].  method: 0 = FP64 SIMT brute force, 1 = tcgen05 TF32 candidates +
- * exact FP64 re-rank with a proven guard band (rows that fail the guard are recomputed by
- * method 0 inside the same call).  workspace: scf_knn_workspace_bytes(nq, nref, dim, k, method). */
+ * out_dist float32 [nq,k].  method: 0 = FP64 SIMT brute force, 1 = tcgen05 FP16 candidates (operands
+ * scaled by an exact power of two and rounded to FP16, FP32 accumulate) + exact FP64 re-rank with a
+ * proven guard band; rows that fail the guard are repaired inside the same call (tensor-core threshold
+ * collect, FP64 scan for the rest).  k <= 24 and dim <= 253 run on the tensor cores, other shapes take
+ * method 0.  workspace: scf_knn_workspace_bytes(nq, nref, dim, k, method). */
 int64_t scf_knn_workspace_bytes(int64_t nq, int64_t nref, int32_t dim, int32_t k, int32_t method);
 /* diagnostics: byte offset inside the workspace of an int32 that, after scf_knn_l2(method 1), holds the
  * number of query rows whose guard band could not be proven (recomputed by method 0); -1 if n/a. */
