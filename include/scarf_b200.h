@@ -158,6 +158,10 @@ int64_t scf_knn_workspace_bytes(int64_t nq, int64_t nref, int32_t dim, int32_t k
 /* diagnostics: byte offset inside the workspace of an int32 that, after scf_knn_l2(method 1), holds the
  * number of query rows whose guard band could not be proven (recomputed by method 0); -1 if n/a. */
 int64_t scf_knn_fail_count_offset(int64_t nq, int64_t nref, int32_t dim, int32_t k, int32_t method);
+/* measurement hook: the next scf_knn_l2(method 1) issued by the calling thread records the two cudaEvent_t (created
+ * by the caller with timing enabled) on its stream around the tcgen05 distance / top-k' kernel alone, so that the
+ * dominant kernel can be timed live without a profiler (bench.py `roofline`).  One shot; NULL, NULL cancels. */
+int32_t scf_knn_time_next_call(void* event_start, void* event_stop);
 int32_t scf_knn_l2(const float* q, int64_t nq, const float* ref, int64_t nref, int32_t dim,
                    int64_t ld, int32_t k, int64_t self_offset, int64_t* out_idx, float* out_dist,
                    int32_t method, void* workspace, int64_t workspace_bytes, void* stream);

@@ -804,6 +804,14 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
 
 }  // namespace
 
+// measurement hook (bench.py): events the next scf_knn_l2(method 1) of this thread records around its tensor kernel
+static thread_local void* g_time_start = nullptr;
+static thread_local void* g_time_stop = nullptr;
+extern "C" int32_t scf_knn_time_next_call(void* event_start, void* event_stop) {
+  g_time_start = event_start, g_time_stop = event_stop;
+  return 0;
+}
+
 int64_t knn_tc_fail_count_offset(int64_t nq, int64_t nref, int dim, int k) {
   Plan pl;
   if (!make_plan(nq, nref, dim, k, pl)) return -1;
@@ -889,7 +897,10 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
+  if (g_time_start) cudaEventRecord((cudaEvent_t)g_time_start, stream);
   kern<<<dim3((unsigned)pl.grid), NTHREADS, pl.smem, stream>>>(tq, tr, prm);
+  if (g_time_stop) cudaEventRecord((cudaEvent_t)g_time_stop, stream);
+  g_time_start = g_time_stop = nullptr;  // one shot
   rc = scf_check_launch("scf_knn_l2(tcgen05)");
   if (rc) return rc;
   if (SCF_KNN_DEBUG & (4 | 8 | 32 | 64 | 128)) return 0;  // timing experiments: candidates are meaningless, stop here

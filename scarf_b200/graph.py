@@ -381,7 +381,12 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
     mark("project")
 
     # ---- exact kNN (K5) ----
-    idx, dist = ops.knn_l2(y, y_all, dims, k, self_offset=row_offset, method=knn_method)
+    kev = None
+    if timers is not None and knn_method == 1:  # the tensor kernel alone, for the roofline of bench.py
+        kev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        kev[0].record(), kev[1].record()  # creates the handles; the library records them again around the kernel
+        timers.append(("knn_kernel_events", kev))
+    idx, dist = ops.knn_l2(y, y_all, dims, k, self_offset=row_offset, method=knn_method, kernel_events=kev)
     mark("knn")
 
     # ---- edge weights (K6, collective 4) ----

@@ -229,9 +229,11 @@ def sym_eig_small(a, info=None, max_n=JACOBI_MAX_N):
 
 
 # ------------------------------------------------------------------------------------------ K5
-def knn_l2(q, ref, dim, k, self_offset=-1, method=0, stats=None):
+def knn_l2(q, ref, dim, k, self_offset=-1, method=0, stats=None, kernel_events=None):
     """Exact kNN (squared L2).  q, ref: float32 [n, ld] sharing the row stride.  -> (int64 idx, float32 dist).
-    ``stats`` (optional dict) receives ``guard_fail_rows`` as a device scalar tensor (method 1)."""
+    ``stats`` (optional dict) receives ``guard_fail_rows`` as a device scalar tensor (method 1).
+    ``kernel_events``: optional pair of recorded ``torch.cuda.Event(enable_timing=True)``; the library re-records them
+    around the tensor-core kernel of this call alone (measurement hook of bench.py)."""
     assert q.dtype == torch.float32 and ref.dtype == torch.float32
     assert q.stride(1) == 1 and ref.stride(1) == 1 and q.stride(0) == ref.stride(0)
     nq, nref = int(q.shape[0]), int(ref.shape[0])
@@ -239,6 +241,8 @@ def knn_l2(q, ref, dim, k, self_offset=-1, method=0, stats=None):
     dist = torch.empty((nq, k), dtype=torch.float32, device=q.device)
     ws_bytes = int(lib.raw("scf_knn_workspace_bytes")(nq, nref, int(dim), int(k), int(method)))
     ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=q.device)
+    if kernel_events is not None and method == 1:
+        lib.call("scf_knn_time_next_call", kernel_events[0].cuda_event, kernel_events[1].cuda_event, launches=0)
     lib.call("scf_knn_l2", q.data_ptr(), nq, ref.data_ptr(), nref, int(dim), int(q.stride(0)), int(k),
              int(self_offset), idx.data_ptr(), dist.data_ptr(), int(method), ws.data_ptr(), ws_bytes, _stream())
     if stats is not None:

@@ -1,6 +1,2 @@
 #!/bin/bash
-for v in 5 6 7 8 9; do
-  echo "== SCF_GS_VARIANT=$v"
-  SCF_GS_VARIANT=$v timeout 120 python tools/csr_probe.py 2>&1 | grep -E "gene_stats w|gene_ncells w"
-done
-SCF_GS_VARIANT=6 timeout 120 python -m pytest tests -m gpu -q -x -k "gene_stats or hvg" 2>&1 | tail -2
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['stage_ms']); r=d['roofline']; print({k:r[k] for k in ('achieved','peak','frac','ms_per_launch','entry_point_ms','entry_point_achieved','tmem_readout_floor_ms')})"
