@@ -205,6 +205,24 @@ int32_t scf_host_lowess(const double* endog, const double* exog, int64_t n, doub
 int32_t scf_lowess(const double* endog, const double* exog, const uint8_t* valid, int32_t n, double frac,
                    int32_t it, double* out, void* stream);
 
+/* ---- mark_hvgs after the statistics pass, fused into one CTA ----------------------------------------
+ * Trend removal (MetaData.remove_trend -> fit_lowess, scarf/metadata.py:586-617, scarf/feat_utils.py:11-45) and the
+ * HVG choice (RNAassay.mark_hvgs, scarf/assay.py:1014-1063 + MetaData.multi_sift, scarf/metadata.py:483-533) on the
+ * per-gene vectors of scf_csr_gene_stats*: avg = sum / n_cells_total, var = sumsq / m_cells - (sum / m_cells)^2,
+ * n_bins equal-width bins on log(avg) over the genes of feat_i with avg > 0 (np.histogram edges, last edge + 0.1), the
+ * minimum-log(var) gene of every bin, LOWESS(frac, it = 100) through them, c_var = exp(log var - fit(bin)); eligible =
+ * min_cells < nnz < max_cells & min_mean < sum/nnz < max_mean (strict; pass -inf / +inf for open bounds) & feat_i &
+ * keep; selected = eligible & c_var > (top_n + 1)-th largest eligible c_var.  All pointers DEVICE; feat_i / keep / hv:
+ * one byte per gene (keep nullable); col_map[g] = rank of gene g among the selected ones or -1; *n_sel = their number.
+ * n_bins <= 512.  workspace: scf_hvg_select_workspace_bytes(n_genes). */
+int64_t scf_hvg_select_workspace_bytes(int32_t n_genes);
+int32_t scf_hvg_select(const unsigned long long* gene_nnz, const double* gene_sum, const double* gene_sumsq,
+                       const uint8_t* feat_i, const uint8_t* keep, int32_t n_genes, double m_cells,
+                       double n_cells_total, int32_t n_bins, double lowess_frac, int32_t top_n,
+                       double min_cells, double max_cells, double min_mean, double max_mean, uint8_t* hv,
+                       int32_t* col_map, int32_t* n_sel, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

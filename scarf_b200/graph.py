@@ -65,6 +65,23 @@ def mark_hvgs_csr(csr: CsrDevice, cell_idx, feat_I, n_counts, n_cells_total, gen
     if min_cells is None:
         min_cells = int(0.01 * n_cells_total)  # datastore.py:291
     dev = csr.device
+    if csr.indptr.is_cuda and not return_stats and top_n is not None and n_bins <= 512:
+        # device path: one statistics pass + ONE fused kernel for trend removal and choice (no synchronisation)
+        row_div = n_counts[cell_idx] if cell_idx is not None else n_counts
+        nnz, sm, sq = ops.csr_gene_stats(csr, cell_idx, row_div.contiguous(), SF)
+        m = csr.n_rows if cell_idx is None else int(cell_idx.numel())
+        if comm is not None and comm.world > 1:
+            mt = torch.tensor([m], dtype=torch.int64, device=dev)
+            comm.allreduce_sum_(nnz), comm.allreduce_sum_(sm), comm.allreduce_sum_(sq), comm.allreduce_sum_(mt)
+            m = int(mt.item())
+        if keep_mask is None:
+            keep_mask = hvg_host.blacklist_keep_mask(gene_names, csr.n_cols, blacklist)
+        to_dev = lambda x: (x if torch.is_tensor(x) else torch.from_numpy(np.asarray(x, dtype=bool))).to(dev)
+        lo_mean = 2.0 ** min_mean if min_mean != -np.inf else -np.inf  # log2 thresholds (scarf/assay.py:1014-1021)
+        hi_mean = 2.0 ** max_mean if max_mean != np.inf else np.inf
+        mask, _, _ = ops.hvg_select(nnz, sm, sq, to_dev(feat_I), to_dev(keep_mask), m, n_cells_total, n_bins,
+                                    lowess_frac, top_n, min_cells, max_cells, lo_mean, hi_mean)
+        return mask if as_tensor else mask.cpu().numpy()
     st = hvg_gene_stats(csr, cell_idx, n_counts, n_cells_total, comm, as_numpy=False)
     if keep_mask is None:
         keep_mask = hvg_host.blacklist_keep_mask(gene_names, csr.n_cols, blacklist)

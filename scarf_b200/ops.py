@@ -106,6 +106,28 @@ def csr_gene_stats(csr: CsrDevice, row_ids=None, row_div=None, sf=1000.0, out=No
     return nnz, sm, sq
 
 
+def hvg_select(nnz, sm, sq, feat_i, keep, m_cells, n_cells_total, n_bins, lowess_frac, top_n, min_cells, max_cells,
+               min_mean, max_mean):
+    """Fused trend removal + HVG choice on the per-gene statistics (one CTA).  ``feat_i`` / ``keep``: bool device
+    vectors (keep may be None); bounds are the final, strict ones (+-inf = open).  -> (mask bool [G], col_map int32 [G],
+    n_selected int32 [1]), all on the device, no synchronisation."""
+    g = int(nnz.numel())
+    dev = nnz.device
+    _chk(nnz, torch.int64, "nnz"), _chk(sm, torch.float64, "sum"), _chk(sq, torch.float64, "sumsq")
+    hv = torch.empty(g, dtype=torch.bool, device=dev)
+    col_map = torch.empty(g, dtype=torch.int32, device=dev)
+    n_sel = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.raw("scf_hvg_select_workspace_bytes")(g))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    fi = feat_i.to(torch.bool).contiguous()
+    kp = keep.to(torch.bool).contiguous() if keep is not None else None
+    lib.call("scf_hvg_select", _ptr(nnz), _ptr(sm), _ptr(sq), fi.data_ptr(), kp.data_ptr() if kp is not None else None,
+             g, float(m_cells), float(n_cells_total), int(n_bins), float(lowess_frac), int(top_n), float(min_cells),
+             float(max_cells), float(min_mean), float(max_mean), hv.data_ptr(), _ptr(col_map), _ptr(n_sel),
+             ws.data_ptr(), ws_bytes, _stream())
+    return hv, col_map, n_sel
+
+
 def lowess(endog, exog, valid=None, frac=0.1, it=100):
     """Robust LOWESS fit at every usable point, on the device (float64 vectors of <= 512 points; NaN elsewhere)."""
     _chk(endog, torch.float64, "endog"), _chk(exog, torch.float64, "exog"), _chk(valid, torch.uint8, "valid")

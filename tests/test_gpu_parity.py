@@ -598,3 +598,37 @@ def test_knn_fp16_scale_handling(gpu, scale, outlier, dim, k):
     idx_o, dist_o = P.exact_knn(y, y, k, self_offset=0)
     assert np.array_equal(idx.cpu().numpy().astype(np.uint64), idx_o)
     assert np.array_equal(dist.cpu().numpy(), dist_o)
+
+
+@pytest.mark.parametrize("top_n,bounds", [(500, {}), (50, {"max_cells": 2000.0, "min_mean": -3.0, "max_mean": 2.0}),
+                                           (100000, {})])
+def test_fused_hvg_selection_equals_tensor_ops(gpu, synth_small, top_n, bounds):
+    """scf_hvg_select (one CTA: bins, LOWESS, corrected variance, bounds, radix select) against the tensor-op
+    formulation of scarf_b200/hvg.py on the same statistics: identical mask, col_map = rank among the selected genes."""
+    from scarf_b200 import hvg
+
+    torch, graph, ops = gpu["torch"], gpu["graph"], gpu["ops"]
+    csr = _dev(gpu, synth_small)
+    n_counts, n_feat = graph.cell_totals(csr)
+    cells = torch.nonzero(n_feat > 10).flatten()
+    g = csr.n_cols
+    feat_I = graph.gene_ncells(csr) > 20
+    keep = torch.rand(g, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) > 0.05
+    nnz, sm, sq = ops.csr_gene_stats(csr, cells, n_counts[cells].contiguous(), 1000.0)
+    m, n_total = int(cells.numel()), synth_small.shape[0]
+    min_cells = int(0.01 * n_total)
+    max_cells = bounds.get("max_cells", np.inf)
+    min_mean, max_mean = bounds.get("min_mean", -np.inf), bounds.get("max_mean", np.inf)
+    lo = 2.0 ** min_mean if min_mean != -np.inf else -np.inf
+    hi = 2.0 ** max_mean if max_mean != np.inf else np.inf
+    mask, col_map, n_sel = ops.hvg_select(nnz, sm, sq, feat_I, keep, m, n_total, 200, 0.1, top_n, min_cells, max_cells,
+                                          lo, hi)
+    st = graph.hvg_gene_stats(csr, cells, n_counts, n_total, as_numpy=False)
+    c_var = hvg.remove_trend_device(st["avg"], st["sigmas"], 200, 0.1, select=feat_I)
+    c_var = torch.where(feat_I, c_var, torch.full_like(c_var, float("nan")))
+    ref = hvg.choose_hvgs_device(st["normed_n"], st["nz_mean"], c_var, feat_I & keep, top_n, min_cells, max_cells,
+                                 min_mean, max_mean)
+    assert torch.equal(mask, ref), int((mask != ref).sum())
+    assert int(n_sel.item()) == int(ref.sum())
+    expect = torch.where(ref, torch.cumsum(ref, 0, dtype=torch.int32) - 1, torch.full((g,), -1, dtype=torch.int32, device="cuda"))
+    assert torch.equal(col_map, expect)
