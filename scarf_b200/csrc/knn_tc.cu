@@ -550,6 +550,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   }
 }
 
+// The oracle's distance: sequential in t, separate multiply and add, in float64.  Rows are read as float4 (the row
+// stride is a multiple of 4 floats and the rows are 16-byte aligned when ld % 4 == 0), four loads in flight, so the
+// dependent FP64 chain does not wait for one scalar load per term.
+__device__ __forceinline__ double oracle_dist(const float* __restrict__ a, const float* __restrict__ b, int dim,
+                                              bool vec) {
+  double acc = 0.0;
+  if (vec) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    const int n4 = dim >> 2;
+#pragma unroll 4
+    for (int t = 0; t < n4; ++t) {
+      const float4 av = a4[t], bv = __ldg(b4 + t);
+      double df = __dsub_rn((double)av.x, (double)bv.x);
+      acc = __dadd_rn(acc, __dmul_rn(df, df));
+      df = __dsub_rn((double)av.y, (double)bv.y);
+      acc = __dadd_rn(acc, __dmul_rn(df, df));
+      df = __dsub_rn((double)av.z, (double)bv.z);
+      acc = __dadd_rn(acc, __dmul_rn(df, df));
+      df = __dsub_rn((double)av.w, (double)bv.w);
+      acc = __dadd_rn(acc, __dmul_rn(df, df));
+    }
+    for (int t = n4 << 2; t < dim; ++t) {
+      const double df = __dsub_rn((double)a[t], (double)__ldg(b + t));
+      acc = __dadd_rn(acc, __dmul_rn(df, df));
+    }
+  } else {
+    for (int t = 0; t < dim; ++t) {
+      const double df = __dsub_rn((double)a[t], (double)__ldg(b + t));
+      acc = __dadd_rn(acc, __dmul_rn(df, df));
+    }
+  }
+  return acc;
+}
+
 // ---------------------------------------------------------------------------------------------- re-rank
 constexpr int MAXU = 8;  // candidates per lane: nsplit * kc <= 256
 
@@ -571,6 +606,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   const int ncand = kc * nsplit;
   const int64_t self = self_offset >= 0 ? qi + self_offset : -1;
   const float* a = q + qi * ld;
+  const bool vec = (ld & 3) == 0 && ((((uintptr_t)q) | ((uintptr_t)ref)) & 15) == 0;
   unsigned long long key[MAXU];
 #pragma unroll
   for (int u = 0; u < MAXU; ++u) {
@@ -579,12 +615,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
     if (c < ncand) {
       const int j = cand_idx[(size_t)qi * ncand + c];
       if (j >= 0 && j < nref && j != self) {
-        const float* b = ref + (int64_t)j * ld;
-        double acc = 0.0;
-        for (int t = 0; t < dim; ++t) {  // the oracle's arithmetic: sequential, separate multiply and add
-          const double df = __dsub_rn((double)a[t], (double)__ldg(b + t));
-          acc = __dadd_rn(acc, __dmul_rn(df, df));
-        }
+        const double acc = oracle_dist(a, ref + (int64_t)j * ld, dim, vec);
         key[u] = ((unsigned long long)__float_as_uint((float)acc) << 32) | (unsigned)j;
       }
     }
@@ -680,6 +711,7 @@ __global__ void __launch_bounds__(256) knn_fix_finish_kernel(const float* __rest
     if (c >= k && c <= FIXTC_CAP) {
       const int64_t self = self_offset >= 0 ? qi + self_offset : -1;
       const float* a = q + qi * ld;
+  const bool vec = (ld & 3) == 0 && ((((uintptr_t)q) | ((uintptr_t)ref)) & 15) == 0;
       unsigned long long key[FIXTC_CAP / 32];
       int live = 0;
 #pragma unroll
@@ -689,12 +721,7 @@ __global__ void __launch_bounds__(256) knn_fix_finish_kernel(const float* __rest
         if (e < c) {
           const int j = fix_list[(size_t)w * FIXTC_CAP + e];
           if (j != self) {
-            const float* b = ref + (int64_t)j * ld;
-            double acc = 0.0;
-            for (int t = 0; t < dim; ++t) {
-              const double df = __dsub_rn((double)a[t], (double)__ldg(b + t));
-              acc = __dadd_rn(acc, __dmul_rn(df, df));
-            }
+            const double acc = oracle_dist(a, ref + (int64_t)j * ld, dim, vec);
             key[u] = ((unsigned long long)__float_as_uint((float)acc) << 32) | (unsigned)j;
             ++live;
           }

@@ -1,2 +1,3 @@
 #!/bin/bash
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['stage_ms']); r=d['roofline']; print({k:r[k] for k in ('achieved','peak','frac','ms_per_launch','entry_point_ms','entry_point_achieved','tmem_readout_floor_ms')})"
+timeout 200 python -m pytest tests -m gpu -q -x -k "knn" 2>&1 | tail -3
+KNN_PROBE_NO_EXACT=1 timeout 200 python tools/knn_probe.py 100000 50 11 1000000 100 21 2>&1 | tail -2
