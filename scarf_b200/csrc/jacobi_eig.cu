@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double*
   __shared__ int s_rank[JE_MAXN + 1];
   const int tid = threadIdx.x;
   const int ne = n + (n & 1);
-  for (int e = tid; e < n * ne; e += JE_THREADS) {
+  const int nthreads = blockDim.x;
+  for (int e = tid; e < n * ne; e += nthreads) {
     const int col = e / n, row = e - col * n;
     // symmetrised read: the caller's matrix is symmetric up to rounding
     w[e] = col < n ? 0.5 * (a[(int64_t)row * lda + col] + a[(int64_t)col * lda + row]) : 0.0;
@@ -98,13 +99,13 @@ __global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double*
     }
   }
   // eigenvalues = column norms; ascending order by rank (ties by column index)
-  for (int c = tid; c < n; c += JE_THREADS) {
+  for (int c = tid; c < n; c += nthreads) {
     double s2 = 0.0;
     for (int r = 0; r < n; ++r) s2 = fma(w[(size_t)c * n + r], w[(size_t)c * n + r], s2);
     s_norm[c] = sqrt(s2);
   }
   __syncthreads();
-  for (int c = tid; c < n; c += JE_THREADS) {
+  for (int c = tid; c < n; c += nthreads) {
     int rank = 0;
     const double mine = s_norm[c];
     for (int o = 0; o < n; ++o) rank += (s_norm[o] < mine) || (s_norm[o] == mine && o < c);
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double*
     evals[rank] = mine;
   }
   __syncthreads();
-  for (int e = tid; e < n * n; e += JE_THREADS) {
+  for (int e = tid; e < n * n; e += nthreads) {
     const int c = e / n, r = e - c * n;
     const double nv = s_norm[c];
     // a zero column can only come from an exactly singular matrix: its direction is undefined, emit a unit vector
@@ -135,6 +136,10 @@ extern "C" int32_t scf_sym_eig_jacobi(const double* a, int32_t n, int64_t lda, d
     scf_set_error("scf_sym_eig_jacobi: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
-  jacobi_eig_kernel<<<1, JE_THREADS, smem, (cudaStream_t)stream>>>(a, n, lda, evals, evecs, ldv, info);
+  // one group of eight threads per column pair: a small matrix runs with few warps (cheaper barriers)
+  const int npairs = (n + 1) / 2;
+  int threads = (npairs * JE_TPP + 31) / 32 * 32;
+  threads = threads < 64 ? 64 : (threads > JE_THREADS ? JE_THREADS : threads);
+  jacobi_eig_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(a, n, lda, evals, evecs, ldv, info);
   return scf_check_launch("scf_sym_eig_jacobi");
 }

@@ -275,7 +275,10 @@ def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
         e = 0.5 * cut
         rho = _cheb_growth((th_max - e) / e) / _cheb_growth((th_dims - e) / e)
         m = int(max(2, min(32, math.floor(math.log(1e20) / math.log(max(rho, 1.0 + 1e-9))))))
-        y_prev = _cheb_filter(cov, q @ s, m, cut, th_max)
+        # Ritz vectors in DESCENDING order: the (Gram-Schmidt-like) orthonormalisation then takes the strong
+        # directions first and removes their leakage from the weak columns, so the new basis stays aligned with the
+        # eigen-directions and the next Rayleigh-Ritz matrix is nearly diagonal (few Jacobi sweeps)
+        y_prev = _cheb_filter(cov, q @ torch.flip(s, dims=[1]), m, cut, th_max)
         q, chol_bad = _cholqr2(y_prev)
     w, v = torch.linalg.eigh(cov)
     if stats is not None:
