@@ -181,7 +181,7 @@ def run_reference(args, cfg, rank):
         "impl": "reference", "metric": "make_graph_cells_per_s", "value": val, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, cfg, 1),
+        "config": workload_config(args, cfg, max(args.gpus, 1)),
         "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference (scarf 0.32.3) cannot be imported here (dask/zarr/hnswlib/umap-learn absent, no network): "
