@@ -89,7 +89,7 @@ class RNAassay:
         self.sf = 1000  # scarf/assay.py:776
         g = self.z["counts_csr"]
         shape = tuple(g.attrs["shape"])
-        self.csr = CsrDevice.from_host(g["indptr"][:], g["indices"][:], g["data"][:], shape, device)
+        self.csr = CsrDevice.from_host(g["indptr"][:], g["indices"][:], g["data"][:], shape, device, validate=True)
 
     @property
     def nCounts(self):

@@ -31,8 +31,24 @@ class CsrDevice:
     def device(self):
         return self.indptr.device
 
+    def check_sorted(self) -> None:
+        """Raises ValueError unless the column ids ascend strictly inside every row (the CSR contract of the library:
+        the windowed gene statistics locate a row's gene windows by binary search).  One pass, for construction time."""
+        nnz = self.nnz
+        if nnz < 2:
+            return
+        step = 1 << 26
+        starts = torch.zeros(nnz + 1, dtype=torch.bool, device=self.device)
+        starts[self.indptr.clamp(max=nnz)] = True  # first position of every row (empty rows repeat a position)
+        for lo in range(1, nnz, step):
+            hi = min(nnz, lo + step)
+            bad = (self.indices[lo:hi] <= self.indices[lo - 1:hi - 1]) & ~starts[lo:hi]
+            if bool(bad.any()):
+                raise ValueError("CSR column ids must ascend strictly inside every row (scipy: `m.sort_indices()` after "
+                                 "`m.sum_duplicates()`)")
+
     @staticmethod
-    def from_host(indptr, indices, data, shape, device="cuda", non_blocking=False) -> "CsrDevice":
+    def from_host(indptr, indices, data, shape, device="cuda", non_blocking=False, validate=False) -> "CsrDevice":
         import numpy as np
 
         def as_t(a, dt):
@@ -42,7 +58,10 @@ class CsrDevice:
         ip = as_t(indptr, np.int64).to(device, non_blocking=non_blocking)
         ix = as_t(indices, np.int32).to(device, non_blocking=non_blocking)
         dv = as_t(data, np.uint32).to(device, non_blocking=non_blocking)
-        return CsrDevice(ip, ix, dv, int(shape[0]), int(shape[1]))
+        out = CsrDevice(ip, ix, dv, int(shape[0]), int(shape[1]))
+        if validate:
+            out.check_sorted()
+        return out
 
     @staticmethod
     def from_scipy(m, device="cuda") -> "CsrDevice":

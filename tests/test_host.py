@@ -183,3 +183,19 @@ def test_eig_topk_cpu_matches_full_eigh():
     np.testing.assert_allclose(ev.numpy(), torch.flip(wf[-dims:], [0]).numpy(), rtol=1e-10)
     ref = graph.sign_rule(torch.flip(vf[:, -dims:], [1]).T.contiguous()).T
     assert float(torch.acos((ref * load).sum(0).abs().clamp(max=1.0)).max()) < 1e-5
+
+
+def test_csr_sortedness_check_on_cpu_tensors():
+    """CsrDevice.check_sorted (device-agnostic torch code): unsorted or duplicated column ids inside a row are refused,
+    empty rows and row boundaries are not mistaken for a descent."""
+    import torch
+
+    from scarf_b200.ops import CsrDevice
+
+    ip = torch.tensor([0, 3, 3, 5, 6], dtype=torch.int64)
+    ok = CsrDevice(ip, torch.tensor([1, 4, 9, 0, 2, 0], dtype=torch.int32), torch.ones(6, dtype=torch.int32), 4, 10)
+    ok.check_sorted()
+    for bad_ix in ([1, 9, 4, 0, 2, 0], [1, 4, 4, 0, 2, 0]):
+        bad = CsrDevice(ip, torch.tensor(bad_ix, dtype=torch.int32), torch.ones(6, dtype=torch.int32), 4, 10)
+        with pytest.raises(ValueError, match="ascend strictly"):
+            bad.check_sorted()
