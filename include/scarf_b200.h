@@ -223,6 +223,26 @@ int32_t scf_hvg_select(const unsigned long long* gene_nnz, const double* gene_su
                        int32_t* col_map, int32_t* n_sel, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
+/* ---- reading stores the reference wrote: chunk codec (host) and dense -> CSR (device) -------------------
+ * scf_host_blosc_*: decoder of the Blosc-1 frames numcodecs.Blosc(cname='lz4', shuffle=SHUFFLE | BITSHUFFLE) writes
+ * for every Zarr chunk of a Scarf store (create_zarr_dataset, scarf/writers.py:58-89; read back through zarr by
+ * Assay.rawData, scarf/assay.py:134).  HOST pointers; pure functions (safe from several threads).  _info reports the
+ * decoded size / element size / flag byte of a frame; _decode needs dst_bytes == that size.  Stored (memcpy) frames
+ * and LZ4 frames are decoded, any other inner codec is an argument error. */
+int32_t scf_host_blosc_info(const void* frame, int64_t frame_bytes, int64_t* nbytes, int32_t* typesize,
+                            int32_t* flags);
+int32_t scf_host_blosc_decode(const void* frame, int64_t frame_bytes, void* dst, int64_t dst_bytes);
+
+/* scf_dense_row_nnz / scf_dense_to_csr: a dense row-major uint32 block [n_rows, ld] of raw counts (the decoded
+ * chunks of `<assay>/counts`, scarf/writers.py:164-204) to the CSR rows the path computes on -- the GPU form of
+ * Assay.to_raw_sparse (scarf/assay.py:175-199).  Pass 1 writes the number of non-zero values of the first n_cols
+ * columns of every row; the caller builds row_ptr (absolute int64 start of every row in indices / data); pass 2
+ * writes column ids (ascending) and counts.  ld % 4 == 0, block 16-byte aligned; columns >= n_cols are ignored. */
+int32_t scf_dense_row_nnz(const uint32_t* dense, int64_t n_rows, int32_t n_cols, int64_t ld, int64_t* row_nnz,
+                          void* stream);
+int32_t scf_dense_to_csr(const uint32_t* dense, int64_t n_rows, int32_t n_cols, int64_t ld, const int64_t* row_ptr,
+                         int32_t* indices, uint32_t* data, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

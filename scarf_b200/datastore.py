@@ -10,8 +10,9 @@ What mirrors what (paths relative to the reference checkout):
   run_mapping             scarf/datastore/mapping_datastore.py:31-209 (+ mapping_utils.align_features :148-214)
   load_graph              scarf/datastore/graph_datastore.py:474-511,1022-1075
 
-Differences that are deliberate (and documented in DESIGN.md): raw counts enter as CSR (``from_csr``) and are kept
-as three 1-D arrays under ``<assay>/counts_csr`` instead of the reference's dense chunked ``counts`` array; the
+Differences that are deliberate (and documented in DESIGN.md): raw counts enter as CSR (``from_csr``) and are then
+kept as three 1-D arrays under ``<assay>/counts_csr``; a store the reference wrote (dense chunked ``<assay>/counts``,
+Blosc) is opened as it is and converted to CSR on the GPU (``ops.csr_from_dense_zarr``); the
 ``ann__...`` group holds the float32 embedding (``embedding``) in place of hnswlib's ``ann_idx`` file; arrays are
 written uncompressed; options the GPU path does not implement raise ``NotImplementedError`` (no CPU fallback).
 """
@@ -69,7 +70,7 @@ class MetaData:
         if column_name in self.z and not overwrite:
             raise ValueError(f"ERROR: {column_name} already exists. Please set `overwrite` to True to overwrite.")
         values = np.asarray(values)
-        idx = self.active_index(key)
+        idx = np.arange(self.N) if len(values) == self.N else self.active_index(key)  # metadata.py:321-323
         if len(values) != len(idx):
             raise ValueError(f"ERROR: `values` are of incorrect length: {len(values)} for {len(idx)} active rows")
         full = np.full(self.N, fill_value, dtype=values.dtype if values.dtype.kind in "bU" else np.float64)
@@ -80,6 +81,21 @@ class MetaData:
         a[:] = full
 
 
+    def sift(self, column, min_v=-np.inf, max_v=np.inf, keep_bounds=False):
+        """metadata.py:483-505."""
+        v = self.fetch_all(column)
+        return (v >= min_v) & (v <= max_v) if keep_bounds else (v > min_v) & (v < max_v)
+
+    def update_key(self, values, key):
+        """metadata.py:437-450: the key column becomes ``key & values`` (values cover all rows)."""
+        values = np.asarray(values, dtype=bool)
+        if len(values) != self.N:
+            raise ValueError(f"ERROR: `values` must cover all {self.N} rows")
+        a = self.z[key]
+        new = values & self.fetch_all(key)
+        a[:] = new
+
+
 class RNAassay:
     """The raw counts of one assay on the device plus its feature table (scarf/assay.py: RNAassay)."""
 
@@ -87,9 +103,15 @@ class RNAassay:
         self.name, self.z, self.cells = name, zroot[name], cells
         self.feats = MetaData(self.z["featureData"])
         self.sf = 1000  # scarf/assay.py:776
-        g = self.z["counts_csr"]
-        shape = tuple(g.attrs["shape"])
-        self.csr = CsrDevice.from_host(g["indptr"][:], g["indices"][:], g["data"][:], shape, device, validate=True)
+        if "counts_csr" in self.z:
+            g = self.z["counts_csr"]
+            shape = tuple(g.attrs["shape"])
+            self.csr = CsrDevice.from_host(g["indptr"][:], g["indices"][:], g["data"][:], shape, device, validate=True)
+        else:  # a store the reference wrote: dense chunked `counts` (scarf/writers.py:164-204, assay.py:134)
+            self.csr = ops.csr_from_dense_zarr(self.z["counts"], device)
+        if self.csr.n_rows != cells.N or self.csr.n_cols != self.feats.N:
+            raise ValueError(f"ERROR: counts of assay {name} are {self.csr.n_rows} x {self.csr.n_cols} but the store "
+                             f"lists {cells.N} cells and {self.feats.N} features")
 
     @property
     def nCounts(self):
@@ -151,7 +173,7 @@ class DataStore:
     """A Scarf-style datastore whose graph path runs on B200.  Create with :meth:`from_csr`, reopen by path."""
 
     def __init__(self, zarr_loc: str, default_assay: str = "RNA", device="cuda", comm: Optional[Comm] = None,
-                 mode: str = "r+"):
+                 mode: str = "r+", min_features_per_cell: int = 10, min_cells_per_feature: int = 20):
         if not torch.cuda.is_available():
             raise RuntimeError("scarf_b200.DataStore needs a CUDA device: the path has no CPU fallback")
         self.zw = open_group(zarr_loc, mode)
@@ -162,6 +184,30 @@ class DataStore:
         self.cells = MetaData(self.zw["cellData"])
         self._assays = {}
         setattr(self, default_assay, self._get_assay(default_assay))
+        self._ini_props(default_assay, min_features_per_cell, min_cells_per_feature)
+
+    def _ini_props(self, from_assay, min_features, min_cells):
+        """First open of a store (base_datastore.py:324-401 `_ini_cell_props`, assay.py:201-225 `_ini_feature_props`):
+        ``<assay>_nCounts`` / ``<assay>_nFeatures`` per cell, ``nCells`` / ``dropOuts`` per feature and the ``I``
+        filters, computed on the GPU from the CSR when the columns are missing.  The reference's percentMito /
+        percentRibo columns are cell annotations outside the graph path and are not written."""
+        assay = self._get_assay(from_assay)
+        have = self.cells.columns
+        if f"{from_assay}_nCounts" not in have or f"{from_assay}_nFeatures" not in have:
+            n_counts, n_feats = graph.cell_totals(assay.csr)
+            self.cells.insert(f"{from_assay}_nCounts", n_counts.cpu().numpy(), overwrite=True)
+            self.cells.insert(f"{from_assay}_nFeatures", n_feats.cpu().numpy().astype(np.float64), overwrite=True)
+        v = self.cells.fetch(f"{from_assay}_nFeatures", key="I")
+        if len(v) and min_features <= np.median(v):  # base_datastore.py:384-399 (every open; a no-op once applied)
+            keep = self.cells.sift(f"{from_assay}_nFeatures", min_features, np.inf)
+            cur = self.cells.fetch_all("I")
+            if not np.array_equal(keep & cur, cur):
+                self.cells.update_key(keep, "I")
+        if "nCells" not in assay.feats.columns or "dropOuts" not in assay.feats.columns:
+            nc = graph.gene_ncells(assay.csr).cpu().numpy().astype(np.float64)
+            assay.feats.insert("nCells", nc, overwrite=True)
+            assay.feats.insert("dropOuts", np.abs(self.cells.N - nc), overwrite=True)
+            assay.feats.update_key(nc > min_cells, "I")  # assay.py:225
 
     # ---------------------------------------------------------------------------------------------------------
     @classmethod
@@ -205,12 +251,13 @@ class DataStore:
         put(rg, "indptr", counts.indptr.astype(np.int64))
         put(rg, "indices", counts.indices.astype(np.int32))
         put(rg, "data", counts.data.astype(np.uint32))
-        return cls(zarr_loc, default_assay=assay_name, device=device, **kw)
+        return cls(zarr_loc, default_assay=assay_name, device=device, min_features_per_cell=min_features_per_cell,
+                   min_cells_per_feature=min_cells_per_feature, **kw)
 
     # ---------------------------------------------------------------------------------------------------------
     def _get_assay(self, from_assay):
         if from_assay not in self._assays:
-            if from_assay not in self.zw or "counts_csr" not in self.zw[from_assay]:
+            if from_assay not in self.zw or not ("counts_csr" in self.zw[from_assay] or "counts" in self.zw[from_assay]):
                 raise ValueError(f"ERROR: Assay {from_assay} was not found.")
             self._assays[from_assay] = RNAassay(self.zw, from_assay, self.cells, self.device)
         return self._assays[from_assay]

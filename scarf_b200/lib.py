@@ -45,6 +45,10 @@ SIGNATURES = {
                        _p, _i64, _p]),
     "scf_host_lowess": (_i32, [_p, _p, _i64, _f64, _i32, _p]),
     "scf_lowess": (_i32, [_p, _p, _p, _i32, _f64, _i32, _p, _p]),
+    "scf_host_blosc_info": (_i32, [_p, _i64, _p, _p, _p]),
+    "scf_host_blosc_decode": (_i32, [_p, _i64, _p, _i64]),
+    "scf_dense_row_nnz": (_i32, [_p, _i64, _i32, _i64, _p, _p]),
+    "scf_dense_to_csr": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
 }
 
 COLSTAT_SHIFT = 34

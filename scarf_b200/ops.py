@@ -90,6 +90,67 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+# ------------------------------------------------------------------------------- dense store -> CSR
+def dense_to_csr(block: torch.Tensor, n_cols: int):
+    """Non-zero values of the first ``n_cols`` columns of a dense uint32 row block ``[rows, ld]`` (int32 storage,
+    ld % 4 == 0) -> (row_nnz int64 [rows], indices int32 [nnz], data uint32-in-int32 [nnz]), columns ascending in a
+    row.  One host synchronisation (the number of stored values sizes the outputs)."""
+    _chk(block, U32, "block")
+    rows, ld = int(block.shape[0]), int(block.stride(0))
+    cnt = torch.empty(rows, dtype=torch.int64, device=block.device)
+    lib.call("scf_dense_row_nnz", _ptr(block), rows, n_cols, ld, _ptr(cnt), _stream())
+    ptr = torch.cumsum(cnt, 0) - cnt
+    nnz = int(cnt.sum().item())
+    idx = torch.empty(nnz, dtype=torch.int32, device=block.device)
+    val = torch.empty(nnz, dtype=U32, device=block.device)
+    if nnz:
+        lib.call("scf_dense_to_csr", _ptr(block), rows, n_cols, ld, _ptr(ptr), _ptr(idx), _ptr(val), _stream())
+    return cnt, idx, val
+
+
+def csr_from_dense_zarr(arr, device="cuda", row_range=None, n_threads=None) -> CsrDevice:
+    """Reads ``<assay>/counts`` of a Scarf store (dense uint32 N x G, chunks (rows, cols), Blosc or plain;
+    scarf/writers.py:164-204) into a CSR on ``device``: per block of chunk rows the column chunks are decoded on host
+    threads (the library's decoder runs without the GIL), copied into a dense staging block in HBM and converted by
+    ``scf_dense_row_nnz`` / ``scf_dense_to_csr``.  ``row_range=(lo, hi)`` reads a shard (chunk-row aligned ``lo``)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+
+    if arr.ndim != 2 or arr.dtype.kind not in "ui" or arr.dtype.itemsize > 4:
+        raise TypeError(f"raw counts must be a 2-D integer array of at most 32 bits, got {arr.dtype} {arr.shape}")
+    n, g = arr.shape
+    lo, hi = (0, n) if row_range is None else row_range
+    cr, cc = arr.chunks
+    if lo % cr:
+        raise ValueError(f"row_range must start on a chunk row boundary ({cr})")
+    dev = torch.device(device)
+    ld = round_up(max(g, 1), 4)
+    stage = torch.zeros((cr, ld), dtype=U32, device=dev)
+    n_cc = (g + cc - 1) // cc
+    counts, idxs, vals = [], [], []
+
+    def load(ci, cj):
+        c = arr.read_chunk((ci, cj))
+        c = np.ascontiguousarray(c, dtype=np.uint32) if c.dtype != np.uint32 else c
+        return torch.from_numpy(c.view(np.int32))
+
+    with ThreadPoolExecutor(max_workers=n_threads or min(16, os.cpu_count() or 1)) as pool:
+        for ci in range(lo // cr, (hi + cr - 1) // cr):
+            r0, r1 = ci * cr, min((ci + 1) * cr, hi)
+            for cj, t in enumerate(pool.map(lambda j: load(ci, j), range(n_cc))):
+                w = min(cc, g - cj * cc)
+                stage[:, cj * cc: cj * cc + w].copy_(t[:, :w], non_blocking=False)
+            c, i, v = dense_to_csr(stage[: r1 - r0], g)
+            counts.append(c), idxs.append(i), vals.append(v)
+    cnt = torch.cat(counts) if counts else torch.zeros(0, dtype=torch.int64, device=dev)
+    indptr = torch.zeros(cnt.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(cnt, 0, out=indptr[1:])
+    cat = lambda xs, dt: torch.cat(xs) if xs else torch.zeros(0, dtype=dt, device=dev)
+    return CsrDevice(indptr, cat(idxs, torch.int32), cat(vals, U32), hi - lo, g)
+
+
 # ------------------------------------------------------------------------------------------ K0
 def csr_row_sums(csr: CsrDevice, row_ids=None, col_map=None):
     """(sum float64, nnz int32) per selected row over the columns with col_map >= 0 (all if None)."""

@@ -2,17 +2,39 @@
 
 The reference persists every stage through `zarr` (<= 2.16) + numcodecs Blosc (`scarf/writers.py:58-89`); neither is
 installed where this runs.  This module writes and reads the same on-disk format -- `.zgroup` / `.zarray` /
-`.zattrs` JSON plus one file per chunk, C order, little endian -- with `compressor: null`, which real zarr opens
-unchanged (readers take the codec from `.zarray`, `graph_datastore.py:474-511`).  Chunk shapes follow the
-reference's `create_zarr_dataset` calls so that chunk-wise consumers see the same blocking.
+`.zattrs` JSON plus one file per chunk, C order, little endian.  New arrays are written with `compressor: null`,
+which real zarr opens unchanged (readers take the codec from `.zarray`, `graph_datastore.py:474-511`).  Arrays the
+reference wrote (`numcodecs.Blosc(cname='lz4', clevel=5, shuffle=...)`, `scarf/writers.py:79-89`) are read through
+the native frame decoder of the C-ABI (`scf_host_blosc_decode`, scarf_b200/csrc/host_blosc.cu); a partial write into
+such an array stores the chunk as a Blosc "memcpy" frame, which c-blosc reads like any other.  Chunk shapes follow
+the reference's `create_zarr_dataset` calls so that chunk-wise consumers see the same blocking.
 """
 from __future__ import annotations
 
+import ctypes
 import json
 import os
 import shutil
+import struct
 
 import numpy as np
+
+from . import lib
+
+
+def blosc_decode(frame: bytes) -> np.ndarray:
+    """One Blosc-1 frame -> its bytes (uint8 array), decoded by the library's host routine."""
+    src = np.frombuffer(frame, dtype=np.uint8)
+    nbytes = ctypes.c_int64()
+    lib.call("scf_host_blosc_info", src.ctypes.data, src.size, ctypes.addressof(nbytes), None, None, launches=0)
+    out = np.empty(nbytes.value, dtype=np.uint8)
+    lib.call("scf_host_blosc_decode", src.ctypes.data, src.size, out.ctypes.data, out.size, launches=0)
+    return out
+
+
+def blosc_store(raw: bytes, typesize: int) -> bytes:
+    """A Blosc-1 frame that carries `raw` uncompressed (flag 0x02, "memcpyed"): version 2, LZ4 format id."""
+    return struct.pack("<BBBBIII", 2, 1, 0x02 | (1 << 5), min(typesize, 255), len(raw), len(raw), len(raw) + 16) + raw
 
 
 def _dtype_str(dt: np.dtype) -> str:
@@ -62,10 +84,14 @@ class Array:
         self.path = path
         with open(os.path.join(path, ".zarray")) as f:
             meta = json.load(f)
-        if meta.get("compressor") is not None:
-            raise NotImplementedError(
-                f"{path}: compressor {meta['compressor'].get('id')} -- this store reads arrays it wrote itself "
-                "(compressor null); Blosc decoding of reference-written stores is the next step of DESIGN.md 9")
+        comp = meta.get("compressor")
+        if comp is not None and comp.get("id") != "blosc":
+            raise NotImplementedError(f"{path}: compressor {comp.get('id')!r}; Scarf stores use Blosc (or none)")
+        if meta.get("filters"):
+            raise NotImplementedError(f"{path}: Zarr filters are not supported")
+        if meta.get("order", "C") != "C":
+            raise NotImplementedError(f"{path}: only C-ordered chunks are supported")
+        self.blosc = comp is not None
         self.shape = tuple(meta["shape"])
         self.chunks = tuple(meta["chunks"])
         self.dtype = np.dtype(meta["dtype"])
@@ -81,6 +107,27 @@ class Array:
 
     def _chunk_file(self, idx):
         return os.path.join(self.path, ".".join(str(i) for i in idx))
+
+    def _fill(self):
+        return np.full(self.chunks, self.fill_value if self.dtype.kind != "U" else "", dtype=self.dtype)
+
+    def read_chunk(self, idx):
+        """The whole chunk `idx` (a tuple) in chunk shape; a missing file reads as the fill value (zarr semantics)."""
+        f = self._chunk_file(idx)
+        if not os.path.exists(f):
+            return self._fill()
+        if not self.blosc:
+            return np.fromfile(f, dtype=self.dtype).reshape(self.chunks)
+        with open(f, "rb") as fh:
+            raw = blosc_decode(fh.read())
+        return raw.view(self.dtype).reshape(self.chunks)
+
+    def _write_chunk(self, idx, chunk):
+        if not self.blosc:
+            chunk.tofile(self._chunk_file(idx))
+            return
+        with open(self._chunk_file(idx), "wb") as fh:
+            fh.write(blosc_store(np.ascontiguousarray(chunk).tobytes(), self.dtype.itemsize))
 
     def __setitem__(self, key, value):
         """Whole-array (`a[:] = x`) or leading-axis row range (`a[lo:hi] = x`, `a[lo:hi, :] = x`) assignment."""
@@ -98,17 +145,13 @@ class Array:
             for cj in range(grid[1] if self.ndim == 2 else 1):
                 idx = (ci, cj) if self.ndim == 2 else (ci,)
                 full = (a == r0 and b == r1)
-                chunk = None
-                if not full and os.path.exists(self._chunk_file(idx)):
-                    chunk = np.fromfile(self._chunk_file(idx), dtype=self.dtype).reshape(self.chunks)
-                if chunk is None:
-                    chunk = np.full(self.chunks, self.fill_value if self.dtype.kind != "U" else "", dtype=self.dtype)
+                chunk = self._fill() if full else np.array(self.read_chunk(idx))
                 if self.ndim == 2:
                     k0, k1 = cj * self.chunks[1], min((cj + 1) * self.chunks[1], self.shape[1])
                     chunk[a - r0:b - r0, : k1 - k0] = value[a - lo:b - lo, k0:k1]
                 else:
                     chunk[a - r0:b - r0] = value[a - lo:b - lo]
-                chunk.tofile(self._chunk_file(idx))
+                self._write_chunk(idx, chunk)
 
     def _rows(self, key):
         if isinstance(key, tuple):
@@ -132,11 +175,7 @@ class Array:
             a, b = max(lo, r0), min(hi, r1)
             for cj in range(grid[1] if self.ndim == 2 else 1):
                 idx = (ci, cj) if self.ndim == 2 else (ci,)
-                f = self._chunk_file(idx)
-                if os.path.exists(f):
-                    chunk = np.fromfile(f, dtype=self.dtype).reshape(self.chunks)
-                else:
-                    chunk = np.full(self.chunks, self.fill_value if self.dtype.kind != "U" else "", dtype=self.dtype)
+                chunk = self.read_chunk(idx)
                 if self.ndim == 2:
                     k0, k1 = cj * self.chunks[1], min((cj + 1) * self.chunks[1], self.shape[1])
                     out[a - lo:b - lo, k0:k1] = chunk[a - r0:b - r0, : k1 - k0]
