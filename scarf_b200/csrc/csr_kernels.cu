@@ -1,12 +1,14 @@
 // K0 / K1: CSR row kernels (warp per cell, persistent grid).  HBM-bound: the algorithmic traffic
 // is 8 B per stored value (int32 gene id + uint32 count) + 8 B of indptr per cell.
 #include <math_constants.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kCompactVariant = 2;  // scf_csr_hvg_compact: see the variant table at its entry point
 
 __device__ __forceinline__ int64_t row_of(const int64_t* row_ids, int64_t r) { return row_ids ? row_ids[r] : r; }
 
@@ -95,6 +97,24 @@ __device__ __forceinline__ double norm_value(uint32_t c, double s, double sf, bo
   return log_transform ? log1p(v) : v;
 }
 
+// Counts are small integers and the divisor is fixed inside a row, so the FP64 division + log1p (~250 instructions,
+// the bulk of what these kernels issued) is evaluated once per row for the counts 1..kNormTab -- two per lane, into a
+// per-warp shared-memory table -- and looked up per stored value; larger counts take the direct evaluation.  Same
+// function on the same arguments: bit-identical values.
+constexpr int kNormTab = 64;
+__device__ __forceinline__ void fill_norm_table(double* tab, int lane, double s, double sf, bool log_transform) {
+  __syncwarp();  // the previous row's lookups are done
+  tab[lane] = norm_value((uint32_t)lane + 1u, s, sf, log_transform);
+  tab[lane + 32] = norm_value((uint32_t)lane + 33u, s, sf, log_transform);
+  __syncwarp();
+}
+__device__ __forceinline__ double norm_lookup(const double* tab, uint32_t c, double s, double sf, bool log_transform) {
+  return c - 1u < (uint32_t)kNormTab ? tab[c - 1u] : norm_value(c, s, sf, log_transform);
+}
+__device__ __forceinline__ unsigned long long colstat_fx(double v) {  // == to_fx(v, SCF_COLSTAT_SHIFT): exact scaling
+  return (unsigned long long)__double2ll_rn(v * (double)(1ull << SCF_COLSTAT_SHIFT));
+}
+
 __global__ void __launch_bounds__(kThreads) hvg_colstats_kernel(const int64_t* __restrict__ indptr,
                                                                 const int32_t* __restrict__ indices,
                                                                 const uint32_t* __restrict__ data,
@@ -105,9 +125,11 @@ __global__ void __launch_bounds__(kThreads) hvg_colstats_kernel(const int64_t* _
                                                                 long long* __restrict__ sumsq_fx, int n_cols,
                                                                 int n_rep) {
   // same-address atomics serialise in L2: every CTA adds into one of n_rep copies of the H-long accumulators
+  __shared__ double s_tab[kWarpsPerCta][kNormTab];
   sum_fx += (int64_t)(blockIdx.x % n_rep) * n_cols;
   sumsq_fx += (int64_t)(blockIdx.x % n_rep) * n_cols;
   const int lane = threadIdx.x & 31;
+  double* tab = s_tab[threadIdx.x >> 5];
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
   for (int64_t r = warp0; r < n_sel; r += nwarps) {
@@ -115,12 +137,13 @@ __global__ void __launch_bounds__(kThreads) hvg_colstats_kernel(const int64_t* _
     const int64_t s = indptr[row], e = indptr[row + 1];
     double sc = row_sum[r];
     if (sc == 0.0) sc = 1.0;  // scalar[scalar == 0] = 1  (scarf/assay.py:821-823)
+    fill_norm_table(tab, lane, sc, sf, log_transform != 0);
     warp_row_scan(indices, data, s, e, lane, [&](int32_t g, uint32_t c) {
       const int col = __ldg(col_map + g);
       if (col < 0 || c == 0) return;
-      const double x = norm_value(c, sc, sf, log_transform != 0);
-      atomicAdd((unsigned long long*)(sum_fx + col), (unsigned long long)to_fx(x, SCF_COLSTAT_SHIFT));
-      atomicAdd((unsigned long long*)(sumsq_fx + col), (unsigned long long)to_fx(x * x, SCF_COLSTAT_SHIFT));
+      const double x = norm_lookup(tab, c, sc, sf, log_transform != 0);
+      atomicAdd((unsigned long long*)(sum_fx + col), colstat_fx(x));
+      atomicAdd((unsigned long long*)(sumsq_fx + col), colstat_fx(x * x));
     });
   }
 }
@@ -143,6 +166,7 @@ __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
   double* s_sigma = s_mu + ldz;
   float* s_base = reinterpret_cast<float*>(s_sigma + ldz);
   float* s_base_lo = s_base + ldz;
+  __shared__ double s_tab[kWarpsPerCta][kNormTab];
   for (int j = threadIdx.x; j < ldz; j += kThreads) {
     const double m = (j < n_cols && mu) ? mu[j] : 0.0;
     const double sd = (j < n_cols && sigma) ? sigma[j] : 1.0;
@@ -173,6 +197,7 @@ __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
       reinterpret_cast<float4*>(zr)[j] = reinterpret_cast<const float4*>(s_base)[j];
       if (zl) reinterpret_cast<float4*>(zl)[j] = reinterpret_cast<const float4*>(s_base_lo)[j];
     }
+    fill_norm_table(s_tab[warp], lane, sc, sf, log_transform != 0);
     __syncwarp();  // orders the base row before the overwrites below (different lanes hit the same addresses)
     warp_row_scan(indices, data, s, e, lane, [&](int32_t g, uint32_t c) {
       const int col = __ldg(col_map + g);
@@ -181,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
         const double f = __ldg(missing_fill + col);
         if (f == f) return;
       }
-      const double x = norm_value(c, sc, sf, log_transform != 0);
+      const double x = norm_lookup(s_tab[warp], c, sc, sf, log_transform != 0);
       const float v = (float)__ddiv_rn(x - s_mu[col], s_sigma[col]);
       zr[col] = v;
       if (zl) zl[col] = tf32_low_part(v);  // what the tensor core's 19-bit read of z drops (3xTF32 low plane)
@@ -195,22 +220,34 @@ __global__ void __launch_bounds__(kThreads) norm_scale_kernel(
 // column sums of x and x^2.  The selected entries are ~10 % of a row and scattered over the lanes, so doing the
 // FP64 division + log1p where they are found would run it at 1/8 lane occupancy; here each warp first packs them
 // (ballot + popc) into a shared-memory batch and then evaluates full batches.  K1b' reads this compact matrix.
-constexpr int kBatch = 512;  // entries per warp batch (flushed when fewer than 128 slots remain)
-
-__global__ void __launch_bounds__(kThreads) hvg_compact_kernel(
+//
+// Column sums: one 64-bit reduction per value and statistic into one of n_rep copies in L2 (106 M at C2).
+// Measured at C2 (100k cells, tools/csr_probe.py; 1.25 ms before): the per-row lookup table above 1.13 ms; eight
+// stored values per lane and step 1.04 ms; the next stretch of the row loading while the current one is looked up
+// and packed 0.85 ms (PREFETCH 1); a third stage that also keeps the col_map look-ups of the next stretch in flight
+// 0.83 ms (PREFETCH 2: no further gain, the two load latencies are hidden by then).  Per-CTA shared-memory
+// accumulators for the column sums (two 32-bit ATOMS.ADD with carry per sum -- shared memory has no native 64-bit
+// add -- flushed once per CTA) were SLOWER (1.47 ms): the L2 reductions are not what bounds the kernel, and the
+// accumulators cost occupancy.
+// dynamic smem: [kWarpsPerCta][kNormTab] double | [kWarpsPerCta][BATCH] int32 col | [kWarpsPerCta][BATCH] uint32 count
+template <int UNROLL, int BATCH, int MIN_CTAS, int PREFETCH>
+__global__ void __launch_bounds__(kThreads, MIN_CTAS) hvg_compact_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const uint32_t* __restrict__ data,
     const int64_t* __restrict__ row_ids, int64_t n_sel, const int32_t* __restrict__ col_map,
     const double* __restrict__ row_sum, double sf, int log_transform, const int64_t* __restrict__ row_off,
     int32_t* __restrict__ out_col, double* __restrict__ out_x, long long* __restrict__ sum_fx,
     long long* __restrict__ sumsq_fx, int n_cols, int n_rep) {
-  __shared__ int32_t s_col[kWarpsPerCta][kBatch];
-  __shared__ uint32_t s_cnt[kWarpsPerCta][kBatch];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_tab = reinterpret_cast<double*>(smem_raw);
+  int32_t* s_col = reinterpret_cast<int32_t*>(s_tab + kWarpsPerCta * kNormTab);
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_col + kWarpsPerCta * BATCH);
   sum_fx += (int64_t)(blockIdx.x % n_rep) * n_cols;
   sumsq_fx += (int64_t)(blockIdx.x % n_rep) * n_cols;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  int32_t* bc = s_col[warp];
-  uint32_t* bn = s_cnt[warp];
+  int32_t* bc = s_col + warp * BATCH;
+  uint32_t* bn = s_cnt + warp * BATCH;
+  double* tab = s_tab + warp * kNormTab;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + warp;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
   for (int64_t r = warp0; r < n_sel; r += nwarps) {
@@ -220,13 +257,15 @@ __global__ void __launch_bounds__(kThreads) hvg_compact_kernel(
     if (sc == 0.0) sc = 1.0;  // scalar[scalar == 0] = 1  (scarf/assay.py:821-823)
     int64_t cursor = row_off[r];
     int pending = 0;
+    fill_norm_table(tab, lane, sc, sf, log_transform != 0);
     auto flush = [&]() {
       __syncwarp();
       for (int i = lane; i < pending; i += 32) {
         const int col = bc[i];
-        const double x = norm_value(bn[i], sc, sf, log_transform != 0);
-        atomicAdd((unsigned long long*)(sum_fx + col), (unsigned long long)to_fx(x, SCF_COLSTAT_SHIFT));
-        atomicAdd((unsigned long long*)(sumsq_fx + col), (unsigned long long)to_fx(x * x, SCF_COLSTAT_SHIFT));
+        const double x = norm_lookup(tab, bn[i], sc, sf, log_transform != 0);
+        const unsigned long long fx = colstat_fx(x), fxx = colstat_fx(x * x);
+        atomicAdd((unsigned long long*)(sum_fx + col), fx);
+        atomicAdd((unsigned long long*)(sumsq_fx + col), fxx);
         out_col[cursor + i] = col;
         out_x[cursor + i] = x;
       }
@@ -234,29 +273,61 @@ __global__ void __launch_bounds__(kThreads) hvg_compact_kernel(
       pending = 0;
       __syncwarp();
     };
-    for (int64_t p = s + lane; p - lane < e; p += 128) {
-      int32_t g[4];
-      uint32_t c[4];
+    // PREFETCH 0: load, look up, pack.  1: the next stretch of the row is in flight while this one is looked up and
+    // packed.  2: three stages -- stretch i + 2 loading, the col_map look-ups of stretch i + 1 in flight, stretch i
+    // packed: neither of the two dependent global latencies is exposed.
+    constexpr int S = 32 * UNROLL;
+    int32_t col[UNROLL], g1[UNROLL], g2[UNROLL];
+    uint32_t c[UNROLL], c1[UNROLL], c2[UNROLL];
+    auto load = [&](int32_t* gg, uint32_t* cc, int64_t p) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         const int64_t pp = p + 32 * u;
         const bool ok = pp < e;
-        g[u] = ok ? ld_stream(indices + pp) : -1;
-        c[u] = ok ? ld_stream(data + pp) : 0u;
+        gg[u] = ok ? ld_stream(indices + pp) : -1;
+        cc[u] = ok ? ld_stream(data + pp) : 0u;
+      }
+    };
+    auto lookup = [&](int32_t* out, const int32_t* gg) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) out[u] = gg[u] >= 0 ? __ldg(col_map + gg[u]) : -1;
+    };
+    const int64_t p0 = s + lane;
+    if (PREFETCH == 1) load(g1, c1, p0);
+    if (PREFETCH == 2) {
+      load(g1, c, p0);
+      load(g2, c2, p0 + S);
+      lookup(col, g1);
+    }
+    for (int64_t p = p0; p - lane < e; p += S) {
+      if (PREFETCH == 0) {
+        load(g1, c, p);
+        lookup(col, g1);
+      } else if (PREFETCH == 1) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) g2[u] = g1[u], c[u] = c1[u];
+        load(g1, c1, p + S);
+        lookup(col, g2);
+      } else {
+        load(g1, c1, p + 2 * S);
+        lookup(g2, g2);  // column ids of the next stretch replace its gene ids; consumed one iteration later
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int col = g[u] >= 0 ? __ldg(col_map + g[u]) : -1;
-        const bool hit = col >= 0 && c[u] != 0u;
+      for (int u = 0; u < UNROLL; ++u) {
+        const bool hit = col[u] >= 0 && c[u] != 0u;
         const unsigned m = __ballot_sync(SCF_FULL, hit);
         if (hit) {
           const int pos = pending + __popc(m & lt_mask);
-          bc[pos] = col;
+          bc[pos] = col[u];
           bn[pos] = c[u];
         }
         pending += __popc(m);
       }
-      if (pending > kBatch - 128) flush();
+      if (pending > BATCH - S) flush();
+      if (PREFETCH == 2) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) col[u] = g2[u], c[u] = c2[u], g2[u] = g1[u], c2[u] = c1[u];
+      }
     }
     flush();
   }
@@ -384,11 +455,34 @@ extern "C" int32_t scf_csr_hvg_compact(const int64_t* indptr, const int32_t* ind
           "null pointer");
   SCF_ARG(n_sel >= 0 && n_cols > 0 && n_rep > 0, "bad sizes");
   if (n_sel == 0) return 0;
-  const int grid = grid_for((const void*)hvg_compact_kernel, kThreads, 0);
-  hvg_compact_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data, row_ids, n_sel, col_map,
-                                                                   row_sum, sf, log_transform, row_off, out_col, out_x,
-                                                                   (long long*)sum_fx, (long long*)sumsq_fx, n_cols,
-                                                                   n_rep);
+  // variants {stored values per lane and step, batch entries per warp, CTAs per SM aimed at, pipeline depth}
+  struct Variant { int batch; const void* fn; };
+  static const Variant kVariants[] = {
+      {512, (const void*)hvg_compact_kernel<4, 512, 4, 0>}, {512, (const void*)hvg_compact_kernel<8, 512, 5, 0>},
+      {512, (const void*)hvg_compact_kernel<8, 512, 3, 1>}, {256, (const void*)hvg_compact_kernel<4, 256, 4, 1>},
+      {512, (const void*)hvg_compact_kernel<8, 512, 3, 2>},
+  };
+  constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+  const char* env = getenv("SCF_COMPACT_VARIANT");  // developer switch (tools/csr_probe.py sweeps it)
+  int variant = env ? atoi(env) : kCompactVariant;
+  if (variant < 0 || variant >= kNumVariants) variant = kCompactVariant;
+  const size_t smem = (size_t)kWarpsPerCta * (kNormTab * 8 + kVariants[variant].batch * 8);
+  const void* fn = kVariants[variant].fn;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    scf_set_error("scf_csr_hvg_compact: %s", cudaGetErrorString(e));
+    return -(int32_t)e;
+  }
+  const int grid = grid_for(fn, kThreads, smem);
+  long long* sfx = (long long*)sum_fx;
+  long long* sqfx = (long long*)sumsq_fx;
+  void* args[] = {&indptr, &indices, &data, &row_ids, &n_sel, &col_map, &row_sum, &sf, &log_transform, &row_off,
+                  &out_col, &out_x, &sfx, &sqfx, &n_cols, &n_rep};
+  e = cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, smem, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    scf_set_error("scf_csr_hvg_compact: %s", cudaGetErrorString(e));
+    return -(int32_t)e;
+  }
   return scf_check_launch("scf_csr_hvg_compact");
 }
 

@@ -46,8 +46,18 @@ timed("gene_stats plain (3 RED/value)", lambda: ops.csr_gene_stats(csr, None, n_
 timed("gene_stats windowed (smem RMW)", lambda: ops.csr_gene_stats(csr, None, n_counts, 1000.0, windowed=True), csr_bytes + 8 * n)
 timed("gene_ncells plain", lambda: ops.csr_gene_stats(csr, None, None, with_moments=False, windowed=False), csr_bytes)
 timed("gene_ncells windowed", lambda: ops.csr_gene_stats(csr, None, None, with_moments=False, windowed=True), csr_bytes)
-comp = timed("hvg_compact", lambda: ops.csr_hvg_compact(csr, None, col_map, 2000, row_sum, row_nnz), csr_bytes + 8 * n)
-row_off, cols, xs, sx, sxx = comp
+ref_sums = None
+for variant in ("0", "1", "2", "3", "4", None):  # None: the library's default
+    if variant is None:
+        os.environ.pop("SCF_COMPACT_VARIANT", None)
+    else:
+        os.environ["SCF_COMPACT_VARIANT"] = variant
+    comp = timed(f"hvg_compact (variant {variant})", lambda: ops.csr_hvg_compact(csr, None, col_map, 2000, row_sum, row_nnz),
+                 csr_bytes + 8 * n + 12.0 * float(row_nnz.sum()))
+    row_off, cols, xs, sx, sxx = comp
+    if ref_sums is None:
+        ref_sums = (sx.clone(), sxx.clone())
+    assert torch.equal(sx, ref_sums[0]) and torch.equal(sxx, ref_sums[1]), "column sums differ between variants"
 hnnz = int(cols.numel())
 print("hvg nnz per cell", hnnz / n)
 mu = torch.zeros(2000, dtype=torch.float64, device=dev)

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python tools/c5_mapping_probe.py 20000 10000 2>&1 | tail -5
-timeout 420 python tools/c5_mapping_probe.py > gpurun_out/c5_mapping.json 2> gpurun_out/c5_mapping.err; tail -3 gpurun_out/c5_mapping.err; cat gpurun_out/c5_mapping.json
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "compact or chain or mu_sigma or normalised or run_mapping" 2>&1 | tail -5
+timeout 200 python tools/csr_probe.py 2>&1 | tee gpurun_out/csr_probe.log | grep -E "compact|norm_scale|dense_scale \(Z \+"
