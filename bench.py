@@ -228,6 +228,8 @@ def run_ours(args, cfg, rank, world, local_rank):
     keep = torch.ones(cfg["genes"], dtype=torch.bool, device=dev)  # synthetic gene names never hit the blacklist
     torch.cuda.synchronize()
 
+    eig_stats = {}
+
     def step(c, tm=None):
         if tm is not None:
             e = torch.cuda.Event(enable_timing=True)
@@ -236,7 +238,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         hv = graph.mark_hvgs_csr(c, None, feat_I, n_counts, n_total, top_n=cfg["hvgs"], comm=comm, as_tensor=True,
                                  keep_mask=keep)
         return graph.make_graph_csr(c, None, hv, dims=cfg["dims"], k=cfg["k"], comm=comm, gram_mode=args.gram_mode,
-                                    knn_method=args.knn_method, timers=tm)
+                                    knn_method=args.knn_method, timers=tm, stats=eig_stats)
 
     def timed(fn, steps):
         comm.barrier()
@@ -357,7 +359,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (f64 gene / column statistics, 3xTF32 Gram and projection, f16 tensor-core kNN candidates + f64 re-rank)",
             "data": "synthetic", "config": workload_config(args, cfg, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu_base, "stage_ms": stages,
+            "roofline": roofline, "cpu_baseline": cpu_base, "stage_ms": stages, "eig": eig_stats,
             "csr_bytes_per_gpu": csr_bytes, "nnz_per_cell": nnz / n_local,
         }))
     if world > 1:

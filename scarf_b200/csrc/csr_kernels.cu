@@ -333,6 +333,8 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) hvg_compact_kernel(
   }
 }
 
+constexpr int kDenseUnroll = 4;
+
 // K1b': Z (and the 3xTF32 low plane) from the compact matrix: base row from shared memory, then the row's entries.
 __global__ void __launch_bounds__(kThreads) hvg_dense_scale_kernel(
     const int64_t* __restrict__ row_off, const int32_t* __restrict__ cols, const double* __restrict__ xs,
@@ -366,12 +368,22 @@ __global__ void __launch_bounds__(kThreads) hvg_dense_scale_kernel(
     }
     __syncwarp();
     const int64_t e = row_off[r + 1];
-    for (int64_t p = row_off[r] + lane; p < e; p += 32) {
-      const int col = ld_stream(cols + p);
-      const double x = __ldcs(xs + p);
-      const float v = (float)__ddiv_rn(x - s_mu[col], s_sigma[col]);
-      zr[col] = v;
-      if (zl) zl[col] = tf32_low_part(v);
+    for (int64_t p = row_off[r] + lane; p < e; p += 32 * kDenseUnroll) {  // all loads of a step before its stores
+      int col[kDenseUnroll];
+      double x[kDenseUnroll];
+#pragma unroll
+      for (int u = 0; u < kDenseUnroll; ++u) {
+        const int64_t pp = p + 32 * u;
+        col[u] = pp < e ? ld_stream(cols + pp) : -1;
+        x[u] = pp < e ? __ldcs(xs + pp) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kDenseUnroll; ++u) {
+        if (col[u] < 0) continue;
+        const float v = (float)__ddiv_rn(x[u] - s_mu[col[u]], s_sigma[col[u]]);
+        zr[col[u]] = v;
+        if (zl) zl[col[u]] = tf32_low_part(v);
+      }
     }
   }
 }

@@ -208,8 +208,8 @@ def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
 
     Only ``dims`` << H pairs are needed, so instead of a full tridiagonalisation (cuSOLVER syevd: ~28 ms at H = 2000
     on B200 -- two thousand dependent BLAS-2 panels) this runs Chebyshev-filtered subspace iteration on a
-    ``b = 2*dims + 64`` wide block: a polynomial of C (GEMMs) that damps the spectrum below the block, a Householder
-    QR, and a Rayleigh-Ritz step per round.  It stops when every kept pair has a residual
+    ``b = 2*dims + 64`` wide block: a polynomial of C (GEMMs) that damps the spectrum below the block, an
+    orthonormalisation (Cholesky-QR2; Householder QR as the checked fallback), and a Rayleigh-Ritz step per round.  It stops when every kept pair has a residual
     ``|C v - lambda v| <= tol * lambda_max`` (angle to the exact eigenvector <= residual * lambda_max / eigengap:
     1e-8 keeps the angle below 1e-5 rad for relative gaps down to 1e-3; the Gram matrix itself carries a 2e-5
     relative error from the 3xTF32 tensor-core accumulation).
@@ -229,12 +229,40 @@ def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
         return _finish_eig(w, v, dims)
     g = torch.Generator(device=cov.device)
     g.manual_seed(4466)
-    q = torch.randn((h, b), dtype=torch.float64, device=cov.device, generator=g)
+    q0 = torch.randn((h, b), dtype=torch.float64, device=cov.device, generator=g)
     # first filter without a Rayleigh-Ritz step: cut at the mean eigenvalue (the wanted ones lie above it), upper
     # bound from the 1-norm; both stay on the device
     trace = torch.diagonal(cov).sum()
-    q = _orthonormalise(_cheb_filter(cov, q, degree, trace / h, cov.abs().sum(dim=0).max()))
-    y_prev, chol_bad = None, torch.zeros((), dtype=torch.int32, device=cov.device)
+    top0 = cov.abs().sum(dim=0).max()
+    zero = torch.zeros((), dtype=torch.int32, device=cov.device)
+
+    def start_block(householder):
+        """Orthonormal basis of the filtered random block.  One degree-``degree`` filter leaves it with a condition
+        number ~1e11: Householder QR territory (~1 ms of dependent panels at C2).  Filtering in steps of degree 3 with
+        a Cholesky-QR2 after each keeps every step at cond <= T_3(t) = 4 t^3 - 3 t, t = (bound - cut / 2) / (cut / 2)
+        (9e6 at C2, inside Cholesky-QR2's range of ~1e8); the product of the steps is nearly as sharp a filter (same
+        number of rounds at C2) and all of it is GEMM-shaped.  Whether the range held is CHECKED, not assumed: the
+        Cholesky status and the measured orthonormality defect travel with the first round's synchronisation, and a
+        failed check repeats the start with Householder."""
+        if householder:
+            return _orthonormalise(_cheb_filter(cov, q0, degree, trace / h, top0)), zero, zero.to(torch.float64)
+        x, bad = q0, zero
+        for d in [3] * (degree // 3) + ([degree % 3] if degree % 3 else []):
+            x, bd = _cholqr2(_cheb_filter(cov, x, d, trace / h, top0))
+            bad = bad + bd
+        defect = (x.T @ x - torch.eye(b, dtype=x.dtype, device=x.device)).abs().max()
+        return x, bad, defect
+
+    # Gate (one small synchronisation; the host waits for the Gram anyway at the end of round 1): the Cholesky route
+    # only when T_3 at the upper bound of lambda_1 -- min(1-norm, Frobenius norm), which overestimates lambda_1 up to
+    # ~3x, T_3 up to ~30x -- stays below 3e9.  A wrong guess costs time, never accuracy (the check above).
+    bound, cut0 = torch.stack([torch.minimum(top0, torch.linalg.matrix_norm(cov)), trace / h]).tolist()
+    t0 = (bound - 0.5 * cut0) / (0.5 * cut0) if cut0 > 0.0 else math.inf
+    chol_start = degree >= 3 and 4.0 * t0 ** 3 <= 3e9
+    q, chol_bad, start_defect = start_block(householder=not chol_start)
+    if stats is not None:
+        stats["eig_start"] = "cholesky-qr2" if chol_start else "householder"
+    y_prev = None
     rounds = 0
     while rounds < max_rounds:
         rounds += 1
@@ -247,11 +275,16 @@ def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
         # the one synchronisation of the round: residual + the Ritz values that fix the next filter
         width = int(q.shape[1])
         keep = min(width, dims + 32)
-        res, th_min, th_max, th_dims, bulk, th_keep, bulk_keep, bad = torch.stack(
+        res, th_min, th_max, th_dims, bulk, th_keep, bulk_keep, bad, defect = torch.stack(
             [res_t, w[0], w[-1], wt[0], (trace - w.sum()) / (h - width), w[-keep],
-             (trace - w[-keep:].sum()) / (h - keep), chol_bad.to(torch.float64)]).tolist()
-        if bad != 0.0 or res != res:  # the Cholesky-QR of this round's basis broke down: Householder, same round again
-            q, chol_bad = _orthonormalise(y_prev), torch.zeros_like(chol_bad)
+             (trace - w[-keep:].sum()) / (h - keep), chol_bad.to(torch.float64), start_defect]).tolist()
+        if bad != 0.0 or res != res or not defect <= 1e-9:
+            # the Cholesky-QR of this round's basis broke down (or the start block is not orthonormal): Householder,
+            # same round again
+            q = _orthonormalise(y_prev) if y_prev is not None else start_block(householder=True)[0]
+            chol_bad, start_defect = zero, torch.zeros_like(start_defect)
+            if stats is not None:
+                stats["eig_householder_repeats"] = stats.get("eig_householder_repeats", 0) + 1
             rounds -= 1
             continue
         if stats is not None:
@@ -313,10 +346,11 @@ def normalise_stats(csr, cell_idx, col_map, n_feat, comm, log_transform=True, re
 def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, bw=1.5, batch_size=1000,
                    log_transform=True, renormalize_subset=True, n_counts=None, comm: Comm | None = None,
                    gram_mode=0, knn_method=0, loadings=None, mu=None, sigma=None, timers=None,
-                   pca_rows=None) -> GraphResult:
+                   pca_rows=None, stats=None) -> GraphResult:
     """normalise -> mu/sigma -> Z -> Gram -> eig -> project -> exact kNN -> edge weights for this rank's rows.
 
     ``timers``: optional list; (stage name, torch.cuda.Event) pairs are appended at every stage boundary.
+    ``stats``: optional dict; receives the eigensolver's route / rounds / residual (see :func:`eig_topk`).
     ``cell_idx``: int64 device tensor of the local CSR rows to use (None = all).  ``feat_mask``: bool over all
     genes (numpy), e.g. from :func:`mark_hvgs_csr`.  With ``comm.world > 1`` every rank passes its own shard and
     receives its own rows of the global graph; neighbour ids are global selected-row ids.
@@ -386,7 +420,7 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
         if col_mean is not None:
             cov = cov - float(n_pca) * torch.outer(col_mean, col_mean)
         cov = cov / max(n_pca - 1, 1)
-        evals, load = eig_topk(cov, dims)
+        evals, load = eig_topk(cov, dims, stats=stats)
         mark("eig")
     else:
         load, evals = loadings, torch.zeros(dims, dtype=torch.float64, device=dev)

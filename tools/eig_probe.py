@@ -35,6 +35,11 @@ for name, fn in (("eigh f64", lambda: torch.linalg.eigh(cov)), ("eigh f32", lamb
                  ("qr f64 Hx164", lambda: torch.linalg.qr(cov[:, :164]))):
     ms, _ = timed(fn)
     print(f"{name:20s} {ms:8.3f} ms")
+y164 = cov[:, :164].contiguous()
+for name, fn in (("cholqr2 Hx164", lambda: graph._cholqr2(y164)), ("cholqr2 Hx82", lambda: graph._cholqr2(y164[:, :82].contiguous())),
+                 ("cheb filter deg 3 Hx164", lambda: graph._cheb_filter(cov, y164, 3, 1.0, 200.0))):
+    ms, _ = timed(fn, reps=10)
+    print(f"{name:28s} {ms:8.3f} ms")
 for dims in (25, 50, 100):
     st = {}
     ms, _ = timed(lambda: graph.eig_topk(cov, dims, stats=st), reps=2)
