@@ -64,8 +64,13 @@ mu = torch.zeros(2000, dtype=torch.float64, device=dev)
 sigma = torch.ones(2000, dtype=torch.float64, device=dev)
 z = torch.empty((n, 2048), dtype=torch.float32, device=dev)
 z_lo = torch.empty_like(z)
-timed("hvg_dense_scale (Z + Z_lo)", lambda: ops.hvg_dense_scale(row_off, cols, xs, 2000, z, mu, sigma, z_lo=z_lo),
-      12.0 * hnnz + 8 * n + 2 * 4.0 * 2048 * n)
+for seg in ("128", "256", "512", "1024", "2048", None):
+    if seg is None:
+        os.environ.pop("SCF_DENSE_SEG", None)
+    else:
+        os.environ["SCF_DENSE_SEG"] = seg
+    timed(f"hvg_dense_scale (Z + Z_lo) seg {seg}", lambda: ops.hvg_dense_scale(row_off, cols, xs, 2000, z, mu, sigma, z_lo=z_lo),
+          12.0 * hnnz + 8 * n + 2 * 4.0 * 2048 * n)
 timed("hvg_dense_scale (Z only)", lambda: ops.hvg_dense_scale(row_off, cols, xs, 2000, z, mu, sigma),
       12.0 * hnnz + 8 * n + 4.0 * 2048 * n)
 timed("csr_norm_scale (Z + Z_lo)", lambda: ops.csr_norm_scale(csr, None, col_map, 2000, row_sum, z, mu=mu, sigma=sigma, z_lo=z_lo),
