@@ -68,11 +68,18 @@ int64_t lz4_block(const uint8_t* ip, int64_t n_in, uint8_t* dst, int64_t n_out) 
     const uint8_t* m = op - offset;
     if (offset >= len) {
       memcpy(op, m, (size_t)len);
-      op += len;
+    } else if (offset == 1) {
+      memset(op, m[0], (size_t)len);  // runs of one byte: most of a bit-shuffled count matrix
     } else {
-      for (int64_t i = 0; i < len; ++i) op[i] = m[i];  // overlapping match: byte order matters
-      op += len;
+      // overlapping match = periodic extension of the last `offset` bytes: one period, then doubling copies
+      memcpy(op, m, (size_t)offset);
+      for (int64_t filled = offset; filled < len;) {
+        const int64_t n = std::min(filled, len - filled);
+        memcpy(op + filled, op, (size_t)n);
+        filled += n;
+      }
     }
+    op += len;
   }
   return op - dst;
 }
@@ -99,14 +106,34 @@ inline uint64_t transpose8x8(uint64_t x) {  // byte r, bit c  <->  byte c, bit r
 // element, element e at bit e % 8 of byte e / 8 of the row; the remaining bytes are verbatim
 void unshuffle_bits(const uint8_t* src, uint8_t* dst, int64_t bsize, int ts) {
   const int64_t nelem = bsize / ts, n8 = nelem - nelem % 8, row = n8 / 8;
-  for (int64_t k = 0; k < row; ++k) {  // eight elements at a time: 8 * ts contiguous output bytes
-    uint8_t* o = dst + k * 8 * ts;
-    for (int b = 0; b < ts; ++b) {
-      const uint8_t* rows = src + (int64_t)b * 8 * row + k;
+  memset(dst, 0, (size_t)(n8 * ts));
+  for (int b = 0; b < ts; ++b) {
+    const uint8_t* rows = src + (int64_t)b * 8 * row;  // the eight bit rows of byte b
+    int64_t k = 0;
+    // 64 elements at a time: one 8-byte word of each bit row.  Count matrices are sparse and their values small, so
+    // most words (all of the high bytes, most high bits) are zero and the elements keep their zero bytes.
+    for (; k + 8 <= row; k += 8) {
+      uint64_t r[8], any = 0;
+      for (int t = 0; t < 8; ++t) {
+        memcpy(&r[t], rows + t * row + k, 8);
+        any |= r[t];
+      }
+      if (!any) continue;
+      for (int j = 0; j < 8; ++j) {
+        uint64_t x = 0;
+        for (int t = 0; t < 8; ++t) x |= ((r[t] >> (8 * j)) & 0xFFull) << (8 * t);
+        if (!x) continue;
+        x = transpose8x8(x);
+        uint8_t* o = dst + (k + j) * 8 * ts + b;
+        for (int e = 0; e < 8; ++e) o[(int64_t)e * ts] = (uint8_t)(x >> (8 * e));
+      }
+    }
+    for (; k < row; ++k) {
       uint64_t x = 0;
-      for (int t = 0; t < 8; ++t) x |= (uint64_t)rows[t * row] << (8 * t);
+      for (int t = 0; t < 8; ++t) x |= (uint64_t)rows[t * row + k] << (8 * t);
       x = transpose8x8(x);
-      for (int e = 0; e < 8; ++e) o[e * ts + b] = (uint8_t)(x >> (8 * e));
+      uint8_t* o = dst + k * 8 * ts + b;
+      for (int e = 0; e < 8; ++e) o[(int64_t)e * ts] = (uint8_t)(x >> (8 * e));
     }
   }
   memcpy(dst + n8 * ts, src + n8 * ts, (size_t)(bsize - n8 * ts));

@@ -60,6 +60,67 @@ def test_blosc_decoder_rejects_what_it_cannot_decode():
     assert blosc_decode(blosc_store(b"", 4)).size == 0
 
 
+def _blosc_encode(raw: bytes, typesize: int, shuffle: int, blocksize: int, dont_split: bool = False) -> bytes:
+    """Test-side Blosc-1 encoder (frame layout as in oracle/blosc_shim.py; LZ4 blocks from pyarrow): shuffle 0 none,
+    1 bytes, 2 bits.  A stream that does not shrink is stored raw (csize == its decoded size), as c-blosc does."""
+    import struct
+
+    import pyarrow as pa
+
+    nbytes = len(raw)
+    flags = (1 << 5) | {0: 0, 1: 0x01, 2: 0x04}[shuffle] | (0x10 if dont_split else 0)
+    nblocks = (nbytes + blocksize - 1) // blocksize
+    body, bstarts = b"", []
+    pos0 = 16 + 4 * nblocks
+    for b in range(nblocks):
+        blk = np.frombuffer(raw[b * blocksize:(b + 1) * blocksize], dtype=np.uint8)
+        bsize = blk.size
+        n = bsize // typesize
+        if shuffle == 1 and typesize > 1:
+            blk = np.concatenate([blk[: n * typesize].reshape(n, typesize).T.reshape(-1), blk[n * typesize:]])
+        elif shuffle == 2:
+            n8 = n - n % 8
+            head = blk[: n8 * typesize]
+            if n8:
+                bits = np.unpackbits(head.reshape(n8, typesize), axis=1, bitorder="little")  # [elem, bit row]
+                head = np.packbits(bits.T.copy(), axis=1, bitorder="little").reshape(-1)
+            blk = np.concatenate([head, blk[n8 * typesize:]])
+        leftover = bsize != blocksize
+        nsplits = typesize if (not dont_split and not leftover and typesize <= 16 and bsize // typesize >= 128) else 1
+        ne = bsize // nsplits
+        bstarts.append(pos0 + len(body))
+        for s_ in range(nsplits):
+            part = blk[s_ * ne:(s_ + 1) * ne].tobytes()
+            comp = pa.compress(part, codec="lz4_raw", asbytes=True)
+            if len(comp) >= ne:
+                comp = part
+            body += struct.pack("<i", len(comp)) + comp
+    head = struct.pack("<BBBBIII", 2, 1, flags, typesize, nbytes, blocksize, pos0 + len(body))
+    return head + struct.pack(f"<{nblocks}i", *bstarts) + body
+
+
+@pytest.mark.parametrize("typesize,shuffle,blocksize,dont_split", [
+    (1, 0, 4096, True), (4, 2, 8192, False), (4, 2, 5000, False), (4, 1, 8192, False), (8, 1, 4096, True),
+    (2, 2, 2048, False), (68, 1, 6800, False), (4, 0, 1 << 20, False), (3, 2, 3000, False)])
+def test_blosc_decoder_round_trips(typesize, shuffle, blocksize, dont_split):
+    """Independent of the reference's fixture: data with every kind of LZ4 match (runs, short periods, long
+    repeats, incompressible stretches), several blocks with a ragged last one, split and unsplit streams."""
+    from oracle.blosc_shim import blosc_decompress
+    from scarf_b200.zarr_store import blosc_decode
+
+    rng = np.random.default_rng(typesize * 100 + shuffle)
+    parts = [np.zeros(3000, np.uint8), rng.integers(0, 256, 2500, dtype=np.uint8)]
+    for period in (1, 2, 3, 5, 7, 8, 9, 16, 33, 200):
+        parts.append(np.tile(rng.integers(0, 256, period, dtype=np.uint8), 4000 // period + 1))
+    counts = (rng.random(6000) < 0.07) * rng.integers(1, 40, 6000)
+    parts.append(counts.astype("<u4").view(np.uint8))
+    raw = np.concatenate(parts).tobytes()
+    raw = raw[: len(raw) - len(raw) % typesize + (typesize // 2)]  # a few bytes past the last whole element
+    frame = _blosc_encode(raw, typesize, shuffle, blocksize, dont_split)
+    assert blosc_decompress(frame) == raw  # the encoder speaks the format the oracle's reader pins on the fixture
+    assert blosc_decode(frame).tobytes() == raw
+
+
 def test_blosc_decoder_threads():
     """the decoder is a pure function: chunks are decoded from a thread pool when a store is read"""
     from concurrent.futures import ThreadPoolExecutor
