@@ -221,6 +221,13 @@ def test_open_reference_written_store(pbmc, tmp_path):
     assert np.array_equal(csr.indptr.cpu().numpy(), want.indptr)
     assert np.array_equal(csr.indices.cpu().numpy(), want.indices)
     assert np.array_equal(csr.data.cpu().numpy().view(np.uint32), want.data)
+    from scarf_b200 import ops
+
+    part = ops.csr_from_dense_zarr(open_group(dst, "r")["RNA/counts"], "cuda", row_range=(0, 500), n_threads=2)
+    assert part.n_rows == 500 and np.array_equal(part.indptr.cpu().numpy(), want.indptr[:501])
+    assert np.array_equal(part.indices.cpu().numpy(), want.indices[: want.indptr[500]])
+    with pytest.raises(ValueError, match="chunk row boundary"):
+        ops.csr_from_dense_zarr(open_group(dst, "r")["RNA/counts"], "cuda", row_range=(100, 500))
     dense = want.toarray().astype(np.int64)
     n_feats = (dense > 0).sum(1)
     assert np.array_equal(ds.cells.fetch_all("RNA_nCounts"), dense.sum(1).astype(np.float64))
