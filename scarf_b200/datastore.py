@@ -612,12 +612,8 @@ class DataStore:
                                       "exclude_missing=False, filter_null=False, feat_scaling=True)")
         target_assay.sf = source.sf
         feat_col = cell_key + "__" + feat_key if feat_key != "I" else "I"
-        s_ids = source.feats.fetch_all("ids")
         s_feat_idx = np.where(source.feats.fetch_all(feat_col))[0]
-        pos = {v: i for i, v in enumerate(target_assay.feats.fetch_all("ids"))}
-        t_col = np.array([pos.get(s_ids[i], -1) for i in s_feat_idx], dtype=np.int64)  # mapping_utils.py:98-145
-        if np.all(t_col == -1):
-            raise ValueError("ERROR: None of the features from reference were found in the target data")
+        t_col = graph.order_features(source.feats.fetch_all("ids"), target_assay.feats.fetch_all("ids"), s_feat_idx)
         ann_obj = self.make_graph(from_assay=from_assay, cell_key=cell_key, feat_key=feat_key,
                                   return_ann_object=True, update_keys=False)
         if save_k > ann_obj.k:

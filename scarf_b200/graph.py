@@ -124,8 +124,10 @@ class GraphResult:
 
 
 def clean_array(x, fill_val=0.0):
-    """scarf/utils.py:143-153."""
-    x = torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)
+    """scarf/utils.py:143-153: NaN -> 0, then zeros -> ``fill_val``.  As executed, the reference's ``np.nan_to_num``
+    has already turned +-inf into +-the largest float64 when its ``x == inf`` line runs, so infinities do NOT become
+    zero (tests/golden/ref_functions.npz, made by running the reference function); same here."""
+    x = torch.nan_to_num(x)
     return torch.where(x == 0, torch.full_like(x, fill_val), x)
 
 
@@ -549,6 +551,17 @@ def run_mapping_csr(target: CsrDevice, target_cell_idx, t_col_of_feature, ref_mu
 # =============================================================================================
 # small pieces of the AnnStream contract
 # =============================================================================================
+def order_features(source_ids, target_ids, source_feat_idx) -> np.ndarray:
+    """``_order_features`` with its defaults exclude_missing=False / filter_null=False (scarf/mapping_utils.py:98-145):
+    for every source feature the graph was built on (``source_feat_idx``: ascending positions in the source feature
+    table), its column in the target matrix, matched by feature id, or -1 when the target lacks it."""
+    pos = {v: i for i, v in enumerate(target_ids)}
+    t_col = np.array([pos.get(source_ids[i], -1) for i in source_feat_idx], dtype=np.int64)
+    if t_col.size == 0 or np.all(t_col == -1):
+        raise ValueError("ERROR: None of the features from reference were found in the target data")
+    return t_col
+
+
 def fix_knn_query(indices: np.ndarray, distances: np.ndarray, ref_idx: np.ndarray):
     """scarf/ann.py:31-52: drop each query's own hit from a (k+1)-neighbour result -- column 0 when it is the query
     itself, else wherever the query is found, else the last column.  Returns (indices, distances, n_not_first)."""

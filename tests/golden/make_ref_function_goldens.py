@@ -1,0 +1,98 @@
+"""Generates tests/golden/ref_functions.npz by EXECUTING reference functions of the path on seeded inputs.
+
+The reference package cannot be imported here (`import scarf` needs dask / zarr / numcodecs / hnswlib), but the
+functions below are plain numpy / pandas code: their source is cut out of the reference files with `ast` and executed
+unchanged (nothing is copied into this repository; the GPU box never runs this script).
+
+    python tests/golden/make_ref_function_goldens.py        (needs /root/reference)
+
+Functions executed (reference file:lines) and the scope-table rows they pin:
+  norm_lib_size, norm_lib_size_log   scarf/assay.py:41-64       a4  (library-size normalisation, log1p)
+  clean_array                        scarf/utils.py:143-153     a6  (mu / sigma clean-up)
+  fix_knn_query                      scarf/ann.py:31-52         a10 (self removal in a k+1 query result)
+  _order_features                    scarf/mapping_utils.py:98-145  a14 (source / target feature alignment)
+The per-cell scalar of the renormalised branch (`RNAassay.normed`, scarf/assay.py:814-823) is inline code of a method
+that needs a store; the three lines are restated below where the scalar is built.
+"""
+import ast
+import os
+from types import SimpleNamespace
+from typing import Tuple
+
+import numpy as np
+import pandas as pd
+
+REF = "/root/reference/scarf"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_functions.npz")
+
+
+def ref_function(rel_path, name, extra=None):
+    with open(os.path.join(REF, rel_path)) as f:
+        src = f.read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"np": np, "pd": pd, "Tuple": Tuple, "daskArrayType": object, "__name__": "ref"}
+    ns.update(extra or {})
+    exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REF, rel_path), "exec"), ns)
+    return ns[name]
+
+
+rng = np.random.default_rng(20261017)
+out = {}
+
+# ---- a4: normalisation ------------------------------------------------------------------------------------------
+norm_lib_size = ref_function("assay.py", "norm_lib_size")
+norm_lib_size_log = ref_function("assay.py", "norm_lib_size_log")
+counts = ((rng.random((60, 90)) < 0.15) * rng.integers(1, 200, (60, 90))).astype(np.uint32)
+counts[7] = 0  # a cell without any count
+feat_idx = np.sort(rng.choice(90, 25, replace=False))
+cell_idx = np.sort(rng.choice(60, 50, replace=False))
+cell_idx = np.union1d(cell_idx, [7])
+sub = counts[cell_idx][:, feat_idx]
+scalar = sub.sum(axis=1)  # assay.py:819-823: counts.sum(axis=1) over the feature subset, zeros replaced by one
+scalar[scalar == 0] = 1
+assay = SimpleNamespace(sf=1000, scalar=scalar)
+out.update(norm_counts=counts, norm_cell_idx=cell_idx, norm_feat_idx=feat_idx,
+           norm_lib_size=np.asarray(norm_lib_size(assay, sub), dtype=np.float64),
+           norm_lib_size_log=np.asarray(norm_lib_size_log(assay, sub), dtype=np.float64))
+n_counts = counts.sum(axis=1).astype(np.float64)  # renormalize_subset=False: scalar = nCounts of the cells
+n_counts[n_counts == 0] = 1
+assay_nc = SimpleNamespace(sf=1000, scalar=n_counts[cell_idx])
+out.update(norm_n_counts=n_counts, norm_lib_size_log_ncounts=np.asarray(norm_lib_size_log(assay_nc, sub), dtype=np.float64))
+
+# ---- a6: clean_array ----------------------------------------------------------------------------------------------
+clean_array = ref_function("utils.py", "clean_array")
+x = rng.normal(size=40)
+x[[1, 5, 9, 13, 17, 21]] = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-300]
+out.update(clean_in=x, clean_fill0=clean_array(x.copy()), clean_fill1=clean_array(x.copy(), 1))
+
+# ---- a10: fix_knn_query -------------------------------------------------------------------------------------------
+fix_knn_query = ref_function("ann.py", "fix_knn_query")
+n, k1 = 30, 6
+ind = np.stack([rng.choice(200, k1, replace=False) for _ in range(n)]).astype(np.uint64)
+ref_idx = np.arange(100, 100 + n).astype(np.uint64)
+dist = np.sort(rng.random((n, k1)).astype(np.float32), axis=1)
+for r in range(n):
+    ind[r][ind[r] == ref_idx[r]] = 999  # no accidental self
+    mode = r % 3
+    if mode == 0:
+        ind[r, 0] = ref_idx[r]  # self found first (the normal case)
+    elif mode == 1:
+        ind[r, 1 + r % (k1 - 1)] = ref_idx[r]  # self found further down (ties / approximate search)
+    # mode 2: self not found at all -> the last neighbour is dropped
+fi, fd, n_mis = fix_knn_query(ind, dist, ref_idx)
+out.update(fix_ind=ind, fix_dist=dist, fix_ref_idx=ref_idx, fix_out_ind=fi, fix_out_dist=fd, fix_n_mis=np.int64(n_mis))
+
+# ---- a14: _order_features -----------------------------------------------------------------------------------------
+order = ref_function("mapping_utils.py", "_order_features", {"logger": SimpleNamespace(warning=lambda *a, **k: None),
+                                                            "controlled_compute": None})
+s_ids = np.array([f"G{i:03d}" for i in range(40)])
+t_ids = np.array([f"G{i:03d}" for i in rng.permutation(60)[:35]] + ["X1", "X2"])  # reordered, some missing, some extra
+s_feat_ids = s_ids[np.sort(rng.choice(40, 18, replace=False))]
+mk = lambda ids: SimpleNamespace(feats=SimpleNamespace(fetch_all=lambda col, ids=ids: ids))
+s_idx, t_re_idx = order(mk(s_ids), mk(t_ids), s_feat_ids, filter_null=False, exclude_missing=False, nthreads=1)
+out.update(order_s_ids=s_ids, order_t_ids=t_ids, order_s_feat_ids=s_feat_ids, order_s_idx=np.asarray(s_idx, dtype=np.int64),
+           order_t_re_idx=np.asarray(t_re_idx, dtype=np.int64))
+
+np.savez_compressed(OUT, **out)
+print("ok", OUT, os.path.getsize(OUT), "bytes;", "mismatching self rows:", int(n_mis), "; missing target features:",
+      int((np.asarray(t_re_idx) == -1).sum()))

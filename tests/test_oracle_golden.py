@@ -4,9 +4,12 @@ The goldens were produced by the reference chain auto_filter_cells -> mark_hvgs(
 make_graph(feat_key='hvgs') (scarf/tests/fixtures_datastore.py:58-73) on the PBMC fixture.
 hnswlib is approximate, so the index pin is a stated recall / identical-row fraction.
 """
+import os
+
 import numpy as np
 import pytest
 
+from conftest import GOLDEN
 from oracle import pipeline as P
 
 
@@ -114,3 +117,56 @@ def test_aligned_target_missing_features_and_order():
     tot = sub.sum(1, keepdims=True)
     tot[tot == 0] = 1
     np.testing.assert_allclose(a[:, [0, 1, 3, 4]], np.log1p(1000 * sub / tot), rtol=1e-12)
+
+
+# ---- goldens produced by EXECUTING reference functions (tests/golden/make_ref_function_goldens.py) -----------------
+@pytest.fixture(scope="module")
+def ref_fn():
+    return np.load(os.path.join(GOLDEN, "ref_functions.npz"))
+
+
+def test_normalisation_equals_reference_functions(ref_fn):
+    """a4: norm_lib_size / norm_lib_size_log (scarf/assay.py:41-64) executed from the reference's source; the oracle
+    restatement gives the same float64 bits, for the renormalised scalar and for nCounts."""
+    import scipy.sparse as sp
+
+    c = sp.csr_matrix(ref_fn["norm_counts"])
+    ci, fi = ref_fn["norm_cell_idx"], ref_fn["norm_feat_idx"]
+    assert np.array_equal(P.normed_hvg(c, ci, fi), ref_fn["norm_lib_size_log"])
+    assert np.array_equal(P.normed_hvg(c, ci, fi, log_transform=False), ref_fn["norm_lib_size"])
+    assert np.array_equal(P.normed_hvg(c, ci, fi, renormalize_subset=False, n_counts=ref_fn["norm_n_counts"]),
+                          ref_fn["norm_lib_size_log_ncounts"])
+    assert (ref_fn["norm_lib_size_log"][list(ci).index(7)] == 0).all()  # the empty cell: scalar 0 -> 1, values 0
+
+
+def test_clean_array_equals_reference_function(ref_fn):
+    """a6: clean_array (scarf/utils.py:143-153): oracle and the product's tensor version."""
+    import torch
+
+    from scarf_b200 import graph
+
+    for fill, key in ((0, "clean_fill0"), (1, "clean_fill1")):
+        assert np.array_equal(P.clean_array(ref_fn["clean_in"].copy(), fill), ref_fn[key])
+        got = graph.clean_array(torch.from_numpy(ref_fn["clean_in"].copy()), float(fill)).numpy()
+        assert np.array_equal(got, ref_fn[key])
+
+
+def test_fix_knn_query_equals_reference_function(ref_fn):
+    """a10: fix_knn_query (scarf/ann.py:31-52) on rows with the self hit first, further down, and missing."""
+    from scarf_b200.graph import fix_knn_query
+
+    i, d, n_mis = fix_knn_query(ref_fn["fix_ind"], ref_fn["fix_dist"], ref_fn["fix_ref_idx"])
+    assert np.array_equal(i, ref_fn["fix_out_ind"]) and np.array_equal(d, ref_fn["fix_out_dist"])
+    assert n_mis == int(ref_fn["fix_n_mis"]) == 20
+
+
+def test_order_features_equals_reference_function(ref_fn):
+    """a14: _order_features (scarf/mapping_utils.py:98-145, defaults): oracle and the product's host routine."""
+    from scarf_b200.graph import order_features
+
+    s_ids, t_ids, want = ref_fn["order_s_ids"], ref_fn["order_t_ids"], ref_fn["order_t_re_idx"]
+    s_idx, t_re = P.order_features(s_ids, t_ids, ref_fn["order_s_feat_ids"])
+    assert np.array_equal(s_idx, ref_fn["order_s_idx"]) and np.array_equal(t_re, want)
+    assert np.array_equal(order_features(s_ids, t_ids, ref_fn["order_s_idx"]), want) and (want == -1).sum() == 7
+    with pytest.raises(ValueError, match="None of the features"):
+        order_features(s_ids, np.array(["Q1", "Q2"]), ref_fn["order_s_idx"])
