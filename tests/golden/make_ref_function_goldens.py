@@ -11,6 +11,10 @@ Functions executed (reference file:lines) and the scope-table rows they pin:
   clean_array                        scarf/utils.py:143-153     a6  (mu / sigma clean-up)
   fix_knn_query                      scarf/ann.py:31-52         a10 (self removal in a k+1 query result)
   _order_features                    scarf/mapping_utils.py:98-145  a14 (source / target feature alignment)
+  fit_lowess                         scarf/feat_utils.py:11-45  a3  (log-log binning, minimum-variance gene per bin,
+                                     corrected variance) -- executed with statsmodels' `lowess` (not installed) replaced
+                                     by the restated smoother oracle/lowess.py: everything around the smoother is the
+                                     reference's own code
 The per-cell scalar of the renormalised branch (`RNAassay.normed`, scarf/assay.py:814-823) is inline code of a method
 that needs a store; the three lines are restated below where the scalar is built.
 """
@@ -92,6 +96,24 @@ mk = lambda ids: SimpleNamespace(feats=SimpleNamespace(fetch_all=lambda col, ids
 s_idx, t_re_idx = order(mk(s_ids), mk(t_ids), s_feat_ids, filter_null=False, exclude_missing=False, nthreads=1)
 out.update(order_s_ids=s_ids, order_t_ids=t_ids, order_s_feat_ids=s_feat_ids, order_s_idx=np.asarray(s_idx, dtype=np.int64),
            order_t_re_idx=np.asarray(t_re_idx, dtype=np.int64))
+
+# ---- a3: fit_lowess (binning + corrected variance; the smoother itself is the oracle's restatement) -------------------
+import sys
+import types
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle.lowess import lowess as oracle_lowess  # noqa: E402
+
+sm = types.ModuleType("statsmodels.nonparametric.smoothers_lowess")
+sm.lowess = lambda endog, exog, return_sorted=False, frac=2.0 / 3.0, it=3: oracle_lowess(endog, exog, frac=frac, it=it)
+for name in ("statsmodels", "statsmodels.nonparametric"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["statsmodels.nonparametric.smoothers_lowess"] = sm
+fit_lowess = ref_function("feat_utils.py", "fit_lowess")
+n_genes = 3000
+mean = rng.gamma(0.3, 1.0, n_genes) + 1e-4  # gene means over four decades, variance ~ mean * (1 + mean * dispersion)
+var = mean * (1.0 + mean * rng.gamma(2.0, 0.5, n_genes)) * np.exp(rng.normal(0.0, 0.3, n_genes))
+out.update(lowess_avg=mean, lowess_var=var, lowess_c_var=np.asarray(fit_lowess(mean, var, 200, 0.1), dtype=np.float64))
 
 np.savez_compressed(OUT, **out)
 print("ok", OUT, os.path.getsize(OUT), "bytes;", "mismatching self rows:", int(n_mis), "; missing target features:",
