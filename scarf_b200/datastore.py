@@ -298,7 +298,8 @@ class DataStore:
         mask, st = graph.mark_hvgs_csr(assay.csr, cells, feat_I, n_counts, self.cells.N,
                                        gene_names=assay.feats.fetch_all("names"), top_n=top_n, min_cells=min_cells,
                                        min_mean=min_mean, max_mean=max_mean, n_bins=n_bins, lowess_frac=lowess_frac,
-                                       blacklist=blacklist, comm=self.comm, return_stats=True)
+                                       blacklist=blacklist, comm=self.comm, return_stats=True, min_var=min_var,
+                                       max_var=max_var)
         ident = f"{cell_key}__"
         for name, col in (("normed_tot", "normed_tot"), ("avg", "avg"), ("nz_mean", "nz_mean"),
                           ("sigmas", "sigmas"), ("normed_n", "normed_n"), ("c_var", f"c_var__{n_bins}__{lowess_frac}")):

@@ -113,29 +113,30 @@ def remove_trend(avg, sigmas, n_bins=200, lowess_frac=0.1, fill_value=0.0):
 
 
 def choose_hvgs(normed_n, nz_mean, c_var, feat_I, gene_names=None, top_n=500, min_cells=0, max_cells=np.inf,
-                min_mean=-np.inf, max_mean=np.inf, min_var=None, max_var=np.inf, blacklist=DEFAULT_BLACKLIST):
-    """scarf/assay.py:1014-1063 + MetaData.multi_sift (scarf/metadata.py:483-533): strict bounds, then the
-    ``top_n`` largest corrected variances.  All vectors cover every gene (NaN outside ``feat_I``)."""
+                min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf, blacklist=DEFAULT_BLACKLIST):
+    """scarf/assay.py:1014-1063 + MetaData.multi_sift (scarf/metadata.py:483-533): strict bounds; with
+    ``min_var == -inf`` (the default) the threshold is the (top_n + 1)-th largest corrected variance of the eligible
+    genes, otherwise ``top_n`` is ignored and ``2**min_var`` is the threshold; ``c_var < 2**max_var`` applies in both
+    modes.  Mean / variance bounds are given in log2 and only exponentiated when finite.  All vectors cover every
+    gene (NaN outside ``feat_I``).  Pinned on the executed reference method (tests/golden/ref_functions.npz)."""
     g = normed_n.size
-    if blacklist and gene_names is not None:
-        pat = re.compile(blacklist)
-        keep = np.fromiter((pat.search(str(x)) is None for x in gene_names), dtype=bool, count=g)
-    else:
-        keep = np.ones(g, dtype=bool)
-    # thresholds are given in log2 and only exponentiated when finite (scarf/assay.py:1014-1021)
+    keep = blacklist_keep_mask(gene_names, g, blacklist)
     min_mean = 2.0 ** min_mean if min_mean != -np.inf else min_mean
     max_mean = 2.0 ** max_mean if max_mean != np.inf else max_mean
+    max_var = 2.0 ** max_var if max_var != np.inf else max_var
     with np.errstate(invalid="ignore"):
         idx = (normed_n > min_cells) & (normed_n < max_cells) & (nz_mean > min_mean) & (nz_mean < max_mean)
         idx &= feat_I & keep
-        if top_n is not None:
+        if min_var == -np.inf:
+            if top_n < 1:
+                raise ValueError("ERROR: Please provide a value greater than 0 for `top_n` parameter")
             n_valid = int(idx.sum())
             if top_n > n_valid:
                 top_n = n_valid - 1
             min_var = np.sort(c_var[idx])[::-1][top_n]
         else:
             min_var = 2.0 ** min_var
-        hv = idx & (c_var > min_var) & (c_var < (np.inf if top_n is not None else 2.0 ** max_var))
+        hv = idx & (c_var > min_var) & (c_var < max_var)
     return hv
 
 
@@ -144,10 +145,12 @@ def choose_hvgs(normed_n, nz_mean, c_var, feat_I, gene_names=None, top_n=500, mi
 # the <= n_bins binned points cross to the host for the LOWESS fit.  Used by graph.mark_hvgs_csr.
 # =============================================================================================
 def blacklist_keep_mask(gene_names, n_genes, blacklist=DEFAULT_BLACKLIST):
-    """bool numpy mask of the genes that survive the blacklist regex (static per dataset)."""
+    """bool numpy mask of the genes that survive the blacklist regex (static per dataset).  As the reference does it
+    (MetaData.grep, scarf/metadata.py:569-584): names AND pattern are upper-cased, the pattern must match at the
+    start of the name (``re.match``)."""
     if blacklist and gene_names is not None:
-        pat = re.compile(blacklist)
-        return np.fromiter((pat.search(str(x)) is None for x in gene_names), dtype=bool, count=n_genes)
+        pat = re.compile(blacklist.upper())
+        return np.fromiter((pat.match(str(x).upper()) is None for x in gene_names), dtype=bool, count=n_genes)
     return np.ones(n_genes, dtype=bool)
 
 
@@ -205,20 +208,23 @@ def remove_trend_device(avg, sigmas, n_bins=200, lowess_frac=0.1, select=None):
 
 
 def choose_hvgs_device(normed_n, nz_mean, c_var, eligible, top_n=500, min_cells=0, max_cells=np.inf,
-                       min_mean=-np.inf, max_mean=np.inf, min_var=None, max_var=np.inf):
+                       min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf):
     """:func:`choose_hvgs` on device vectors; ``eligible`` = feat_I & blacklist-keep (bool tensor).  No
     synchronisation: the (top_n+1)-th largest corrected variance is picked with a device-side index."""
     import torch
 
     min_mean = 2.0 ** min_mean if min_mean != -np.inf else min_mean
     max_mean = 2.0 ** max_mean if max_mean != np.inf else max_mean
+    max_var = 2.0 ** max_var if max_var != np.inf else max_var
     idx = (normed_n > min_cells) & (normed_n < max_cells) & (nz_mean > min_mean) & (nz_mean < max_mean) & eligible
     idx = idx & ~torch.isnan(c_var)
-    if top_n is not None:
+    if min_var == -np.inf:
+        if top_n < 1:
+            raise ValueError("ERROR: Please provide a value greater than 0 for `top_n` parameter")
         ninf = torch.full_like(c_var, float("-inf"))
         cv = torch.sort(torch.where(idx, c_var, ninf), descending=True).values
         n_valid = idx.sum()
         kk = torch.minimum(torch.full_like(n_valid, int(top_n)), n_valid - 1).clamp(min=0)  # assay.py:1035-1040
         thr = cv[kk]
-        return idx & (c_var > thr)
-    return idx & (c_var > 2.0 ** min_var) & (c_var < 2.0 ** max_var)
+        return idx & (c_var > thr) & (c_var < max_var)
+    return idx & (c_var > 2.0 ** min_var) & (c_var < max_var)

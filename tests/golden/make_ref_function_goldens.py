@@ -15,6 +15,10 @@ Functions executed (reference file:lines) and the scope-table rows they pin:
                                      corrected variance) -- executed with statsmodels' `lowess` (not installed) replaced
                                      by the restated smoother oracle/lowess.py: everything around the smoother is the
                                      reference's own code
+  RNAassay.mark_hvgs                 scarf/assay.py:945-1063    a3  (HVG choice) -- the method body after
+                                     `set_summary_stats`, run on a stub assay whose feature table serves columns from
+                                     a dict through the reference's own MetaData.sift / multi_sift / grep /
+                                     get_index_by / index_to_bool (scarf/metadata.py:339-394,483-533,569-584)
 The per-cell scalar of the renormalised branch (`RNAassay.normed`, scarf/assay.py:814-823) is inline code of a method
 that needs a store; the three lines are restated below where the scalar is built.
 """
@@ -30,10 +34,14 @@ REF = "/root/reference/scarf"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_functions.npz")
 
 
-def ref_function(rel_path, name, extra=None):
+def ref_function(rel_path, name, extra=None, cls=None):
+    """The function `name` of a reference file (a method of class `cls` when given), compiled from its own source."""
     with open(os.path.join(REF, rel_path)) as f:
         src = f.read()
-    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    body = ast.parse(src).body
+    if cls is not None:
+        body = next(n for n in body if isinstance(n, ast.ClassDef) and n.name == cls).body
+    node = next(n for n in body if isinstance(n, ast.FunctionDef) and n.name == name)
     ns = {"np": np, "pd": pd, "Tuple": Tuple, "daskArrayType": object, "__name__": "ref"}
     ns.update(extra or {})
     exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REF, rel_path), "exec"), ns)
@@ -114,6 +122,62 @@ n_genes = 3000
 mean = rng.gamma(0.3, 1.0, n_genes) + 1e-4  # gene means over four decades, variance ~ mean * (1 + mean * dispersion)
 var = mean * (1.0 + mean * rng.gamma(2.0, 0.5, n_genes)) * np.exp(rng.normal(0.0, 0.3, n_genes))
 out.update(lowess_avg=mean, lowess_var=var, lowess_c_var=np.asarray(fit_lowess(mean, var, 200, 0.1), dtype=np.float64))
+
+# ---- a3: RNAassay.mark_hvgs (the HVG choice) -------------------------------------------------------------------------
+import re
+from typing import Any, Iterable, List, Optional
+
+quiet = SimpleNamespace(info=lambda *a, **k: None, warning=lambda *a, **k: None)
+md_ns = {"re": re, "Iterable": Iterable, "List": List, "Any": Any, "Optional": Optional, "logger": quiet,
+         "_all_true": ref_function("metadata.py", "_all_true")}
+
+
+class FeatureTable:
+    """Columns from a dict; every other method is the reference's MetaData code."""
+
+    def __init__(self, cols):
+        self.cols, self.N = dict(cols), len(cols["I"])
+
+    def fetch_all(self, column):
+        return self.cols[column]
+
+    def insert(self, column_name, values, fill_value=np.nan, key="I", overwrite=False, location="primary"):
+        self.cols[column_name] = np.asarray(values)
+
+
+for m in ("sift", "multi_sift", "grep", "get_index_by", "index_to_bool"):
+    setattr(FeatureTable, m, ref_function("metadata.py", m, md_ns, cls="MetaData"))
+mark_hvgs = ref_function("assay.py", "mark_hvgs", {"logger": quiet}, cls="RNAassay")
+
+g = 1200
+names = np.array([f"Gene{i}" for i in range(g)], dtype=object)
+for i, nm in zip(rng.choice(g, 14, replace=False), ["MT-CO1", "mt-Co2", "Rps3", "RPL13", "Mrps7", "MRPL2", "Ccnb1", "HLA-A",
+                                                     "H2-K1", "Hist1h1a", "hist2h2aa", "xMT-1", "RPS", "Hla-dra"]):
+    names[i] = nm
+names = names.astype("U")
+feat_I = rng.random(g) < 0.85
+normed_n = np.floor(rng.gamma(2.0, 200.0, g))
+nz_mean = rng.gamma(1.5, 1.0, g) + 0.05
+c_var = np.exp(rng.normal(0.0, 0.6, g))
+c_var[rng.choice(g, 6, replace=False)] = c_var[0]  # ties at arbitrary places
+c_var[~feat_I] = 0.0  # what MetaData.insert leaves outside the active rows (fill value of remove_trend's column)
+cases = [dict(top_n=100, min_cells=8, max_cells=np.inf, min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf),
+         dict(top_n=40, min_cells=50, max_cells=900.0, min_mean=-2.0, max_mean=1.5, min_var=-np.inf, max_var=np.inf),
+         dict(top_n=5000, min_cells=8, max_cells=np.inf, min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf),
+         dict(top_n=10, min_cells=8, max_cells=np.inf, min_mean=-np.inf, max_mean=np.inf, min_var=-0.5, max_var=1.0)]
+out.update(hvg_names=names, hvg_feat_I=feat_I, hvg_normed_n=normed_n, hvg_nz_mean=nz_mean, hvg_c_var=c_var,
+           hvg_blacklist=np.array("^MT-|^RPS|^RPL|^MRPS|^MRPL|^CCN|^HLA-|^H2-|^HIST"))
+for ci, case in enumerate(cases):
+    feats = FeatureTable({"I": feat_I, "names": names, "I__normed_n": normed_n, "I__nz_mean": nz_mean,
+                          "I__c_var__200__0.1": c_var})
+    stub = SimpleNamespace(feats=feats, set_summary_stats=lambda ck, nb, lf: ("I_", "c_var__200__0.1"))
+    # col_renamer gives f"{identifier}_{x}": identifier "I_" -> columns "I__normed_n", ... (scarf/assay.py:1007-1011)
+    mark_hvgs(stub, cell_key="I", n_bins=200, lowess_frac=0.1, blacklist=str(out["hvg_blacklist"]), hvg_key_name="hvgs",
+              keep_bounds=False, show_plot=False, **case)
+    out[f"hvg_case{ci}_params"] = np.array([case[k_] for k_ in ("top_n", "min_cells", "max_cells", "min_mean", "max_mean",
+                                                               "min_var", "max_var")], dtype=np.float64)
+    out[f"hvg_case{ci}_mask"] = feats.cols["I__hvgs"].astype(bool)
+    print("hvg case", ci, int(out[f"hvg_case{ci}_mask"].sum()))
 
 np.savez_compressed(OUT, **out)
 print("ok", OUT, os.path.getsize(OUT), "bytes;", "mismatching self rows:", int(n_mis), "; missing target features:",

@@ -183,3 +183,32 @@ def test_fit_lowess_equals_reference_function(ref_fn):
     np.testing.assert_allclose(P.fit_lowess(a, b, 200, 0.1), want, rtol=5e-16, atol=0)
     np.testing.assert_allclose(hvg.fit_lowess(a, b, 200, 0.1), want, rtol=1e-10)
     assert np.isfinite(want).all() and want.min() > 0
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_hvg_choice_equals_reference_method(ref_fn, case):
+    """a3: RNAassay.mark_hvgs (scarf/assay.py:945-1063) executed on a stub assay through the reference's own
+    MetaData.sift / multi_sift / grep / get_index_by: default top-n rule, log2 mean bounds with max_cells, top_n larger
+    than the number of eligible genes, explicit min_var / max_var (top_n then ignored).  Gene names include lower-case
+    spellings the blacklist still catches (names and pattern are upper-cased, `re.match`).  Oracle, product host
+    routine and product tensor routine give the same mask."""
+    import torch
+
+    from scarf_b200 import hvg
+
+    top_n, min_cells, max_cells, min_mean, max_mean, min_var, max_var = ref_fn[f"hvg_case{case}_params"]
+    want = ref_fn[f"hvg_case{case}_mask"]
+    names, feat_I = ref_fn["hvg_names"], ref_fn["hvg_feat_I"]
+    nn, nz, cv = ref_fn["hvg_normed_n"], ref_fn["hvg_nz_mean"], ref_fn["hvg_c_var"]
+    bl = str(ref_fn["hvg_blacklist"])
+    kw = dict(top_n=int(top_n), min_cells=min_cells, max_cells=max_cells, min_mean=min_mean, max_mean=max_mean,
+              min_var=min_var, max_var=max_var)
+    assert np.array_equal(P.choose_hvgs(nn, nz, cv, feat_I, names, blacklist=bl, **kw), want)
+    assert np.array_equal(hvg.choose_hvgs(nn, nz, cv, feat_I, names, blacklist=bl, **kw), want)
+    keep = hvg.blacklist_keep_mask(names, len(names), bl)
+    assert (~keep).sum() == 13  # every planted name but "xMT-1" (the pattern is anchored at the start)
+    t = lambda a: torch.from_numpy(np.asarray(a))
+    got = hvg.choose_hvgs_device(t(nn), t(nz), t(cv), t(feat_I & keep), **kw).numpy()
+    assert np.array_equal(got, want)
+    with pytest.raises(ValueError, match="greater than 0"):
+        hvg.choose_hvgs(nn, nz, cv, feat_I, names, top_n=0)
