@@ -19,6 +19,10 @@ Functions executed (reference file:lines) and the scope-table rows they pin:
                                      `set_summary_stats`, run on a stub assay whose feature table serves columns from
                                      a dict through the reference's own MetaData.sift / multi_sift / grep /
                                      get_index_by / index_to_bool (scarf/metadata.py:339-394,483-533,569-584)
+  AnnStream._fit_pca, transform_z    scarf/ann.py:191-192,207-256  a8 (the block loop around sklearn's IncrementalPCA:
+                                     first block kept as the end reservoir, carry-over of blocks shorter than
+                                     dims + 1, one extra component dropped) -- run on a stub stream of numpy blocks
+                                     with the installed scikit-learn (1.9; the reference pins 1.6.1, same algorithm)
 The per-cell scalar of the renormalised branch (`RNAassay.normed`, scarf/assay.py:814-823) is inline code of a method
 that needs a store; the three lines are restated below where the scalar is built.
 """
@@ -178,6 +182,33 @@ for ci, case in enumerate(cases):
                                                                "min_var", "max_var")], dtype=np.float64)
     out[f"hvg_case{ci}_mask"] = feats.cols["I__hvgs"].astype(bool)
     print("hvg case", ci, int(out[f"hvg_case{ci}_mask"].sum()))
+
+# ---- a8: AnnStream._fit_pca (IncrementalPCA block loop) --------------------------------------------------------------
+ann_ns = {"logger": quiet}
+fit_pca = ref_function("ann.py", "_fit_pca", ann_ns, cls="AnnStream")
+transform_z = ref_function("ann.py", "transform_z", ann_ns, cls="AnnStream")
+n_pca, h_pca, dims_pca, bs = 2005, 40, 7, 1000  # blocks of 1000, 1000 and 5 rows: the last one is shorter than dims + 1
+lat = rng.normal(size=(n_pca, 10)) * (3.0 * 0.8 ** np.arange(10))
+x_pca = np.abs(lat @ rng.normal(size=(10, h_pca)) + rng.normal(size=(n_pca, h_pca)))
+mu_pca, sigma_pca = x_pca.mean(axis=0), x_pca.std(axis=0)
+
+
+class Stream:
+    def __init__(self):
+        self.dims, self.batchSize, self.nCells, self.mu, self.sigma = dims_pca, bs, n_pca, mu_pca, sigma_pca
+
+    def iter_blocks(self, msg=""):
+        for s_ in range(0, n_pca, bs):
+            yield x_pca[s_:s_ + bs]
+
+    transform_z = transform_z
+
+
+st = Stream()
+fit_pca(st, False, np.ones(n_pca, dtype=bool))
+out.update(pca_x=x_pca, pca_mu=mu_pca, pca_sigma=sigma_pca, pca_dims=np.int64(dims_pca), pca_batch=np.int64(bs),
+           pca_loadings=st.loadings.copy())
+print("ipca loadings", st.loadings.shape)
 
 np.savez_compressed(OUT, **out)
 print("ok", OUT, os.path.getsize(OUT), "bytes;", "mismatching self rows:", int(n_mis), "; missing target features:",

@@ -212,3 +212,13 @@ def test_hvg_choice_equals_reference_method(ref_fn, case):
     assert np.array_equal(got, want)
     with pytest.raises(ValueError, match="greater than 0"):
         hvg.choose_hvgs(nn, nz, cv, feat_I, names, top_n=0)
+
+
+def test_ipca_loop_equals_reference_method(ref_fn):
+    """a8: AnnStream._fit_pca (scarf/ann.py:207-256) executed on a stub stream of numpy blocks -- first block held back
+    as the end reservoir, a last block shorter than dims + 1 carried over, dims + 1 components fitted and the last one
+    dropped -- against the oracle's restatement of the loop (same scikit-learn underneath)."""
+    got = P.ipca_loadings(ref_fn["pca_x"], ref_fn["pca_mu"], ref_fn["pca_sigma"], int(ref_fn["pca_dims"]),
+                          int(ref_fn["pca_batch"]))
+    assert got.shape == ref_fn["pca_loadings"].shape == (40, 7)
+    np.testing.assert_allclose(got, ref_fn["pca_loadings"], rtol=0, atol=1e-12)
