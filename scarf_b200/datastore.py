@@ -566,11 +566,11 @@ class DataStore:
         return self.zw[knn_loc].attrs["latest_graph"]
 
     def load_graph(self, from_assay: Optional[str] = None, cell_key: Optional[str] = None,
-                   feat_key: Optional[str] = None, symmetric: bool = True, upper_only: bool = True,
-                   use_k: Optional[int] = None, graph_loc: Optional[str] = None):
-        """graph_datastore.py:1022-1075 + _store_to_sparse :474-511 -> scipy CSR."""
-        from scipy.sparse import csr_matrix, triu
-
+                   feat_key: Optional[str] = None, symmetric: Optional[bool] = None,
+                   upper_only: Optional[bool] = None, use_k: Optional[int] = None, graph_loc: Optional[str] = None):
+        """graph_datastore.py:1022-1075 + _store_to_sparse :474-511 -> scipy sparse matrix.  As in the reference the
+        defaults (None) return the stored, directed graph; ``symmetric=True`` gives ``g + g.T - g * g.T`` and
+        ``upper_only=True`` its upper triangle (what run_leiden / run_umap ask for)."""
         from_assay, cell_key, feat_key = self._get_latest_keys(from_assay, cell_key, feat_key)
         if graph_loc is None:
             graph_loc = self._get_latest_graph_loc(from_assay, cell_key, feat_key)
@@ -580,17 +580,7 @@ class DataStore:
         knn_loc = graph_loc.rsplit("/", 1)[0]
         n_cells, k = self.zw[knn_loc]["indices"].shape
         store = self.zw[graph_loc]
-        edges, weights = store["edges"][:], store["weights"][:]
-        if use_k is not None and 0 < use_k < k:  # the first use_k of every row's k entries
-            keep = (np.arange(edges.shape[0]) % k) < use_k
-            edges, weights = edges[keep], weights[keep]
-        g = csr_matrix((weights, (edges[:, 0].astype(np.int64), edges[:, 1].astype(np.int64))),
-                       shape=(n_cells, n_cells))
-        if symmetric:
-            g = g + g.T - g.multiply(g.T)  # graph_datastore.py:1067-1070
-            if upper_only:
-                g = triu(g)
-        return g.tocsr()
+        return graph.graph_to_sparse(store["edges"][:], store["weights"][:], n_cells, k, use_k, symmetric, upper_only)
 
     # ---------------------------------------------------------------------------------------------------------
     def run_mapping(self, target_assay: RNAassay, target_name: str, target_feat_key: str,

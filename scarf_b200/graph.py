@@ -554,6 +554,24 @@ def run_mapping_csr(target: CsrDevice, target_cell_idx, t_col_of_feature, ref_mu
 # =============================================================================================
 # small pieces of the AnnStream contract
 # =============================================================================================
+def graph_to_sparse(edges, weights, n_cells, k, use_k=None, symmetric=None, upper_only=None):
+    """The stored COO graph as a scipy CSR matrix: ``_store_to_sparse`` (scarf/datastore/graph_datastore.py:474-511:
+    ``use_k`` clamped into [1, k], the first ``use_k`` of every row's k entries kept) and ``load_graph``'s
+    symmetrisation ``g + g.T - g * g.T`` with the optional upper triangle (graph_datastore.py:1052-1075)."""
+    from scipy.sparse import csr_matrix, triu
+
+    use_k = k if use_k is None else min(max(int(use_k), 1), k)
+    if use_k != k:
+        keep = np.tile([True] * use_k + [False] * (k - use_k), n_cells)
+        edges, weights = edges[keep], weights[keep]
+    g = csr_matrix((weights, (edges[:, 0].astype(np.int64), edges[:, 1].astype(np.int64))), shape=(n_cells, n_cells))
+    if symmetric is True:
+        g = g + g.T - g.multiply(g.T)
+        if upper_only is True:
+            g = triu(g)
+    return g
+
+
 def order_features(source_ids, target_ids, source_feat_idx) -> np.ndarray:
     """``_order_features`` with its defaults exclude_missing=False / filter_null=False (scarf/mapping_utils.py:98-145):
     for every source feature the graph was built on (``source_feat_idx``: ascending positions in the source feature

@@ -23,6 +23,9 @@ Functions executed (reference file:lines) and the scope-table rows they pin:
                                      first block kept as the end reservoir, carry-over of blocks shorter than
                                      dims + 1, one extra component dropped) -- run on a stub stream of numpy blocks
                                      with the installed scikit-learn (1.9; the reference pins 1.6.1, same algorithm)
+  GraphDataStore._store_to_sparse, load_graph   scarf/datastore/graph_datastore.py:474-511,1022-1075  f-4 (use_k
+                                     clamping and row-wise truncation, g + g.T - g * g.T, upper triangle) -- run on a
+                                     stub store holding the edges / weights arrays in a dict
 The per-cell scalar of the renormalised branch (`RNAassay.normed`, scarf/assay.py:814-823) is inline code of a method
 that needs a store; the three lines are restated below where the scalar is built.
 """
@@ -209,6 +212,38 @@ fit_pca(st, False, np.ones(n_pca, dtype=bool))
 out.update(pca_x=x_pca, pca_mu=mu_pca, pca_sigma=sigma_pca, pca_dims=np.int64(dims_pca), pca_batch=np.int64(bs),
            pca_loadings=st.loadings.copy())
 print("ipca loadings", st.loadings.shape)
+
+# ---- f-4: _store_to_sparse + load_graph ---------------------------------------------------------------------------------
+from scipy.sparse import coo_matrix, csr_matrix  # noqa: E402
+
+gd_ns = {"logger": SimpleNamespace(debug=lambda *a, **k: None), "csr_matrix": csr_matrix, "coo_matrix": coo_matrix,
+         "Optional": Optional}
+store_to_sparse = ref_function("datastore/graph_datastore.py", "_store_to_sparse", gd_ns, cls="GraphDataStore")
+load_graph = ref_function("datastore/graph_datastore.py", "load_graph", gd_ns, cls="GraphDataStore")
+n_g, k_g = 60, 5
+nbrs = np.stack([rng.choice(np.delete(np.arange(n_g), r), k_g, replace=False) for r in range(n_g)])
+edges = np.stack([np.repeat(np.arange(n_g), k_g), nbrs.reshape(-1)], axis=1).astype(np.uint64)
+weights = np.sort(rng.random((n_g, k_g)), axis=1)[:, ::-1].reshape(-1).copy()
+
+
+class GraphStore:
+    zw = {"g": {"edges": edges, "weights": weights}}
+    _store_to_sparse = store_to_sparse
+
+    def _get_graph_ncells_k(self, loc):
+        return n_g, k_g
+
+    def _get_latest_keys(self, a, c, f):
+        return "RNA", "I", "hvgs"
+
+
+out.update(graph_edges=edges, graph_weights=weights, graph_n=np.int64(n_g), graph_k=np.int64(k_g))
+for tag, kw in (("default", dict()), ("sym_upper", dict(symmetric=True, upper_only=True)),
+                ("sym_full", dict(symmetric=True, upper_only=False)), ("raw_k3", dict(symmetric=False, use_k=3)),
+                ("sym_k0", dict(symmetric=True, use_k=0)), ("sym_upper_k9", dict(symmetric=True, upper_only=True, use_k=9))):
+    gmat = load_graph(GraphStore(), graph_loc="g", **kw)
+    out[f"graph_{tag}"] = np.asarray(gmat.todense())
+    print("graph", tag, type(gmat).__name__, gmat.nnz)
 
 np.savez_compressed(OUT, **out)
 print("ok", OUT, os.path.getsize(OUT), "bytes;", "mismatching self rows:", int(n_mis), "; missing target features:",

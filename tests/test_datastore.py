@@ -106,8 +106,9 @@ def test_datastore_chain_layout_and_cache(tmp_path, pbmc):
     assert np.array_equal(edges[:, 1].reshape(808, 11), idx)
     _, w_o = P.smoothen_dists(idx, z[knn]["distances"][:], 1.0, 1.5, 1000)
     assert np.abs(weights - w_o).max() < 1e-5
-    g = ds.load_graph()
+    g = ds.load_graph(symmetric=True, upper_only=True)
     assert sp.issparse(g) and g.shape == (808, 808) and (g - sp.triu(g)).nnz == 0
+    assert ds.load_graph().nnz == 808 * 11  # the reference's defaults (None): the stored, directed graph
     # Assay.save_normalized_data: the materialised normalised matrix (row a5) against the oracle, 1e-5 relative
     loc = ds.save_normalized_data(feat_key="hvgs")
     arr = z[loc.rsplit("/", 1)[0]]["data"]

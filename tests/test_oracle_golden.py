@@ -222,3 +222,17 @@ def test_ipca_loop_equals_reference_method(ref_fn):
                           int(ref_fn["pca_batch"]))
     assert got.shape == ref_fn["pca_loadings"].shape == (40, 7)
     np.testing.assert_allclose(got, ref_fn["pca_loadings"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag,kw", [("default", {}), ("sym_upper", dict(symmetric=True, upper_only=True)),
+                                    ("sym_full", dict(symmetric=True, upper_only=False)),
+                                    ("raw_k3", dict(symmetric=False, use_k=3)), ("sym_k0", dict(symmetric=True, use_k=0)),
+                                    ("sym_upper_k9", dict(symmetric=True, upper_only=True, use_k=9))])
+def test_load_graph_equals_reference_method(ref_fn, tag, kw):
+    """f-4: GraphDataStore._store_to_sparse + load_graph (scarf/datastore/graph_datastore.py:474-511,1022-1075)
+    executed on a stub store: the defaults return the stored directed graph, use_k is clamped into [1, k] and keeps the
+    first use_k entries of every row, symmetric=True gives g + g.T - g * g.T, upper_only its upper triangle."""
+    from scarf_b200.graph import graph_to_sparse
+
+    g = graph_to_sparse(ref_fn["graph_edges"], ref_fn["graph_weights"], int(ref_fn["graph_n"]), int(ref_fn["graph_k"]), **kw)
+    assert np.array_equal(np.asarray(g.todense()), ref_fn[f"graph_{tag}"])
