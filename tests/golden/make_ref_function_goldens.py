@@ -26,6 +26,11 @@ Functions executed (reference file:lines) and the scope-table rows they pin:
   GraphDataStore._store_to_sparse, load_graph   scarf/datastore/graph_datastore.py:474-511,1022-1075  f-4 (use_k
                                      clamping and row-wise truncation, g + g.T - g * g.T, upper triangle) -- run on a
                                      stub store holding the edges / weights arrays in a dict
+  smoothen_dists                     scarf/knn_utils.py:89-159  a11 (the chunk loop: chunk-local row ids shifted by
+                                     `last_row`, per-chunk float32 cast, zero-weight entries set to the smallest
+                                     non-zero weight seen) -- run with umap-learn's two numba functions (not
+                                     installed) replaced by the restatements that reproduce the reference's
+                                     `knn_weights.npy` golden (oracle/pipeline.py), on a stub store of numpy arrays
 The per-cell scalar of the renormalised branch (`RNAassay.normed`, scarf/assay.py:814-823) is inline code of a method
 that needs a store; the three lines are restated below where the scalar is built.
 """
@@ -244,6 +249,43 @@ for tag, kw in (("default", dict()), ("sym_upper", dict(symmetric=True, upper_on
     gmat = load_graph(GraphStore(), graph_loc="g", **kw)
     out[f"graph_{tag}"] = np.asarray(gmat.todense())
     print("graph", tag, type(gmat).__name__, gmat.nnz)
+
+# ---- a11: smoothen_dists (chunk loop around the two umap-learn functions) ------------------------------------------------
+from oracle import pipeline as oracle_pipeline  # noqa: E402
+
+umap_mod = types.ModuleType("umap.umap_")
+umap_mod.smooth_knn_dist = oracle_pipeline.smooth_knn_dist_vec
+umap_mod.compute_membership_strengths = oracle_pipeline.compute_membership_strengths
+sys.modules.setdefault("umap", types.ModuleType("umap"))
+sys.modules["umap.umap_"] = umap_mod
+created = {}
+
+
+def create_zarr_dataset(store, name, chunks, dtype, shape):
+    created[name] = np.zeros(shape, dtype=np.uint64 if isinstance(dtype, tuple) else dtype)
+    return created[name]
+
+
+smoothen = ref_function("knn_utils.py", "smoothen_dists", {"create_zarr_dataset": create_zarr_dataset,
+                                                           "tqdmbar": lambda it, **k: it,
+                                                           "_is_umap_version_new": lambda: False})
+n_s, k_s, chunk = 2300, 6, 1000  # three chunks, the last one ragged
+idx_s = np.stack([rng.choice(np.delete(np.arange(n_s), r), k_s, replace=False) for r in range(n_s)]).astype(np.uint64)
+dist_s = np.sort(rng.gamma(2.0, 1.0, (n_s, k_s)), axis=1).astype(np.float32).astype(np.float64)
+dist_s[[5, 1200, 2299], -2:] = [4.0e4, 9.0e5]  # two very far neighbours
+dist_s[77] = dist_s[77, 0]  # all neighbours equally far
+dist_s[9, :3] = 0.0  # zero distances (duplicate cells)
+dist_s[1500] = 0.0
+# umap's membership function zeroes an entry whose neighbour id equals the row id INSIDE THE CHUNK it is called on:
+# with chunks this hits global ids that are no self loops; such zeros are then raised to the smallest non-zero weight
+idx_s[1007, 4] = 7
+idx_s[2100, 0] = 100
+idx_s[3, 2] = 3
+smoothen(None, idx_s, dist_s, 1.0, 1.5, chunk)
+out.update(smooth_idx=idx_s, smooth_dist=dist_s, smooth_chunk=np.int64(chunk), smooth_edges=created["edges"].copy(),
+           smooth_weights=created["weights"].copy())
+print("smoothen_dists: entries at the floor:", int((created["weights"] == created["weights"].min()).sum()),
+      "floor", created["weights"].min())
 
 np.savez_compressed(OUT, **out)
 print("ok", OUT, os.path.getsize(OUT), "bytes;", "mismatching self rows:", int(n_mis), "; missing target features:",

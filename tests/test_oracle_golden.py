@@ -236,3 +236,15 @@ def test_load_graph_equals_reference_method(ref_fn, tag, kw):
 
     g = graph_to_sparse(ref_fn["graph_edges"], ref_fn["graph_weights"], int(ref_fn["graph_n"]), int(ref_fn["graph_k"]), **kw)
     assert np.array_equal(np.asarray(g.todense()), ref_fn[f"graph_{tag}"])
+
+
+def test_smoothen_dists_loop_equals_reference_function(ref_fn):
+    """a11: smoothen_dists (scarf/knn_utils.py:89-159) executed around the restated umap functions on a stub store:
+    three chunks (the last ragged), chunk-local 'neighbour id == row id' zeroing that hits non-self entries in later
+    chunks, the floor at the smallest non-zero weight, zero distances.  The oracle's loop gives the same arrays."""
+    e, w = P.smoothen_dists(ref_fn["smooth_idx"], ref_fn["smooth_dist"], 1.0, 1.5, int(ref_fn["smooth_chunk"]))
+    assert np.array_equal(e, ref_fn["smooth_edges"]) and np.array_equal(w, ref_fn["smooth_weights"])
+    wr = ref_fn["smooth_weights"].reshape(-1, 6)
+    floor = wr.min()
+    assert wr[1007, 4] == floor and wr[2100, 0] == floor and wr[3, 2] == floor  # the planted chunk-local collisions
+    assert (wr == floor).sum() == 9 and (wr == 0).sum() == 0  # + chance collisions (e.g. row 1017 -> cell 17) + the floor's source
