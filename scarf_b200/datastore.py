@@ -327,11 +327,12 @@ class DataStore:
         c_dims = c_pca = None
         if normed_loc in zw and "latest_reduction" in zw[normed_loc].attrs:
             c_dims, c_pca = zw[normed_loc].attrs["latest_reduction"].rsplit("__", 2)[1:]
+        dims_given = dims is not None
         if dims is None:
             dims = int(c_dims) if c_dims is not None else dv["dims"]
         if pca_cell_key is None:
             pca_cell_key = c_pca if c_pca is not None else cell_key
-        else:
+        elif not dims_given:  # as executed, the reference checks the column only when `dims` is not given (:188-208)
             if pca_cell_key not in self.cells.columns:
                 raise ValueError(f"ERROR: `pca_use_cell_key` {pca_cell_key} does not exist in cell metadata")
             if self.cells.get_dtype(pca_cell_key) != bool:

@@ -31,6 +31,10 @@ Functions executed (reference file:lines) and the scope-table rows they pin:
                                      non-zero weight seen) -- run with umap-learn's two numba functions (not
                                      installed) replaced by the restatements that reproduce the reference's
                                      `knn_weights.npy` golden (oracle/pipeline.py), on a stub store of numpy arrays
+  GraphDataStore._set_graph_params, _choose_reduction_method   scarf/datastore/graph_datastore.py:24-363  a12 (explicit ->
+                                     cached -> default resolution of make_graph's parameters and the group names built
+                                     from them) -- run on stub stores (a dict of nodes with attrs); the scenarios and
+                                     the resolved tuples go to tests/golden/ref_graph_params.json
 The per-cell scalar of the renormalised branch (`RNAassay.normed`, scarf/assay.py:814-823) is inline code of a method
 that needs a store; the three lines are restated below where the scalar is built.
 """
@@ -286,6 +290,61 @@ out.update(smooth_idx=idx_s, smooth_dist=dist_s, smooth_chunk=np.int64(chunk), s
            smooth_weights=created["weights"].copy())
 print("smoothen_dists: entries at the floor:", int((created["weights"] == created["weights"].min()).sum()),
       "floor", created["weights"].min())
+
+# ---- a12: _set_graph_params ----------------------------------------------------------------------------------------------
+import json
+
+gp_ns = {"logger": SimpleNamespace(debug=lambda *a, **k: None, info=lambda *a, **k: None), "Assay": object}
+set_graph_params = ref_function("datastore/graph_datastore.py", "_set_graph_params", gp_ns, cls="GraphDataStore")
+choose_reduction = ref_function("datastore/graph_datastore.py", "_choose_reduction_method", gp_ns, cls="GraphDataStore")
+
+
+class RNAassay:  # the class NAME is what `_choose_reduction_method` looks at
+    pass
+
+
+def graph_store(tree):
+    cells = SimpleNamespace(columns=["I", "ids", "names", "sub", "RNA_nCounts"],
+                            get_dtype=lambda c: bool if c in ("I", "sub") else float)
+    return SimpleNamespace(zw={k_: SimpleNamespace(attrs=dict(v)) for k_, v in tree.items()}, cells=cells,
+                           _get_assay=lambda a: RNAassay(), _choose_reduction_method=choose_reduction)  # (a staticmethod there)
+
+
+base = "RNA/normed__I__hvgs"
+red = f"{base}/reduction__pca__25__I"
+ann = f"{red}/ann__l2__63__70__48__99"
+knn = f"{ann}/knn__21"
+cached_tree = {base: {"subset_params": {"log_transform": False, "renormalize_subset": True}, "latest_reduction": red},
+               red: {"latest_ann": ann, "latest_kmeans": f"{red}/kmeans__300__99"},
+               ann: {"latest_knn": knn}, knn: {"latest_graph": f"{knn}/graph__2.0__1.25"}}
+scenarios = [
+    {"tree": {}, "kwargs": {}},
+    {"tree": {}, "kwargs": {"dims": 60, "k": 40, "reduction_method": "PCA"}},
+    {"tree": {}, "kwargs": {"dims": 30, "pca_cell_key": "sub", "ann_m": 20, "ann_efc": 10, "ann_ef": 12, "rand_state": 7,
+                            "n_centroids": 50, "local_connectivity": 2.5, "bandwidth": 0.5, "log_transform": False,
+                            "renormalize_subset": False, "ann_metric": "l2"}},
+    {"tree": cached_tree, "kwargs": {}},
+    {"tree": cached_tree, "kwargs": {"k": 11}},
+    {"tree": cached_tree, "kwargs": {"dims": 11}},
+    {"tree": cached_tree, "kwargs": {"log_transform": True, "bandwidth": 3.0}},
+    # pca_cell_key is validated only when dims is NOT given (the check sits in the else of an inner if,
+    # graph_datastore.py:188-208): the outcomes below are recorded, not presumed
+    {"tree": {}, "kwargs": {"dims": 5, "pca_cell_key": "nope"}},
+    {"tree": {}, "kwargs": {"dims": 5, "pca_cell_key": "RNA_nCounts"}},
+    {"tree": {}, "kwargs": {"pca_cell_key": "nope"}},
+    {"tree": {}, "kwargs": {"pca_cell_key": "RNA_nCounts"}},
+    {"tree": {}, "kwargs": {"pca_cell_key": "sub"}},
+    {"tree": {}, "kwargs": {"reduction_method": "umap"}},
+]
+for sc in scenarios:
+    try:
+        res_t = set_graph_params(graph_store(sc["tree"]), "RNA", "I", "hvgs", **sc["kwargs"])
+        sc["result"] = [bool(v) if isinstance(v, (bool, np.bool_)) else v for v in res_t]
+    except (ValueError, TypeError) as err:
+        sc["raises"] = type(err).__name__
+with open(os.path.join(os.path.dirname(OUT), "ref_graph_params.json"), "w") as f:
+    json.dump(scenarios, f, indent=1)
+print("graph params scenarios:", len(scenarios))
 
 np.savez_compressed(OUT, **out)
 print("ok", OUT, os.path.getsize(OUT), "bytes;", "mismatching self rows:", int(n_mis), "; missing target features:",

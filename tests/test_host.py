@@ -199,3 +199,35 @@ def test_csr_sortedness_check_on_cpu_tensors():
         bad = CsrDevice(ip, torch.tensor(bad_ix, dtype=torch.int32), torch.ones(6, dtype=torch.int32), 4, 10)
         with pytest.raises(ValueError, match="ascend strictly"):
             bad.check_sorted()
+
+
+def test_graph_parameter_resolution_equals_reference_method():
+    """a12: GraphDataStore._set_graph_params (scarf/datastore/graph_datastore.py:63-363) was executed on stub stores
+    (tests/golden/make_ref_function_goldens.py -> ref_graph_params.json): fresh store, explicit values, values cached by
+    an earlier run at every level of the tree, partial overrides, and the error cases as they really fall out (the
+    pca_cell_key column is only checked when `dims` is not given).  DataStore._set_graph_params resolves the same tuples
+    on the same stubs."""
+    import json
+    import os
+    from types import SimpleNamespace
+
+    from conftest import GOLDEN
+    from scarf_b200.datastore import DataStore
+
+    class Tree(dict):
+        pass
+
+    cells = SimpleNamespace(columns=["I", "ids", "names", "sub", "RNA_nCounts"],
+                            get_dtype=lambda c: bool if c in ("I", "sub") else float)
+    with open(os.path.join(GOLDEN, "ref_graph_params.json")) as f:
+        scenarios = json.load(f)
+    assert len(scenarios) == 13
+    for sc in scenarios:
+        stub = SimpleNamespace(zw=Tree({k: SimpleNamespace(attrs=dict(v)) for k, v in sc["tree"].items()}), cells=cells)
+        if "raises" in sc:
+            with pytest.raises({"ValueError": ValueError, "TypeError": TypeError}[sc["raises"]]):
+                DataStore._set_graph_params(stub, "RNA", "I", "hvgs", **sc["kwargs"])
+        else:
+            got = DataStore._set_graph_params(stub, "RNA", "I", "hvgs", **sc["kwargs"])
+            assert list(got) == sc["result"], (sc["kwargs"], got, sc["result"])
+            assert [type(v) for v in got] == [type(v) for v in sc["result"]]
