@@ -103,12 +103,13 @@ def remove_trend(avg, sigmas, n_bins=200, lowess_frac=0.1, fill_value=0.0):
 # A.4  HVG choice                    scarf/assay.py:1014-1063, scarf/datastore/datastore.py:282-314
 # ----------------------------------------------------------------------------------------------
 def choose_hvgs(normed_n, nz_mean, c_var, feat_I, gene_names=None, top_n=500, min_cells=0, max_cells=np.inf,
-                min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf, blacklist=DEFAULT_BLACKLIST):
+                min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf, blacklist=DEFAULT_BLACKLIST,
+                keep_bounds=False):
     """The HVG choice of RNAassay.mark_hvgs (scarf/assay.py:1014-1063) on full-length per-gene vectors: log2 bounds
     exponentiated when finite, blacklist through MetaData.grep (names and pattern upper-cased, re.match;
-    scarf/metadata.py:569-584), strict multi_sift bounds (metadata.py:483-533), and either the (top_n + 1)-th largest
-    eligible corrected variance or ``2**min_var`` as the threshold.  Pinned on the reference method executed on a
-    stub assay (tests/golden/make_ref_function_goldens.py)."""
+    scarf/metadata.py:569-584), multi_sift bounds (strict unless ``keep_bounds``; metadata.py:483-533), and either
+    the (top_n + 1)-th largest eligible corrected variance or ``2**min_var`` as the threshold.  Pinned on the
+    reference method executed on a stub assay (tests/golden/make_ref_function_goldens.py)."""
     G = len(normed_n)
     if max_mean != np.inf:
         max_mean = 2 ** max_mean
@@ -123,18 +124,20 @@ def choose_hvgs(normed_n, nz_mean, c_var, feat_I, gene_names=None, top_n=500, mi
         bl = np.array([pat.match(str(x).upper()) is None for x in gene_names])
     else:
         bl = np.ones(G, dtype=bool)
+
+    def sift(v, lo, hi):
+        return (v >= lo) & (v <= hi) if keep_bounds else (v > lo) & (v < hi)
+
     with np.errstate(invalid="ignore"):
         if min_var == -np.inf:
             if top_n < 1:
                 raise ValueError("ERROR: Please provide a value greater than 0 for `top_n` parameter")
-            idx = (normed_n > min_cells) & (normed_n < max_cells) & (nz_mean > min_mean) & (nz_mean < max_mean)
-            idx = idx & feat_I & bl
+            idx = sift(normed_n, min_cells, max_cells) & sift(nz_mean, min_mean, max_mean) & feat_I & bl
             n_valid = idx.sum()
             if top_n > n_valid:
                 top_n = n_valid - 1
             min_var = np.sort(c_var[idx])[::-1][top_n]
-        hvgs = ((normed_n > min_cells) & (normed_n < max_cells) & (nz_mean > min_mean) & (nz_mean < max_mean)
-                & (c_var > min_var) & (c_var < max_var))
+        hvgs = sift(normed_n, min_cells, max_cells) & sift(nz_mean, min_mean, max_mean) & sift(c_var, min_var, max_var)
         return hvgs & feat_I & bl
 
 

@@ -276,13 +276,18 @@ class DataStore:
         return from_assay, cell_key, feat_key
 
     # ---------------------------------------------------------------------------------------------------------
-    def mark_hvgs(self, from_assay: Optional[str] = None, cell_key: str = "I", min_cells: Optional[int] = None,
-                  top_n: int = 500, min_var: float = -np.inf, max_var: float = np.inf, min_mean: float = -np.inf,
-                  max_mean: float = np.inf, n_bins: int = 200, lowess_frac: float = 0.1,
-                  blacklist: str = hvg_host.DEFAULT_BLACKLIST, show_plot: bool = False,
-                  hvg_key_name: str = "hvgs", **plot_kwargs) -> None:
-        """scarf/datastore/datastore.py:223-314.  Stores ``<cell_key>__<hvg_key_name>`` (bool) and the statistics
-        columns of ``set_summary_stats`` in the feature table."""
+    def mark_hvgs(self, from_assay: Optional[str] = None, cell_key: Optional[str] = None,
+                  min_cells: Optional[int] = None, top_n: int = 500, min_var: float = -np.inf, max_var: float = np.inf,
+                  min_mean: float = -np.inf, max_mean: float = np.inf, n_bins: int = 200, lowess_frac: float = 0.1,
+                  blacklist: str = hvg_host.DEFAULT_BLACKLIST, keep_bounds: bool = False, show_plot: bool = True,
+                  hvg_key_name: str = "hvgs", max_cells: Optional[float] = np.inf, **plot_kwargs) -> None:
+        """scarf/datastore/datastore.py:223-314 (same parameters and defaults).  Stores ``<cell_key>__<hvg_key_name>``
+        (bool) and the statistics columns of ``set_summary_stats`` in the feature table.  ``show_plot`` / plot
+        arguments are accepted and ignored: plotting is not part of this path."""
+        if cell_key is None:
+            cell_key = "I"
+        if max_cells is None:
+            max_cells = np.inf
         if cell_key not in self.cells.columns:
             raise ValueError(f"ERROR: cell_key {cell_key} not found in cell metadata")
         if from_assay is None:
@@ -299,7 +304,7 @@ class DataStore:
                                        gene_names=assay.feats.fetch_all("names"), top_n=top_n, min_cells=min_cells,
                                        min_mean=min_mean, max_mean=max_mean, n_bins=n_bins, lowess_frac=lowess_frac,
                                        blacklist=blacklist, comm=self.comm, return_stats=True, min_var=min_var,
-                                       max_var=max_var)
+                                       max_var=max_var, max_cells=max_cells, keep_bounds=keep_bounds)
         ident = f"{cell_key}__"
         for name, col in (("normed_tot", "normed_tot"), ("avg", "avg"), ("nz_mean", "nz_mean"),
                           ("sigmas", "sigmas"), ("normed_n", "normed_n"), ("c_var", f"c_var__{n_bins}__{lowess_frac}")):

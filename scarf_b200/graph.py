@@ -58,17 +58,19 @@ def hvg_gene_stats(csr: CsrDevice, cell_idx, n_counts, n_cells_total: int, comm:
 def mark_hvgs_csr(csr: CsrDevice, cell_idx, feat_I, n_counts, n_cells_total, gene_names=None, top_n=500,
                   min_cells=None, max_cells=np.inf, min_mean=-np.inf, max_mean=np.inf, n_bins=200, lowess_frac=0.1,
                   blacklist=hvg_host.DEFAULT_BLACKLIST, comm: Comm | None = None, return_stats=False,
-                  as_tensor=False, keep_mask=None, min_var=-np.inf, max_var=np.inf):
+                  as_tensor=False, keep_mask=None, min_var=-np.inf, max_var=np.inf, keep_bounds=False):
     """DataStore.mark_hvgs (scarf/datastore/datastore.py:223-314) -> bool mask over all genes (numpy, or a device
     tensor with ``as_tensor``).  The per-gene vectors never leave the GPU; only the <= n_bins binned points of the
     trend fit visit the host (LOWESS).  ``keep_mask`` = precomputed blacklist survivors (static per dataset).
-    ``min_var`` / ``max_var`` (log2; scarf/assay.py:1014-1063): a finite ``min_var`` replaces the top-n rule."""
+    ``min_var`` / ``max_var`` (log2; scarf/assay.py:1014-1063): a finite ``min_var`` replaces the top-n rule;
+    ``keep_bounds``: bounds inclusive (MetaData.sift).  Both leave the fused kernel for the tensor formulation."""
     if min_cells is None:
         min_cells = int(0.01 * n_cells_total)  # datastore.py:291
     dev = csr.device
     if min_var == -np.inf and top_n < 1:
         raise ValueError("ERROR: Please provide a value greater than 0 for `top_n` parameter")  # assay.py:1030-1033
-    if csr.indptr.is_cuda and not return_stats and min_var == -np.inf and max_var == np.inf and n_bins <= 512:
+    if (csr.indptr.is_cuda and not return_stats and min_var == -np.inf and max_var == np.inf and not keep_bounds
+            and n_bins <= 512):
         # device path: one statistics pass + ONE fused kernel for trend removal and choice (no synchronisation)
         row_div = n_counts[cell_idx] if cell_idx is not None else n_counts
         nnz, sm, sq = ops.csr_gene_stats(csr, cell_idx, row_div.contiguous(), SF)
@@ -94,7 +96,7 @@ def mark_hvgs_csr(csr: CsrDevice, cell_idx, feat_I, n_counts, n_cells_total, gen
     c_var = hvg_host.remove_trend_device(st["avg"], st["sigmas"], n_bins, lowess_frac, select=feat_I_t)
     c_var = torch.where(feat_I_t, c_var, torch.full_like(c_var, math.nan))
     mask = hvg_host.choose_hvgs_device(st["normed_n"], st["nz_mean"], c_var, feat_I_t & keep_t, top_n, min_cells,
-                                       max_cells, min_mean, max_mean, min_var, max_var)
+                                       max_cells, min_mean, max_mean, min_var, max_var, keep_bounds)
     out = mask if as_tensor else mask.cpu().numpy()
     if return_stats:
         st = {k: v.cpu().numpy() for k, v in st.items()}

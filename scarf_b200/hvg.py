@@ -112,20 +112,27 @@ def remove_trend(avg, sigmas, n_bins=200, lowess_frac=0.1, fill_value=0.0):
     return ret
 
 
+def _sift(v, lo, hi, keep_bounds):
+    """MetaData.sift (scarf/metadata.py:483-505); works on numpy arrays and torch tensors."""
+    return (v >= lo) & (v <= hi) if keep_bounds else (v > lo) & (v < hi)
+
+
 def choose_hvgs(normed_n, nz_mean, c_var, feat_I, gene_names=None, top_n=500, min_cells=0, max_cells=np.inf,
-                min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf, blacklist=DEFAULT_BLACKLIST):
-    """scarf/assay.py:1014-1063 + MetaData.multi_sift (scarf/metadata.py:483-533): strict bounds; with
-    ``min_var == -inf`` (the default) the threshold is the (top_n + 1)-th largest corrected variance of the eligible
-    genes, otherwise ``top_n`` is ignored and ``2**min_var`` is the threshold; ``c_var < 2**max_var`` applies in both
-    modes.  Mean / variance bounds are given in log2 and only exponentiated when finite.  All vectors cover every
-    gene (NaN outside ``feat_I``).  Pinned on the executed reference method (tests/golden/ref_functions.npz)."""
+                min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf, blacklist=DEFAULT_BLACKLIST,
+                keep_bounds=False):
+    """scarf/assay.py:1014-1063 + MetaData.multi_sift (scarf/metadata.py:483-533): bounds strict unless
+    ``keep_bounds``; with ``min_var == -inf`` (the default) the threshold is the (top_n + 1)-th largest corrected
+    variance of the eligible genes, otherwise ``top_n`` is ignored and ``2**min_var`` is the threshold;
+    ``c_var < 2**max_var`` applies in both modes.  Mean / variance bounds are given in log2 and only exponentiated when
+    finite.  All vectors cover every gene (NaN outside ``feat_I``).  Pinned on the executed reference method
+    (tests/golden/ref_functions.npz)."""
     g = normed_n.size
     keep = blacklist_keep_mask(gene_names, g, blacklist)
     min_mean = 2.0 ** min_mean if min_mean != -np.inf else min_mean
     max_mean = 2.0 ** max_mean if max_mean != np.inf else max_mean
     max_var = 2.0 ** max_var if max_var != np.inf else max_var
     with np.errstate(invalid="ignore"):
-        idx = (normed_n > min_cells) & (normed_n < max_cells) & (nz_mean > min_mean) & (nz_mean < max_mean)
+        idx = _sift(normed_n, min_cells, max_cells, keep_bounds) & _sift(nz_mean, min_mean, max_mean, keep_bounds)
         idx &= feat_I & keep
         if min_var == -np.inf:
             if top_n < 1:
@@ -136,7 +143,7 @@ def choose_hvgs(normed_n, nz_mean, c_var, feat_I, gene_names=None, top_n=500, mi
             min_var = np.sort(c_var[idx])[::-1][top_n]
         else:
             min_var = 2.0 ** min_var
-        hv = idx & (c_var > min_var) & (c_var < max_var)
+        hv = idx & _sift(c_var, min_var, max_var, keep_bounds)
     return hv
 
 
@@ -208,7 +215,7 @@ def remove_trend_device(avg, sigmas, n_bins=200, lowess_frac=0.1, select=None):
 
 
 def choose_hvgs_device(normed_n, nz_mean, c_var, eligible, top_n=500, min_cells=0, max_cells=np.inf,
-                       min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf):
+                       min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf, keep_bounds=False):
     """:func:`choose_hvgs` on device vectors; ``eligible`` = feat_I & blacklist-keep (bool tensor).  No
     synchronisation: the (top_n+1)-th largest corrected variance is picked with a device-side index."""
     import torch
@@ -216,7 +223,7 @@ def choose_hvgs_device(normed_n, nz_mean, c_var, eligible, top_n=500, min_cells=
     min_mean = 2.0 ** min_mean if min_mean != -np.inf else min_mean
     max_mean = 2.0 ** max_mean if max_mean != np.inf else max_mean
     max_var = 2.0 ** max_var if max_var != np.inf else max_var
-    idx = (normed_n > min_cells) & (normed_n < max_cells) & (nz_mean > min_mean) & (nz_mean < max_mean) & eligible
+    idx = _sift(normed_n, min_cells, max_cells, keep_bounds) & _sift(nz_mean, min_mean, max_mean, keep_bounds) & eligible
     idx = idx & ~torch.isnan(c_var)
     if min_var == -np.inf:
         if top_n < 1:
@@ -226,5 +233,5 @@ def choose_hvgs_device(normed_n, nz_mean, c_var, eligible, top_n=500, min_cells=
         n_valid = idx.sum()
         kk = torch.minimum(torch.full_like(n_valid, int(top_n)), n_valid - 1).clamp(min=0)  # assay.py:1035-1040
         thr = cv[kk]
-        return idx & (c_var > thr) & (c_var < max_var)
-    return idx & (c_var > 2.0 ** min_var) & (c_var < max_var)
+        return idx & ((c_var >= thr) & (c_var <= max_var) if keep_bounds else (c_var > thr) & (c_var < max_var))
+    return idx & _sift(c_var, 2.0 ** min_var, max_var, keep_bounds)

@@ -180,7 +180,10 @@ c_var[~feat_I] = 0.0  # what MetaData.insert leaves outside the active rows (fil
 cases = [dict(top_n=100, min_cells=8, max_cells=np.inf, min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf),
          dict(top_n=40, min_cells=50, max_cells=900.0, min_mean=-2.0, max_mean=1.5, min_var=-np.inf, max_var=np.inf),
          dict(top_n=5000, min_cells=8, max_cells=np.inf, min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf),
-         dict(top_n=10, min_cells=8, max_cells=np.inf, min_mean=-np.inf, max_mean=np.inf, min_var=-0.5, max_var=1.0)]
+         dict(top_n=10, min_cells=8, max_cells=np.inf, min_mean=-np.inf, max_mean=np.inf, min_var=-0.5, max_var=1.0),
+         # keep_bounds=True: >= / <= in every sift; bounds placed ON values of the data so that it matters
+         dict(top_n=60, min_cells=float(np.sort(normed_n)[300]), max_cells=float(np.sort(normed_n)[1100]),
+              min_mean=-np.inf, max_mean=np.inf, min_var=-np.inf, max_var=np.inf, keep_bounds=True)]
 out.update(hvg_names=names, hvg_feat_I=feat_I, hvg_normed_n=normed_n, hvg_nz_mean=nz_mean, hvg_c_var=c_var,
            hvg_blacklist=np.array("^MT-|^RPS|^RPL|^MRPS|^MRPL|^CCN|^HLA-|^H2-|^HIST"))
 for ci, case in enumerate(cases):
@@ -188,10 +191,13 @@ for ci, case in enumerate(cases):
                           "I__c_var__200__0.1": c_var})
     stub = SimpleNamespace(feats=feats, set_summary_stats=lambda ck, nb, lf: ("I_", "c_var__200__0.1"))
     # col_renamer gives f"{identifier}_{x}": identifier "I_" -> columns "I__normed_n", ... (scarf/assay.py:1007-1011)
+    case = dict(case)
+    keep_bounds = case.pop("keep_bounds", False)
     mark_hvgs(stub, cell_key="I", n_bins=200, lowess_frac=0.1, blacklist=str(out["hvg_blacklist"]), hvg_key_name="hvgs",
-              keep_bounds=False, show_plot=False, **case)
+              keep_bounds=keep_bounds, show_plot=False, **case)
     out[f"hvg_case{ci}_params"] = np.array([case[k_] for k_ in ("top_n", "min_cells", "max_cells", "min_mean", "max_mean",
-                                                               "min_var", "max_var")], dtype=np.float64)
+                                                               "min_var", "max_var")] + [float(keep_bounds)],
+                                           dtype=np.float64)
     out[f"hvg_case{ci}_mask"] = feats.cols["I__hvgs"].astype(bool)
     print("hvg case", ci, int(out[f"hvg_case{ci}_mask"].sum()))
 

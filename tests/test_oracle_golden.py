@@ -185,24 +185,26 @@ def test_fit_lowess_equals_reference_function(ref_fn):
     assert np.isfinite(want).all() and want.min() > 0
 
 
-@pytest.mark.parametrize("case", [0, 1, 2, 3])
+@pytest.mark.parametrize("case", [0, 1, 2, 3, 4])
 def test_hvg_choice_equals_reference_method(ref_fn, case):
     """a3: RNAassay.mark_hvgs (scarf/assay.py:945-1063) executed on a stub assay through the reference's own
     MetaData.sift / multi_sift / grep / get_index_by: default top-n rule, log2 mean bounds with max_cells, top_n larger
-    than the number of eligible genes, explicit min_var / max_var (top_n then ignored).  Gene names include lower-case
+    than the number of eligible genes, explicit min_var / max_var (top_n then ignored), keep_bounds=True with bounds
+    placed on values of the data (61 genes for top_n = 60: the threshold gene is kept).  Gene names include lower-case
     spellings the blacklist still catches (names and pattern are upper-cased, `re.match`).  Oracle, product host
     routine and product tensor routine give the same mask."""
     import torch
 
     from scarf_b200 import hvg
 
-    top_n, min_cells, max_cells, min_mean, max_mean, min_var, max_var = ref_fn[f"hvg_case{case}_params"]
+    top_n, min_cells, max_cells, min_mean, max_mean, min_var, max_var, keep_bounds = ref_fn[f"hvg_case{case}_params"]
     want = ref_fn[f"hvg_case{case}_mask"]
     names, feat_I = ref_fn["hvg_names"], ref_fn["hvg_feat_I"]
     nn, nz, cv = ref_fn["hvg_normed_n"], ref_fn["hvg_nz_mean"], ref_fn["hvg_c_var"]
     bl = str(ref_fn["hvg_blacklist"])
     kw = dict(top_n=int(top_n), min_cells=min_cells, max_cells=max_cells, min_mean=min_mean, max_mean=max_mean,
-              min_var=min_var, max_var=max_var)
+              min_var=min_var, max_var=max_var, keep_bounds=bool(keep_bounds))
+    assert want.sum() == [100, 40, 997, 565, 61][case]
     assert np.array_equal(P.choose_hvgs(nn, nz, cv, feat_I, names, blacklist=bl, **kw), want)
     assert np.array_equal(hvg.choose_hvgs(nn, nz, cv, feat_I, names, blacklist=bl, **kw), want)
     keep = hvg.blacklist_keep_mask(names, len(names), bl)
