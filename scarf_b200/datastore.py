@@ -589,12 +589,11 @@ class DataStore:
         return graph.graph_to_sparse(store["edges"][:], store["weights"][:], n_cells, k, use_k, symmetric, upper_only)
 
     # ---------------------------------------------------------------------------------------------------------
-    def run_mapping(self, target_assay: RNAassay, target_name: str, target_feat_key: str,
+    def run_mapping(self, target_assay: RNAassay, target_name: str, target_feat_key: str, target_cell_key: str = "I",
                     from_assay: Optional[str] = None, cell_key: str = "I", feat_key: Optional[str] = None,
                     save_k: int = 3, batch_size: int = 1000, ref_mu: bool = True, ref_sigma: bool = True,
                     run_coral: bool = False, exclude_missing: bool = False, filter_null: bool = False,
-                    feat_scaling: bool = True, ann_index_fetcher=None, ann_index_saver=None,
-                    target_cell_key: str = "I") -> None:
+                    feat_scaling: bool = True, ann_index_fetcher=None, ann_index_saver=None) -> None:
         """mapping_datastore.py:31-209: project the cells of ``target_assay`` onto this store's graph and store
         ``projections/<target_name>/{indices (u8), distances (f8)}``."""
         from_assay, cell_key, feat_key = self._get_latest_keys(from_assay, cell_key, feat_key)

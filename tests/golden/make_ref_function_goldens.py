@@ -352,6 +352,21 @@ with open(os.path.join(os.path.dirname(OUT), "ref_graph_params.json"), "w") as f
     json.dump(scenarios, f, indent=1)
 print("graph params scenarios:", len(scenarios))
 
+# ---- (b): public signatures ----------------------------------------------------------------------------------------------
+signatures = {}
+for rel, cls, name in (("datastore/graph_datastore.py", "GraphDataStore", "make_graph"),
+                       ("datastore/graph_datastore.py", "GraphDataStore", "load_graph"),
+                       ("datastore/mapping_datastore.py", "MappingDatastore", "run_mapping"),
+                       ("datastore/datastore.py", "DataStore", "mark_hvgs")):
+    with open(os.path.join(REF, rel)) as f:
+        cdef = next(n for n in ast.parse(f.read()).body if isinstance(n, ast.ClassDef) and n.name == cls)
+    fdef = next(n for n in cdef.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    args = fdef.args.args[1:]
+    defaults = [None] * (len(args) - len(fdef.args.defaults)) + [ast.unparse(d) for d in fdef.args.defaults]
+    signatures[name] = [[a.arg, d] for a, d in zip(args, defaults)]
+with open(os.path.join(os.path.dirname(OUT), "ref_signatures.json"), "w") as f:
+    json.dump(signatures, f, indent=1)
+
 np.savez_compressed(OUT, **out)
 print("ok", OUT, os.path.getsize(OUT), "bytes;", "mismatching self rows:", int(n_mis), "; missing target features:",
       int((np.asarray(t_re_idx) == -1).sum()))

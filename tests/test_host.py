@@ -231,3 +231,28 @@ def test_graph_parameter_resolution_equals_reference_method():
             got = DataStore._set_graph_params(stub, "RNA", "I", "hvgs", **sc["kwargs"])
             assert list(got) == sc["result"], (sc["kwargs"], got, sc["result"])
             assert [type(v) for v in got] == [type(v) for v in sc["result"]]
+
+
+def test_public_signatures_equal_the_reference():
+    """(b): parameter names, order and defaults of the four drop-in entry points, as recorded from the reference's
+    source (scarf/datastore/{datastore,graph_datastore,mapping_datastore}.py, parsed with `ast` when the goldens were
+    made: tests/golden/ref_signatures.json)."""
+    import inspect
+    import json
+    import os
+
+    from conftest import GOLDEN
+    from scarf_b200.datastore import DataStore
+
+    with open(os.path.join(GOLDEN, "ref_signatures.json")) as f:
+        ref = json.load(f)
+    assert sorted(ref) == ["load_graph", "make_graph", "mark_hvgs", "run_mapping"]
+    for name, params in ref.items():
+        sig = [p for p in list(inspect.signature(getattr(DataStore, name)).parameters.values())[1:]
+               if p.kind != p.VAR_KEYWORD]
+        assert [p.name for p in sig] == [a for a, _ in params], name
+        for p, (a, default) in zip(sig, params):
+            if default is None:
+                assert p.default is inspect.Parameter.empty, (name, a)
+            else:
+                assert p.default == eval(default, {"np": np}), (name, a, p.default, default)
