@@ -118,6 +118,13 @@ class RNAassay:
         return self.cells.fetch_all(f"{self.name}_nCounts")
 
 
+class _PcaSummary:
+    """Stands where sklearn's IncrementalPCA object stood for the attributes callers read."""
+
+    def __init__(self, explained_variance, explained_variance_ratio):
+        self.explained_variance_, self.explained_variance_ratio_ = explained_variance, explained_variance_ratio
+
+
 class _KMeans:
     def __init__(self, centers):
         self.cluster_centers_ = centers
@@ -152,6 +159,12 @@ class AnnStream:
         self.annIdx = _ExactIndex(res.embedding_all, res.dims)
         self.kmeans, self.clusterLabels = kmeans, labels
         self._res = res
+        # what the reference's elbow plot reads (graph_datastore.py:1013-1016): variance explained by every kept
+        # component.  Exact-PCA values lambda_i / trace(cov); the z-scaled columns have unit variance, so the trace is
+        # nFeats * n / (n - 1) (constant columns, kept at sigma = 1, make this a slight over-estimate of the total).
+        ev = res.eigenvalues.detach().cpu().numpy().astype(np.float64)
+        total = float(self.nFeats) * res.n_cells / max(res.n_cells - 1, 1)
+        self._pca = _PcaSummary(ev, ev / total)
 
     def reducer(self, x):
         """``transform_z(x).dot(loadings)`` (scarf/ann.py:138,191-192); accepts a block or one row."""
