@@ -165,7 +165,7 @@ extern "C" int32_t scf_host_blosc_decode(const void* frame, int64_t frame_bytes,
     return 0;
   }
   SCF_ARG(((h.flags >> 5) & 7) == 1, "only the lz4 codec of Blosc is decoded (cname='lz4', scarf/writers.py:79-89)");
-  SCF_ARG(h.blocksize > 0 && h.typesize > 0, "bad header");
+  SCF_ARG(h.blocksize > 0 && h.blocksize <= h.nbytes && h.typesize > 0, "bad header");
   const int64_t nblocks = ((int64_t)h.nbytes + h.blocksize - 1) / h.blocksize;
   SCF_ARG(16 + 4 * nblocks <= frame_bytes, "frame truncated (block table)");
   const int ts = h.typesize;
