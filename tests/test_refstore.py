@@ -68,7 +68,9 @@ def _blosc_encode(raw: bytes, typesize: int, shuffle: int, blocksize: int, dont_
     import pyarrow as pa
 
     nbytes = len(raw)
-    blocksize = min(blocksize, nbytes)  # c-blosc never announces a block larger than the buffer
+    blocksize = min(blocksize, nbytes)  # c-blosc: a block is never larger than the buffer and holds whole elements
+    if blocksize > typesize:
+        blocksize -= blocksize % typesize
     flags = (1 << 5) | {0: 0, 1: 0x01, 2: 0x04}[shuffle] | (0x10 if dont_split else 0)
     nblocks = (nbytes + blocksize - 1) // blocksize
     body, bstarts = b"", []
