@@ -256,3 +256,37 @@ def test_public_signatures_equal_the_reference():
                 assert p.default is inspect.Parameter.empty, (name, a)
             else:
                 assert p.default == eval(default, {"np": np}), (name, a, p.default, default)
+
+
+def test_mark_hvgs_glue_on_cpu_tensors(pbmc, monkeypatch):
+    """graph.mark_hvgs_csr's tensor route (what DataStore.mark_hvgs runs: statistics wanted, or min_var / max_var /
+    keep_bounds given) with the statistics kernel replaced by the oracle's numbers, so that the glue -- argument
+    passing, blacklist, trend removal, choice, returned statistics -- runs here without a GPU."""
+    import torch
+
+    from oracle import pipeline as P
+    from scarf_b200 import graph
+    from scarf_b200.ops import CsrDevice
+
+    counts, cell_idx, names = pbmc["counts"], pbmc["cell_idx"], pbmc["names"]
+    feat_I = P.gene_ncells(counts) > 20
+    hv_o, st_o = P.mark_hvgs(counts, cell_idx, feat_I, gene_names=names, top_n=100, return_stats=True)
+    full = {k: torch.from_numpy(np.nan_to_num(np.asarray(st_o[k], dtype=np.float64)))
+            for k in ("normed_n", "normed_tot", "sigmas", "avg", "nz_mean")}
+    monkeypatch.setattr(graph, "hvg_gene_stats", lambda *a, **k: dict(full))
+    csr = CsrDevice(torch.zeros(893, dtype=torch.int64), torch.zeros(0, dtype=torch.int32),
+                    torch.zeros(0, dtype=torch.int32), 892, counts.shape[1])  # never read: the statistics are patched
+    n_counts = torch.ones(892, dtype=torch.float64)
+    cells = torch.from_numpy(cell_idx)
+    mask, st = graph.mark_hvgs_csr(csr, cells, feat_I, n_counts, 892, gene_names=names, top_n=100, return_stats=True)
+    assert np.array_equal(mask, hv_o) and set(st) >= {"c_var", "avg", "sigmas", "normed_n", "nz_mean", "normed_tot"}
+    np.testing.assert_allclose(st["c_var"][feat_I], st_o["c_var"][feat_I], rtol=1e-10)
+    kw = dict(min_cells=8, max_cells=700.0, min_mean=-3.0, max_mean=2.0)
+    hi = float(np.log2(np.nanpercentile(st_o["c_var"][feat_I], 99.8)))  # cuts the very top of the corrected variances
+    for extra in (dict(top_n=50), dict(top_n=50, keep_bounds=True), dict(top_n=50, max_var=hi),
+                  dict(top_n=50, min_var=0.0, max_var=hi)):
+        got = graph.mark_hvgs_csr(csr, cells, feat_I, n_counts, 892, gene_names=names, **kw, **extra)
+        want = P.choose_hvgs(st_o["normed_n"], st_o["nz_mean"], st_o["c_var"], feat_I, names, **kw, **extra)
+        assert np.array_equal(got, want) and want.sum() > 0, extra
+    with pytest.raises(ValueError, match="greater than 0"):
+        graph.mark_hvgs_csr(csr, cells, feat_I, n_counts, 892, gene_names=names, top_n=0)
