@@ -290,3 +290,51 @@ def test_mark_hvgs_glue_on_cpu_tensors(pbmc, monkeypatch):
         assert np.array_equal(got, want) and want.sum() > 0, extra
     with pytest.raises(ValueError, match="greater than 0"):
         graph.mark_hvgs_csr(csr, cells, feat_I, n_counts, 892, gene_names=names, top_n=0)
+
+
+def test_datastore_mark_hvgs_front_end_on_a_stub_store(pbmc, monkeypatch):
+    """DataStore.mark_hvgs (reference signature: cell_key None, max_cells, keep_bounds, min_var / max_var) driven on a
+    stub store with CPU tensors and the statistics kernel patched with the oracle's numbers: the columns written to the
+    feature table and the HVG mask are the oracle's."""
+    import torch
+    from types import SimpleNamespace
+
+    from oracle import pipeline as P
+    from scarf_b200 import graph
+    from scarf_b200.datastore import DataStore, RNAassay
+    from scarf_b200.ops import CsrDevice
+
+    counts, cell_idx, names = pbmc["counts"], pbmc["cell_idx"], pbmc["names"]
+    g = counts.shape[1]
+    feat_I = P.gene_ncells(counts) > 20
+    hv_o, st_o = P.mark_hvgs(counts, cell_idx, feat_I, gene_names=names, top_n=100, return_stats=True)
+    full = {k: torch.from_numpy(np.nan_to_num(np.asarray(st_o[k], dtype=np.float64)))
+            for k in ("normed_n", "normed_tot", "sigmas", "avg", "nz_mean")}
+    monkeypatch.setattr(graph, "hvg_gene_stats", lambda *a, **k: dict(full))
+    keep = np.zeros(892, dtype=bool)
+    keep[cell_idx] = True
+    written = {}
+
+    def insert(name, values, fill_value=np.nan, key="I", overwrite=False):
+        written[name] = np.asarray(values)
+
+    feats = SimpleNamespace(fetch_all=lambda c: {"I": feat_I, "names": names}[c], insert=insert, N=g)
+    assay = object.__new__(RNAassay)
+    assay.feats, assay.name, assay.sf = feats, "RNA", 1000
+    assay.csr = CsrDevice(torch.zeros(893, dtype=torch.int64), torch.zeros(0, dtype=torch.int32),
+                          torch.zeros(0, dtype=torch.int32), 892, g)
+    assay.cells = SimpleNamespace(fetch_all=lambda c: np.ones(892))  # RNA_nCounts (unused: statistics are patched)
+    cells = SimpleNamespace(columns=["I", "ids", "names"], N=892, active_index=lambda k: np.where(keep)[0])
+    store = SimpleNamespace(cells=cells, _defaultAssay="RNA", _get_assay=lambda a: assay, device=torch.device("cpu"),
+                            comm=None)
+    assert DataStore.mark_hvgs(store, top_n=100) is None  # cell_key None -> "I", min_cells None -> int(0.01 * N)
+    assert np.array_equal(written["I__hvgs"], hv_o[feat_I]) and written["I__hvgs"].sum() == 100
+    assert set(written) == {"I__normed_tot", "I__avg", "I__nz_mean", "I__sigmas", "I__normed_n", "I__c_var__200__0.1",
+                            "I__hvgs"}
+    np.testing.assert_allclose(written["I__c_var__200__0.1"], st_o["c_var"][feat_I], rtol=1e-10)
+    DataStore.mark_hvgs(store, top_n=30, max_cells=600.0, keep_bounds=True, hvg_key_name="few", show_plot=False)
+    want = P.choose_hvgs(st_o["normed_n"], st_o["nz_mean"], st_o["c_var"], feat_I, names, top_n=30, min_cells=8,
+                         max_cells=600.0, keep_bounds=True)
+    assert np.array_equal(written["I__few"], want[feat_I]) and want.sum() == 31
+    with pytest.raises(ValueError, match="not found in cell metadata"):
+        DataStore.mark_hvgs(store, cell_key="nope")
