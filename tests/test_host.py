@@ -338,3 +338,35 @@ def test_datastore_mark_hvgs_front_end_on_a_stub_store(pbmc, monkeypatch):
     assert np.array_equal(written["I__few"], want[feat_I]) and want.sum() == 31
     with pytest.raises(ValueError, match="not found in cell metadata"):
         DataStore.mark_hvgs(store, cell_key="nope")
+
+
+def test_datastore_load_graph_on_a_store_without_a_gpu(tmp_path):
+    """DataStore.load_graph reads the Zarr layout make_graph writes (knn__k/indices, graph__lc__bw/{edges,weights}) and
+    returns what the reference's load_graph returned on the same arrays (tests/golden/ref_functions.npz)."""
+    import os
+    from types import SimpleNamespace
+
+    from conftest import GOLDEN
+    from scarf_b200.datastore import DataStore
+    from scarf_b200.zarr_store import open_group
+
+    ref = np.load(os.path.join(GOLDEN, "ref_functions.npz"))
+    n, k = int(ref["graph_n"]), int(ref["graph_k"])
+    root = open_group(str(tmp_path / "g.zarr"), "w")
+    knn = "RNA/normed__I__hvgs/reduction__pca__11__I/ann__l2__50__50__48__4466/knn__5"
+    gl = f"{knn}/graph__1.0__1.5"
+    root.create_group(gl)
+    a = root[knn].create_dataset("indices", (n, k), "u8", (1000, k))
+    a[:] = ref["graph_edges"][:, 1].reshape(n, k)
+    e = root[gl].create_dataset("edges", (n * k, 2), "u8", (1000 * k, 2))
+    e[:] = ref["graph_edges"]
+    w = root[gl].create_dataset("weights", (n * k,), "f8", (1000 * k,))
+    w[:] = ref["graph_weights"]
+    store = SimpleNamespace(zw=root, _get_latest_keys=lambda a_, c, f: ("RNA", "I", "hvgs"),
+                            _get_latest_graph_loc=lambda a_, c, f: gl)
+    for tag, kw in (("default", {}), ("sym_upper", dict(symmetric=True, upper_only=True)),
+                    ("raw_k3", dict(symmetric=False, use_k=3)), ("sym_k0", dict(symmetric=True, use_k=0))):
+        g = DataStore.load_graph(store, **kw)
+        assert np.array_equal(np.asarray(g.todense()), ref[f"graph_{tag}"]), tag
+    with pytest.raises(ValueError, match="not found in zarr location"):
+        DataStore.load_graph(store, graph_loc="RNA/none")
