@@ -185,19 +185,58 @@ class AnnStream:
 class DataStore:
     """A Scarf-style datastore whose graph path runs on B200.  Create with :meth:`from_csr`, reopen by path."""
 
-    def __init__(self, zarr_loc: str, default_assay: str = "RNA", device="cuda", comm: Optional[Comm] = None,
-                 mode: str = "r+", min_features_per_cell: int = 10, min_cells_per_feature: int = 20):
+    def __init__(self, zarr_loc: str, assay_types: Optional[dict] = None, default_assay: Optional[str] = None,
+                 min_features_per_cell: int = 10, min_cells_per_feature: int = 20, mito_pattern: Optional[str] = None,
+                 ribo_pattern: Optional[str] = None, nthreads: int = 2, zarr_mode: str = "r+",
+                 workspace: Optional[str] = None, synchronizer=None, *, device="cuda", comm: Optional[Comm] = None):
+        """scarf/datastore/datastore.py:46-90 + base_datastore.py:77-186 (same parameters, order and defaults; ``device``
+        and ``comm`` are keyword-only additions).  ``mito_pattern`` / ``ribo_pattern`` (percentMito / percentRibo
+        annotations), ``nthreads`` and ``synchronizer`` (dask / zarr plumbing) have nothing to act on here and are
+        accepted for compatibility; ``workspace`` and non-RNA ``assay_types`` raise."""
         if not torch.cuda.is_available():
             raise RuntimeError("scarf_b200.DataStore needs a CUDA device: the path has no CPU fallback")
-        self.zw = open_group(zarr_loc, mode)
+        if zarr_mode not in ["r", "r+"]:
+            raise ValueError("ERROR: Zarr file can only be accessed using either 'r' or 'r+' mode")
+        if workspace is not None:
+            raise NotImplementedError("scarf_b200.DataStore: `workspace` sub-hierarchies are not implemented")
+        self.zw = open_group(zarr_loc, zarr_mode)
         self.z = self.zw
-        self._defaultAssay = default_assay
+        self.nthreads = nthreads
         self.device = torch.device(device)
         self.comm = comm
+        if "cellData" not in self.zw:
+            raise KeyError(f"cellData not found in zarr file at {self.zw.path}")
         self.cells = MetaData(self.zw["cellData"])
+        self._defaultAssay = self._load_default_assay(default_assay)
+        if assay_types is not None and str(assay_types.get(self._defaultAssay, "RNA")).upper() != "RNA":
+            raise NotImplementedError("scarf_b200.DataStore implements the RNAassay path only")
         self._assays = {}
-        setattr(self, default_assay, self._get_assay(default_assay))
-        self._ini_props(default_assay, min_features_per_cell, min_cells_per_feature)
+        setattr(self, self._defaultAssay, self._get_assay(self._defaultAssay))
+        self._ini_props(self._defaultAssay, min_features_per_cell, min_cells_per_feature)
+
+    @property
+    def assay_names(self):
+        """Groups that carry the writers' ``is_assay`` attribute (base_datastore.py:127-141)."""
+        return [k for k in self.zw.keys() if isinstance(self.zw[k], Group) and "is_assay" in self.zw[k].attrs]
+
+    def _load_default_assay(self, assay_name: Optional[str] = None) -> str:
+        """base_datastore.py:143-182: explicit name (must exist) -> the store's ``defaultAssay`` attribute -> the only
+        assay; the choice is remembered in the root attributes."""
+        names = self.assay_names
+        if assay_name is None:
+            if "defaultAssay" in self.zw.attrs:
+                return self.zw.attrs["defaultAssay"]
+            if len(names) != 1:
+                raise ValueError("ERROR: You have more than one assay data. "
+                                 f"Choose one from: {' '.join(names)}\n using 'default_assay' parameter. "
+                                 "Please note that names are case-sensitive.")
+            assay_name = names[0]
+        elif assay_name not in names:
+            raise ValueError(f"ERROR: The provided default assay name: {assay_name} was not found. "
+                             f"Please Choose one from: {' '.join(names)}\n"
+                             "Please note that the names are case-sensitive.")
+        self.zw.attrs["defaultAssay"] = assay_name
+        return assay_name
 
     def _ini_props(self, from_assay, min_features, min_cells):
         """First open of a store (base_datastore.py:324-401 `_ini_cell_props`, assay.py:201-225 `_ini_feature_props`):

@@ -370,3 +370,74 @@ def test_datastore_load_graph_on_a_store_without_a_gpu(tmp_path):
         assert np.array_equal(np.asarray(g.todense()), ref[f"graph_{tag}"]), tag
     with pytest.raises(ValueError, match="not found in zarr location"):
         DataStore.load_graph(store, graph_loc="RNA/none")
+
+
+def test_datastore_constructor_follows_the_reference(tmp_path, monkeypatch):
+    """DataStore.__init__ (scarf/datastore/datastore.py:46-90, base_datastore.py:77-186): the reference's parameter
+    list, default-assay resolution (explicit -> `defaultAssay` attribute -> the only assay), the every-open cell filter
+    on nFeatures, the error cases.  Runs on CPU tensors: the store already holds every first-open column, so no kernel
+    is needed (the CUDA check is patched out for this test only)."""
+    import inspect
+    import json
+    import os
+
+    import scipy.sparse as sp
+    import torch
+
+    from scarf_b200.datastore import DataStore
+    from scarf_b200.zarr_store import open_group
+
+    params = list(inspect.signature(DataStore.__init__).parameters.values())[1:]
+    assert [p.name for p in params if p.kind == p.POSITIONAL_OR_KEYWORD] == [
+        "zarr_loc", "assay_types", "default_assay", "min_features_per_cell", "min_cells_per_feature", "mito_pattern",
+        "ribo_pattern", "nthreads", "zarr_mode", "workspace", "synchronizer"]
+    rng = np.random.default_rng(5)
+    m = sp.random(40, 30, density=0.4, random_state=5, format="csr", dtype=np.float64)
+    m.data = np.ceil(m.data * 5).astype(np.uint32)
+    m = m.astype(np.uint32)
+    m.sort_indices()
+    dense = m.toarray()
+    loc = str(tmp_path / "s.zarr")
+    root = open_group(loc, "w")
+
+    def put(grp, name, arr):
+        grp.create_dataset(name, arr.shape, arr.dtype, (100000,))[:] = arr
+
+    cg = root.create_group("cellData")
+    put(cg, "I", np.ones(40, dtype=bool)), put(cg, "ids", np.array([f"c{i}" for i in range(40)]))
+    put(cg, "names", np.array([f"c{i}" for i in range(40)]))
+    put(cg, "RNA_nCounts", dense.sum(1).astype(np.float64)), put(cg, "RNA_nFeatures", (dense > 0).sum(1).astype(np.float64))
+    for name in ("RNA", "ADT"):
+        ag = root.create_group(name)
+        ag.attrs["is_assay"] = True
+        fg = ag.create_group("featureData")
+        put(fg, "I", np.ones(30, dtype=bool)), put(fg, "ids", np.array([f"g{i}" for i in range(30)]))
+        put(fg, "names", np.array([f"g{i}" for i in range(30)]))
+        put(fg, "nCells", (dense > 0).sum(0).astype(np.float64)), put(fg, "dropOuts", 40.0 - (dense > 0).sum(0))
+        rg = ag.create_group("counts_csr")
+        rg.attrs["shape"] = [40, 30]
+        put(rg, "indptr", m.indptr.astype(np.int64)), put(rg, "indices", m.indices.astype(np.int32))
+        put(rg, "data", m.data.astype(np.uint32))
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    with pytest.raises(ValueError, match="more than one assay"):
+        DataStore(loc, device="cpu")
+    with pytest.raises(ValueError, match="was not found"):
+        DataStore(loc, default_assay="rna", device="cpu")
+    with pytest.raises(ValueError, match="'r' or 'r\\+'"):
+        DataStore(loc, default_assay="RNA", zarr_mode="w", device="cpu")
+    with pytest.raises(NotImplementedError):
+        DataStore(loc, {"RNA": "ATAC"}, "RNA", device="cpu")
+    n_feat = (dense > 0).sum(1)
+    cut = int(np.sort(n_feat)[5])  # a threshold below the median: the filter applies (base_datastore.py:384-399)
+    ds = DataStore(loc, None, "RNA", cut, 20, None, None, 4, "r+", device="cpu")  # positional, as the reference takes them
+    assert ds._defaultAssay == "RNA" and ds.nthreads == 4 and ds.assay_names == ["ADT", "RNA"]
+    assert json.load(open(os.path.join(loc, ".zattrs")))["defaultAssay"] == "RNA"
+    assert np.array_equal(ds.cells.fetch_all("I"), n_feat > cut) and 0 < (n_feat > cut).sum() < 40
+    assert np.array_equal(ds.RNA.csr.indices.numpy(), m.indices) and ds.RNA.csr.n_cols == 30
+    # reopening: the remembered default assay, and the filter runs again with the default threshold of 10 (it is
+    # applied at every open, base_datastore.py:384-399); a threshold above the median of the kept cells changes nothing
+    ds2 = DataStore(loc, device="cpu")
+    assert cut < 10 <= np.median(n_feat[n_feat > cut])
+    assert ds2._defaultAssay == "RNA" and np.array_equal(ds2.cells.fetch_all("I"), n_feat > 10)
+    ds3 = DataStore(loc, min_features_per_cell=10 ** 6, device="cpu")
+    assert np.array_equal(ds3.cells.fetch_all("I"), n_feat > 10)
