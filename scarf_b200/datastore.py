@@ -201,6 +201,7 @@ class DataStore:
             raise NotImplementedError("scarf_b200.DataStore: `workspace` sub-hierarchies are not implemented")
         self.zw = open_group(zarr_loc, zarr_mode)
         self.z = self.zw
+        self._zarr_mode = zarr_mode
         self.nthreads = nthreads
         self.device = torch.device(device)
         self.comm = comm
@@ -235,7 +236,8 @@ class DataStore:
             raise ValueError(f"ERROR: The provided default assay name: {assay_name} was not found. "
                              f"Please Choose one from: {' '.join(names)}\n"
                              "Please note that the names are case-sensitive.")
-        self.zw.attrs["defaultAssay"] = assay_name
+        if self._zarr_mode != "r":  # a read-only store keeps its attributes
+            self.zw.attrs["defaultAssay"] = assay_name
         return assay_name
 
     def _ini_props(self, from_assay, min_features, min_cells):
