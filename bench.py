@@ -7,9 +7,22 @@
 One "step" = mark_hvgs + make_graph on one synthetic CSR batch: raw CSR -> weighted kNN graph.  As in the
 reference, the per-cell nCounts and the per-gene nCells mask `I` are attributes the DataStore computed when the
 store was created (scarf/datastore/base_datastore.py:324-401, scarf/assay.py:201-225): both arms receive them.
+
+Workloads (BASELINE.json `configs`):
+  N = 1   headline C2 (100k cells x 30k genes, 2k HVGs, dims 50, k 11); extra leg `legs.C3`: the 1M-cell C3 workload on
+          this one GPU -- the N = 1 point of the strong-scaling series the N > 1 lines continue.
+  N > 1   headline C3, STRONG scaling: 1M cells in total, rows sharded over the ranks (aligned to 1000), dims 100, k 21.
+  N = 8   extra leg `legs.C4`: 4M cells x 30k genes, dims 100, k 11, one pass, seconds per phase against the 30 s target.
+
 `value`  : cells/s with the CSR shard already resident in HBM (CUDA events, max over ranks).
-`e2e`    : the same through the public API with HOST (pinned) CSR buffers, H2D + D2H inside the timed region.
+`e2e`    : the same through the public API with HOST (pinned) CSR buffers; every step copies its inputs host->device and
+           its graph device->host inside the timed region; uploads are double buffered (the copy of step i+1 overlaps
+           the compute of step i); `e2e.latency_ms` is one step alone, copies and compute back to back.
 `roofline`: the dominant kernel (exact kNN) timed live with CUDA events on its launch stream.
+`parity` : computed in the run on the last step's result: (a) 256 local rows re-solved by the FP64 brute-force kernel
+           against the all-gathered embedding, compared bit for bit; (b) an order-independent 64-bit hash of
+           indices / distances / weights summed over ranks -- equal for every N on the same total workload, and
+           compared with profiles/expected_hashes.json when that holds an entry for the workload.
 `cpu_baseline`: the CPU oracle (restated reference path, "port") on a bounded sample of the same workload.
 """
 import argparse
@@ -25,11 +38,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    "C1": dict(cells=5_000, genes=20_000, hvgs=2_000, dims=25, k=11, factors=40),
     # BASELINE.json configs[1]: the configuration the metric is quoted on for one GPU
     "C2": dict(cells=100_000, genes=30_000, hvgs=2_000, dims=50, k=11, factors=65),
-    "C1": dict(cells=5_000, genes=20_000, hvgs=2_000, dims=25, k=11, factors=40),
     "C3": dict(cells=1_000_000, genes=30_000, hvgs=2_000, dims=100, k=21, factors=115),
+    "C4": dict(cells=4_000_000, genes=30_000, hvgs=2_000, dims=100, k=11, factors=115),
 }
+GEN_BLOCK = 1000  # rows per generator block == shard alignment: any shard of the global matrix is reproducible
+SEED = 4466
 
 
 def parse():
@@ -38,13 +54,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cells", type=int, default=None, help="cells per GPU (overrides the workload)")
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="headline workload (default: C2 on one GPU, C3 strong scaling on several)")
+    ap.add_argument("--cells", type=int, default=None, help="total cells (overrides the workload)")
+    ap.add_argument("--legs", default="auto", help="extra legs: auto | none | comma list of C3,C4,datastore")
     ap.add_argument("--gram-mode", type=int, default=int(os.environ.get("SCF_GRAM_MODE", "3")))
     ap.add_argument("--knn-method", type=int, default=int(os.environ.get("SCF_KNN_METHOD", "1")))
     ap.add_argument("--cpu-sample", type=int, default=4000, help="cells in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -54,35 +73,50 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "src": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
-def measure_f16_peak(torch, dev):
-    """cuBLAS FP16 dense GEMM 8192^3 (FP32 accumulate), best of 10 -- the method MEASURED_PEAKS.json uses for bf16;
-    the kNN kernel issues tcgen05.mma kind::f16, which runs at the same rate: TFLOP/s."""
-    a = torch.randn((8192, 8192), device=dev, dtype=torch.float16)
-    b = torch.randn((8192, 8192), device=dev, dtype=torch.float16)
-    for _ in range(3):
-        a @ b
-    best = float("inf")
-    for _ in range(10):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        a @ b
-        e1.record()
-        torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
+def measure_gemm_peak(torch, dev, dtype, tf32=False):
+    """cuBLAS dense GEMM 8192^3, best of 10 -- the method MEASURED_PEAKS.json uses for bf16: TFLOP/s."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    try:
+        a = torch.randn((8192, 8192), device=dev, dtype=dtype)
+        b = torch.randn((8192, 8192), device=dev, dtype=dtype)
+        for _ in range(3):
+            a @ b
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
     return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
-def ncu_traffic(kernel_key):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full summary (profiles/)."""
+def ncu_traffic(kernel_key, shape_key):
+    """DRAM bytes per launch of the dominant kernel from a committed `ncu --set full` capture of the SAME launch shape
+    (profiles/ncu_full_summary.json: {kernel: {shape_key: {dram_bytes_read, dram_bytes_write}}}); None when the shape of
+    this run has no capture (a number taken at another shape would not describe this launch)."""
     p = os.path.join(ROOT, "profiles", "ncu_full_summary.json")
     if os.path.exists(p):
-        d = json.load(open(p)).get(kernel_key)
+        d = json.load(open(p)).get(kernel_key, {})
+        d = d.get("by_shape", {}).get(shape_key)
         if d:
             return d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0)
+    return None
+
+
+def expected_hash(key):
+    p = os.path.join(ROOT, "profiles", "expected_hashes.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(key)
     return None
 
 
@@ -142,7 +176,36 @@ class ClockSampler:
         return out
 
 
+def pin_to_gpu_numa(index):
+    """Best effort: run this rank on the cores next to its GPU, so that its pinned host buffers are allocated on the
+    GPU's NUMA node (first touch) and the H2D copies of the ranks do not share one socket's memory controllers."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------------------------------
+def describe(name, cfg, n_total, world, scaling, sample=None):
+    w = (f"{name}: synthetic {n_total} cells x {cfg['genes']} genes raw CSR in total"
+         f"{' over ' + str(world) + ' GPUs (rows sharded, ' + scaling + ' scaling)' if world > 1 else ''}, "
+         f"{cfg['hvgs']} HVGs, dims={cfg['dims']}, k={cfg['k']} (mark_hvgs + make_graph)")
+    if sample is not None:
+        w += f"; CPU arm: the first {sample} cells of it (same generator / seed, all genes) per step"
+    return w
+
+
 def cpu_reference_run(cfg, sample, threads):
     """The reference's algorithm on host cores (oracle port): mark_hvgs + make_graph on `sample` cells of the
     workload (same generator / seed, first `sample` rows).  Returns (seconds, cells)."""
@@ -150,9 +213,9 @@ def cpu_reference_run(cfg, sample, threads):
     from threadpoolctl import threadpool_limits
 
     from oracle import pipeline as P
-    from scarf_b200 import synth
+    from scarf_b200 import synth  # pure torch / numpy: does not load the CUDA library
 
-    m = synth.make_counts_scipy(sample, cfg["genes"], cfg["factors"], seed=4466, block=2000)
+    m = synth.make_counts_scipy(sample, cfg["genes"], cfg["factors"], seed=SEED, block=GEN_BLOCK)
     P.exact_knn(np.zeros((4, 2), np.float32), np.zeros((4, 2), np.float32), 1)  # builds/loads the C part untimed
     cell_idx = np.arange(sample)
     n_counts, _ = P.cell_totals(m)     # DataStore-creation attributes: outside the timed region on both arms
@@ -164,83 +227,137 @@ def cpu_reference_run(cfg, sample, threads):
     return time.perf_counter() - t0, sample
 
 
-def run_reference(args, cfg, rank):
+def run_reference(args, rank):
     if rank != 0:
         return
+    name = args.workload or ("C2" if args.gpus == 1 else "C3")
+    cfg = dict(WORKLOADS[name])
+    n_total = args.cells or cfg["cells"]
+    sample = min(args.cpu_sample, n_total)
     threads = os.cpu_count() or 1
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_run(cfg, min(1000, args.cpu_sample), threads)
+        cpu_reference_run(cfg, min(1000, sample), threads)
     times = []
     for _ in range(args.steps):
-        dt, n = cpu_reference_run(cfg, args.cpu_sample, threads)
+        dt, n = cpu_reference_run(cfg, sample, threads)
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    val = args.cpu_sample / (ms / 1e3)
-    sample = f"first {args.cpu_sample} cells of the workload (same generator/seed), full gene set"
+    val = sample / (ms / 1e3)
+    sample_txt = f"first {sample} cells of the workload (same generator/seed), full gene set, per step"
+    scaling = "weak" if args.gpus == 1 else "strong"
     print(json.dumps({
         "impl": "reference", "metric": "make_graph_cells_per_s", "value": val, "unit": "cells/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, cfg, max(args.gpus, 1)),
-        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": describe(name, cfg, n_total, max(args.gpus, 1), scaling, sample=sample),
+                   "total_cells": n_total, "cells_timed_per_step": sample, "genes": cfg["genes"], "hvgs": cfg["hvgs"],
+                   "dims": cfg["dims"], "k": cfg["k"]},
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample_txt},
         "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference (scarf 0.32.3) cannot be imported here (dask/zarr/hnswlib/umap-learn absent, no network): "
                 "this arm times the CPU restatement of its algorithm (oracle/, IncrementalPCA in Scarf's block order + "
-                "exact kNN + umap smoothing) on all host cores",
+                "exact kNN + umap smoothing) on all host cores, on a bounded sample of the workload: its cells/s is an "
+                "UPPER bound of the CPU's rate on the whole workload (the exact search is O(N^2))",
     }))
 
 
-def workload_config(args, cfg, world):
-    return {"workload": f"{args.workload}: synthetic {cfg['cells']} cells/GPU x {cfg['genes']} genes raw CSR, "
-                        f"{cfg['hvgs']} HVGs, dims={cfg['dims']}, k={cfg['k']} (mark_hvgs + make_graph)",
-            "cells_per_gpu": cfg["cells"], "total_cells": cfg["cells"] * world, "genes": cfg["genes"],
-            "hvgs": cfg["hvgs"], "dims": cfg["dims"], "k": cfg["k"],
-            "l2": "inputs larger than L2 (CSR shard >> 126 MB is re-read from HBM every step)",
-            "gram_mode": args.gram_mode, "knn_method": args.knn_method}
+# ---------------------------------------------------------------------------------------------------
+def _mix64(torch, x):
+    """splitmix64 finaliser on int64 tensors (two's-complement wrap-around arithmetic)."""
+    x = (x ^ (x >> 30)) * -4658895280553007687   # 0xBF58476D1CE4E5B9
+    x = (x ^ (x >> 27)) * -7723592293110705685   # 0x94D049BB133111EB
+    return x ^ (x >> 31)
+
+
+def array_hash(torch, t, first_row, salt):
+    """Order-independent 64-bit hash of a [rows, cols] (or flat per-row) array whose first row has global id
+    `first_row`: sum over the elements of mix(global position, value bits), modulo 2^64 -> int64 scalar tensor."""
+    if t.dtype == torch.float32:
+        bits = t.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    elif t.dtype == torch.float64:
+        bits = t.contiguous().view(torch.int64)
+    else:
+        bits = t.to(torch.int64)
+    bits = bits.reshape(-1)
+    pos = torch.arange(bits.numel(), dtype=torch.int64, device=t.device) + int(first_row)
+    h = _mix64(torch, pos * -7046029254386353131 + _mix64(torch, bits + int(salt)))  # 0x9E3779B97F4A7C15
+    return h.sum()
+
+
+def parity_check(torch, ops, res, comm, k, dims, hash_key):
+    """(a) FP64 brute-force spot check of 256 local rows, (b) the all-rank hash (see the module docstring)."""
+    dev = res.indices.device
+    n_local = int(res.indices.shape[0])
+    rows_checked, equal = 0, True
+    if n_local > 0:
+        blocks = 4 if n_local >= 256 else 1
+        per = min(64, n_local)
+        for b in range(blocks):
+            s = (n_local - per) * b // max(blocks - 1, 1)
+            qi, qd = ops.knn_l2(res.embedding[s:s + per], res.embedding_all, dims, k, self_offset=res.row_offset + s,
+                                method=0)
+            equal &= bool(torch.equal(qi, res.indices[s:s + per])) and bool(torch.equal(qd, res.distances[s:s + per]))
+            rows_checked += per
+    flag = torch.tensor([1 if equal else 0, rows_checked], dtype=torch.int64, device=dev)
+    hs = torch.stack([array_hash(torch, res.indices, res.row_offset * k, 1),
+                      array_hash(torch, res.distances, res.row_offset * k, 2),
+                      array_hash(torch, res.weights, res.row_offset * k, 3)])
+    if comm.world > 1:
+        import torch.distributed as td
+
+        td.all_reduce(flag[:1], op=td.ReduceOp.MIN)
+        comm.allreduce_sum_(flag[1:])
+        comm.allreduce_sum_(hs)
+    names = ("indices", "distances", "weights")
+    hashes = {n_: f"{int(v) & 0xFFFFFFFFFFFFFFFF:016x}" for n_, v in zip(names, hs.tolist())}
+    exp = expected_hash(hash_key)
+    out = {"fp64_spot_rows": int(flag[1].item()), "fp64_spot_equal": bool(flag[0].item()), "hash": hashes,
+           "hash_key": hash_key, "hash_expected": exp,
+           "hash_match": (None if exp is None else all(exp.get(n_) == hashes[n_] for n_ in names))}
+    out["ok"] = out["fp64_spot_equal"] and out["hash_match"] is not False
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
-def run_ours(args, cfg, rank, world, local_rank):
-    import numpy as np
-    import torch
-    import torch.distributed as td
+class Runner:
+    """One workload on this rank's shard: generation, the step, timing, roofline, e2e, parity."""
 
-    from scarf_b200 import graph, lib, synth
-    from scarf_b200.dist import Comm
-    from scarf_b200.ops import CsrDevice
+    def __init__(self, args, name, cfg, n_total, rank, world, dev, comm, scaling):
+        import torch
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        td.init_process_group("nccl", device_id=dev)
-    comm = Comm()
-    n_local = cfg["cells"]
-    n_total = n_local * world
-    block = 2000
-    csr = synth.make_counts_device(n_local, cfg["genes"], cfg["factors"], seed=4466, device=dev, block=block,
-                                   row_start=rank * n_local)
-    torch.cuda.synchronize()
-    nnz = csr.nnz
-    timers = []
+        from scarf_b200 import graph, synth
+        from scarf_b200.dist import ShardPlan
 
-    n_counts, _ = graph.cell_totals(csr)  # DataStore-creation attributes (see the module docstring)
-    feat_I = graph.gene_ncells(csr, comm) > 20  # bool device tensor
-    keep = torch.ones(cfg["genes"], dtype=torch.bool, device=dev)  # synthetic gene names never hit the blacklist
-    torch.cuda.synchronize()
+        self.torch, self.graph = torch, graph
+        self.args, self.name, self.cfg, self.n_total = args, name, cfg, n_total
+        self.rank, self.world, self.dev, self.comm, self.scaling = rank, world, dev, comm, scaling
+        a, b = ShardPlan.make(n_total, world, GEN_BLOCK).rows(rank)
+        self.row0, self.n_local = a, b - a
+        t0 = time.time()
+        self.csr = synth.make_counts_device(self.n_local, cfg["genes"], cfg["factors"], seed=SEED, device=dev,
+                                            block=GEN_BLOCK, row_start=a)
+        torch.cuda.synchronize()
+        self.gen_s = time.time() - t0
+        self.n_counts, _ = graph.cell_totals(self.csr)  # DataStore-creation attributes (see the module docstring)
+        self.feat_I = graph.gene_ncells(self.csr, comm) > 20  # bool device tensor
+        self.keep = torch.ones(cfg["genes"], dtype=torch.bool, device=dev)  # synthetic names never hit the blacklist
+        self.eig_stats = {}
+        torch.cuda.synchronize()
 
-    eig_stats = {}
-
-    def step(c, tm=None):
+    def step(self, c, tm=None):
+        torch, graph, cfg, args = self.torch, self.graph, self.cfg, self.args
         if tm is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             tm.append(("step_start", e))
-        hv = graph.mark_hvgs_csr(c, None, feat_I, n_counts, n_total, top_n=cfg["hvgs"], comm=comm, as_tensor=True,
-                                 keep_mask=keep)
-        return graph.make_graph_csr(c, None, hv, dims=cfg["dims"], k=cfg["k"], comm=comm, gram_mode=args.gram_mode,
-                                    knn_method=args.knn_method, timers=tm, stats=eig_stats)
+        hv = graph.mark_hvgs_csr(c, None, self.feat_I, self.n_counts, self.n_total, top_n=cfg["hvgs"], comm=self.comm,
+                                 as_tensor=True, keep_mask=self.keep)
+        return graph.make_graph_csr(c, None, hv, dims=cfg["dims"], k=cfg["k"], comm=self.comm,
+                                    gram_mode=args.gram_mode, knn_method=args.knn_method, timers=tm,
+                                    stats=self.eig_stats)
 
-    def timed(fn, steps):
+    def timed(self, fn, steps):
+        torch, comm = self.torch, self.comm
         comm.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -250,139 +367,373 @@ def run_ours(args, cfg, rank, world, local_rank):
         e1.record()
         torch.cuda.synchronize()
         comm.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
         comm.allreduce_max_(ms)
         return float(ms.item())
 
-    res = None
-    for _ in range(max(args.warmup, 1)):
-        res = step(csr)
-    torch.cuda.synchronize()
-    # stored values that fall on the selected features (the compact matrix the normalise stage reads): counted once,
-    # outside the timed region, for the HBM-side roofline of that stage
-    fmask = torch.zeros(cfg["genes"], dtype=torch.bool, device=dev)
-    fmask[torch.from_numpy(res.feat_idx).to(dev)] = True
-    hvg_nnz = 0
-    for s0 in range(0, nnz, 1 << 26):
-        hvg_nnz += int(fmask[csr.indices[s0:s0 + (1 << 26)].long()].sum())
-    del fmask
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.5)  # nvidia-smi needs a moment before its first sample
-    lib.LAUNCHES["n"] = 0
-    if args.profiler_range:
-        torch.cuda.profiler.start()
-    wall0 = time.time()
-    ms_total = timed(lambda: step(csr, timers), args.steps)
-    wall1 = time.time()
-    if args.profiler_range:
-        torch.cuda.profiler.stop()
-    launches = lib.LAUNCHES["n"]
-    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    ms_step = ms_total / args.steps
-    value = n_total / (ms_step / 1e3)
+    def run(self, steps, warmup, with_e2e, with_parity, sampler=None):
+        import numpy as np  # noqa: F401
 
-    # per-stage CUDA-event times of the timed steps (events were recorded on the launching stream)
-    kernel_ms = [a.elapsed_time(b) for name, (a, b) in ((n_, e_) for n_, e_ in timers if n_ == "knn_kernel_events")]
-    timers = [t for t in timers if t[0] != "knn_kernel_events"]
-    stage_ms = {}
-    for (n0, a), (n1, b) in zip(timers[:-1], timers[1:]):
-        if n1 != "step_start":
-            stage_ms.setdefault("mark_hvgs" if n1 == "start" else n1, []).append(a.elapsed_time(b))
-    stage_ms = {k_: sum(v) / len(v) for k_, v in stage_ms.items()}
-    pk = peaks()
-    knn_ms = stage_ms.get("knn", float("nan"))  # whole entry point
-    knn_kernel_ms = sum(kernel_ms) / len(kernel_ms) if kernel_ms else knn_ms  # knn_tc_kernel alone (events in the library)
-    knn_flop = 2.0 * n_total * cfg["dims"] * n_local  # 2*N_ref*D per query, true D
-    f16_peak_run = measure_f16_peak(torch, dev)
-    # the driver-measured dense 16-bit peak is the denominator (burst figure: the kNN entry point runs for a few ms);
-    # the in-run cuBLAS FP16 number is reported next to it
-    tensor_peak = pk["bf16_tflops"]
-    # the fused top-k' epilogue has to read every FP32 accumulator out of TMEM: 4 B per (query, reference) pair at the
-    # 64 B/clk/SM tcgen05.ld rate (B300_MICROARCH.md) bounds the kernel from below whatever the tensor pipe does
-    sm_hz = 1e6 * float((clocks or {}).get("sm_max_mhz") or 1965.0)
-    tmem_floor_ms = 4.0 * n_total * n_local / (64.0 * 148 * sm_hz) * 1e3
-    roofline = {"kernel": "knn_tc_kernel (tcgen05 kind::f16 distance contraction with fused top-k', the dominant kernel of "
-                          "scf_knn_l2; timed with CUDA events recorded by the library around this launch alone; "
-                          "entry_point_* = the whole call incl. operand prep, FP64 re-rank and guard repair)",
-                "bound": "tensor", "achieved": knn_flop / (knn_kernel_ms * 1e-3) / 1e12, "peak": tensor_peak,
-                "unit": "TFLOP/s", "frac": knn_flop / (knn_kernel_ms * 1e-3) / 1e12 / tensor_peak,
-                "traffic": ncu_traffic("knn_tc_kernel"),
-                "peak_note": f"dense 16-bit tensor peak from MEASURED_PEAKS.json ({pk['src']}; bf16 cuBLAS 8192^3, burst); "
-                             f"cuBLAS FP16 8192^3 measured in this run: {f16_peak_run:.1f} TFLOP/s; HBM {pk['hbm_gbs']} GB/s. "
-                             "achieved = 2*N_query*N_ref*D (true D, no padding credit) / CUDA-event time of the kernel",
-                "ms_per_launch": knn_kernel_ms,
-                "entry_point_ms": knn_ms,
-                "entry_point_achieved": knn_flop / (knn_ms * 1e-3) / 1e12,
-                "tmem_readout_floor_ms": tmem_floor_ms,
-                "hbm_side": {k_: {"ms": stage_ms.get(k_), "algorithmic_GBs": v / (stage_ms[k_] * 1e-3) / 1e9,
-                                  "frac_of_hbm_peak": v / (stage_ms[k_] * 1e-3) / 1e9 / pk["hbm_gbs"]}
-                             for k_, v in (("normalise", 12.0 * hvg_nnz + 8.0 * n_local + 4.0 * 2048 * n_local *
-                                            (2 if args.gram_mode == 3 else 1)),) if stage_ms.get(k_)}}
-    csr_bytes = 8.0 * nnz + 8.0 * (n_local + 1)
-    stages = {k_: round(v, 4) for k_, v in stage_ms.items()}
+        from scarf_b200 import lib, ops
 
-    # ---- e2e: host (pinned) CSR -> device -> graph -> host ----
-    e2e = None
-    if not args.no_e2e:
-        h_ip, h_ix, h_dv = (t.cpu().pin_memory() for t in (csr.indptr, csr.indices, csr.data))
-        out_host = {}
+        torch, args, cfg, dev = self.torch, self.args, self.cfg, self.dev
+        timers = []
+        res = None
+        for _ in range(max(warmup, 1)):
+            res = self.step(self.csr)
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.5)  # nvidia-smi needs a moment before its first sample
+        lib.LAUNCHES["n"] = 0
+        if args.profiler_range:
+            torch.cuda.profiler.start()
+        wall0 = time.time()
+        ms_total = self.timed(lambda: self.step(self.csr, timers), steps)
+        wall1 = time.time()
+        if args.profiler_range:
+            torch.cuda.profiler.stop()
+        launches = lib.LAUNCHES["n"]
+        clocks = sampler.stop(wall0, wall1) if sampler is not None else None
+        ms_step = ms_total / steps
+        out = {"value": self.n_total / (ms_step / 1e3), "ms_per_step": ms_step, "gpu_launches": launches,
+               "clocks": clocks, "cells_per_gpu": self.n_local, "generation_s": round(self.gen_s, 3)}
 
-        def e2e_step():
-            c = CsrDevice(h_ip.to(dev, non_blocking=True), h_ix.to(dev, non_blocking=True),
-                          h_dv.to(dev, non_blocking=True), n_local, cfg["genes"])
-            r = step(c)
-            for name in ("indices", "distances", "weights"):
-                t = getattr(r, name)
-                if name not in out_host:
-                    out_host[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                out_host[name].copy_(t, non_blocking=True)
+        # per-stage CUDA-event times of the timed steps (events were recorded on the launching stream)
+        kernel_ms = [a.elapsed_time(b) for n_, (a, b) in ((n_, e_) for n_, e_ in timers if n_ == "knn_kernel_events")]
+        tms = [t for t in timers if t[0] != "knn_kernel_events"]
+        stage_ms = {}
+        for (n0, a), (n1, b) in zip(tms[:-1], tms[1:]):
+            if n1 != "step_start":
+                stage_ms.setdefault("mark_hvgs" if n1 == "start" else n1, []).append(a.elapsed_time(b))
+        stage_ms = {k_: sum(v) / len(v) for k_, v in stage_ms.items()}
+        out["stage_ms"] = {k_: round(v, 4) for k_, v in stage_ms.items()}
+        out["eig"] = dict(self.eig_stats)
+        pk = peaks()
+        knn_ms = stage_ms.get("knn", float("nan"))  # whole entry point
+        knn_kernel_ms = sum(kernel_ms) / len(kernel_ms) if kernel_ms else knn_ms  # the tensor kernel alone
+        knn_flop = 2.0 * self.n_total * cfg["dims"] * self.n_local  # 2*N_ref*D per query, true D
+        # a kernel that runs for a few ms is compared with the burst figure, one that runs for tens of ms or more
+        # with the sustained one (B200_PROFILING.md)
+        sustained = knn_kernel_ms > 20.0 and pk.get("bf16_tflops_sustained")
+        tensor_peak = pk["bf16_tflops_sustained"] if sustained else pk["bf16_tflops"]
+        kc = 16 if cfg["k"] + 1 <= 12 else 32
+        shape_key = f"nq{self.n_local}_nref{self.n_total}_d{cfg['dims']}_k{cfg['k']}"
+        out["roofline"] = {
+            "kernel": f"knn_tc_kernel<{kc}> (tcgen05 kind::f16 distance contraction with fused top-k', the dominant "
+                      "kernel of scf_knn_l2; timed with CUDA events recorded by the library around this launch alone; "
+                      "entry_point_* = the whole call incl. operand prep, FP64 re-rank and guard repair)",
+            "bound": "tensor", "achieved": knn_flop / (knn_kernel_ms * 1e-3) / 1e12, "peak": tensor_peak,
+            "unit": "TFLOP/s", "frac": knn_flop / (knn_kernel_ms * 1e-3) / 1e12 / tensor_peak,
+            "traffic": ncu_traffic("knn_tc_kernel", shape_key), "traffic_shape": shape_key,
+            "peak_note": f"dense 16-bit tensor peak from MEASURED_PEAKS.json ({pk['src']}; bf16 cuBLAS 8192^3, "
+                         f"{'sustained' if sustained else 'burst'} figure); achieved = 2*N_query*N_ref*D (true D, no "
+                         "padding credit) / CUDA-event time of the kernel",
+            "ms_per_launch": knn_kernel_ms, "entry_point_ms": knn_ms,
+            "entry_point_achieved": knn_flop / (knn_ms * 1e-3) / 1e12,
+        }
+        nnz = self.csr.nnz
+        out["csr_bytes_per_gpu"] = 8.0 * nnz + 8.0 * (self.n_local + 1)
+        out["nnz_per_cell"] = nnz / max(self.n_local, 1)
+        # HBM side of the step: the algorithm needs two passes over the raw CSR (gene statistics; everything after the
+        # HVG choice) -- bytes the stages mark_hvgs + stats + normalise have to move at least, against their time
+        csr_side_ms = sum(stage_ms.get(k_, 0.0) for k_ in ("mark_hvgs", "stats", "normalise"))
+        planes = 2 if args.gram_mode == 3 else 1
+        csr_side_bytes = 2.0 * out["csr_bytes_per_gpu"] + 4.0 * 2048 * self.n_local * planes
+        if csr_side_ms > 0:
+            out["roofline"]["hbm_side"] = {
+                "stages": "mark_hvgs + stats + normalise", "ms": csr_side_ms, "algorithmic_bytes": csr_side_bytes,
+                "algorithmic_GBs": csr_side_bytes / (csr_side_ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": csr_side_bytes / (csr_side_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                "note": "two passes over the raw CSR + one write of the Z planes"}
 
-        e2e_step()
-        ms_e2e = timed(e2e_step, args.steps) / args.steps
-        h2d = sum(t.numel() * t.element_size() for t in (h_ip, h_ix, h_dv))
+        if with_parity:
+            out["parity"] = parity_check(torch, ops, res, self.comm, res.k, res.dims,
+                                         f"{self.name}_n{self.n_total}_g{cfg['genes']}_d{cfg['dims']}_k{cfg['k']}")
+        if with_e2e:
+            out["e2e"] = self.e2e(steps, res)
+        return out
+
+    def e2e(self, steps, res):
+        """Host (pinned) CSR -> device -> graph -> host (pinned).  Two device CSR buffers: the upload of step i + 1 runs
+        on a copy stream while step i computes; the result of step i is read back (indices, distances, edges, weights)
+        before its buffer is reused."""
+        from scarf_b200.ops import CsrDevice
+
+        torch, dev, cfg = self.torch, self.dev, self.cfg
+        h = [t.cpu().pin_memory() for t in (self.csr.indptr, self.csr.indices, self.csr.data)]
+        names = ("indices", "distances", "edges", "weights")
+        out_host = {n_: torch.empty(getattr(res, n_).shape, dtype=getattr(res, n_).dtype, pin_memory=True)
+                    for n_ in names}
+        dbuf = [[torch.empty_like(t, device=dev) for t in h] for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream()
+        ready = [torch.cuda.Event(), torch.cuda.Event()]   # upload into buffer b complete
+        freed = [torch.cuda.Event(), torch.cuda.Event()]   # compute on buffer b complete
+        state = {"i": 0, "primed": False}
+
+        def upload(b):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[b])
+                for d, s in zip(dbuf[b], h):
+                    d.copy_(s, non_blocking=True)
+                ready[b].record(copy_stream)
+
+        def compute(b):
+            main.wait_event(ready[b])
+            c = CsrDevice(dbuf[b][0], dbuf[b][1], dbuf[b][2], self.n_local, cfg["genes"])
+            r = self.step(c)
+            freed[b].record(main)
+            for n_ in names:
+                out_host[n_].copy_(getattr(r, n_), non_blocking=True)
+
+        def serial_step():  # latency of one step: upload, compute, read back, nothing overlapped
+            upload(0)
+            compute(0)
+
+        def pipelined_step():
+            b = state["i"] & 1
+            if not state["primed"]:
+                upload(b)
+                state["primed"] = True
+            upload(b ^ 1)   # next step's inputs: overlaps this step's compute
+            compute(b)
+            state["i"] += 1
+
+        for b in range(2):
+            freed[b].record(main)
+        serial_step()
+        lat_ms = self.timed(serial_step, max(2, steps // 3)) / max(2, steps // 3)
+        torch.cuda.synchronize()
+        for b in range(2):
+            freed[b].record(main)
+        state.update(i=0, primed=False)
+        pipelined_step()  # primes the pipeline (buffer 1 holds the next step's inputs)
+        ms_e2e = self.timed(pipelined_step, steps) / steps
+        torch.cuda.synchronize()
+        h2d = sum(t.numel() * t.element_size() for t in h)
         d2h = sum(t.numel() * t.element_size() for t in out_host.values())
-        e2e = {"value": n_total / (ms_e2e / 1e3), "unit": "cells/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e}
+        return {"value": self.n_total / (ms_e2e / 1e3), "unit": "cells/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "latency_ms": lat_ms,
+                "pipeline": "double buffered: every step uploads one full CSR shard from pinned host memory and reads "
+                            "its graph back; the upload of step i+1 overlaps the compute of step i (steady state "
+                            "timed; one extra upload primes the pipeline outside the timed region)",
+                "h2d_GBs_at_latency": None}
+
+    def close(self):
+        del self.csr, self.n_counts, self.feat_I
+        self.torch.cuda.empty_cache()
+
+
+def c4_leg(args, rank, world, dev, comm):
+    """C4 (4M cells x 30k genes, dims 100, k 11) once through, seconds per phase against the 30 s target:
+    generation (on the device), host->device of the shard's bytes, compute (mark_hvgs + make_graph), device->host of
+    the graph, sharded Zarr write of the graph arrays."""
+    import shutil
+
+    import torch
+
+    from scarf_b200 import ops
+    from scarf_b200.datastore import write_graph_arrays
+    from scarf_b200.zarr_store import open_group
+
+    cfg = dict(WORKLOADS["C4"])
+    n_total = args.cells or cfg["cells"]
+    r = Runner(args, "C4", cfg, n_total, rank, world, dev, comm, "strong")
+
+    def mx(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        comm.allreduce_max_(t)
+        return float(t.item())
+
+    # host -> device: the shard's bytes through a pinned staging buffer of 256 MiB (the host copy of an 8 x 10 GB data
+    # set is not kept: the link rate is what is measured)
+    stage = torch.empty(1 << 26, dtype=torch.int32).pin_memory()
+    nbytes = int(r.csr.indices.numel()) * 8
+    flat = [r.csr.indices, r.csr.data]
+    comm.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for t in flat:
+        for lo in range(0, t.numel(), stage.numel()):
+            n = min(stage.numel(), t.numel() - lo)
+            t[lo:lo + n].copy_(stage[:n], non_blocking=True)  # overwrites the shard with the staging bytes ...
+    torch.cuda.synchronize()
+    h2d_s = mx(time.time() - t0)
+    r.close()
+    r = Runner(args, "C4", cfg, n_total, rank, world, dev, comm, "strong")  # ... so the shard is generated again
+    gen_s = mx(r.gen_s)
+    out = {"workload": describe("C4", cfg, n_total, world, "strong"), "cells_per_gpu": r.n_local,
+           "generation_s": gen_s, "h2d_s": h2d_s, "h2d_bytes_per_gpu": nbytes,
+           "h2d_note": "the shard's indices + data byte count streamed through a 256 MiB pinned staging buffer"}
+    phases = []
+    res = None
+    for it in range(2):  # first pass cold (kernel attributes, NCCL channels), second warm
+        comm.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        res = r.step(r.csr)
+        torch.cuda.synchronize()
+        phases.append(mx(time.time() - t0))
+    out["compute_s_cold"], out["compute_s"] = phases
+    out["parity"] = parity_check(torch, ops, res, comm, res.k, res.dims,
+                                 f"C4_n{n_total}_g{cfg['genes']}_d{cfg['dims']}_k{cfg['k']}")
+    # device -> host + sharded Zarr write (every rank writes the chunks of its own rows)
+    path = os.path.join(os.environ.get("SCF_BENCH_TMP", tempfile.gettempdir()), "scarf_b200_c4_graph.zarr")
+    if rank == 0:
+        open_group(path, "w")
+    comm.barrier()
+    t0 = time.time()
+    knn_loc = f"RNA/normed__I__hvgs/reduction__pca__{res.dims}__I/ann__l2__50__50__64__4466/knn__{res.k}"
+    nb = write_graph_arrays(open_group(path, "r+"), knn_loc, knn_loc + "/graph__1.0__1.5", res, comm, batch_size=1000)
+    comm.barrier()
+    out["d2h_and_zarr_write_s"] = mx(time.time() - t0)
+    out["zarr_bytes_per_gpu"] = nb
+    out["zarr_path_fs"] = path
+    comm.barrier()
+    if rank == 0:
+        shutil.rmtree(path, ignore_errors=True)
+    out["total_s"] = out["h2d_s"] + out["compute_s"] + out["d2h_and_zarr_write_s"]
+    out["target_s"] = 30.0
+    out["cells_per_s"] = n_total / out["total_s"]
+    r.close()
+    return out
+
+
+def datastore_leg(args, dev):
+    """The drop-in call itself, once: DataStore.mark_hvgs + DataStore.make_graph on a store holding the C2 counts --
+    incl. the k-means arrays the reference always writes, the widening to u8 / f8 and the Zarr write."""
+    import shutil
+
+    import torch
+
+    from scarf_b200 import synth
+    from scarf_b200.datastore import DataStore
+
+    cfg = dict(WORKLOADS["C2"])
+    n = min(args.cells or cfg["cells"], cfg["cells"])
+    csr = synth.make_counts_device(n, cfg["genes"], cfg["factors"], seed=SEED, device=dev, block=GEN_BLOCK)
+    m = synth.to_scipy(csr)
+    del csr
+    path = os.path.join(os.environ.get("SCF_BENCH_TMP", tempfile.gettempdir()), "scarf_b200_c2_store.zarr")
+    t0 = time.time()
+    ds = DataStore.from_csr(path, m, [f"g{i}" for i in range(cfg["genes"])], device=dev)
+    torch.cuda.synchronize()
+    out = {"workload": f"DataStore.mark_hvgs + DataStore.make_graph, {n} cells x {cfg['genes']} genes, top_n={cfg['hvgs']}, "
+                       f"dims={cfg['dims']}, k={cfg['k']}, n_centroids=1000 (k-means and Zarr write included)",
+           "store_create_s": round(time.time() - t0, 3)}
+    t0 = time.time()
+    ds.mark_hvgs(top_n=cfg["hvgs"], show_plot=False)
+    torch.cuda.synchronize()
+    out["mark_hvgs_s"] = round(time.time() - t0, 4)
+    t0 = time.time()
+    ds.make_graph(feat_key="hvgs", dims=cfg["dims"], k=cfg["k"])
+    torch.cuda.synchronize()
+    out["make_graph_s"] = round(time.time() - t0, 4)
+    out["make_graph_phases_s"] = dict(getattr(ds, "last_make_graph_timing", {}))
+    out["cells_per_s"] = n / (out["mark_hvgs_s"] + out["make_graph_s"])
+    shutil.rmtree(path, ignore_errors=True)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as td
+
+    from scarf_b200.dist import Comm
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    numa_cpus = pin_to_gpu_numa(local_rank)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    comm = Comm()
+    name = args.workload or ("C2" if world == 1 else "C3")
+    cfg = dict(WORKLOADS[name])
+    n_total = args.cells or cfg["cells"]
+    scaling = "weak" if world == 1 else "strong"
+    legs = (["C3", "datastore"] if world == 1 else (["C4"] if world == 8 else [])) if args.legs == "auto" else \
+        [x for x in args.legs.split(",") if x and x != "none"]
+    if name in legs:
+        legs.remove(name)
+
+    r = Runner(args, name, cfg, n_total, rank, world, dev, comm, scaling)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    m = r.run(args.steps, args.warmup, not args.no_e2e, not args.no_parity, sampler)
+    r.close()
+    f16_peak_run = measure_gemm_peak(torch, dev, torch.float16)
+    tf32_peak_run = measure_gemm_peak(torch, dev, torch.float32, tf32=True)
+    m["roofline"]["peaks_measured_in_run"] = {"cublas_f16_tflops": f16_peak_run, "cublas_tf32_tflops": tf32_peak_run,
+                                              "method": "torch.matmul 8192^3, best of 10, CUDA events"}
+
+    leg_out = {}
+    for leg in legs:
+        try:
+            if leg == "C3":
+                c3 = dict(WORKLOADS["C3"])
+                lr = Runner(args, "C3", c3, c3["cells"], rank, world, dev, comm, scaling)
+                lm = lr.run(max(2, min(args.steps, 3)), max(1, min(args.warmup, 2)), False, not args.no_parity)
+                lr.close()
+                lm["workload"] = describe("C3", c3, c3["cells"], world, scaling)
+                leg_out["C3"] = lm
+            elif leg == "C4":
+                leg_out["C4"] = c4_leg(args, rank, world, dev, comm)
+            elif leg == "datastore" and world == 1:
+                leg_out["datastore_e2e"] = datastore_leg(args, dev)
+        except Exception as e:  # a leg must not take the headline line down with it
+            leg_out[leg] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        dt, n = cpu_reference_run(cfg, args.cpu_sample, threads)
+        dt, n = cpu_reference_run(cfg, min(args.cpu_sample, n_total), threads)
         cpu_base = {"value": n / dt, "unit": "cells/s", "cores": threads, "kind": "port",
                     "sample": f"first {n} cells of the workload (same generator/seed), one pass, {dt:.1f} s"}
+    parity = m.get("parity")
     if rank == 0:
-        print(json.dumps({
-            "metric": "make_graph_cells_per_s", "value": value, "unit": "cells/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (f64 gene / column statistics, 3xTF32 Gram and projection, f16 tensor-core kNN candidates + f64 re-rank)",
-            "data": "synthetic", "config": workload_config(args, cfg, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu_base, "stage_ms": stages, "eig": eig_stats,
-            "csr_bytes_per_gpu": csr_bytes, "nnz_per_cell": nnz / n_local,
-        }))
+        line = {
+            "metric": "make_graph_cells_per_s", "value": m["value"], "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None,
+            "dtype": "f32 (f64 gene / column statistics, 3xTF32 Gram and projection, f64 eigensolve, f16 tensor-core kNN "
+                     "candidates + f64 re-rank)",
+            "data": "synthetic",
+            "config": {"workload": describe(name, cfg, n_total, world, scaling), "total_cells": n_total,
+                       "cells_per_gpu": m["cells_per_gpu"], "genes": cfg["genes"], "hvgs": cfg["hvgs"],
+                       "dims": cfg["dims"], "k": cfg["k"],
+                       "l2": "inputs larger than L2 (the CSR shard >> 126 MB is re-read from HBM every step)",
+                       "gram_mode": args.gram_mode, "knn_method": args.knn_method,
+                       "strong_scaling_series": "C3 at N = 1 is legs.C3 of the --gpus 1 line; N > 1 lines carry it as "
+                                                "the headline value",
+                       "numa_cpus_rank0": numa_cpus},
+            "clocks": m["clocks"], "e2e": m.get("e2e"), "gpu_launches": m["gpu_launches"], "roofline": m["roofline"],
+            "cpu_baseline": cpu_base, "parity": parity, "stage_ms": m["stage_ms"], "eig": m["eig"],
+            "csr_bytes_per_gpu": m["csr_bytes_per_gpu"], "nnz_per_cell": m["nnz_per_cell"],
+            "generation_s": m["generation_s"], "legs": leg_out,
+        }
+        print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit("parity check failed: " + json.dumps(parity))
 
 
 def main():
     args = parse()
-    cfg = dict(WORKLOADS[args.workload])
-    if args.cells:
-        cfg["cells"] = args.cells
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, cfg, rank)
+        run_reference(args, rank)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         # convenience: relaunch under torchrun
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                                    "29531", os.path.abspath(__file__)] + sys.argv[1:])
-    run_ours(args, cfg, rank, world, local_rank)
+    run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

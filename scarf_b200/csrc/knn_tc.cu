@@ -38,14 +38,15 @@ namespace {
 __device__ unsigned long long g_dbg[8];  // SCF_KNN_DEBUG & 16: event counters (developer diagnostics)
 
 constexpr int BM = 128;        // queries per MMA (= TMEM lanes)
-constexpr int QT = 2;          // query tiles per CTA: both reuse every reference tile staged in shared memory
-constexpr int BN = 128;        // references per MMA / accumulator tile (TMEM columns)
 constexpr int KCH = 64;        // FP16 values per 128-byte swizzle row
 constexpr int KSTEP = 16;      // K per tcgen05.mma kind::f16 (32 bytes of every operand row)
 constexpr int A_CHUNK_BYTES = BM * 128;
-constexpr int B_STAGE_BYTES = BN * 128;
-constexpr int NTHREADS = 320;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue
-constexpr int NLISTS = QT * BM;  // one candidate list per query row of the CTA
+constexpr int ACC_COLS = 256;  // TMEM columns of one accumulator buffer: QT query tiles x BN references
+constexpr int GCOLS = 64;      // accumulator columns one epilogue thread examines per reference tile
+constexpr int NEPI_WARPS = 16;
+constexpr int NTHREADS = 64 + 32 * NEPI_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-17: epilogue
+constexpr int NL = 32 * NEPI_WARPS;             // epilogue threads = candidate lists per CTA
+constexpr int HB = 8;          // buffered hits per epilogue thread
 
 // error model of the tensor-core score (see DESIGN.md "kNN guard band"), all in scaled units (a := s a, b := s b),
 // a~ = fp16(a), da = a - a~ (known exactly):
@@ -169,10 +170,11 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------- main
-// Per-thread UNSORTED candidate list: the KC scores live in registers, the ids in shared memory (entry e of
-// list l at [e * NLISTS + l], conflict free).  The slot number is carried in the low mantissa bits of every kept
-// score (<= 31 ulp perturbation; the threshold is rounded down past the tag, so every rejected score is >= thr),
-// so one FMNMX3 tree yields both the largest kept score and the slot that holds it: a new candidate overwrites it.
+// Per-thread UNSORTED candidate list: the KC scores live in registers, the ids in global memory (entry e of the list
+// at gid[e]; written only when a candidate is inserted, L2 absorbs it).  The slot number is carried in the low
+// mantissa bits of every kept score (<= 31 ulp perturbation; the threshold is rounded down past the tag, so every
+// rejected score is >= thr), so one FMNMX3 tree yields both the largest kept score and the slot that holds it: a new
+// candidate overwrites it.
 template <int KC>
 struct CandList {
   static constexpr uint32_t SLOT_MASK = KC - 1;
@@ -200,9 +202,9 @@ struct CandList {
     for (int e = 0; e < KC; ++e) r[e] = __uint_as_float((0x7F7FFFFFu & ~SLOT_MASK) | (uint32_t)e);
     recompute();
   }
-  __device__ __forceinline__ void replace_max(float s, int j, int* li_slot) {
+  __device__ __forceinline__ void replace_max(float s, int j, int* __restrict__ gid) {
     const uint32_t pmax = __float_as_uint(tmax) & SLOT_MASK;
-    li_slot[pmax * NLISTS] = j;
+    gid[pmax] = j;
     const float tagged = __uint_as_float((__float_as_uint(s) & ~SLOT_MASK) | pmax);
     const uint32_t onehot = 1u << pmax;  // selects, not a dynamically indexed store (keeps r[] in registers)
 #pragma unroll
@@ -211,79 +213,21 @@ struct CandList {
   }
 };
 
-__device__ __forceinline__ float min8(const uint32_t* v) {
-  const float a = fminf(fminf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
-  const float b = fminf(fminf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
-  return fminf(fminf(a, b), fminf(__uint_as_float(v[6]), __uint_as_float(v[7])));
-}
-
-// One 32-column chunk of one query row.  Group-of-8 minima prefilter (FMNMX3); rows with a candidate stage the
-// values of their hit groups in shared memory ([column][thread], conflict free) and set a 32-bit hit mask; then
-// every lane drains its own hits concurrently from the staged copy (dynamic column index without local memory).
-// All branches that contain warp votes are warp-uniform.  Returns after the registers v are dead, so the caller
-// can issue the next TMEM load before calling drain_hits().
-template <int KC>
-__device__ __forceinline__ uint32_t stage_hits(const uint32_t (&v)[32], float thr, float* st_slot, int dbg) {
-  if (dbg & 8) return 0u;  // timing experiment: TMEM traffic only
-  float g[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) g[i] = min8(v + 8 * i);
-  const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
-  if (!__any_sync(SCF_FULL, m < thr) || (dbg & 4)) return 0u;  // no candidate in this chunk for any row of the warp
-  const bool cnt = (dbg & 16) && (threadIdx.x & 31) == 0;
-  if (cnt) atomicAdd(&g_dbg[0], 1ull);
-  uint32_t mask = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (!__any_sync(SCF_FULL, g[i] < thr)) continue;
-    if (cnt) atomicAdd(&g_dbg[1], 1ull);
-    if (g[i] < thr) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float x = __uint_as_float(v[8 * i + c]);
-        if (x < thr) {
-          st_slot[(8 * i + c) * NLISTS] = x;
-          mask |= 1u << (8 * i + c);
-        }
-      }
-    }
-  }
-  return mask;
-}
-
-template <int KC>
-__device__ __forceinline__ void drain_hits(uint32_t mask, int jbase, int nref, CandList<KC>& cl, int* li_slot,
-                                           const float* st_slot, int dbg) {
-  const bool cnt = (dbg & 16) && (threadIdx.x & 31) == 0;
-  while (__any_sync(SCF_FULL, mask != 0u)) {
-    if (cnt) atomicAdd(&g_dbg[2], 1ull);
-    if (mask) {
-      const int c = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const float sc = st_slot[c * NLISTS];
-      if (sc < cl.thr && jbase + c < nref) {
-        if (dbg & 16) atomicAdd(&g_dbg[3], 1ull);
-        cl.replace_max(sc, jbase + c, li_slot);
-      }
-    }
-  }
-}
-
 struct KnnTcParams {
-  int kchunks;          // Kp / 32
-  int ksteps_last;      // 8-wide K steps that hold data in the last chunk (all-zero padding steps are skipped)
+  int kchunks;          // Kp / 64
+  int ksteps_last;      // 16-wide K steps that hold data in the last chunk (all-zero padding steps are skipped)
   int stages;           // B pipeline depth
   int n_ref_tiles;      // nr_pad / BN
   int tiles_per_split;
-  int nsplit;
-  float* cand_score;    // [nq_pad, nsplit, KC]  (unsorted)
+  int nlists;           // candidate lists per query row: nsplit (reference ranges) x HALVES (column halves)
+  float* cand_score;    // [nq_pad, nlists, KC]  (unsorted)
   int* cand_idx;
-  float* cand_tau;      // [nq_pad, nsplit]  largest kept score = lower bound of every rejected score
+  float* cand_tau;      // [nq_pad, nlists]  largest kept score = lower bound of every rejected score
   int balanced;         // 1: the (query tile, reference tile) space is cut into gridDim.x equal contiguous ranges
   long long total_work; //    n_q_tiles * n_ref_tiles (balanced mode)
   int nq;               // live query rows (pad rows keep nothing)
   int nref;             // live reference rows (pad rows are rejected by index)
-  int flags;            // developer switches (SCF_KNN_FLAGS): 2 = back off in waits, 4/8 = timing experiments, 16 = counters
+  int flags;            // developer switches (SCF_KNN_FLAGS): 2 = back off in waits
   // collect pass (repair of guard failures): query row r of this launch is failed row r of the fail list
   const int* fail_count;   // device count of failed rows (rows >= min(count, FIXTC_ROWS) do nothing)
   const float* fix_thr;    // [FIXTC_ROWS] score threshold: every reference scoring below it is collected
@@ -295,10 +239,86 @@ constexpr int FIXTC_ROWS = 32768;  // failed rows repaired by the tensor-core co
 constexpr int FIXTC_CAP = 64;     // collected references per failed row
 constexpr int FIXTC_NSPLIT = 16;  // reference ranges per query tile in the collect pass
 
-template <int KC, bool COLLECT>
+__device__ __forceinline__ float min4(const uint32_t* v) {
+  return fminf(fminf(__uint_as_float(v[0]), __uint_as_float(v[1])), fminf(__uint_as_float(v[2]), __uint_as_float(v[3])));
+}
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// Epilogue state of one thread: the candidate list of (its query row, its 64-column group) plus a small buffer of
+// hits in shared memory.  A score below the threshold is APPENDED to the buffer (three predicated instructions); the
+// buffers of a warp are drained together -- every lane inserts its own entries into its own register list at the same
+// time -- when one of them is nearly full.  In the steady state of a search hits are rare and scattered over the
+// lanes: an immediate insert costs the whole warp ~KC + 30 instructions for one lane's benefit, the buffered one is
+// shared by all lanes that have collected something since the last drain.  The threshold is stale between drains
+// (never too small): entries are checked again against the fresh one when they are drained.
+template <int KC>
+struct Epi {
+  CandList<KC> cl;
+  float thr;        // comparison threshold in use (>= cl.thr; with two lists per row also <= the partner's)
+  int cnt;          // buffered hits
+  float* hs;        // hit scores  [HB][NL] (this thread's column)
+  int* hc;          // hit reference ids
+  int* gid;         // this list's candidate ids in global memory
+  int nref;
+  __device__ __forceinline__ void drain() {
+    for (int i = 0; __any_sync(SCF_FULL, i < cnt); ++i) {
+      if (i < cnt) {
+        const float sc = hs[i * NL];
+        const int j = hc[i * NL];
+        if (sc < cl.thr && j < nref) cl.replace_max(sc, j, gid);
+      }
+    }
+    cnt = 0;
+  }
+};
+
+// One 16-column chunk of one query row: min tree (FMNMX3) against the threshold, groups of four columns; a group is
+// visited only when some lane of the warp has a candidate in it (warp-uniform branches around every vote).
+template <int KC, bool SHARED_THR>
+__device__ __forceinline__ void process16(const uint32_t (&v)[16], int jb, Epi<KC>& ep, float* thr_pub,
+                                          const volatile float* thr_partner) {
+  float g[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = min4(v + 4 * i);
+  const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
+  if (!__any_sync(SCF_FULL, m < ep.thr)) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (!__any_sync(SCF_FULL, g[i] < ep.thr)) continue;
+    if (__any_sync(SCF_FULL, ep.cnt > HB - 4)) {
+      ep.drain();
+      ep.thr = ep.cl.thr;
+      if constexpr (SHARED_THR) {
+        *thr_pub = ep.cl.thr;
+        ep.thr = fminf(ep.thr, *thr_partner);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float x = __uint_as_float(v[4 * i + c]);
+      if (x < ep.thr) {
+        ep.hs[ep.cnt * NL] = x;
+        ep.hc[ep.cnt * NL] = jb + 4 * i + c;
+        ++ep.cnt;
+      }
+    }
+  }
+}
+
+// QT query tiles of 128 rows per CTA x reference tiles of BN = 256 / QT rows: QT = 4 (BN = 64) when the operand rows
+// fit one 128-byte swizzle row (Kp = 64: a reference tile is re-used by 512 queries, half the L2 -> shared-memory
+// traffic of QT = 2), QT = 2 (BN = 128) for longer rows (the query operand of 512 rows would not fit).
+// 18 warps: warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-17 epilogue.  Epilogue warp w reads TMEM lane quarter
+// (warp id % 4) and the 64 accumulator columns [64 g, 64 g + 64), g = w / 4, of the 256-column buffer: with QT = 4
+// that is query tile g (one list per row), with QT = 2 query tile g / 2, column half g % 2 (two lists per row, which
+// share their thresholds through shared memory).
+template <int KC, int QT, bool COLLECT>
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                              const __grid_constant__ CUtensorMap tmap_r,
                                                              const KnnTcParams p) {
+  constexpr int BN = ACC_COLS / QT;
+  constexpr int HALVES = QT == 2 ? 2 : 1;
+  constexpr int B_STAGE_BYTES = BN * 128;
   int n_fix = 0;
   if constexpr (COLLECT) {  // whole CTA leaves before any barrier / TMEM setup when its query tile is empty
     n_fix = min(*p.fail_count, FIXTC_ROWS);
@@ -308,10 +328,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   // the 128-byte swizzle is a function of the shared-memory address: tiles must sit on 1024-byte boundaries
   unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;                                             // [QT][kchunks][128 rows x 128 B]
-  unsigned char* sB = sA + (size_t)QT * p.kchunks * A_CHUNK_BYTES;      // [stages][128 rows x 128 B]
-  int* li = reinterpret_cast<int*>(sB + (size_t)p.stages * B_STAGE_BYTES);  // candidate ids [KC][NLISTS]
-  float* st = reinterpret_cast<float*>(li + (size_t)KC * NLISTS);           // staged chunk values [32][NLISTS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(st + (size_t)32 * NLISTS);
+  unsigned char* sB = sA + (size_t)QT * p.kchunks * A_CHUNK_BYTES;      // [stages][BN rows x 128 B]
+  float* hb_score = reinterpret_cast<float*>(sB + (size_t)p.stages * B_STAGE_BYTES);  // hit buffers [HB][NL]
+  int* hb_col = reinterpret_cast<int*>(hb_score + (size_t)HB * NL);
+  float* thr_x = reinterpret_cast<float*>(hb_col + (size_t)HB * NL);    // published list thresholds [NL]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thr_x + NL);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + 1;
   uint64_t* full = bars + 2;
@@ -323,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t backoff = (p.flags & 2) ? 32u : 0u;
   // Work of this CTA: a contiguous range [w0, w1) of the linearised (query tile, reference tile) space, walked as
-  // segments that stay inside one query tile.  Legacy grid (blockIdx.x = query tile, blockIdx.y = reference split):
+  // segments that stay inside one query tile.  Static grid (blockIdx.x = query tile, blockIdx.y = reference split):
   // exactly one segment.  Balanced grid: every CTA gets total_work / gridDim.x tile steps, so all SMs finish
   // together whatever the number of query tiles; a query tile cut by a range boundary keeps one candidate list per
   // part (slot = this CTA's index minus the index of the CTA that holds the tile's first step).
@@ -356,7 +377,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tmem_full + a, 1);
-      tc::mbar_init(tmem_empty + a, NLISTS);
+      tc::mbar_init(tmem_empty + a, NL);
     }
     tc::fence_barrier_init();
   }
@@ -364,7 +385,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     tc::tma_prefetch_desc(&tmap_q);
     tc::tma_prefetch_desc(&tmap_r);
   }
-  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);  // 2 buffers x QT tiles x 128 columns
+  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);  // 2 buffers x 256 columns
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -372,38 +393,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================  (whole warp, one elected lane issues)
-    {
-      const bool leader = tc::elect_one();
-      int it = 0, seg = 0;
-      for (long long cur = w0; cur < w1; ++seg) {
-        const int q = (int)(cur / T), t0 = (int)(cur % T);
-        const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
-        cur += t1 - t0;
-        if (seg > 0) tc::mbar_wait(a_empty, (uint32_t)(seg - 1) & 1u, backoff);  // MMAs of the last segment done with sA
-        if (leader) {
-          tc::mbar_expect_tx(a_full, (uint32_t)(QT * p.kchunks * A_CHUNK_BYTES));
-          for (int t = 0; t < QT; ++t)
-            for (int c = 0; c < p.kchunks; ++c)
-              tc::tma_load_2d(sA + (size_t)(t * p.kchunks + c) * A_CHUNK_BYTES, &tmap_q, a_full, c * KCH,
-                              q * (QT * BM) + t * BM);
-        }
-        __syncwarp();
-        for (int t = t0; t < t1; ++t)
-          for (int c = 0; c < p.kchunks; ++c, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            tc::mbar_wait(empty + s, ph ^ 1u, backoff);
-            if (leader) {
-              if (SCF_KNN_DEBUG & 128) {  // timing experiment: no reference traffic, the MMAs run on stale tiles
-                tc::mbar_arrive(full + s);
-              } else {
-                tc::mbar_expect_tx(full + s, B_STAGE_BYTES);
-                tc::tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmap_r, full + s, c * KCH, t * BN);
-              }
-            }
-            __syncwarp();
-          }
+    const bool leader = tc::elect_one();
+    int it = 0, seg = 0;
+    for (long long cur = w0; cur < w1; ++seg) {
+      const int q = (int)(cur / T), t0 = (int)(cur % T);
+      const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
+      cur += t1 - t0;
+      if (seg > 0) tc::mbar_wait(a_empty, (uint32_t)(seg - 1) & 1u, backoff);  // MMAs of the last segment done with sA
+      if (leader) {
+        tc::mbar_expect_tx(a_full, (uint32_t)(QT * p.kchunks * A_CHUNK_BYTES));
+        for (int t = 0; t < QT; ++t)
+          for (int c = 0; c < p.kchunks; ++c)
+            tc::tma_load_2d(sA + (size_t)(t * p.kchunks + c) * A_CHUNK_BYTES, &tmap_q, a_full, c * KCH,
+                            q * (QT * BM) + t * BM);
       }
+      __syncwarp();
+      for (int t = t0; t < t1; ++t)
+        for (int c = 0; c < p.kchunks; ++c, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          tc::mbar_wait(empty + s, ph ^ 1u, backoff);
+          if (leader) {
+            if (SCF_KNN_DEBUG & 128) {  // timing experiment: no reference traffic, the MMAs run on stale tiles
+              tc::mbar_arrive(full + s);
+            } else {
+              tc::mbar_expect_tx(full + s, B_STAGE_BYTES);
+              tc::tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmap_r, full + s, c * KCH, t * BN);
+            }
+          }
+          __syncwarp();
+        }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -411,88 +430,91 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     // instructions: descriptors then live in uniform registers.  Issuing from inside an `if (lane == 0)` region makes
     // the compiler move every descriptor from vector to uniform registers through a waterfall loop per MMA (~110
     // idle cycles between 64-cycle instructions, measured).
-    {
-      constexpr uint32_t idesc = tc::umma_idesc_f16(BM, BN, false, false);
-      const bool leader = tc::elect_one();
-      const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
-      int it = 0, lt = 0, seg = 0;
-      for (long long cur = w0; cur < w1; ++seg) {
-        const int t0 = (int)(cur % T);
-        const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
-        cur += t1 - t0;
-        tc::mbar_wait(a_full, (uint32_t)seg & 1u);
+    constexpr uint32_t idesc = tc::umma_idesc_f16(BM, BN, false, false);
+    const bool leader = tc::elect_one();
+    const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
+    int it = 0, lt = 0, seg = 0;
+    for (long long cur = w0; cur < w1; ++seg) {
+      const int t0 = (int)(cur % T);
+      const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
+      cur += t1 - t0;
+      tc::mbar_wait(a_full, (uint32_t)seg & 1u);
+      tc::tc_fence_after();
+      for (int t = t0; t < t1; ++t, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
+        tc::mbar_wait(tmem_empty + acc, acc_ph ^ 1u, backoff);
         tc::tc_fence_after();
-        for (int t = t0; t < t1; ++t, ++lt) {
-          const int acc = lt & 1;
-          const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
-          tc::mbar_wait(tmem_empty + acc, acc_ph ^ 1u, backoff);
+        for (int c = 0; c < p.kchunks; ++c, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          tc::mbar_wait(full + s, ph, backoff);
           tc::tc_fence_after();
-          for (int c = 0; c < p.kchunks; ++c, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            tc::mbar_wait(full + s, ph, backoff);
-            tc::tc_fence_after();
-            const uint64_t db = tc::umma_desc_k_sw128_u32(sB_u + (uint32_t)s * B_STAGE_BYTES);
-            const int nk = c + 1 == p.kchunks ? p.ksteps_last : KCH / KSTEP;
+          const uint64_t db = tc::umma_desc_k_sw128_u32(sB_u + (uint32_t)s * B_STAGE_BYTES);
+          const int nk = c + 1 == p.kchunks ? p.ksteps_last : KCH / KSTEP;
 #pragma unroll
-            for (int tq = 0; tq < QT; ++tq) {
-              const uint64_t da = tc::umma_desc_k_sw128_u32(sA_u + (uint32_t)(tq * p.kchunks + c) * A_CHUNK_BYTES);
-              const uint32_t d_tmem = tmem_base + (uint32_t)((acc * QT + tq) * BN);
+          for (int tq = 0; tq < QT; ++tq) {
+            const uint64_t da = tc::umma_desc_k_sw128_u32(sA_u + (uint32_t)(tq * p.kchunks + c) * A_CHUNK_BYTES);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + tq * BN);
 #pragma unroll
-              for (int kk = 0; kk < KCH / KSTEP; ++kk)  // K = 16 fp16 = 32 bytes per instruction: +2 in 16-byte units
-                if (kk < nk && !(SCF_KNN_DEBUG & 64) && leader)
-                  tc::umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (c | kk) != 0);
-            }
-            if (leader) tc::umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
-            __syncwarp();
+            for (int kk = 0; kk < KCH / KSTEP; ++kk)  // K = 16 fp16 = 32 bytes per instruction: +2 in 16-byte units
+              if (kk < nk && !(SCF_KNN_DEBUG & 64) && leader)
+                tc::umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (c | kk) != 0);
           }
-          if (leader) tc::umma_commit(tmem_full + acc);  // both accumulators of this reference tile complete
+          if (leader) tc::umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
           __syncwarp();
         }
-        if (leader) tc::umma_commit(a_empty);  // the query operand may be replaced once every MMA of the segment has run
+        if (leader) tc::umma_commit(tmem_full + acc);  // all accumulators of this reference tile complete
         __syncwarp();
       }
+      if (leader) tc::umma_commit(a_empty);  // the query operand may be replaced once every MMA of the segment has run
+      __syncwarp();
     }
   } else {
-    // ===================== epilogue: one query row per thread, top-k' of the segment's reference range ===========
+    // ===================== epilogue: 64 accumulator columns of one query row per thread =====================
+    const int w = warp - 2;
     const int quarter = warp & 3;      // TMEM lane quarter this warp may read
-    const int qt = (warp - 2) >> 2;    // which of the CTA's query tiles
+    const int g = w >> 2;              // column group
+    const int l = w * 32 + lane;       // epilogue thread id
     const int row = quarter * 32 + lane;
-    int* li_slot = li + qt * BM + row;
-    float* st_slot = st + qt * BM + row;
+    const int qt = QT == 4 ? g : (g >> 1);
+    const int half = QT == 4 ? 0 : (g & 1);
+    const int col0 = half * GCOLS;     // first reference of this thread inside a reference tile
+    float* thr_pub = thr_x + l;
+    const volatile float* thr_partner = thr_x + (l ^ 128);  // same row, other column half (QT = 2): warp w ^ 4
+    const int pair_id = 1 + (w & 3) + 4 * (w >> 3);
     int lt = 0;
     for (long long cur = w0; cur < w1;) {
       const int q = (int)(cur / T), t0 = (int)(cur % T);
       const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
       cur += t1 - t0;
-      const int q0 = q * (QT * BM);
+      const int qrow = q * (QT * BM) + qt * BM + row;
       if constexpr (COLLECT) {
         // fixed per-row threshold, append-only: every reference whose score is below it goes on the row's list
-        const int slot = q0 + qt * BM + row;
-        const float thr = slot < n_fix ? p.fix_thr[slot] : -FLT_MAX;
+        const float thr = qrow < n_fix ? p.fix_thr[qrow] : -FLT_MAX;
         for (int t = t0; t < t1; ++t, ++lt) {
           const int acc = lt & 1;
           const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
           tc::mbar_wait(tmem_full + acc, acc_ph);
           tc::tc_fence_after();
-          const int j0 = t * BN;
-          const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
+          const int j0 = t * BN + col0;
+          const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + g * GCOLS);
 #pragma unroll 1
-          for (int cc = 0; cc < BN / 32; ++cc) {
-            uint32_t v[32];
-            tc::tmem_ld32(t_row + (uint32_t)(cc * 32), v);
+          for (int cc = 0; cc < GCOLS / 16; ++cc) {
+            uint32_t v[16];
+            tc::tmem_ld16(t_row + (uint32_t)(cc * 16), v);
             tc::tmem_ld_wait();
-            float g[4];
+            float gm[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) g[i] = min8(v + 8 * i);
-            const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
+            for (int i = 0; i < 4; ++i) gm[i] = min4(v + 4 * i);
+            const float m = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
             if (!__any_sync(SCF_FULL, m < thr)) continue;
             if (m < thr) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (__uint_as_float(v[c]) < thr && j0 + cc * 32 + c < p.nref) {
-                  const int pos = atomicAdd(p.fix_cnt + slot, 1);
-                  if (pos < FIXTC_CAP) p.fix_list[(size_t)slot * FIXTC_CAP + pos] = j0 + cc * 32 + c;
+              for (int c = 0; c < 16; ++c)
+                if (__uint_as_float(v[c]) < thr && j0 + cc * 16 + c < p.nref) {
+                  const int pos = atomicAdd(p.fix_cnt + qrow, 1);
+                  if (pos < FIXTC_CAP) p.fix_list[(size_t)qrow * FIXTC_CAP + pos] = j0 + cc * 16 + c;
                 }
             }
           }
@@ -501,44 +523,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
         }
       } else {
         const int split = split_of(q);
-        CandList<KC> cl;
-        cl.init();
-        if (q0 + qt * BM + row >= p.nq) cl.thr = -FLT_MAX;  // pad row: never a candidate
-#pragma unroll
-        for (int e = 0; e < KC; ++e) li_slot[e * NLISTS] = -1;
+        const size_t sub = (size_t)qrow * p.nlists + (size_t)(split * HALVES + half);
+        Epi<KC> ep;
+        ep.cl.init();
+        if (qrow >= p.nq) ep.cl.thr = -FLT_MAX;  // pad row: never a candidate
+        ep.thr = ep.cl.thr;
+        ep.cnt = 0;
+        ep.hs = hb_score + l;
+        ep.hc = hb_col + l;
+        ep.gid = p.cand_idx + sub * KC;
+        ep.nref = p.nref;
+        if constexpr (HALVES == 2) {
+          // both lists of a row publish the threshold of THIS segment before either reads the other's
+          *thr_pub = ep.cl.thr;
+          pair_barrier(pair_id);
+        }
         for (int t = t0; t < t1; ++t, ++lt) {
           const int acc = lt & 1;
           const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
           tc::mbar_wait(tmem_full + acc, acc_ph);
           tc::tc_fence_after();
-          const int j0 = t * BN;
-          const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + qt) * BN);
-          uint32_t v[32];
           if (SCF_KNN_DEBUG & 32) {  // timing experiment: no accumulator read-out at all
             tc::tc_fence_before();
             tc::mbar_arrive(tmem_empty + acc);
             continue;
           }
-          tc::tmem_ld32(t_row, v);
+          const int j0 = t * BN + col0;
+          const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + g * GCOLS);
+          if constexpr (HALVES == 2) ep.thr = fminf(ep.cl.thr, *thr_partner);
+          uint32_t va[16], vb[16];
+          tc::tmem_ld16(t_row, va);
 #pragma unroll
-          for (int cc = 0; cc < BN / 32; ++cc) {
+          for (int cc = 0; cc < GCOLS / 16; ++cc) {
             tc::tmem_ld_wait();
-            const uint32_t mask = stage_hits<KC>(v, cl.thr, st_slot, SCF_KNN_DEBUG);
-            // v is dead: the TMEM load of the next chunk overlaps the drain of this one
-            if (cc + 1 < BN / 32) tc::tmem_ld32(t_row + (uint32_t)((cc + 1) * 32), v);
-            drain_hits<KC>(mask, j0 + cc * 32, p.nref, cl, li_slot, st_slot, SCF_KNN_DEBUG);
+            // the load of the next chunk is in flight while this one is examined
+            if (cc + 1 < GCOLS / 16) tc::tmem_ld16(t_row + (uint32_t)((cc + 1) * 16), (cc & 1) ? va : vb);
+            if (!(SCF_KNN_DEBUG & 8))
+              process16<KC, HALVES == 2>((cc & 1) ? vb : va, j0 + cc * 16, ep, thr_pub, thr_partner);
           }
           tc::tc_fence_before();
           tc::mbar_arrive(tmem_empty + acc);
         }
-        // candidates out: [query, split, KC]
-        const size_t sub = (size_t)(q0 + qt * BM + row) * p.nsplit + split;
+        ep.drain();
+        if constexpr (HALVES == 2) *thr_pub = ep.cl.thr;
+        // candidates out: [query, list, KC]; the ids are already in place
 #pragma unroll
-        for (int e = 0; e < KC; ++e) {
-          p.cand_score[sub * KC + e] = cl.r[e];
-          p.cand_idx[sub * KC + e] = li_slot[e * NLISTS];
-        }
-        p.cand_tau[sub] = cl.thr;
+        for (int e = 0; e < KC; ++e) p.cand_score[sub * KC + e] = ep.cl.r[e];
+        p.cand_tau[sub] = ep.cl.thr;
       }
     }
   }
@@ -765,7 +796,7 @@ int pick_kc(int k) {
 }
 
 struct Plan {
-  int kp, kchunks, kc, stages, nsplit, tiles_per_split, n_ref_tiles, grid;
+  int kp, kchunks, kc, qt, bn, halves, stages, nsplit, nlists, tiles_per_split, n_ref_tiles, grid;
   long long total_work;
   int64_t nq_pad, nr_pad;
   size_t smem;
@@ -779,42 +810,47 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.kp = (dim + 3 + KCH - 1) / KCH * KCH;
   pl.kchunks = pl.kp / KCH;
   if (pl.kc == 0 || pl.kchunks > 4) return false;  // k > 24 or dim > 253: method 0 handles those
-  pl.nq_pad = (nq + QT * BM - 1) / (QT * BM) * (QT * BM);
-  pl.nr_pad = (nref + BN - 1) / BN * BN;
-  pl.n_ref_tiles = (int)(pl.nr_pad / BN);
-  const int64_t q_tiles = pl.nq_pad / (QT * BM);
+  pl.qt = pl.kchunks == 1 ? 4 : 2;  // see knn_tc_kernel
+  pl.bn = ACC_COLS / pl.qt;
+  pl.halves = pl.qt == 2 ? 2 : 1;
+  const int rows = pl.qt * BM;
+  pl.nq_pad = (nq + rows - 1) / rows * rows;
+  pl.nr_pad = (nref + pl.bn - 1) / pl.bn * pl.bn;
+  pl.n_ref_tiles = (int)(pl.nr_pad / pl.bn);
+  const int64_t q_tiles = pl.nq_pad / rows;
   // Balanced schedule: the q_tiles x n_ref_tiles tile steps are cut into `grid` equal contiguous ranges (one CTA per
-  // SM, at least 8 steps each).  A query tile spans at most nsplit = ceil(T / L) + 1 ranges (L = steps per range) and
-  // keeps one candidate list per range; with at least as many query tiles as SMs that is 2.  One list over (nearly)
-  // the whole reference range keeps the number of list updates at k' ln(N/k').
+  // SM, at least 8 steps of 128 references each).  A query tile spans at most nsplit = ceil(T / L) + 1 ranges (L = steps
+  // per range) and keeps one candidate list per range (and column half); with at least as many query tiles as SMs
+  // that is 2.  One list over (nearly) the whole reference range keeps the number of list updates at k' ln(N/k').
   const long long work = (long long)q_tiles * pl.n_ref_tiles;
-  long long grid = std::max<long long>(1, std::min<long long>(SCF_NUM_SMS, work / 8));
+  long long grid = std::max<long long>(1, std::min<long long>(SCF_NUM_SMS, work / (8 * 128 / pl.bn)));
   for (;;) {
     const long long L = work / grid;
     pl.nsplit = (int)((pl.n_ref_tiles + L - 1) / L) + 1;
-    if (pl.nsplit * pl.kc <= 32 * MAXU || grid == 1) break;
+    if (pl.nsplit * pl.halves * pl.kc <= 32 * MAXU || grid == 1) break;
     --grid;
   }
+  pl.nlists = pl.nsplit * pl.halves;
   pl.grid = (int)grid;
   pl.total_work = work;
   pl.tiles_per_split = pl.n_ref_tiles;
   auto smem_for = [&](int stages) {
-    return (size_t)QT * pl.kchunks * A_CHUNK_BYTES + (size_t)stages * B_STAGE_BYTES + (size_t)pl.kc * NLISTS * 4 +
-           (size_t)32 * NLISTS * 4 + (size_t)(2 + 2 * stages + 4) * 8 + 64;
+    return (size_t)pl.qt * pl.kchunks * A_CHUNK_BYTES + (size_t)stages * pl.bn * 128 + (size_t)2 * HB * NL * 4 +
+           (size_t)NL * 4 + (size_t)(2 + 2 * stages + 4) * 8 + 64;
   };
-  pl.stages = 6;
+  pl.stages = pl.qt == 4 ? 10 : 6;
   while (pl.stages > 2 && smem_for(pl.stages) + 1024 > 227 * 1024) --pl.stages;
   pl.smem = smem_for(pl.stages) + 1024;  // slack for the 1024-byte alignment of the swizzled tiles
   if (pl.smem > 227 * 1024) return false;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t o = 0;
-  pl.off_qop = o, o = al(o + (size_t)pl.nq_pad * pl.kp * 2);
+  pl.off_qop = o, o = al(o + (size_t)std::max<int64_t>(pl.nq_pad, 512) * pl.kp * 2);
   pl.off_rop = o, o = al(o + (size_t)pl.nr_pad * pl.kp * 2);
   pl.off_qn = o, o = al(o + (size_t)pl.nq_pad * 8);
   pl.off_qe = o, o = al(o + (size_t)pl.nq_pad * 4);
-  pl.off_cs = o, o = al(o + (size_t)pl.nq_pad * pl.nsplit * pl.kc * 4);
-  pl.off_ci = o, o = al(o + (size_t)pl.nq_pad * pl.nsplit * pl.kc * 4);
-  pl.off_tau = o, o = al(o + (size_t)pl.nq_pad * pl.nsplit * 4);
+  pl.off_cs = o, o = al(o + (size_t)pl.nq_pad * pl.nlists * pl.kc * 4);
+  pl.off_ci = o, o = al(o + (size_t)pl.nq_pad * pl.nlists * pl.kc * 4);
+  pl.off_tau = o, o = al(o + (size_t)pl.nq_pad * pl.nlists * 4);
   pl.off_fail = o, o = al(o + (size_t)nq * 8);
   pl.off_fkey = o, o = al(o + (size_t)nq * 8);
   pl.off_misc = o, o = al(o + 256);
@@ -827,6 +863,13 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.off_rkey = o, o = al(o + (size_t)nq * 8);
   pl.total = o;
   return true;
+}
+
+typedef void (*KnnKernel)(const CUtensorMap, const CUtensorMap, const KnnTcParams);
+KnnKernel pick_kernel(int kc, int qt, bool collect) {
+  if (collect) return qt == 4 ? (KnnKernel)knn_tc_kernel<16, 4, true> : (KnnKernel)knn_tc_kernel<16, 2, true>;
+  if (qt == 4) return kc == 16 ? (KnnKernel)knn_tc_kernel<16, 4, false> : (KnnKernel)knn_tc_kernel<32, 4, false>;
+  return kc == 16 ? (KnnKernel)knn_tc_kernel<16, 2, false> : (KnnKernel)knn_tc_kernel<32, 2, false>;
 }
 
 }  // namespace
@@ -898,17 +941,17 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   CUtensorMap tq, tr;
   rc = scf_make_tmap_2d_f16(&tq, qop, (uint64_t)pl.nq_pad, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BM);
   if (rc) return rc;
-  rc = scf_make_tmap_2d_f16(&tr, rop, (uint64_t)pl.nr_pad, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, BN);
+  rc = scf_make_tmap_2d_f16(&tr, rop, (uint64_t)pl.nr_pad, (uint64_t)pl.kp, (uint64_t)pl.kp, KCH, (uint32_t)pl.bn);
   if (rc) return rc;
   KnnTcParams prm;
   prm.kchunks = pl.kchunks, prm.stages = pl.stages, prm.n_ref_tiles = pl.n_ref_tiles;
   prm.nq = (int)nq, prm.nref = (int)nref;
   prm.ksteps_last = ((dim + 3 + KSTEP - 1) / KSTEP) - (pl.kchunks - 1) * (KCH / KSTEP);
-  prm.tiles_per_split = pl.tiles_per_split, prm.nsplit = pl.nsplit, prm.cand_score = cs, prm.cand_idx = ci, prm.cand_tau = ctau;
+  prm.tiles_per_split = pl.tiles_per_split, prm.nlists = pl.nlists, prm.cand_score = cs, prm.cand_idx = ci, prm.cand_tau = ctau;
   prm.balanced = 1, prm.total_work = pl.total_work;
   // list slots that no range fills (a query tile that is not cut uses one of its nsplit slots): ids -1, tau "nothing rejected"
-  e = cudaMemsetAsync(ci, 0xFF, (size_t)pl.nq_pad * pl.nsplit * pl.kc * 4, stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(ctau, 0x7F, (size_t)pl.nq_pad * pl.nsplit * 4, stream);
+  e = cudaMemsetAsync(ci, 0xFF, (size_t)pl.nq_pad * pl.nlists * pl.kc * 4, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctau, 0x7F, (size_t)pl.nq_pad * pl.nlists * 4, stream);
   if (e != cudaSuccess) {
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
@@ -918,7 +961,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     prm.flags = f ? atoi(f) : 2;
   }
   prm.fail_count = nullptr, prm.fix_thr = nullptr, prm.fix_cnt = nullptr, prm.fix_list = nullptr;
-  auto kern = pl.kc == 16 ? knn_tc_kernel<16, false> : knn_tc_kernel<32, false>;
+  KnnKernel kern = pick_kernel(pl.kc, pl.qt, false);
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) {
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
@@ -932,7 +975,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   if (rc) return rc;
   if (SCF_KNN_DEBUG & (4 | 8 | 32 | 64 | 128)) return 0;  // timing experiments: candidates are meaningless, stop here
   knn_rerank_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(q, nq, ref, nref, dim, ld, k, self_offset, pl.kc,
-                                                                  pl.nsplit, pl.kp, cs, ci, ctau, qn, qe, bmax, out_idx, out_dist,
+                                                                  pl.nlists, pl.kp, cs, ci, ctau, qn, qe, bmax, out_idx, out_dist,
                                                                   fail_ids, fail_keys, fix_thr, fail_count);
   rc = scf_check_launch("scf_knn_l2(rerank)");
   if (rc) return rc;
@@ -956,17 +999,17 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   KnnTcParams fp = prm;
   fp.nq = FIXTC_ROWS;
   fp.balanced = 0, fp.total_work = 0;  // collect pass: static (query tile, reference split) grid
-  fp.nsplit = std::max(1, std::min(FIXTC_NSPLIT, pl.n_ref_tiles));
-  fp.tiles_per_split = (pl.n_ref_tiles + fp.nsplit - 1) / fp.nsplit;
-  fp.nsplit = (pl.n_ref_tiles + fp.tiles_per_split - 1) / fp.tiles_per_split;
+  int fsplit = std::max(1, std::min(FIXTC_NSPLIT, pl.n_ref_tiles));
+  fp.tiles_per_split = (pl.n_ref_tiles + fsplit - 1) / fsplit;
+  fsplit = (pl.n_ref_tiles + fp.tiles_per_split - 1) / fp.tiles_per_split;
   fp.fail_count = fail_count, fp.fix_thr = fix_thr, fp.fix_cnt = fix_cnt, fp.fix_list = fix_list;
-  auto fkern = knn_tc_kernel<16, true>;
+  KnnKernel fkern = pick_kernel(16, pl.qt, true);
   e = cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) {
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
-  fkern<<<dim3(FIXTC_ROWS / (QT * BM), (unsigned)fp.nsplit), NTHREADS, pl.smem, stream>>>(tf, tr, fp);
+  fkern<<<dim3(FIXTC_ROWS / (pl.qt * BM), (unsigned)fsplit), NTHREADS, pl.smem, stream>>>(tf, tr, fp);
   rc = scf_check_launch("scf_knn_l2(fix,collect)");
   if (rc) return rc;
   knn_fix_finish_kernel<<<SCF_NUM_SMS, 256, 0, stream>>>(q, ref, dim, ld, k, self_offset, fail_ids, fail_keys, fail_count,

@@ -18,8 +18,8 @@ written uncompressed; options the GPU path does not implement raise ``NotImpleme
 """
 from __future__ import annotations
 
-import hashlib
 import os
+import time
 from typing import Optional
 
 import numpy as np
@@ -28,7 +28,7 @@ import torch
 from . import graph
 from . import hvg as hvg_host
 from . import ops
-from .dist import Comm
+from .dist import Comm, ShardPlan
 from .ops import CsrDevice
 from .zarr_store import Group, open_group
 
@@ -73,9 +73,19 @@ class MetaData:
         idx = np.arange(self.N) if len(values) == self.N else self.active_index(key)  # metadata.py:321-323
         if len(values) != len(idx):
             raise ValueError(f"ERROR: `values` are of incorrect length: {len(values)} for {len(idx)} active rows")
-        full = np.full(self.N, fill_value, dtype=values.dtype if values.dtype.kind in "bU" else np.float64)
+        # metadata.py:308-318 (_fill_to_index): bool columns are always filled with False, integer columns with 0 and
+        # keep their dtype, everything else with `fill_value`
         if values.dtype.kind == "b":
-            full = np.zeros(self.N, dtype=bool) | bool(fill_value)
+            fill_value = False
+        elif values.dtype.kind in "iu":
+            try:
+                if np.isnan(fill_value):
+                    if len(values) and values.min() <= -1:
+                        raise ValueError("`fill_value should be an integer value. ")
+                    fill_value = 0
+            except TypeError:
+                raise ValueError("`fill_value should be an interger value. ")
+        full = np.full(self.N, fill_value, dtype=values.dtype)
         full[idx] = values
         a = self.z.create_dataset(column_name, full.shape, full.dtype, (100000,))
         a[:] = full
@@ -96,22 +106,67 @@ class MetaData:
         a[:] = new
 
 
-class RNAassay:
-    """The raw counts of one assay on the device plus its feature table (scarf/assay.py: RNAassay)."""
+def create_subset_hash(cell_idx, feat_idx) -> int:
+    """Assay._create_subset_hash (scarf/assay.py:317-329): Python's hash of the two index tuples -- deterministic for
+    integers, so a store written by the reference and one written here recognise each other's cached groups."""
+    return hash(tuple([hash(tuple(np.asarray(cell_idx).tolist())), hash(tuple(np.asarray(feat_idx).tolist()))]))
 
-    def __init__(self, zroot: Group, name: str, cells: MetaData, device):
-        self.name, self.z, self.cells = name, zroot[name], cells
+
+def _slice_csr_rows(c: CsrDevice, a: int, b: int) -> CsrDevice:
+    ip = c.indptr[a:b + 1]
+    lo, hi = int(ip[0].item()), int(ip[-1].item())
+    return CsrDevice((ip - lo).contiguous(), c.indices[lo:hi].contiguous(), c.data[lo:hi].contiguous(), b - a, c.n_cols)
+
+
+class RNAassay:
+    """The raw counts of one assay on the device plus its feature table (scarf/assay.py: RNAassay).  ``csr`` holds all
+    rows (loaded on first use); ``csr_rows(lo, hi)`` loads a contiguous span of rows only -- what one rank of a sharded
+    run needs (the last span is cached)."""
+
+    def __init__(self, zroot: Group, name: str, cells: MetaData, device, lazy: bool = False):
+        self.name, self.z, self.cells, self.device = name, zroot[name], cells, device
         self.feats = MetaData(self.z["featureData"])
         self.sf = 1000  # scarf/assay.py:776
+        self._span, self._span_csr = None, None
         if "counts_csr" in self.z:
-            g = self.z["counts_csr"]
-            shape = tuple(g.attrs["shape"])
-            self.csr = CsrDevice.from_host(g["indptr"][:], g["indices"][:], g["data"][:], shape, device, validate=True)
+            self._indptr = self.z["counts_csr"]["indptr"][:].astype(np.int64)
+            shape = tuple(self.z["counts_csr"].attrs["shape"])
+            self.chunk_rows = 1000
         else:  # a store the reference wrote: dense chunked `counts` (scarf/writers.py:164-204, assay.py:134)
-            self.csr = ops.csr_from_dense_zarr(self.z["counts"], device)
-        if self.csr.n_rows != cells.N or self.csr.n_cols != self.feats.N:
-            raise ValueError(f"ERROR: counts of assay {name} are {self.csr.n_rows} x {self.csr.n_cols} but the store "
+            self._indptr = None
+            shape = tuple(self.z["counts"].shape)
+            self.chunk_rows = int(self.z["counts"].chunks[0])
+        self.n_rows, self.n_cols = int(shape[0]), int(shape[1])
+        if self.n_rows != cells.N or self.n_cols != self.feats.N:
+            raise ValueError(f"ERROR: counts of assay {name} are {self.n_rows} x {self.n_cols} but the store "
                              f"lists {cells.N} cells and {self.feats.N} features")
+        if not lazy:
+            self.csr  # noqa: B018  (loads and validates)
+
+    def csr_rows(self, lo: int, hi: int) -> CsrDevice:
+        lo, hi = int(lo), int(hi)
+        if self._span == (lo, hi):
+            return self._span_csr
+        if self._span is not None and self._span[0] <= lo and hi <= self._span[1]:
+            c = _slice_csr_rows(self._span_csr, lo - self._span[0], hi - self._span[0])
+        elif self._indptr is not None:
+            g = self.z["counts_csr"]
+            ip = self._indptr[lo:hi + 1]
+            a, b = (int(ip[0]), int(ip[-1])) if hi > lo else (0, 0)
+            c = CsrDevice.from_host(ip - a if hi > lo else np.zeros(1, np.int64), g["indices"][a:b], g["data"][a:b],
+                                    (hi - lo, self.n_cols), self.device, validate=True)
+        else:
+            al = lo - lo % self.chunk_rows  # the dense reader starts on a chunk-row boundary
+            c = ops.csr_from_dense_zarr(self.z["counts"], self.device, row_range=(al, hi))
+            if al != lo:
+                c = _slice_csr_rows(c, lo - al, hi - al)
+        if self._span is None or (hi - lo) >= (self._span[1] - self._span[0]):
+            self._span, self._span_csr = (lo, hi), c
+        return c
+
+    @property
+    def csr(self) -> CsrDevice:
+        return self.csr_rows(0, self.n_rows)
 
     @property
     def nCounts(self):
@@ -148,23 +203,32 @@ class _ExactIndex:
 
 
 class AnnStream:
-    """What ``make_graph(return_ann_object=True)`` hands back (scarf/ann.py:55): same attribute names."""
+    """What ``make_graph(return_ann_object=True)`` hands back (scarf/ann.py:55): same attribute names.  Built either
+    from a fresh :class:`graph.GraphResult` or from the arrays a previous run left in the store (cache hit)."""
 
-    def __init__(self, res: graph.GraphResult, k: int, kmeans=None, labels=None):
-        self.k, self.method, self.dims = k, "pca", res.dims
-        self.mu, self.sigma = res.mu.cpu().numpy(), res.sigma.cpu().numpy()
-        self.loadings = res.loadings.cpu().numpy()
-        self.nCells, self.nFeats = res.n_cells, int(res.mu.numel())
+    def __init__(self, k: int, dims: int, mu: torch.Tensor, sigma: torch.Tensor, loadings: torch.Tensor, n_cells: int,
+                 embedding_all: torch.Tensor, kmeans=None, labels=None, eigenvalues=None):
+        self.k, self.method, self.dims = k, "pca", dims
+        self.mu_d, self.sigma_d, self.loadings_d = mu, sigma, loadings  # float64 device tensors (run_mapping)
+        self.mu, self.sigma = mu.cpu().numpy(), sigma.cpu().numpy()
+        self.loadings = loadings.cpu().numpy()
+        self.nCells, self.nFeats = n_cells, int(mu.numel())
         self.harmonizedData, self.data = None, None
-        self.annIdx = _ExactIndex(res.embedding_all, res.dims)
+        self.annIdx = _ExactIndex(embedding_all, dims)
         self.kmeans, self.clusterLabels = kmeans, labels
-        self._res = res
-        # what the reference's elbow plot reads (graph_datastore.py:1013-1016): variance explained by every kept
-        # component.  Exact-PCA values lambda_i / trace(cov); the z-scaled columns have unit variance, so the trace is
-        # nFeats * n / (n - 1) (constant columns, kept at sigma = 1, make this a slight over-estimate of the total).
-        ev = res.eigenvalues.detach().cpu().numpy().astype(np.float64)
-        total = float(self.nFeats) * res.n_cells / max(res.n_cells - 1, 1)
-        self._pca = _PcaSummary(ev, ev / total)
+        self._pca = None
+        if eigenvalues is not None:
+            # what the reference's elbow plot reads (graph_datastore.py:1013-1016): variance explained by every kept
+            # component.  Exact-PCA values lambda_i / trace(cov); the z-scaled columns have unit variance, so the trace
+            # is nFeats * n / (n - 1) (constant columns, kept at sigma = 1, make this a slight over-estimate).
+            ev = eigenvalues.detach().cpu().numpy().astype(np.float64)
+            total = float(self.nFeats) * n_cells / max(n_cells - 1, 1)
+            self._pca = _PcaSummary(ev, ev / total)
+
+    @classmethod
+    def from_result(cls, res: graph.GraphResult, kmeans=None, labels=None):
+        return cls(res.k, res.dims, res.mu, res.sigma, res.loadings, res.n_cells, res.embedding_all, kmeans, labels,
+                   res.eigenvalues)
 
     def reducer(self, x):
         """``transform_z(x).dot(loadings)`` (scarf/ann.py:138,191-192); accepts a block or one row."""
@@ -180,6 +244,39 @@ class AnnStream:
         from .graph import fix_knn_query
 
         return fix_knn_query(i, d, np.asarray(self_indices))
+
+
+def write_graph_arrays(zw: Group, knn_loc: str, graph_loc: str, res: graph.GraphResult, comm: Optional[Comm] = None,
+                       batch_size: int = 1000) -> int:
+    """The row-sharded arrays of the graph (scarf/knn_utils.py:54-59,108-117: ``indices`` u8 / ``distances`` f8 in
+    chunks of ``batch_size`` rows, ``edges`` u8 / ``weights`` f8 in chunks of ``batch_size * k``): rank 0 creates the
+    datasets, then every rank writes the chunks of its own rows [row_offset, row_offset + n_local) -- shards are aligned
+    to ``batch_size`` rows (dist.ShardPlan), so no chunk file has two writers.  Returns the bytes this rank wrote."""
+    comm = comm or Comm()
+    n_local, k = (int(x) for x in res.indices.shape)
+    n = res.n_cells
+    specs = (("indices", knn_loc, (n, k), "u8", (batch_size,)), ("distances", knn_loc, (n, k), "f8", (batch_size,)),
+             ("edges", graph_loc, (n * k, 2), "u8", (batch_size * k,)),
+             ("weights", graph_loc, (n * k,), "f8", (batch_size * k,)))
+    if comm.rank == 0:
+        for name, loc, shape, dt, chunks in specs:
+            if loc not in zw:
+                zw.create_group(loc)
+            zw[loc].create_dataset(name, shape, dt, chunks)
+    comm.barrier()
+    if comm.world > 1 and res.row_offset % batch_size:
+        raise ValueError("sharded graph write: shard boundaries must fall on chunk rows")
+    nbytes = 0
+    r0 = res.row_offset
+    for name, loc, shape, dt, chunks in specs:
+        t = getattr(res, name)
+        mul = k if name in ("edges", "weights") else 1
+        if n_local:
+            a = t.cpu().numpy().astype(dt)
+            zw[loc][name][r0 * mul:(r0 + n_local) * mul] = a
+            nbytes += a.nbytes
+    comm.barrier()
+    return nbytes
 
 
 class DataStore:
@@ -205,6 +302,9 @@ class DataStore:
         self.nthreads = nthreads
         self.device = torch.device(device)
         self.comm = comm
+        self._world = comm.world if comm is not None else 1
+        self._rank = comm.rank if comm is not None else 0
+        self.last_make_graph_timing = {}
         if "cellData" not in self.zw:
             raise KeyError(f"cellData not found in zarr file at {self.zw.path}")
         self.cells = MetaData(self.zw["cellData"])
@@ -236,32 +336,62 @@ class DataStore:
             raise ValueError(f"ERROR: The provided default assay name: {assay_name} was not found. "
                              f"Please Choose one from: {' '.join(names)}\n"
                              "Please note that the names are case-sensitive.")
-        if self._zarr_mode != "r":  # a read-only store keeps its attributes
+        if self._zarr_mode != "r" and self._rank == 0:  # a read-only store keeps its attributes
             self.zw.attrs["defaultAssay"] = assay_name
         return assay_name
+
+    def _barrier(self):
+        if self.comm is not None:
+            self.comm.barrier()
+
+    def _shard(self, cell_idx: np.ndarray, align: int):
+        """This rank's part of the selected cells: rows [s, e) of ``cell_idx`` (contiguous, aligned to ``align`` selected
+        rows: the Zarr chunk rows, so that every chunk file has one writer) and the span [lo, hi) of raw rows that
+        holds them.  One rank: everything."""
+        if self._world == 1:
+            return 0, int(cell_idx.size), 0, self.cells.N
+        s0, e0 = ShardPlan.make(int(cell_idx.size), self._world, align).rows(self._rank)
+        lo, hi = (int(cell_idx[s0]), int(cell_idx[e0 - 1]) + 1) if e0 > s0 else (0, 0)
+        return s0, e0, lo, hi
 
     def _ini_props(self, from_assay, min_features, min_cells):
         """First open of a store (base_datastore.py:324-401 `_ini_cell_props`, assay.py:201-225 `_ini_feature_props`):
         ``<assay>_nCounts`` / ``<assay>_nFeatures`` per cell, ``nCells`` / ``dropOuts`` per feature and the ``I``
-        filters, computed on the GPU from the CSR when the columns are missing.  The reference's percentMito /
-        percentRibo columns are cell annotations outside the graph path and are not written."""
+        filters, computed on the GPU from the CSR when the columns are missing (every rank scans its own block of raw
+        rows; rank 0 writes).  The reference's percentMito / percentRibo columns are cell annotations outside the graph
+        path and are not written."""
         assay = self._get_assay(from_assay)
         have = self.cells.columns
-        if f"{from_assay}_nCounts" not in have or f"{from_assay}_nFeatures" not in have:
-            n_counts, n_feats = graph.cell_totals(assay.csr)
-            self.cells.insert(f"{from_assay}_nCounts", n_counts.cpu().numpy(), overwrite=True)
-            self.cells.insert(f"{from_assay}_nFeatures", n_feats.cpu().numpy().astype(np.float64), overwrite=True)
+        need_cells = f"{from_assay}_nCounts" not in have or f"{from_assay}_nFeatures" not in have
+        need_feats = "nCells" not in assay.feats.columns or "dropOuts" not in assay.feats.columns
+        self._barrier()  # every rank has looked before rank 0 starts writing
+        if need_cells or need_feats:
+            a, b = ShardPlan.make(self.cells.N, self._world, assay.chunk_rows).rows(self._rank)
+            csr = assay.csr_rows(a, b)
+            if need_cells:
+                n_counts, n_feats = graph.cell_totals(csr)
+                if self.comm is not None and self._world > 1:
+                    n_counts, n_feats = self.comm.allgather_rows(n_counts), self.comm.allgather_rows(n_feats)
+                if self._rank == 0:
+                    self.cells.insert(f"{from_assay}_nCounts", n_counts.cpu().numpy(), overwrite=True)
+                    self.cells.insert(f"{from_assay}_nFeatures", n_feats.cpu().numpy().astype(np.float64),
+                                      overwrite=True)
+            if need_feats:
+                nc = graph.gene_ncells(csr, self.comm).cpu().numpy().astype(np.float64)
+                if self._rank == 0:
+                    assay.feats.insert("nCells", nc, overwrite=True)
+                    assay.feats.insert("dropOuts", np.abs(self.cells.N - nc), overwrite=True)
+                    assay.feats.update_key(nc > min_cells, "I")  # assay.py:225
+            self._barrier()
         v = self.cells.fetch(f"{from_assay}_nFeatures", key="I")
         if len(v) and min_features <= np.median(v):  # base_datastore.py:384-399 (every open; a no-op once applied)
             keep = self.cells.sift(f"{from_assay}_nFeatures", min_features, np.inf)
             cur = self.cells.fetch_all("I")
-            if not np.array_equal(keep & cur, cur):
+            changed = not np.array_equal(keep & cur, cur)
+            self._barrier()
+            if changed and self._rank == 0 and self._zarr_mode != "r":
                 self.cells.update_key(keep, "I")
-        if "nCells" not in assay.feats.columns or "dropOuts" not in assay.feats.columns:
-            nc = graph.gene_ncells(assay.csr).cpu().numpy().astype(np.float64)
-            assay.feats.insert("nCells", nc, overwrite=True)
-            assay.feats.insert("dropOuts", np.abs(self.cells.N - nc), overwrite=True)
-            assay.feats.update_key(nc > min_cells, "I")  # assay.py:225
+            self._barrier()
 
     # ---------------------------------------------------------------------------------------------------------
     @classmethod
@@ -313,7 +443,7 @@ class DataStore:
         if from_assay not in self._assays:
             if from_assay not in self.zw or not ("counts_csr" in self.zw[from_assay] or "counts" in self.zw[from_assay]):
                 raise ValueError(f"ERROR: Assay {from_assay} was not found.")
-            self._assays[from_assay] = RNAassay(self.zw, from_assay, self.cells, self.device)
+            self._assays[from_assay] = RNAassay(self.zw, from_assay, self.cells, self.device, lazy=self._world > 1)
         return self._assays[from_assay]
 
     def _get_latest_keys(self, from_assay, cell_key, feat_key):
@@ -351,19 +481,26 @@ class DataStore:
             raise TypeError(f"ERROR: This method of feature selection can only be applied to RNAassay type of assay.")
         if min_cells is None:
             min_cells = int(0.01 * self.cells.N)  # datastore.py:291
-        cells = torch.from_numpy(self.cells.active_index(cell_key)).to(self.device)
-        n_counts = torch.from_numpy(assay.nCounts).to(self.device)
+        cell_idx = self.cells.active_index(cell_key)
+        s0, e0, lo, hi = self._shard(cell_idx, assay.chunk_rows)
+        cells = torch.from_numpy(cell_idx[s0:e0] - lo).to(self.device)
+        n_counts = torch.from_numpy(assay.nCounts[lo:hi]).to(self.device)
         feat_I = assay.feats.fetch_all("I")
-        mask, st = graph.mark_hvgs_csr(assay.csr, cells, feat_I, n_counts, self.cells.N,
+        mask, st = graph.mark_hvgs_csr(assay.csr_rows(lo, hi), cells, feat_I, n_counts, self.cells.N,
                                        gene_names=assay.feats.fetch_all("names"), top_n=top_n, min_cells=min_cells,
                                        min_mean=min_mean, max_mean=max_mean, n_bins=n_bins, lowess_frac=lowess_frac,
                                        blacklist=blacklist, comm=self.comm, return_stats=True, min_var=min_var,
                                        max_var=max_var, max_cells=max_cells, keep_bounds=keep_bounds)
+        self._barrier()
+        if self._rank != 0:  # the statistics are identical on every rank after the all-reduce: one writer
+            self._barrier()
+            return None
         ident = f"{cell_key}__"
         for name, col in (("normed_tot", "normed_tot"), ("avg", "avg"), ("nz_mean", "nz_mean"),
                           ("sigmas", "sigmas"), ("normed_n", "normed_n"), ("c_var", f"c_var__{n_bins}__{lowess_frac}")):
             assay.feats.insert(ident + col, st[name][feat_I], overwrite=True)  # assay.py:884-897, metadata.py:612
         assay.feats.insert(ident + hvg_key_name, mask[feat_I], fill_value=False, overwrite=True)
+        self._barrier()
         return None
 
     # ---------------------------------------------------------------------------------------------------------
@@ -461,7 +598,7 @@ class DataStore:
             from_assay = self._defaultAssay
         assay = self._get_assay(from_assay)
         if batch_size is None:
-            batch_size = 1000  # assay.rawData.chunksize[0] of a reference store (writers.py:164-204)
+            batch_size = assay.chunk_rows  # assay.rawData.chunksize[0] (graph_datastore.py:738-745; writers.py:164-204)
         if cell_key is None:
             cell_key = "I"
         if feat_key is None:
@@ -500,46 +637,86 @@ class DataStore:
         if feat_mask.dtype != bool:
             raise ValueError(f"ERROR: {feat_col} is not of boolean type. Cannot perform fetch operation")
         feat_idx = np.where(feat_mask)[0]
-        subset_hash = hashlib.md5((str(cell_idx.tolist()) + str(feat_idx.tolist())).encode()).hexdigest()
+        subset_hash = create_subset_hash(cell_idx, feat_idx)
         subset_params = {"log_transform": log_transform, "renormalize_subset": renormalize_subset}
-        if normed_loc in zw and (zw[normed_loc].attrs.get("subset_hash") != subset_hash or
-                                 zw[normed_loc].attrs.get("subset_params") != subset_params):
-            zw.create_group(normed_loc, overwrite=True)  # stale cache: everything below it is recomputed
-        if normed_loc not in zw:
-            zw.create_group(normed_loc)
-        zw[normed_loc].attrs["subset_hash"] = subset_hash
-        zw[normed_loc].attrs["subset_params"] = subset_params
-        if update_keys:
-            zw[from_assay].attrs["latest_cell_key"] = cell_key
-            zw[from_assay].attrs["latest_feat_key"] = feat_key
+        self._barrier()  # every rank has read the store's state before rank 0 changes it
+        stale = False
+        if normed_loc in zw:
+            at = zw[normed_loc].attrs
+            # a cached group is stale when it records a different subset or different parameters (assay.py:446-460);
+            # a group without a record (foreign or legacy content) is left alone
+            stale = ("subset_hash" in at and at["subset_hash"] != subset_hash) or \
+                    ("subset_params" in at and at["subset_params"] != subset_params)
+        cached = (not stale) and all(x in zw for x in (reduction_loc, ann_loc, knn_loc, graph_loc, kmeans_loc)) and \
+            "embedding" in zw[ann_loc] and "mu" in zw[normed_loc] and "reduction" in zw[reduction_loc]
+        self._barrier()
+        if self._rank == 0:
+            if stale:
+                zw.create_group(normed_loc, overwrite=True)  # everything below it is recomputed
+            if normed_loc not in zw:
+                zw.create_group(normed_loc)
+            zw[normed_loc].attrs["subset_hash"] = subset_hash
+            zw[normed_loc].attrs["subset_params"] = subset_params
+            if update_keys:
+                zw[from_assay].attrs["latest_cell_key"] = cell_key
+                zw[from_assay].attrs["latest_feat_key"] = feat_key
+        self._barrier()
 
-        cached = all(x in zw for x in (reduction_loc, ann_loc, knn_loc, graph_loc, kmeans_loc)) and \
-            "embedding" in zw[ann_loc] and "mu" in zw[normed_loc]
-        if cached and not return_ann_object:
-            self._set_latest(normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc)
-            return None
+        if cached:
+            # the Zarr tree is the checkpoint (graph_datastore.py:797-881, 916-1001): nothing is recomputed; the object
+            # run_mapping needs is rebuilt from the stored mu / sigma / loadings / embedding
+            if self._rank == 0:
+                self._set_latest(normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc)
+            self._barrier()
+            self.last_make_graph_timing = {"cache_hit": True}
+            return self._load_ann_object(normed_loc, reduction_loc, ann_loc, kmeans_loc, dims, k) \
+                if return_ann_object else None
 
-        cells_t = torch.from_numpy(cell_idx).to(self.device)
-        n_counts = torch.from_numpy(assay.nCounts).to(self.device)
+        t_start = time.time()
+        s0, e0, lo, hi = self._shard(cell_idx, batch_size)
+        cells_t = torch.from_numpy(cell_idx[s0:e0] - lo).to(self.device)
+        n_counts = torch.from_numpy(assay.nCounts[lo:hi]).to(self.device)
         pca_rows = None
         if pca_cell_key != cell_key:  # use_for_pca = cells.fetch(pca_cell_key, key=cell_key)  (graph_datastore.py:764)
             use_for_pca = self.cells.fetch_all(pca_cell_key)[cell_idx]
             if use_for_pca.dtype != bool:
                 raise ValueError(f"ERROR: `pca_use_cell_key` {pca_cell_key} is not of boolean type")
             if not use_for_pca.all():
-                pca_rows = torch.from_numpy(np.where(use_for_pca)[0]).to(self.device)
-        res = graph.make_graph_csr(assay.csr, cells_t, feat_mask, dims=dims, k=k, lc=local_connectivity,
+                pca_rows = torch.from_numpy(np.where(use_for_pca[s0:e0])[0]).to(self.device)
+        res = graph.make_graph_csr(assay.csr_rows(lo, hi), cells_t, feat_mask, dims=dims, k=k, lc=local_connectivity,
                                    bw=bandwidth, batch_size=batch_size, log_transform=log_transform,
                                    renormalize_subset=renormalize_subset, n_counts=n_counts, comm=self.comm,
                                    gram_mode=3, knn_method=1, pca_rows=pca_rows)
+        torch.cuda.synchronize()
+        t_graph = time.time()
         centers, labels = graph.fit_kmeans(res.embedding_all, res.dims, max(n_centroids, 2), rand_state)
-        ann_obj = AnnStream(res, res.k, _KMeans(centers.cpu().numpy().astype(np.float64)),
-                            labels.cpu().numpy().astype(np.float64))
-        if self.comm is None or self.comm.rank == 0 or self.comm.world == 1:
-            self._write_graph(res, ann_obj, normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc,
-                              batch_size)
-        self._set_latest(normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc)
+        ann_obj = AnnStream.from_result(res, _KMeans(centers.cpu().numpy().astype(np.float64)),
+                                        labels.cpu().numpy().astype(np.float64))
+        t_kmeans = time.time()
+        self._write_graph(res, ann_obj, normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc, batch_size)
+        if self._rank == 0:
+            self._set_latest(normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc)
+        self._barrier()
+        t_end = time.time()
+        self.last_make_graph_timing = {"graph_s": round(t_graph - t_start, 4), "kmeans_s": round(t_kmeans - t_graph, 4),
+                                       "zarr_write_s": round(t_end - t_kmeans, 4)}
         return ann_obj if return_ann_object else None
+
+    def _load_ann_object(self, normed_loc, reduction_loc, ann_loc, kmeans_loc, dims, k) -> AnnStream:
+        """AnnStream from the arrays of a finished run (mapping_datastore.py:143 reaches make_graph only to get this
+        object: loadings, mu / sigma and the index are loaded, not recomputed -- graph_datastore.py:797-881)."""
+        zw, dev = self.zw, self.device
+        mu = torch.from_numpy(zw[normed_loc]["mu"][:]).to(dev)
+        sigma = torch.from_numpy(zw[normed_loc]["sigma"][:]).to(dev)
+        load = torch.from_numpy(np.ascontiguousarray(zw[reduction_loc]["reduction"][:])).to(dev)
+        emb = zw[ann_loc]["embedding"][:]
+        n, d = emb.shape
+        y = torch.zeros((n, ops.round_up(d, 32)), dtype=torch.float32, device=dev)
+        y[:, :d] = torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float32)).to(dev)
+        km = _KMeans(zw[kmeans_loc]["cluster_centers"][:]) if "cluster_centers" in zw[kmeans_loc] else None
+        lb = zw[kmeans_loc]["cluster_labels"][:] if "cluster_labels" in zw[kmeans_loc] else None
+        k_eff = int(zw[ann_loc.rstrip("/") + f"/knn__{k}"]["indices"].shape[1])
+        return AnnStream(k_eff, int(d), mu, sigma, load, int(n), y, km, lb)
 
     def save_normalized_data(self, from_assay: Optional[str] = None, cell_key: str = "I", feat_key: str = "hvgs",
                              batch_size: int = 1000, log_transform: bool = True, renormalize_subset: bool = True):
@@ -560,6 +737,13 @@ class DataStore:
         feat_idx = np.where(feat_mask)[0]
         n_feat = int(feat_idx.size)
         normed_loc = f"{from_assay}/normed__{cell_key}__{feat_key}"
+        subset_hash = create_subset_hash(cell_idx, feat_idx)
+        subset_params = {"log_transform": bool(log_transform), "renormalize_subset": bool(renormalize_subset)}
+        if normed_loc in zw:
+            at = zw[normed_loc].attrs
+            if ("subset_hash" in at and at["subset_hash"] != subset_hash) or \
+                    ("subset_params" in at and at["subset_params"] != subset_params):
+                zw.create_group(normed_loc, overwrite=True)  # assay.py:459-460: a different subset owns the group
         if normed_loc not in zw:
             zw.create_group(normed_loc)
         dev = self.device
@@ -579,6 +763,8 @@ class DataStore:
             ops.csr_norm_scale(assay.csr, cells_t[lo:hi].contiguous(), col_map, n_feat, row_sum[lo:hi].contiguous(), buf,
                                graph.SF, log_transform)
             out[lo:hi] = buf[: hi - lo, :n_feat].cpu().numpy().astype(np.float64)
+        zw[normed_loc].attrs["subset_hash"] = subset_hash      # assay.py:471-472
+        zw[normed_loc].attrs["subset_params"] = subset_params
         return f"{normed_loc}/data"
 
     def _set_latest(self, normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc):
@@ -592,11 +778,10 @@ class DataStore:
 
     def _write_graph(self, res, ann_obj, normed_loc, reduction_loc, ann_loc, kmeans_loc, knn_loc, graph_loc,
                      batch_size):
-        """Array names / dtypes / chunks of SURVEY.md App. B (single writer: with several ranks the caller gathers)."""
+        """Array names / dtypes / chunks of SURVEY.md App. B.  The replicated arrays (mu, sigma, loadings, k-means, the
+        embedding -- every rank holds all of it after the all-gather) are written by rank 0, the row-sharded ones by the
+        rank that owns the rows (:func:`write_graph_arrays`)."""
         zw = self.zw
-        if self.comm is not None and self.comm.world > 1:
-            raise NotImplementedError("writing the store from a sharded run: gather the GraphResult rows on rank 0 "
-                                      "(rank r owns rows [start_r, stop_r) of every array)")
 
         def put(loc, name, arr, chunks, dtype):
             if loc not in zw:
@@ -604,17 +789,14 @@ class DataStore:
             a = zw[loc].create_dataset(name, arr.shape, dtype, chunks)
             a[:] = arr.astype(dtype)
 
-        n, k = res.indices.shape
-        put(normed_loc, "mu", ann_obj.mu, (100000,), "f8")            # graph_datastore.py:778-796
-        put(normed_loc, "sigma", ann_obj.sigma, (100000,), "f8")
-        put(reduction_loc, "reduction", ann_obj.loadings, (batch_size, ann_obj.loadings.shape[0]), "f8")  # :921-928
-        put(ann_loc, "embedding", res.embedding_all[:, : res.dims].cpu().numpy(), (batch_size,), "f4")
-        put(kmeans_loc, "cluster_centers", ann_obj.kmeans.cluster_centers_, (1000, 1000), "f8")           # :958-976
-        put(kmeans_loc, "cluster_labels", ann_obj.clusterLabels, (100000,), "f8")
-        put(knn_loc, "indices", res.indices.cpu().numpy(), (batch_size,), "u8")                          # knn_utils.py:54-59
-        put(knn_loc, "distances", res.distances.cpu().numpy(), (batch_size,), "f8")
-        put(graph_loc, "edges", res.edges.cpu().numpy(), (batch_size * k,), "u8")                        # knn_utils.py:108-117
-        put(graph_loc, "weights", res.weights.cpu().numpy(), (batch_size * k,), "f8")
+        if self._rank == 0:
+            put(normed_loc, "mu", ann_obj.mu, (100000,), "f8")            # graph_datastore.py:778-796
+            put(normed_loc, "sigma", ann_obj.sigma, (100000,), "f8")
+            put(reduction_loc, "reduction", ann_obj.loadings, (batch_size, ann_obj.loadings.shape[0]), "f8")  # :921-928
+            put(ann_loc, "embedding", res.embedding_all[:, : res.dims].cpu().numpy(), (batch_size,), "f4")
+            put(kmeans_loc, "cluster_centers", ann_obj.kmeans.cluster_centers_, (1000, 1000), "f8")       # :958-976
+            put(kmeans_loc, "cluster_labels", ann_obj.clusterLabels, (100000,), "f8")
+        write_graph_arrays(zw, knn_loc, graph_loc, res, self.comm, batch_size)
 
     # ---------------------------------------------------------------------------------------------------------
     def _get_latest_graph_loc(self, from_assay, cell_key, feat_key):
@@ -670,19 +852,30 @@ class DataStore:
             save_k = ann_obj.k
         normed_loc = f"{from_assay}/normed__{cell_key}__{feat_key}"
         params = self.zw[normed_loc].attrs["subset_params"]
-        res = ann_obj._res
-        t_cells = torch.from_numpy(target_assay.cells.active_index(target_cell_key)).to(self.device)
-        t_counts = torch.from_numpy(target_assay.nCounts).to(self.device)
-        m = graph.run_mapping_csr(target_assay.csr, t_cells, t_col, res.mu, res.sigma, res.loadings,
-                                  res.embedding_all, res.dims, save_k=save_k, use_ref_mu=ref_mu,
-                                  use_ref_sigma=ref_sigma, log_transform=params["log_transform"],
+        t_idx = target_assay.cells.active_index(target_cell_key)
+        if self._world == 1:
+            q0, q1, lo, hi = 0, int(t_idx.size), 0, target_assay.n_rows
+        else:  # every rank maps a block of the target cells (aligned to the projection arrays' chunk rows)
+            q0, q1 = ShardPlan.make(int(t_idx.size), self._world, batch_size).rows(self._rank)
+            lo, hi = (int(t_idx[q0]), int(t_idx[q1 - 1]) + 1) if q1 > q0 else (0, 0)
+        t_cells = torch.from_numpy(t_idx[q0:q1] - lo).to(self.device)
+        t_counts = torch.from_numpy(target_assay.nCounts[lo:hi]).to(self.device)
+        m = graph.run_mapping_csr(target_assay.csr_rows(lo, hi), t_cells, t_col, ann_obj.mu_d, ann_obj.sigma_d,
+                                  ann_obj.loadings_d, ann_obj.annIdx.embedding, ann_obj.dims, save_k=save_k,
+                                  use_ref_mu=ref_mu, use_ref_sigma=ref_sigma, log_transform=params["log_transform"],
                                   renormalize_subset=params["renormalize_subset"], n_counts=t_counts, comm=self.comm)
-        if "projections" not in self.zw[from_assay]:
-            self.zw[from_assay].create_group("projections")
-        store = self.zw[from_assay]["projections"].create_group(target_name, overwrite=True)
-        nc = int(t_cells.numel())
-        zi = store.create_dataset("indices", (nc, save_k), "u8", (batch_size,))
-        zd = store.create_dataset("distances", (nc, save_k), "f8", (batch_size,))
-        zi[:] = m.indices.cpu().numpy().astype(np.uint64)
-        zd[:] = m.distances.cpu().numpy().astype(np.float64)
+        nc = int(t_idx.size)
+        self._barrier()
+        if self._rank == 0:
+            if "projections" not in self.zw[from_assay]:
+                self.zw[from_assay].create_group("projections")
+            store = self.zw[from_assay]["projections"].create_group(target_name, overwrite=True)
+            store.create_dataset("indices", (nc, save_k), "u8", (batch_size,))
+            store.create_dataset("distances", (nc, save_k), "f8", (batch_size,))
+        self._barrier()
+        store = self.zw[from_assay]["projections"][target_name]
+        if q1 > q0:
+            store["indices"][q0:q1] = m.indices.cpu().numpy().astype(np.uint64)
+            store["distances"][q0:q1] = m.distances.cpu().numpy().astype(np.float64)
+        self._barrier()
         return None

@@ -41,28 +41,43 @@ class Comm:
         self.group = group
         self.rank = td.get_rank(group) if self.enabled else 0
         self.world = td.get_world_size(group) if self.enabled else 1
+        # gloo moves host memory: device tensors are staged through the host (used to run several ranks on ONE GPU in
+        # the tests, where NCCL refuses two ranks per device; the production backend is NCCL)
+        self.staged = self.enabled and td.get_backend(group) == "gloo"
+
+    def _allreduce_(self, t, op):
+        if self.world > 1:
+            if self.staged and t.is_cuda:
+                h = t.cpu()
+                td.all_reduce(h, op=op, group=self.group)
+                t.copy_(h)
+            else:
+                td.all_reduce(t, op=op, group=self.group)
+        return t
 
     def allreduce_sum_(self, t):
-        if self.world > 1:
-            td.all_reduce(t, op=td.ReduceOp.SUM, group=self.group)
-        return t
+        return self._allreduce_(t, td.ReduceOp.SUM)
 
     def allreduce_min_(self, t):
-        if self.world > 1:
-            td.all_reduce(t, op=td.ReduceOp.MIN, group=self.group)
-        return t
+        return self._allreduce_(t, td.ReduceOp.MIN)
 
     def allreduce_max_(self, t):
-        if self.world > 1:
-            td.all_reduce(t, op=td.ReduceOp.MAX, group=self.group)
-        return t
+        return self._allreduce_(t, td.ReduceOp.MAX)
+
+    def _allgather_into(self, out, t):
+        if self.staged and t.is_cuda:
+            ho = torch.empty(out.shape, dtype=out.dtype)
+            td.all_gather_into_tensor(ho, t.cpu().contiguous(), group=self.group)
+            out.copy_(ho)
+        else:
+            td.all_gather_into_tensor(out, t.contiguous(), group=self.group)
 
     def allgather_counts(self, n: int, device) -> list:
         if self.world == 1:
             return [n]
         mine = torch.tensor([n], dtype=torch.int64, device=device)
         out = torch.empty(self.world, dtype=torch.int64, device=device)
-        td.all_gather_into_tensor(out, mine, group=self.group)
+        self._allgather_into(out, mine)
         return [int(x) for x in out.tolist()]
 
     def allgather_rows(self, t, counts=None):
@@ -74,12 +89,12 @@ class Comm:
         mx = max(counts)
         if all(c == mx for c in counts):
             out = torch.empty((self.world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            td.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+            self._allgather_into(out, t)
             return out
         pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         pad[: t.shape[0]] = t
         buf = torch.empty((self.world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        td.all_gather_into_tensor(buf, pad, group=self.group)
+        self._allgather_into(buf, pad)
         return torch.cat([buf[r * mx: r * mx + c] for r, c in enumerate(counts)], dim=0)
 
     def barrier(self):

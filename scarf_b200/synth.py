@@ -12,7 +12,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .ops import CsrDevice
+# NOTE: nothing here may import .ops / .lib at module level: the CPU arm of bench.py uses this generator and must not
+# map the CUDA library
 
 
 def gene_model(n_genes: int, n_factors: int, seed: int):
@@ -58,7 +59,9 @@ def make_counts_torch(n_cells: int, n_genes: int, n_factors: int = 65, seed: int
     return indptr, torch.cat(idx_parts), torch.cat(val_parts)
 
 
-def make_counts_device(n_cells, n_genes, n_factors=65, seed=4466, device="cuda", **kw) -> CsrDevice:
+def make_counts_device(n_cells, n_genes, n_factors=65, seed=4466, device="cuda", **kw):
+    from .ops import CsrDevice
+
     ip, ix, dv = make_counts_torch(n_cells, n_genes, n_factors, seed, device, **kw)
     return CsrDevice(ip, ix, dv, n_cells, n_genes)
 
@@ -71,7 +74,7 @@ def make_counts_scipy(n_cells, n_genes, n_factors=65, seed=4466, **kw):
     return sp.csr_matrix((dv.numpy().astype(np.uint32), ix.numpy(), ip.numpy()), shape=(n_cells, n_genes))
 
 
-def to_scipy(csr: CsrDevice):
+def to_scipy(csr):
     import scipy.sparse as sp
 
     return sp.csr_matrix((csr.data.cpu().numpy().view(np.uint32), csr.indices.cpu().numpy(),

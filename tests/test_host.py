@@ -144,20 +144,66 @@ c.allreduce_sum_(g)
 assert int(g[0]) == 2 ** 41 + 1            # int64 fixed-point sums are exact
 m = torch.tensor([1.0 + c.rank, 5.0 - c.rank]); c.allreduce_min_(m); assert m.tolist() == [1.0, 4.0]
 z = torch.tensor([c.rank], dtype=torch.int32); c.allreduce_max_(z); assert int(z) == 1
+# sharded write of the graph arrays (scarf/knn_utils.py:54-59,108-117): rank 0 creates, every rank writes its own rows
+import numpy as np
+from types import SimpleNamespace
+from scarf_b200.datastore import write_graph_arrays
+from scarf_b200.zarr_store import open_group
+k, path = 3, sys.argv[4]
+if c.rank == 0:
+    open_group(path, "w")
+c.barrier()
+gi = torch.arange(a, b, dtype=torch.int64)
+res = SimpleNamespace(n_cells=2500, row_offset=a, indices=gi[:, None] * 10 + torch.arange(k),
+                      distances=(gi[:, None] + torch.arange(k) / 4.0).to(torch.float32),
+                      edges=torch.stack([gi.repeat_interleave(k), (gi[:, None] * 10 + torch.arange(k)).flatten()], 1),
+                      weights=(gi.repeat_interleave(k) / 2.0).to(torch.float32))
+nb = write_graph_arrays(open_group(path, "r+"), "A/knn__3", "A/knn__3/graph__1.0__1.5", res, c, batch_size=1000)
+assert nb == (b - a) * k * (8 + 8 + 16 + 8), nb
+if c.rank == 0:
+    z = open_group(path, "r")
+    full = np.arange(2500)
+    assert z["A/knn__3"]["indices"].dtype == np.dtype("u8") and z["A/knn__3"]["indices"].chunks == (1000, 3)
+    assert np.array_equal(z["A/knn__3"]["indices"][:], full[:, None] * 10 + np.arange(k))
+    assert np.array_equal(z["A/knn__3"]["distances"][:], full[:, None] + np.arange(k) / 4.0)
+    e = z["A/knn__3/graph__1.0__1.5"]["edges"]
+    assert e.shape == (7500, 2) and e.chunks == (3000, 2) and np.array_equal(e[:][:, 0], np.repeat(full, k))
+    assert np.array_equal(z["A/knn__3/graph__1.0__1.5"]["weights"][:], np.repeat(full, k) / 2.0)
 c.barrier(); td.destroy_process_group(); print("ok")
 '''
 
 
 def test_comm_world2_gloo(tmp_path):
-    """The N>1 host logic (uneven all-gather, exact int64 all-reduce, min/max floor exchange) on CPU over gloo."""
+    """The N>1 host logic (uneven all-gather, exact int64 all-reduce, min/max floor exchange, the sharded write of the
+    graph arrays) on CPU over gloo."""
     script = tmp_path / "w.py"
     script.write_text(_GLOO_WORKER)
     port = str(29600 + os.getpid() % 300)
-    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(tmp_path / "g.zarr")],
+                              stdout=subprocess.PIPE,
                               stderr=subprocess.PIPE, text=True) for r in range(2)]
     for p in procs:
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out, err
+
+
+def test_subset_hash_and_shard_spans():
+    """The subset hash is the reference's (scarf/assay.py:317-329: Python's hash of the two index tuples, an int), and
+    DataStore._shard cuts the selected cells into chunk-aligned blocks with the raw-row span that holds each."""
+    from types import SimpleNamespace
+
+    from scarf_b200.datastore import DataStore, create_subset_hash
+
+    ci, fi = np.array([0, 2, 5, 9], dtype=np.int64), np.array([1, 3], dtype=np.int64)
+    assert create_subset_hash(ci, fi) == hash(tuple([hash(tuple(ci)), hash(tuple(fi))]))
+    assert isinstance(create_subset_hash(ci, fi), int) and create_subset_hash(ci, fi) != create_subset_hash(ci[:3], fi)
+    cells = np.arange(0, 7000, 2)  # 3500 selected cells out of 7000 raw rows
+    spans = [DataStore._shard(SimpleNamespace(_world=3, _rank=r, cells=SimpleNamespace(N=7000)), cells, 1000)
+             for r in range(3)]
+    assert [(s, e) for s, e, _, _ in spans] == [(0, 2000), (2000, 3000), (3000, 3500)]
+    assert spans[1][2:] == (4000, 5999) and spans[2][2:] == (6000, 6999)
+    assert DataStore._shard(SimpleNamespace(_world=1, _rank=0, cells=SimpleNamespace(N=7000)), cells, 1000) == \
+        (0, 3500, 0, 7000)
 
 
 def test_eig_topk_cpu_matches_full_eigh():
@@ -321,12 +367,15 @@ def test_datastore_mark_hvgs_front_end_on_a_stub_store(pbmc, monkeypatch):
     feats = SimpleNamespace(fetch_all=lambda c: {"I": feat_I, "names": names}[c], insert=insert, N=g)
     assay = object.__new__(RNAassay)
     assay.feats, assay.name, assay.sf = feats, "RNA", 1000
-    assay.csr = CsrDevice(torch.zeros(893, dtype=torch.int64), torch.zeros(0, dtype=torch.int32),
-                          torch.zeros(0, dtype=torch.int32), 892, g)
+    assay._span = (0, 892)  # the whole (empty) matrix counts as loaded
+    assay._span_csr = CsrDevice(torch.zeros(893, dtype=torch.int64), torch.zeros(0, dtype=torch.int32),
+                                torch.zeros(0, dtype=torch.int32), 892, g)
+    assay.chunk_rows, assay.n_rows, assay.n_cols = 1000, 892, g
     assay.cells = SimpleNamespace(fetch_all=lambda c: np.ones(892))  # RNA_nCounts (unused: statistics are patched)
     cells = SimpleNamespace(columns=["I", "ids", "names"], N=892, active_index=lambda k: np.where(keep)[0])
     store = SimpleNamespace(cells=cells, _defaultAssay="RNA", _get_assay=lambda a: assay, device=torch.device("cpu"),
-                            comm=None)
+                            comm=None, _world=1, _rank=0, _barrier=lambda: None,
+                            _shard=lambda ci, al: (0, int(ci.size), 0, 892))
     assert DataStore.mark_hvgs(store, top_n=100) is None  # cell_key None -> "I", min_cells None -> int(0.01 * N)
     assert np.array_equal(written["I__hvgs"], hv_o[feat_I]) and written["I__hvgs"].sum() == 100
     assert set(written) == {"I__normed_tot", "I__avg", "I__nz_mean", "I__sigmas", "I__normed_n", "I__c_var__200__0.1",

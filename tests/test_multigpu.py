@@ -21,3 +21,18 @@ def test_sharded_equals_single_gpu():
                         "--master-addr", "127.0.0.1", "--master-port", "29517",
                         os.path.join(ROOT, "tools", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
     assert "MULTIGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_sharded_two_ranks_on_one_gpu_equal_single_rank():
+    """The same check on ONE GPU: two ranks share cuda:0 and exchange over gloo (host-staged collectives), so the
+    sharded code path -- shard-local kernels, int64 Gram all-reduce, embedding all-gather, sharded DataStore writes --
+    is compared bit for bit with the single-rank result on a box with a single GPU."""
+    env = dict(os.environ, MG_ONE_GPU="1", MG_CELLS="11500")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29519",
+                        os.path.join(ROOT, "tools", "multigpu_check.py")], capture_output=True, text=True, timeout=900,
+                       env=env)
+    with open(os.path.join(ROOT, "gpurun_out", "multigpu_one_gpu.log") if os.path.isdir(os.path.join(ROOT, "gpurun_out"))
+              else os.devnull, "w") as f:
+        f.write(r.stdout[-5000:] + "\n" + r.stderr[-5000:])
+    assert "MULTIGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

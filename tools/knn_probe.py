@@ -1,5 +1,6 @@
 """Developer probe (GPU): scf_knn_l2 method 1 (tcgen05) against method 0 (FP64 brute force) with timings and
-guard-failure counts.  usage: python tools/knn_probe.py [n dim k]..."""
+guard-failure counts.  usage: python tools/knn_probe.py [n dim k]...   (KNN_PROBE_NQ=<rows>: only the first <rows>
+cells are queries -- the shape one rank of a sharded run sees)"""
 import os
 import sys
 import time
@@ -40,13 +41,20 @@ def main():
         cases = [tuple(a[i:i + 3]) for i in range(0, len(a), 3)]
     for n, dim, k in cases:
         y = embedding(n, dim)
+        nq = min(n, int(os.environ.get("KNN_PROBE_NQ", n)))
+        yq = y[:nq]
         st = {}
-        t1, (i1, d1) = timed(lambda: ops.knn_l2(y, y, dim, k, self_offset=0, method=1, stats=st))
+        kev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        kev[0].record(), kev[1].record()
+        t1, (i1, d1) = timed(lambda: ops.knn_l2(yq, y, dim, k, self_offset=0, method=1, stats=st, kernel_events=kev))
+        torch.cuda.synchronize()
+        tk = kev[0].elapsed_time(kev[1])
         fails = int(st["guard_fail_rows"].item()) if st.get("guard_fail_rows") is not None else -1
-        flop = 2.0 * n * n * dim
-        line = f"n={n} dim={dim} k={k}: tc {t1:.3f} ms ({flop / t1 / 1e9:.1f} TFLOP/s alg), guard fails {fails}"
-        if n <= 200000 and not os.environ.get("KNN_PROBE_NO_EXACT"):
-            t0, (i0, d0) = timed(lambda: ops.knn_l2(y, y, dim, k, self_offset=0, method=0), reps=1)
+        flop = 2.0 * nq * n * dim
+        line = (f"nq={nq} n={n} dim={dim} k={k}: tc {t1:.3f} ms ({flop / t1 / 1e9:.1f} TFLOP/s alg), tensor kernel "
+                f"{tk:.3f} ms ({flop / tk / 1e9:.1f} TFLOP/s alg), guard fails {fails}")
+        if nq * n <= 4e10 and not os.environ.get("KNN_PROBE_NO_EXACT"):
+            t0, (i0, d0) = timed(lambda: ops.knn_l2(yq, y, dim, k, self_offset=0, method=0), reps=1)
             same_i = bool(torch.equal(i0, i1))
             same_d = bool(torch.equal(d0, d1))
             line += f" | exact {t0:.1f} ms | idx equal {same_i} dist equal {same_d}"

@@ -1,6 +1,9 @@
 """Multi-GPU == single-GPU check (launched by tests/test_multigpu.py or by hand under torchrun):
 every rank builds the same synthetic matrix, runs make_graph (+ mark_hvgs, run_mapping) once alone on its GPU and once
-sharded over all ranks, and compares its shard of the sharded result bit for bit with the single-GPU rows."""
+sharded over all ranks, and compares its shard of the sharded result bit for bit with the single-GPU rows.
+MG_ONE_GPU=1: all ranks share cuda:0 and talk over gloo (host-staged collectives) -- the same sharded code path, the
+same kernels, on a box with a single GPU.  Then the Scarf-style front end: the sharded DataStore (every rank loads its
+rows, writes its chunks) must leave the same store as a single-rank one."""
 import os
 import sys
 
@@ -16,6 +19,9 @@ from scarf_b200.ops import CsrDevice  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    one_gpu = os.environ.get("MG_ONE_GPU") == "1"
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     n, g, top_n, dims, k = int(os.environ.get("MG_CELLS", "23500")), 8000, 800, 30, 11
@@ -34,7 +40,10 @@ def main():
         return hv, res, mp
 
     hv1, r1, m1 = run(full, tgt, None, n)
-    td.init_process_group("nccl", device_id=dev)
+    if one_gpu:
+        td.init_process_group("gloo")
+    else:
+        td.init_process_group("nccl", device_id=dev)
     comm = Comm()
     plan, qplan = ShardPlan.make(n, world, 1000), ShardPlan.make(nq, world, 1000)
     (a, b), (qa, qb) = plan.rows(rank), qplan.rows(rank)
@@ -63,12 +72,72 @@ def main():
     check("indices", r1.indices[a:b], rp.indices), check("distances", r1.distances[a:b], rp.distances)
     check("edges", r1.edges[a * k:b * k], rp.edges), check("weights", r1.weights[a * k:b * k], rp.weights)
     check("map indices", m1.indices[qa:qb], mp.indices), check("map distances", m1.distances[qa:qb], mp.distances)
+    ok &= datastore_check(full, tgt, hv1, r1, m1, comm, dev, rank, top_n, dims, k)
     flag = torch.tensor([1 if ok else 0], device=dev)
-    td.all_reduce(flag, op=td.ReduceOp.MIN)
+    comm.allreduce_min_(flag)
     if rank == 0:
         print("MULTIGPU_OK" if int(flag.item()) == 1 else "MULTIGPU_FAIL", f"world={world} cells={n}", flush=True)
     td.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+def datastore_check(full, tgt, hv1, r1, m1, comm, dev, rank, top_n, dims, k):
+    """DataStore(comm=...) on a store in a directory all ranks see: mark_hvgs + make_graph + run_mapping sharded; rank 0
+    compares the arrays in the store with the single-rank device results (widened like the store widens them)."""
+    import shutil
+    import tempfile
+
+    from scarf_b200.datastore import DataStore
+
+    path = os.path.join(tempfile.gettempdir(), "scarf_b200_mg_store.zarr")
+    tpath = os.path.join(tempfile.gettempdir(), "scarf_b200_mg_target.zarr")
+    g = full.n_cols
+    ids = [f"g{i}" for i in range(g)]
+    if rank == 0:
+        for p_, c_ in ((path, full), (tpath, tgt)):
+            shutil.rmtree(p_, ignore_errors=True)
+            DataStore.from_csr(p_, synth.to_scipy(c_), ids, device=dev, min_features_per_cell=0)
+    comm.barrier()
+    ds = DataStore(path, device=dev, comm=comm, min_features_per_cell=0)
+    ds.mark_hvgs(top_n=top_n, min_cells=None, show_plot=False)
+    ds.make_graph(feat_key="hvgs", dims=dims, k=k, n_centroids=50)
+    tds = DataStore(tpath, device=dev, comm=comm, min_features_per_cell=0)
+    ds.run_mapping(tds.RNA, "tgt", "hvgs_tgt", save_k=3)
+    comm.barrier()
+    ok = True
+    if rank == 0:
+        z = ds.zw
+        base = f"RNA/normed__I__hvgs/reduction__pca__{dims}__I/ann__l2__50__50__48__4466"
+        knn = f"{base}/knn__{k}"
+        want = {f"{knn}/indices": r1.indices.cpu().numpy().astype("u8"),
+                f"{knn}/distances": r1.distances.cpu().numpy().astype("f8"),
+                f"{knn}/graph__1.0__1.5/edges": r1.edges.cpu().numpy().astype("u8"),
+                f"{knn}/graph__1.0__1.5/weights": r1.weights.cpu().numpy().astype("f8"),
+                f"{base}/embedding": r1.embedding_all[:, :dims].cpu().numpy(),
+                "RNA/projections/tgt/indices": m1.indices.cpu().numpy().astype("u8"),
+                "RNA/projections/tgt/distances": m1.distances.cpu().numpy().astype("f8")}
+        import numpy as np
+        for loc, w in want.items():
+            grp, name = loc.rsplit("/", 1)
+            got = z[grp][name][:]
+            same = got.shape == w.shape and np.array_equal(got, w)
+            ok &= same
+            if not same:
+                print(f"[datastore] MISMATCH {loc}: {got.shape} vs {w.shape}", flush=True)
+        hv_store = ds.RNA.feats.fetch_all("I__hvgs")
+        same = np.array_equal(hv_store, hv1.cpu().numpy())
+        ok &= same
+        if not same:
+            print("[datastore] MISMATCH I__hvgs", flush=True)
+        # a second make_graph finds its groups (cache hit) and run_mapping does not recompute the graph
+        ds.make_graph(feat_key="hvgs", dims=dims, k=k, n_centroids=50)
+    else:
+        ds.make_graph(feat_key="hvgs", dims=dims, k=k, n_centroids=50)
+    ok &= ds.last_make_graph_timing.get("cache_hit") is True
+    comm.barrier()
+    if rank == 0:
+        shutil.rmtree(path, ignore_errors=True), shutil.rmtree(tpath, ignore_errors=True)
+    return ok
 
 
 if __name__ == "__main__":
