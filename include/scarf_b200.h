@@ -144,6 +144,28 @@ int32_t scf_sym_eig_max_n(void);
 int32_t scf_sym_eig_jacobi(const double* a, int32_t n, int64_t lda, double* evals, double* evecs, int64_t ldv,
                            int32_t* info, void* stream);
 
+/* ---- K3: top eigenpairs of the PCA covariance -------------------------------------------------------
+ * Replaces the fit of sklearn's IncrementalPCA (AnnStream._fit_pca, scarf/ann.py:207-256) on the exact-covariance route:
+ *   cov = gram_fx * scale - mean_weight * col_mean col_mean^T        (col_mean nullable)
+ * with gram_fx the mirrored int64 fixed-point Gram of scf_gram_accumulate / scf_gram_symmetrize (row stride ldg), e.g.
+ * scale = 2^-36 / (n - 1), mean_weight = n / (n - 1) for a PCA fitted on n rows whose column mean is col_mean.
+ * Chebyshev-filtered subspace iteration on dims + 32 columns in FP64, every kernel in this library (no cuSOLVER /
+ * cuBLAS): evals[dims] descending, evecs [h, dims] row major with sklearn's sign rule (svd_flip, v-based: the entry of
+ * largest magnitude of every component is positive), residual |C v - lambda v| <= tol * lambda_1 for every pair;
+ * evecs_f32 (nullable): the same loadings rounded to float32, [h, ld32] row major with zeroed pad columns -- the
+ * operand of scf_project / scf_project_tc.
+ * Deterministic (ranks that hold the same Gram get bit-identical loadings).  dims + 8 <= 160 columns.
+ * The call synchronises the stream once per round; host_report (host memory, >= 176 doubles) receives
+ * [0] residual, [1] trace, [2] norm bound, [3] Cholesky break-down flag, [4] smallest Cholesky pivot, [5] rounds
+ * (negative: not converged), [6] restarts, [7] 1 if the eigenvalue-based orthonormalisation was used,
+ * [8 ...) the Ritz values of the last round, [168] kernels launched.  Returns 2 for a zero / non-finite covariance, 3 without convergence
+ * within max_rounds.  workspace (device): scf_eig_topk_workspace_bytes(h, dims) (-1: unsupported sizes). */
+int64_t scf_eig_topk_workspace_bytes(int32_t h, int32_t dims);
+int32_t scf_eig_topk(const int64_t* gram_fx, int64_t ldg, int32_t h, double scale, const double* col_mean,
+                     double mean_weight, int32_t dims, double tol, int32_t max_rounds, double* evals, double* evecs,
+                     float* evecs_f32, int64_t ld32, double* host_report, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+
 /* ---- K5: exact k nearest neighbours, squared L2 --------------------------------------------------
  * Replaces hnswlib Index(space='l2').knn_query + fix_knn_query (scarf/ann.py:14-52,194-205):
  *   d(a,b) = (float) sum_t ((double)a_t - (double)b_t)^2   (t ascending), order by (d, index),

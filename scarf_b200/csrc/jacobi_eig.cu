@@ -31,7 +31,7 @@ __device__ __forceinline__ double group_sum8(double v, unsigned mask) {
 __global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double* __restrict__ a, int n, int64_t lda,
                                                                    double* __restrict__ evals,
                                                                    double* __restrict__ evecs, int64_t ldv,
-                                                                   int* __restrict__ info) {
+                                                                   int* __restrict__ info, int descending) {
   extern __shared__ __align__(16) double w[];  // column major, n rows x ne columns (ne = n rounded up to even)
   __shared__ int s_rotated;
   __shared__ double s_norm[JE_MAXN + 1];
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double*
     int rank = 0;
     const double mine = s_norm[c];
     for (int o = 0; o < n; ++o) rank += (s_norm[o] < mine) || (s_norm[o] == mine && o < c);
+    if (descending) rank = n - 1 - rank;
     s_rank[c] = rank;
     evals[rank] = mine;
   }
@@ -124,10 +125,19 @@ __global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double*
 
 }  // namespace
 
+int32_t jacobi_eig_launch(const double* a, int n, int64_t lda, double* evals, double* evecs, int64_t ldv, int* info,
+                          int descending, cudaStream_t stream);
+
 extern "C" int32_t scf_sym_eig_max_n(void) { return JE_MAXN; }
 
 extern "C" int32_t scf_sym_eig_jacobi(const double* a, int32_t n, int64_t lda, double* evals, double* evecs, int64_t ldv,
                                       int32_t* info, void* stream) {
+  return jacobi_eig_launch(a, n, lda, evals, evecs, ldv, info, 0, (cudaStream_t)stream);
+}
+
+// descending != 0: eigenvalues (and the matching eigenvector columns) in descending order (eig_topk.cu)
+int32_t jacobi_eig_launch(const double* a, int n, int64_t lda, double* evals, double* evecs, int64_t ldv, int* info,
+                          int descending, cudaStream_t stream) {
   SCF_ARG(a && evals && evecs, "null pointer");
   SCF_ARG(n >= 1 && n <= JE_MAXN && lda >= n && ldv >= n, "n must be within [1, 168]");
   const size_t smem = (size_t)n * (n + (n & 1)) * sizeof(double);
@@ -140,6 +150,6 @@ extern "C" int32_t scf_sym_eig_jacobi(const double* a, int32_t n, int64_t lda, d
   const int npairs = (n + 1) / 2;
   int threads = (npairs * JE_TPP + 31) / 32 * 32;
   threads = threads < 64 ? 64 : (threads > JE_THREADS ? JE_THREADS : threads);
-  jacobi_eig_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(a, n, lda, evals, evecs, ldv, info);
+  jacobi_eig_kernel<<<1, threads, smem, stream>>>(a, n, lda, evals, evecs, ldv, info, descending);
   return scf_check_launch("scf_sym_eig_jacobi");
 }

@@ -239,8 +239,17 @@ constexpr int FIXTC_ROWS = 32768;  // failed rows repaired by the tensor-core co
 constexpr int FIXTC_CAP = 64;     // collected references per failed row
 constexpr int FIXTC_NSPLIT = 16;  // reference ranges per query tile in the collect pass
 
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }  // one FMNMX3
 __device__ __forceinline__ float min4(const uint32_t* v) {
-  return fminf(fminf(__uint_as_float(v[0]), __uint_as_float(v[1])), fminf(__uint_as_float(v[2]), __uint_as_float(v[3])));
+  return fminf(fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2])), __uint_as_float(v[3]));
+}
+__device__ __forceinline__ float min16(const uint32_t* v) {  // eight FMNMX3 / FMNMX
+  const float t0 = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+  const float t1 = fmin3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+  const float t2 = fmin3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+  const float t3 = fmin3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+  const float t4 = fmin3(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]));
+  return fminf(fmin3(t0, t1, t2), fmin3(t3, t4, __uint_as_float(v[15])));
 }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
@@ -261,45 +270,56 @@ struct Epi {
   int* gid;         // this list's candidate ids in global memory
   int nref;
   __device__ __forceinline__ void drain() {
+    const bool count = (SCF_KNN_DEBUG & 16) && (threadIdx.x & 31) == 0;
+    if (count) atomicAdd(&g_dbg[3], 1ull);
     for (int i = 0; __any_sync(SCF_FULL, i < cnt); ++i) {
+      if (count) atomicAdd(&g_dbg[4], 1ull);
       if (i < cnt) {
         const float sc = hs[i * NL];
         const int j = hc[i * NL];
-        if (sc < cl.thr && j < nref) cl.replace_max(sc, j, gid);
+        if (SCF_KNN_DEBUG & 16) atomicAdd(&g_dbg[5], 1ull);
+        if (sc < cl.thr && j < nref) {
+          if (SCF_KNN_DEBUG & 16) atomicAdd(&g_dbg[6], 1ull);
+          cl.replace_max(sc, j, gid);
+        }
       }
     }
     cnt = 0;
   }
 };
 
-// One 16-column chunk of one query row: min tree (FMNMX3) against the threshold, groups of four columns; a group is
-// visited only when some lane of the warp has a candidate in it (warp-uniform branches around every vote).
+// The rare path of a 32-column pass: some lane of the warp has a score below its threshold among v[0..32).  Chunks of
+// 16 and groups of 4 columns are visited only when a lane has a candidate in them (the branches around the votes are
+// warp-uniform); before a group is appended the buffers are drained if one of them could overflow.
 template <int KC, bool SHARED_THR>
-__device__ __forceinline__ void process16(const uint32_t (&v)[16], int jb, Epi<KC>& ep, float* thr_pub,
-                                          const volatile float* thr_partner) {
-  float g[4];
+__device__ __forceinline__ void hits32(const uint32_t (&v)[32], float m_lo, float m_hi, int jb, Epi<KC>& ep, float* thr_pub,
+                                    const volatile float* thr_partner) {
+  const bool count = (SCF_KNN_DEBUG & 16) && (threadIdx.x & 31) == 0;
+  if (count) atomicAdd(&g_dbg[1], 1ull);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) g[i] = min4(v + 4 * i);
-  const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
-  if (!__any_sync(SCF_FULL, m < ep.thr)) return;
+  for (int h = 0; h < 2; ++h) {
+    if (!__any_sync(SCF_FULL, (h ? m_hi : m_lo) < ep.thr)) continue;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (!__any_sync(SCF_FULL, g[i] < ep.thr)) continue;
-    if (__any_sync(SCF_FULL, ep.cnt > HB - 4)) {
-      ep.drain();
-      ep.thr = ep.cl.thr;
-      if constexpr (SHARED_THR) {
-        *thr_pub = ep.cl.thr;
-        ep.thr = fminf(ep.thr, *thr_partner);
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t* vg = v + 16 * h + 4 * i;
+      if (!__any_sync(SCF_FULL, min4(vg) < ep.thr)) continue;
+      if (count) atomicAdd(&g_dbg[2], 1ull);
+      if (__any_sync(SCF_FULL, ep.cnt > HB - 4)) {
+        ep.drain();
+        ep.thr = ep.cl.thr;
+        if constexpr (SHARED_THR) {
+          *thr_pub = ep.cl.thr;
+          ep.thr = fminf(ep.thr, *thr_partner);
+        }
       }
-    }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float x = __uint_as_float(v[4 * i + c]);
-      if (x < ep.thr) {
-        ep.hs[ep.cnt * NL] = x;
-        ep.hc[ep.cnt * NL] = jb + 4 * i + c;
-        ++ep.cnt;
+      for (int c = 0; c < 4; ++c) {
+        const float x = __uint_as_float(vg[c]);
+        if (x < ep.thr) {
+          ep.hs[ep.cnt * NL] = x;
+          ep.hc[ep.cnt * NL] = jb + 16 * h + 4 * i + c;
+          ++ep.cnt;
+        }
       }
     }
   }
@@ -341,7 +361,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: the compiler then knows that the role branches below are warp-uniform and may
+  // use the uniform datapath inside them (UTCHMMA takes its descriptors from uniform registers; in a branch it
+  // considers divergent every operand of every MMA goes through an R2UR move: ~100 cycles per instruction, measured)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t backoff = (p.flags & 2) ? 32u : 0u;
   // Work of this CTA: a contiguous range [w0, w1) of the linearised (query tile, reference tile) space, walked as
   // segments that stay inside one query tile.  Static grid (blockIdx.x = query tile, blockIdx.y = reference split):
@@ -377,7 +400,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tmem_full + a, 1);
-      tc::mbar_init(tmem_empty + a, NL);
+      tc::mbar_init(tmem_empty + a, NEPI_WARPS);  // one arrive per epilogue warp
     }
     tc::fence_barrier_init();
   }
@@ -394,7 +417,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================  (whole warp, one elected lane issues)
     const bool leader = tc::elect_one();
-    int it = 0, seg = 0;
+    int seg = 0;
+    uint32_t s = 0, ph = 0;  // pipeline stage and its phase, advanced without divisions (stay in uniform registers)
     for (long long cur = w0; cur < w1; ++seg) {
       const int q = (int)(cur / T), t0 = (int)(cur % T);
       const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
@@ -409,9 +433,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
       }
       __syncwarp();
       for (int t = t0; t < t1; ++t)
-        for (int c = 0; c < p.kchunks; ++c, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        for (int c = 0; c < p.kchunks; ++c) {
           tc::mbar_wait(empty + s, ph ^ 1u, backoff);
           if (leader) {
             if (SCF_KNN_DEBUG & 128) {  // timing experiment: no reference traffic, the MMAs run on stale tiles
@@ -422,6 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
             }
           }
           __syncwarp();
+          if (++s == (uint32_t)p.stages) s = 0, ph ^= 1u;
         }
     }
   } else if (warp == 1) {
@@ -432,37 +455,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     // idle cycles between 64-cycle instructions, measured).
     constexpr uint32_t idesc = tc::umma_idesc_f16(BM, BN, false, false);
     const bool leader = tc::elect_one();
-    const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
-    int it = 0, lt = 0, seg = 0;
+    // Everything the instructions take is derived from warp-uniform counters with add / shift / select only, so that
+    // the descriptors stay in uniform registers (a division, e.g. `it % stages`, sends them through vector registers
+    // and every MMA then waits for a chain of R2UR moves: ~100 cycles per instruction instead of 32 - 64, measured).
+    const uint32_t a_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sA));
+    const uint32_t b_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sB));
+    const uint32_t nk_last = (uint32_t)p.ksteps_last, kchunks = (uint32_t)p.kchunks, stages = (uint32_t)p.stages;
+    uint32_t s = 0, ph = 0, lt = 0, seg = 0;
     for (long long cur = w0; cur < w1; ++seg) {
       const int t0 = (int)(cur % T);
       const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
       cur += t1 - t0;
-      tc::mbar_wait(a_full, (uint32_t)seg & 1u);
+      tc::mbar_wait(a_full, seg & 1u);
       tc::tc_fence_after();
       for (int t = t0; t < t1; ++t, ++lt) {
-        const int acc = lt & 1;
-        const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
-        tc::mbar_wait(tmem_empty + acc, acc_ph ^ 1u, backoff);
+        const uint32_t acc = lt & 1u;
+        tc::mbar_wait(tmem_empty + acc, ((lt >> 1) & 1u) ^ 1u, backoff);
         tc::tc_fence_after();
-        for (int c = 0; c < p.kchunks; ++c, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        for (uint32_t c = 0; c < kchunks; ++c) {
           tc::mbar_wait(full + s, ph, backoff);
           tc::tc_fence_after();
-          const uint64_t db = tc::umma_desc_k_sw128_u32(sB_u + (uint32_t)s * B_STAGE_BYTES);
-          const int nk = c + 1 == p.kchunks ? p.ksteps_last : KCH / KSTEP;
+          const uint32_t b_lo = b_lo0 + s * (uint32_t)(B_STAGE_BYTES >> 4);
+          const uint32_t nk = c + 1 == kchunks ? nk_last : (uint32_t)(KCH / KSTEP);
 #pragma unroll
-          for (int tq = 0; tq < QT; ++tq) {
-            const uint64_t da = tc::umma_desc_k_sw128_u32(sA_u + (uint32_t)(tq * p.kchunks + c) * A_CHUNK_BYTES);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + tq * BN);
+          for (uint32_t tq = 0; tq < (uint32_t)QT; ++tq) {
+            const uint32_t a_lo = a_lo0 + (tq * kchunks + c) * (uint32_t)(A_CHUNK_BYTES >> 4);
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)ACC_COLS + tq * (uint32_t)BN;
 #pragma unroll
-            for (int kk = 0; kk < KCH / KSTEP; ++kk)  // K = 16 fp16 = 32 bytes per instruction: +2 in 16-byte units
-              if (kk < nk && !(SCF_KNN_DEBUG & 64) && leader)
-                tc::umma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (c | kk) != 0);
+            for (uint32_t kk = 0; kk < (uint32_t)(KCH / KSTEP); ++kk)  // K = 16 fp16 = 32 bytes: +2 in 16-byte units
+              if (kk < nk && !(SCF_KNN_DEBUG & 64)) {
+                if (leader) tc::umma_f16_lo(d_tmem, a_lo + kk * 2u, b_lo + kk * 2u, idesc, (c | kk) != 0u);
+              }
           }
           if (leader) tc::umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
           __syncwarp();
+          if (++s == stages) s = 0, ph ^= 1u;
         }
         if (leader) tc::umma_commit(tmem_full + acc);  // all accumulators of this reference tile complete
         __syncwarp();
@@ -519,7 +546,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
             }
           }
           tc::tc_fence_before();
-          tc::mbar_arrive(tmem_empty + acc);
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
         }
       } else {
         const int split = split_of(q);
@@ -545,24 +573,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
           tc::tc_fence_after();
           if (SCF_KNN_DEBUG & 32) {  // timing experiment: no accumulator read-out at all
             tc::tc_fence_before();
-            tc::mbar_arrive(tmem_empty + acc);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
             continue;
           }
           const int j0 = t * BN + col0;
           const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + g * GCOLS);
           if constexpr (HALVES == 2) ep.thr = fminf(ep.cl.thr, *thr_partner);
-          uint32_t va[16], vb[16];
-          tc::tmem_ld16(t_row, va);
-#pragma unroll
-          for (int cc = 0; cc < GCOLS / 16; ++cc) {
-            tc::tmem_ld_wait();
-            // the load of the next chunk is in flight while this one is examined
-            if (cc + 1 < GCOLS / 16) tc::tmem_ld16(t_row + (uint32_t)((cc + 1) * 16), (cc & 1) ? va : vb);
-            if (!(SCF_KNN_DEBUG & 8))
-              process16<KC, HALVES == 2>((cc & 1) ? vb : va, j0 + cc * 16, ep, thr_pub, thr_partner);
+          // Common case: no lane of the warp has a candidate among its 64 columns.  The two halves are reduced to
+          // their minima one after the other through ONE 32-register buffer (the list itself needs k' registers), then
+          // one vote decides.  A half with a candidate is simply read again: the accumulator stays in TMEM until this
+          // warp has arrived on tmem_empty.
+          uint32_t v[32];
+          tc::tmem_ld32(t_row, v);
+          tc::tmem_ld_wait();
+          float m0 = 0.f, m1 = 0.f;
+          if (!(SCF_KNN_DEBUG & 8)) m0 = fminf(min16(v), min16(v + 16));
+          tc::tmem_ld32(t_row + 32u, v);
+          tc::tmem_ld_wait();
+          if (!(SCF_KNN_DEBUG & 8)) {
+            const float b0 = min16(v), b1 = min16(v + 16);
+            m1 = fminf(b0, b1);
+            if ((SCF_KNN_DEBUG & 16) && lane == 0) atomicAdd(&g_dbg[0], 1ull);
+            if (__any_sync(SCF_FULL, fminf(m0, m1) < ep.thr)) {
+              if (__any_sync(SCF_FULL, m1 < ep.thr))
+                hits32<KC, HALVES == 2>(v, b0, b1, j0 + 32, ep, thr_pub, thr_partner);
+              if (__any_sync(SCF_FULL, m0 < ep.thr)) {
+                tc::tmem_ld32(t_row, v);
+                tc::tmem_ld_wait();
+                hits32<KC, HALVES == 2>(v, min16(v), min16(v + 16), j0, ep, thr_pub, thr_partner);
+              }
+            }
           }
           tc::tc_fence_before();
-          tc::mbar_arrive(tmem_empty + acc);
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
         }
         ep.drain();
         if constexpr (HALVES == 2) *thr_pub = ep.cl.thr;
@@ -983,9 +1028,10 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     unsigned long long h[8];
     cudaStreamSynchronize(stream);
     cudaMemcpyFromSymbol(h, g_dbg, sizeof(h));
-    const double chunks = (double)pl.nq_pad / 32.0 * (double)pl.nr_pad / 32.0;  // (32 rows x 32 columns) units
-    fprintf(stderr, "[knn dbg] nsplit %d kc %d warp-chunks %.3g hit-chunks %llu (%.1f%%) hit-groups %llu drain-iters %llu inserts %llu (%.1f / query)\n",
-            pl.nsplit, pl.kc, chunks, h[0], 100.0 * h[0] / chunks, h[1], h[2], h[3], (double)h[3] / (double)nq);
+    fprintf(stderr, "[knn dbg] qt %d kc %d nlists %d | warp-steps %llu, hit halves %llu (%.1f%% of steps), hit groups %llu, "
+            "drains %llu, drain iterations %llu, buffered entries %llu, inserts %llu (%.1f / query)\n",
+            pl.qt, pl.kc, pl.nlists, h[0], h[1], 100.0 * h[1] / (double)std::max(1ull, h[0]), h[2], h[3], h[4], h[5], h[6],
+            (double)h[6] / (double)nq);
     memset(h, 0, sizeof(h));
     cudaMemcpyToSymbol(g_dbg, h, sizeof(h));
   }

@@ -153,179 +153,6 @@ def sign_rule(vt):
     return vt * s
 
 
-def _finish_eig(w, v, dims):
-    w = torch.flip(w[-dims:], dims=[0])
-    vt = sign_rule(torch.flip(v[:, -dims:], dims=[1]).T.contiguous())
-    return w, vt.T.contiguous()
-
-
-def _cheb_filter(cov, x, degree, cut, top):
-    """Scaled Chebyshev filter p(C) x (Zhou & Saad): damps the spectrum in [0, cut] (covariances are PSD), keeps the
-    component at ``top`` near unit size, amplifies everything above ``cut`` like T_degree.  ``cut`` / ``top`` may be
-    Python floats or 0-dim device tensors: the coefficients of the three-term recurrence are evaluated on the device
-    in closed form (sigma_j = T_{j-1}(t) / T_j(t), t = (top - c) / e), so the filter never synchronises."""
-    dev, dt = cov.device, cov.dtype
-    cut = torch.as_tensor(cut, dtype=dt, device=dev)
-    top = torch.as_tensor(top, dtype=dt, device=dev)
-    e = 0.5 * cut  # centre c == half width e: the damped interval is [0, cut]
-    t = (top - e) / e
-    r = 1.0 / (t + torch.sqrt(t * t - 1.0))  # exp(-acosh t)
-    j = torch.arange(1, degree + 1, dtype=dt, device=dev)
-    sig = r * (1.0 + r ** (2.0 * (j - 1.0))) / (1.0 + r ** (2.0 * j))  # sigma_1 .. sigma_degree
-    a = 2.0 * sig[1:] / e          # step j: y_{j+1} = a_j (C - c) y_j - d_j y_{j-1}
-    d = sig[:-1] * sig[1:]
-    cs = cov - torch.diag_embed(e.expand(cov.shape[0]))
-    y = (cs @ x) * (sig[0] / e)
-    for i in range(degree - 1):
-        y_new = (cs @ y).mul_(a[i]).addcmul_(x, d[i], value=-1.0)
-        x, y = y, y_new
-    return y
-
-
-def _orthonormalise(y):
-    """Orthonormal basis of range(y): Householder QR.  (Cholesky-QR is cheaper but breaks down here: after a filter
-    the unconverged tail columns of the block are dominated by leaked top eigenvectors and become nearly parallel.)"""
-    return torch.linalg.qr(y)[0]
-
-
-def _cholqr2(y):
-    """Orthonormal basis of range(y) by column scaling + two Cholesky-QR passes (GEMM, a b x b Cholesky and a
-    triangular solve each: a fraction of the Householder QR's latency).  Safe for a filtered block of Ritz vectors
-    under eig_topk's degree rule (columns are nearly parallel to at most ~1e4 : 1, i.e. cond^2 <= 1e8); a start block
-    filtered from random columns (cond ~ 1e11) needs the Householder QR.  -> (q, bad): ``bad`` is a device scalar,
-    non-zero when a Cholesky factorisation broke down (the caller then repeats with Householder)."""
-    y = y / y.norm(dim=0, keepdim=True)
-    bad = None
-    for _ in range(2):
-        l, info = torch.linalg.cholesky_ex(y.T @ y)
-        bad = info if bad is None else bad + info
-        y = torch.linalg.solve_triangular(l, y.T, upper=False).T
-    return y.contiguous(), bad
-
-
-def _cheb_growth(x):
-    """|T_m(x)|^(1/m) for large m: x + sqrt(x^2 - 1) (x >= 1)."""
-    return x + math.sqrt(max(x * x - 1.0, 0.0))
-
-
-def eig_topk(cov, dims, tol=1e-8, degree=6, max_rounds=5, stats=None):
-    """K3: top-``dims`` eigenpairs of the symmetric PSD float64 matrix ``cov`` (replicated on every rank; the inputs
-    are bit-identical after the integer all-reduce and the start block is seeded, so every rank gets the same
-    loadings).
-
-    Only ``dims`` << H pairs are needed, so instead of a full tridiagonalisation (cuSOLVER syevd: ~28 ms at H = 2000
-    on B200 -- two thousand dependent BLAS-2 panels) this runs Chebyshev-filtered subspace iteration on a
-    ``b = 2*dims + 64`` wide block: a polynomial of C (GEMMs) that damps the spectrum below the block, an
-    orthonormalisation (Cholesky-QR2; Householder QR as the checked fallback), and a Rayleigh-Ritz step per round.  It stops when every kept pair has a residual
-    ``|C v - lambda v| <= tol * lambda_max`` (angle to the exact eigenvector <= residual * lambda_max / eigengap:
-    1e-8 keeps the angle below 1e-5 rad for relative gaps down to 1e-3; the Gram matrix itself carries a 2e-5
-    relative error from the 3xTF32 tensor-core accumulation).
-
-    Filter degree.  The wanted spectrum is wide (lambda_1 / lambda_dims ~ 50), and T_m grows like rho^m faster at
-    lambda_1 than at lambda_dims (rho ~ 60 per degree here).  From a random start every column mixes all
-    eigenvectors, so the weak directions survive only down to eps * rho^m: the first filter keeps m = ``degree``.
-    After a Rayleigh-Ritz rotation column i is its own Ritz vector with eps-sized leakage along the strong ones; the
-    filter blows that leakage up by rho^m, and the Householder QR still resolves the weak direction to
-    eps * (eps * rho^m).  Each later round therefore takes the largest m with rho^m <= 1e20 (rho from the current
-    Ritz values): the iteration cannot bury the weak pairs, whatever the spectrum.  Small matrices, and the (never
-    observed) case of max_rounds without convergence, take the full ``eigh``."""
-    h = cov.shape[0]
-    b = 2 * dims + 64
-    if h < 4 * b:
-        w, v = torch.linalg.eigh(cov)
-        return _finish_eig(w, v, dims)
-    g = torch.Generator(device=cov.device)
-    g.manual_seed(4466)
-    q0 = torch.randn((h, b), dtype=torch.float64, device=cov.device, generator=g)
-    # first filter without a Rayleigh-Ritz step: cut at the mean eigenvalue (the wanted ones lie above it), upper
-    # bound from the 1-norm; both stay on the device
-    trace = torch.diagonal(cov).sum()
-    top0 = cov.abs().sum(dim=0).max()
-    zero = torch.zeros((), dtype=torch.int32, device=cov.device)
-
-    def start_block(householder):
-        """Orthonormal basis of the filtered random block.  One degree-``degree`` filter leaves it with a condition
-        number ~1e11: Householder QR territory (~1 ms of dependent panels at C2).  Filtering in steps of degree 3 with
-        a Cholesky-QR2 after each keeps every step at cond <= T_3(t) = 4 t^3 - 3 t, t = (bound - cut / 2) / (cut / 2)
-        (9e6 at C2, inside Cholesky-QR2's range of ~1e8); the product of the steps is nearly as sharp a filter (same
-        number of rounds at C2) and all of it is GEMM-shaped.  Whether the range held is CHECKED, not assumed: the
-        Cholesky status and the measured orthonormality defect travel with the first round's synchronisation, and a
-        failed check repeats the start with Householder."""
-        if householder:
-            return _orthonormalise(_cheb_filter(cov, q0, degree, trace / h, top0)), zero, zero.to(torch.float64)
-        x, bad = q0, zero
-        for d in [3] * (degree // 3) + ([degree % 3] if degree % 3 else []):
-            x, bd = _cholqr2(_cheb_filter(cov, x, d, trace / h, top0))
-            bad = bad + bd
-        defect = (x.T @ x - torch.eye(b, dtype=x.dtype, device=x.device)).abs().max()
-        return x, bad, defect
-
-    # Gate (one small synchronisation; the host waits for the Gram anyway at the end of round 1): the Cholesky route
-    # only when T_3 at the upper bound of lambda_1 -- min(1-norm, Frobenius norm), which overestimates lambda_1 up to
-    # ~3x, T_3 up to ~30x -- stays below 3e9.  A wrong guess costs time, never accuracy (the check above).
-    bound, cut0 = torch.stack([torch.minimum(top0, torch.linalg.matrix_norm(cov)), trace / h]).tolist()
-    t0 = (bound - 0.5 * cut0) / (0.5 * cut0) if cut0 > 0.0 else math.inf
-    chol_start = degree >= 3 and 4.0 * t0 ** 3 <= 3e9
-    q, chol_bad, start_defect = start_block(householder=not chol_start)
-    if stats is not None:
-        stats["eig_start"] = "cholesky-qr2" if chol_start else "householder"
-    y_prev = None
-    rounds = 0
-    while rounds < max_rounds:
-        rounds += 1
-        aq = cov @ q
-        t = torch.nan_to_num(q.T @ aq)  # a broken-down Cholesky-QR must reach the check below, not make eigh throw
-        w, s = ops.sym_eig_small(t)  # one-CTA Jacobi for the shrunk blocks of the later rounds, library eigh else
-        top, wt = s[:, -dims:], w[-dims:]
-        v = q @ top
-        res_t = (aq @ top - v * wt).norm(dim=0).max() / w[-1]
-        # the one synchronisation of the round: residual + the Ritz values that fix the next filter
-        width = int(q.shape[1])
-        keep = min(width, dims + 32)
-        res, th_min, th_max, th_dims, bulk, th_keep, bulk_keep, bad, defect = torch.stack(
-            [res_t, w[0], w[-1], wt[0], (trace - w.sum()) / (h - width), w[-keep],
-             (trace - w[-keep:].sum()) / (h - keep), chol_bad.to(torch.float64), start_defect]).tolist()
-        if bad != 0.0 or res != res or not defect <= 1e-9:
-            # the Cholesky-QR of this round's basis broke down (or the start block is not orthonormal): Householder,
-            # same round again
-            q = _orthonormalise(y_prev) if y_prev is not None else start_block(householder=True)[0]
-            chol_bad, start_defect = zero, torch.zeros_like(start_defect)
-            if stats is not None:
-                stats["eig_householder_repeats"] = stats.get("eig_householder_repeats", 0) + 1
-            rounds -= 1
-            continue
-        if stats is not None:
-            stats["eig_rounds"], stats["eig_residual"] = rounds, res
-        if res <= tol:
-            return _finish_eig(wt, v, dims)
-        if rounds == max_rounds or not (th_dims > 0.0 and th_max > th_dims):
-            break
-        # The wide start block is only needed to catch the wanted directions: once the block is rotated to Ritz
-        # vectors, and if the spectrum has a gap below the wanted pairs (theta_{dims+32} < 0.8 theta_dims), the later
-        # rounds keep the top dims + 32 Ritz vectors only.  The damped interval then ends at the smallest KEPT Ritz
-        # value, closer to lambda_dims: faster convergence for half the GEMM / QR / eigh work.  Without such a gap
-        # (wanted pairs inside a dense bulk) the full block stays.
-        if keep < width and th_keep < 0.8 * th_dims:
-            s = s[:, -keep:]
-            th_min, bulk = th_keep, bulk_keep
-        # damped interval [0, cut]: the block's smallest Ritz value, or the mean of the spectrum outside the block
-        # when that is larger (it never exceeds lambda_{b+1}); kept clear of the wanted Ritz values
-        cut = max(th_min, min(bulk, 0.5 * (th_min + th_dims)))
-        cut = min(max(cut, 1e-3 * th_dims), 0.9 * th_dims)
-        e = 0.5 * cut
-        rho = _cheb_growth((th_max - e) / e) / _cheb_growth((th_dims - e) / e)
-        m = int(max(2, min(32, math.floor(math.log(1e20) / math.log(max(rho, 1.0 + 1e-9))))))
-        # Ritz vectors in DESCENDING order: the (Gram-Schmidt-like) orthonormalisation then takes the strong
-        # directions first and removes their leakage from the weak columns, so the new basis stays aligned with the
-        # eigen-directions and the next Rayleigh-Ritz matrix is nearly diagonal (few Jacobi sweeps)
-        y_prev = _cheb_filter(cov, q @ torch.flip(s, dims=[1]), m, cut, th_max)
-        q, chol_bad = _cholqr2(y_prev)
-    w, v = torch.linalg.eigh(cov)
-    if stats is not None:
-        stats["eig_rounds"] = -1 - stats.get("eig_rounds", 0)
-    return _finish_eig(w, v, dims)
-
-
 def normalise_stats(csr, cell_idx, col_map, n_feat, comm, log_transform=True, renormalize_subset=True,
                     n_counts=None):
     """Row scalars, mu / sigma of the normalised feature matrix (graph_datastore.py:767-796) and -- from the same
@@ -423,17 +250,16 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
         comm.allreduce_sum_(g_fx)
         ops.gram_symmetrize(g_fx, n_feat)
         mark("gram")
-        cov = g_fx[:n_feat, :n_feat].to(torch.float64) * 2.0 ** -lib.GRAM_SHIFT
-        if col_mean is not None:
-            cov = cov - float(n_pca) * torch.outer(col_mean, col_mean)
-        cov = cov / max(n_pca - 1, 1)
-        evals, load = eig_topk(cov, dims, stats=stats)
+        # K3, native (scf_eig_topk): cov = G 2^-shift / (n - 1) [- n / (n - 1) mean mean^T for a PCA on a cell subset]
+        den = float(max(n_pca - 1, 1))
+        evals, load, v32 = ops.eig_topk(g_fx, n_feat, dims, 2.0 ** -lib.GRAM_SHIFT / den, col_mean,
+                                        float(n_pca) / den if col_mean is not None else 0.0, stats=stats,
+                                        ld32=round_up(dims, 4))
         mark("eig")
     else:
         load, evals = loadings, torch.zeros(dims, dtype=torch.float64, device=dev)
-    ldv = round_up(dims, 4)
-    v32 = torch.zeros((n_feat, ldv), dtype=torch.float32, device=dev)
-    v32[:, :dims] = load.to(torch.float32)
+        v32 = torch.zeros((n_feat, round_up(dims, 4)), dtype=torch.float32, device=dev)
+        v32[:, :dims] = load.to(torch.float32)
 
     # ---- embedding (K4) + exchange (collective 3) ----
     y = ops.project(z, n_local, n_feat, v32, dims, z_lo=z_lo)  # tensor cores when the 3xTF32 plane exists

@@ -312,15 +312,44 @@ def project(z, n_rows, n_cols, v, dims, y=None, ldy=None, z_lo=None):
     return y
 
 
-JACOBI_MAX_N = 96  # beyond this the one-CTA Jacobi kernel loses to the library eigh (3 n^3 * 8 B through smem per sweep)
+def eig_topk(g_fx, n_cols, dims, scale, col_mean=None, mean_weight=0.0, tol=1e-8, max_rounds=24, stats=None,
+             ld32=None):
+    """K3 (scf_eig_topk): top-``dims`` eigenpairs of ``g_fx[:n_cols, :n_cols] * scale - mean_weight * outer(col_mean)``
+    (g_fx: the mirrored int64 fixed-point Gram).  -> (eigenvalues float64 [dims] descending, eigenvectors float64
+    [n_cols, dims], sklearn sign rule[, float32 copy [n_cols, ld32] with zero pad columns when ``ld32`` is given]).
+    Native Chebyshev-filtered subspace iteration; one stream synchronisation per round.  ``stats`` (dict) receives
+    rounds / residual / restarts."""
+    assert g_fx.dtype == torch.int64 and g_fx.is_cuda and g_fx.stride(1) == 1
+    dev = g_fx.device
+    ws_bytes = int(lib.raw("scf_eig_topk_workspace_bytes")(int(n_cols), int(dims)))
+    if ws_bytes < 0:
+        raise NotImplementedError(f"scf_eig_topk: dims = {dims} of {n_cols} features is outside the native solver "
+                                  "(dims + 8 <= 160 columns)")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    evals = torch.empty(dims, dtype=torch.float64, device=dev)
+    evecs = torch.empty((n_cols, dims), dtype=torch.float64, device=dev)
+    v32 = torch.empty((n_cols, int(ld32)), dtype=torch.float32, device=dev) if ld32 else None
+    report = torch.zeros(176, dtype=torch.float64).pin_memory()
+    _chk(col_mean, torch.float64, "col_mean")
+    try:
+        lib.call("scf_eig_topk", g_fx.data_ptr(), int(g_fx.stride(0)), int(n_cols), float(scale), _ptr(col_mean),
+                 float(mean_weight), int(dims), float(tol), int(max_rounds), evals.data_ptr(), evecs.data_ptr(),
+                 _ptr(v32), int(ld32 or 0), report.data_ptr(), ws.data_ptr(), ws_bytes, _stream(), launches=0)
+    finally:
+        lib.LAUNCHES["n"] += int(report[168])
+        if stats is not None:
+            stats["eig_rounds"], stats["eig_residual"] = int(report[5]), float(report[0])
+            stats["eig_restarts"], stats["eig_robust"] = int(report[6]), bool(report[7])
+            stats["eig_min_pivot"] = float(report[4])
+    return (evals, evecs, v32) if ld32 else (evals, evecs)
 
 
-def sym_eig_small(a, info=None, max_n=JACOBI_MAX_N):
+def sym_eig_small(a, info=None):
     """(eigenvalues ascending, eigenvectors as columns) of a small symmetric PSD float64 matrix on the device: the
-    one-CTA Jacobi kernel for n <= ``max_n``, ``torch.linalg.eigh`` otherwise (and for CPU tensors)."""
+    one-CTA Jacobi kernel the native eigensolver uses for its Rayleigh-Ritz matrices (n <= scf_sym_eig_max_n())."""
     n = int(a.shape[0])
-    if not a.is_cuda or n > min(max_n, int(lib.raw("scf_sym_eig_max_n")())):
-        return torch.linalg.eigh(0.5 * (a + a.T))
+    if n > int(lib.raw("scf_sym_eig_max_n")()):
+        raise NotImplementedError(f"scf_sym_eig_jacobi: n = {n} exceeds {int(lib.raw('scf_sym_eig_max_n')())}")
     _chk(a, torch.float64, "a")
     a = a.contiguous()
     w = torch.empty(n, dtype=torch.float64, device=a.device)

@@ -206,31 +206,6 @@ def test_subset_hash_and_shard_spans():
         (0, 3500, 0, 7000)
 
 
-def test_eig_topk_cpu_matches_full_eigh():
-    """K3's subspace iteration (device-agnostic torch code) on a CPU covariance: a wide wanted spectrum next to a dense
-    bulk converges without the full-eigh fallback, and a second start seed gives the same pairs."""
-    import torch
-
-    from scarf_b200 import graph
-
-    g = torch.Generator().manual_seed(3)
-    n, h, nf = 4000, 700, 30
-    z = torch.randn((n, h), dtype=torch.float64, generator=g)
-    f = torch.randn((n, nf), dtype=torch.float64, generator=g)
-    w = torch.randn((nf, h), dtype=torch.float64, generator=g) * (torch.rand((nf, h), generator=g) < 0.15)
-    z = z + f @ (w * (2.5 * 0.9 ** torch.arange(nf))[:, None])
-    z = (z - z.mean(0)) / z.std(0)
-    cov = (z.T @ z) / (n - 1)
-    wf, vf = torch.linalg.eigh(cov)
-    dims = 12
-    st = {}
-    ev, load = graph.eig_topk(cov, dims, stats=st)
-    assert st["eig_rounds"] > 0, st
-    np.testing.assert_allclose(ev.numpy(), torch.flip(wf[-dims:], [0]).numpy(), rtol=1e-10)
-    ref = graph.sign_rule(torch.flip(vf[:, -dims:], [1]).T.contiguous()).T
-    assert float(torch.acos((ref * load).sum(0).abs().clamp(max=1.0)).max()) < 1e-5
-
-
 def test_csr_sortedness_check_on_cpu_tensors():
     """CsrDevice.check_sorted (device-agnostic torch code): unsorted or duplicated column ids inside a row are refused,
     empty rows and row boundaries are not mistaken for a descent."""

@@ -1,46 +1,41 @@
-"""Developer probe (GPU): time symmetric eigensolvers on an H x H covariance-like matrix."""
+"""Developer probe (GPU): scf_eig_topk on the covariance of a C2 step (tools/build/c2_cov.npy, dumped in round 1) --
+time, rounds, residual, agreement with torch.linalg.eigh.  usage: python tools/eig_probe.py [dims ...]"""
+import os
 import sys
 import time
 
+import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from scarf_b200 import graph  # noqa: E402
-
-h = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-g = torch.Generator(device="cuda").manual_seed(0)
-z = torch.randn((20000, h), device="cuda", dtype=torch.float64, generator=g)
-f = torch.randn((20000, 65), device="cuda", dtype=torch.float64, generator=g)
-w = torch.randn((65, h), device="cuda", dtype=torch.float64, generator=g) * (1.2 * 0.93 ** torch.arange(65, device="cuda"))[:, None]
-z = z + f @ w
-z = (z - z.mean(0)) / z.std(0)
-cov = (z.T @ z) / (z.shape[0] - 1)
+from scarf_b200 import lib, ops  # noqa: E402
 
 
-def timed(fn, reps=3):
-    fn()
-    torch.cuda.synchronize()
-    t = time.perf_counter()
-    for _ in range(reps):
-        out = fn()
-    torch.cuda.synchronize()
-    return (time.perf_counter() - t) / reps * 1e3, out
+def main():
+    path = os.path.join("tools", "build", "c2_cov.npy")
+    cov = torch.from_numpy(np.load(path)).cuda()
+    h = cov.shape[0]
+    n = 100000
+    ld = (h + 31) // 32 * 32
+    g = torch.zeros((ld, ld), dtype=torch.int64, device="cuda")
+    g[:h, :h] = torch.round(cov * (n - 1) * 2.0 ** lib.GRAM_SHIFT).to(torch.int64)
+    scale = 2.0 ** -lib.GRAM_SHIFT / (n - 1)
+    wf, vf = torch.linalg.eigh(g[:h, :h].double() * scale)
+    for dims in [int(x) for x in sys.argv[1:]] or [50, 100]:
+        st = {}
+        ops.eig_topk(g, h, dims, scale, stats=st)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        reps = 5
+        for _ in range(reps):
+            ev, load = ops.eig_topk(g, h, dims, scale, stats=st)
+        torch.cuda.synchronize()
+        ms = (time.time() - t0) / reps * 1e3
+        err = float((ev - torch.flip(wf[-dims:], [0])).abs().max() / wf[-1])
+        ref = torch.flip(vf[:, -dims:], [1])
+        ang = float(torch.acos((ref * load).sum(0).abs().clamp(max=1.0)).max())
+        print(f"dims={dims}: {ms:.3f} ms, {st}, eigenvalue error {err:.2e}, max angle {ang:.2e} rad", flush=True)
 
 
-for name, fn in (("eigh f64", lambda: torch.linalg.eigh(cov)), ("eigh f32", lambda: torch.linalg.eigh(cov.float())),
-                 ("eigvalsh f64", lambda: torch.linalg.eigvalsh(cov)),
-                 ("gemm f64 HxHx164", lambda: cov @ cov[:, :164]), ("gemm f64 HxHxH", lambda: cov @ cov),
-                 ("eigh f64 164", lambda: torch.linalg.eigh(cov[:164, :164])),
-                 ("eigh f64 512", lambda: torch.linalg.eigh(cov[:512, :512])),
-                 ("qr f64 Hx164", lambda: torch.linalg.qr(cov[:, :164]))):
-    ms, _ = timed(fn)
-    print(f"{name:20s} {ms:8.3f} ms")
-y164 = cov[:, :164].contiguous()
-for name, fn in (("cholqr2 Hx164", lambda: graph._cholqr2(y164)), ("cholqr2 Hx82", lambda: graph._cholqr2(y164[:, :82].contiguous())),
-                 ("cheb filter deg 3 Hx164", lambda: graph._cheb_filter(cov, y164, 3, 1.0, 200.0))):
-    ms, _ = timed(fn, reps=10)
-    print(f"{name:28s} {ms:8.3f} ms")
-for dims in (25, 50, 100):
-    st = {}
-    ms, _ = timed(lambda: graph.eig_topk(cov, dims, stats=st), reps=2)
-    print(f"eig_topk dims={dims}: {ms:.2f} ms {st}")
+if __name__ == "__main__":
+    main()

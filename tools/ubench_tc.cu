@@ -128,6 +128,88 @@ __global__ void __launch_bounds__(32 * W + 64, 1) ubench(int mode, int reps_ld, 
   }
 }
 
+// The issue pattern of knn_tc_kernel: descriptors advance with a stage counter (uniform arithmetic), a commit after
+// every `per_commit` instructions, nothing else running.  variant 0: 64-bit descriptors built per instruction,
+// variant 1: 32-bit low words + constant high word (umma_f16_lo).
+template <int N>
+__global__ void __launch_bounds__(64, 1) ubench_issue(int variant, int reps, int per_commit, int stages,
+                                                      long long* cyc_mma) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar, sink_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (16384 + 6 * N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init(&sink_bar, 1 << 20);
+    tc::fence_barrier_init();
+  }
+  tc::fence_proxy_async();
+  if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    constexpr uint32_t idesc = tc::umma_idesc_f16(128, N, false, false);
+    const bool leader = tc::elect_one();
+    const uint32_t a_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(smem));
+    const uint32_t b_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(smem + 16384));
+    uint32_t s = 0;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r += per_commit) {
+      const uint32_t b_lo = b_lo0 + s * (uint32_t)(N * 128 >> 4);
+      const uint32_t d = tmem_base + (uint32_t)((r / per_commit) & 1) * 256u;
+      for (int kk = 0; kk < per_commit; ++kk) {
+        if (variant == 0) {
+          const uint64_t da = ((uint64_t)tc::UMMA_DESC_HI_K_SW128 << 32) | (a_lo0 + (uint32_t)(kk & 3) * 2u);
+          const uint64_t db = ((uint64_t)tc::UMMA_DESC_HI_K_SW128 << 32) | (b_lo + (uint32_t)(kk & 3) * 2u);
+          if (leader) tc::umma_f16(d + (uint32_t)(kk >> 2) * N % 256u, da, db, idesc, (kk & 3) != 0);
+        } else {
+          if (leader)
+            tc::umma_f16_lo(d + (uint32_t)(kk >> 2) * N % 256u, a_lo0 + (uint32_t)(kk & 3) * 2u,
+                            b_lo + (uint32_t)(kk & 3) * 2u, idesc, (kk & 3) != 0);
+        }
+      }
+      if (leader) tc::umma_commit(&sink_bar);
+      __syncwarp();
+      if (++s == (uint32_t)stages) s = 0;
+    }
+    if (leader) tc::umma_commit(&bar);
+    __syncwarp();
+    tc::mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (lane == 0) cyc_mma[blockIdx.x] = t1 - t0;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int N>
+void run_issue(int variant, int per_commit) {
+  const int reps = 8192;
+  long long* c_mma;
+  CK(cudaMalloc(&c_mma, 148 * 8));
+  CK(cudaMemset(c_mma, 0, 148 * 8));
+  const int smem = 16384 + 6 * N * 128 + 1024;
+  CK(cudaFuncSetAttribute(ubench_issue<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int it = 0; it < 2; ++it) {
+    ubench_issue<N><<<148, 64, smem>>>(variant, reps, per_commit, 6, c_mma);
+    CK(cudaDeviceSynchronize());
+  }
+  std::vector<long long> h(148);
+  CK(cudaMemcpy(h.data(), c_mma, 148 * 8, cudaMemcpyDeviceToHost));
+  std::sort(h.begin(), h.end());
+  printf("issue pattern: N=%3d variant %d (%s), commit every %2d | %.1f cyc per MMA\n", N, variant,
+         variant ? "32-bit descriptor words" : "64-bit descriptors", per_commit, (double)h[74] / reps);
+  CK(cudaFree(c_mma));
+}
+
 template <int W, int N>
 void run(int mode, const char* label) {
   const int reps_ld = 4096, reps_mma = 2048;
@@ -176,6 +258,13 @@ int main() {
   cudaDeviceProp p;
   CK(cudaGetDeviceProperties(&p, 0));
   printf("device %s, %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
+  for (int v = 0; v < 2; ++v) {
+    run_issue<64>(v, 16);
+    run_issue<128>(v, 8);
+    run_issue<128>(v, 4);
+    run_issue<256>(v, 4);
+  }
+  run<8, 64>(4, "MMA only, SS operands");
   run<4, 128>(1, "TMEM read only, load+wait");
   run<8, 128>(1, "TMEM read only, load+wait");
   run<16, 128>(1, "TMEM read only, load+wait");
