@@ -174,7 +174,7 @@ int32_t scf_eig_topk(const int64_t* gram_fx, int64_t ldg, int32_t h, double scal
  * out_dist float32 [nq,k].  method: 0 = FP64 SIMT brute force, 1 = tcgen05 FP16 candidates (operands
  * scaled by an exact power of two and rounded to FP16, FP32 accumulate) + exact FP64 re-rank with a
  * proven guard band; rows that fail the guard are repaired inside the same call (tensor-core threshold
- * collect, FP64 scan for the rest).  k <= 24 and dim <= 253 run on the tensor cores, other shapes take
+ * collect, FP64 scan for the rest).  k <= 24 and dim <= 189 run on the tensor cores, other shapes take
  * method 0.  workspace: scf_knn_workspace_bytes(nq, nref, dim, k, method). */
 int64_t scf_knn_workspace_bytes(int64_t nq, int64_t nref, int32_t dim, int32_t k, int32_t method);
 /* diagnostics: byte offset inside the workspace of an int32 that, after scf_knn_l2(method 1), holds the
@@ -209,6 +209,12 @@ int32_t scf_membership_coo(const int64_t* idx, const float* dist, const float* s
                            const float* rho, int64_t n, int32_t k, int64_t row_offset,
                            int64_t chunk_size, int64_t* edges, float* weights, float* chunk_min,
                            int32_t* chunk_has_zero, void* stream);
+/* load_graph's symmetrisation (scarf/datastore/graph_datastore.py:1052-1075: g + g.T - g.multiply(g.T), optionally
+ * scipy.sparse.triu) of the stored graph: idx int64 [n, k] neighbour ids (the second column of `edges`), weights
+ * float64 [n, k]; only the first use_k neighbours of a row take part (_store_to_sparse, :474-511).  Writes 2 n use_k
+ * COO slots (out_row / out_col int64, out_val float64); slots with out_row < 0 are unused. */
+int32_t scf_graph_symmetrize(const int64_t* idx, const double* weights, int64_t n, int32_t k, int32_t use_k,
+                             int32_t upper_only, int64_t* out_row, int64_t* out_col, double* out_val, void* stream);
 /* zero weights := floor (scarf/knn_utils.py:154-158); floor is a host value */
 int32_t scf_fill_zero_weights(float* weights, int64_t n, float floor_value, void* stream);
 

@@ -116,14 +116,20 @@ __global__ void __launch_bounds__(256) eig_init_kernel(double* __restrict__ x, i
 // grid = (row tiles of 64, K splits).  A CTA accumulates its K range for the whole width (thread (ty, tx): rows
 // 4 ty .. 4 ty + 3, columns tx + 16 j, j < NJ), writes the partial tile to `part` and bumps the tile's counter; the CTA
 // that arrives last adds the partials in split order and applies the epilogue.
-template <int NJ>
-__global__ void __launch_bounds__(EG_THREADS) eig_dgemm_kernel(const double* __restrict__ a, int64_t lda,
-                                                               const double* __restrict__ bm, int64_t ldn, int m, int k,
-                                                               double alpha, const double* __restrict__ pm, double gamma,
-                                                               const double* __restrict__ qm, double delta,
-                                                               double* __restrict__ out, double* __restrict__ part,
-                                                               unsigned int* __restrict__ counters, int k_per_split) {
+template <int NJ, int RPT>
+__global__ void __launch_bounds__(16 * (EG_TM / RPT)) eig_dgemm_kernel(const double* __restrict__ a, int64_t lda,
+                                                                      const double* __restrict__ bm, int64_t ldn, int m,
+                                                                      int k, double alpha, const double* __restrict__ pm,
+                                                                      double gamma, const double* __restrict__ qm,
+                                                                      double delta, double* __restrict__ out,
+                                                                      double* __restrict__ part,
+                                                                      unsigned int* __restrict__ counters,
+                                                                      int k_per_split) {
   constexpr int N = NJ * 16;
+  constexpr int THREADS = 16 * (EG_TM / RPT);
+  constexpr int A_PER = EG_TM * EG_KT / THREADS;  // doubles of the A tile per thread (consecutive k of one row)
+  constexpr int B_PER = EG_KT * N / THREADS;
+  static_assert(A_PER <= EG_KT && EG_KT % A_PER == 0, "A staging");
   extern __shared__ __align__(16) double eg_smem[];
   double (*sa)[EG_TM][EG_KT + 2] = reinterpret_cast<double (*)[EG_TM][EG_KT + 2]>(eg_smem);
   double (*sb)[EG_KT][N] = reinterpret_cast<double (*)[EG_KT][N]>(eg_smem + 2 * EG_TM * (EG_KT + 2));
@@ -131,27 +137,26 @@ __global__ void __launch_bounds__(EG_THREADS) eig_dgemm_kernel(const double* __r
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int row0 = blockIdx.x * EG_TM;
   const int k0 = blockIdx.y * k_per_split, k1 = min(k, k0 + k_per_split);
-  double acc[4][NJ];
+  double acc[RPT][NJ];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RPT; ++i)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0;
 
-  // staging: A tile 64 x 16 (thread: row tid / 4, four consecutive k at 4 (tid % 4)); B tile 16 x N (N / 16 = NJ
-  // doubles per thread as NJ / 2 pairs ... kept simple: element e = tid + 256 i of the 16 x N tile)
-  const int a_r = tid >> 2, a_c = (tid & 3) * 4;
-  double ra[4];
-  double rb[NJ];
+  // staging through registers: the global loads of the next tile are in flight during the products of this one
+  const int a_r = tid / (EG_KT / A_PER), a_c = (tid % (EG_KT / A_PER)) * A_PER;
+  double ra[A_PER];
+  double rb[B_PER];
   auto load_tiles = [&](int kk) {
     const int gr = row0 + a_r;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < A_PER; ++i) {
       const int gk = kk + a_c + i;
       ra[i] = (gr < m && gk < k1) ? a[(int64_t)gr * lda + gk] : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-      const int e = tid + EG_THREADS * i;  // 16 * N = 256 * NJ elements
+    for (int i = 0; i < B_PER; ++i) {
+      const int e = tid + THREADS * i;
       const int br = e / N, bc = e - br * N;
       const int gk = kk + br;
       rb[i] = gk < k1 ? bm[(int64_t)gk * ldn + bc] : 0.0;
@@ -159,10 +164,10 @@ __global__ void __launch_bounds__(EG_THREADS) eig_dgemm_kernel(const double* __r
   };
   auto store_tiles = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sa[buf][a_r][a_c + i] = ra[i];
+    for (int i = 0; i < A_PER; ++i) sa[buf][a_r][a_c + i] = ra[i];
 #pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-      const int e = tid + EG_THREADS * i;
+    for (int i = 0; i < B_PER; ++i) {
+      const int e = tid + THREADS * i;
       const int br = e / N, bc = e - br * N;
       sb[buf][br][bc] = rb[i];
     }
@@ -175,16 +180,16 @@ __global__ void __launch_bounds__(EG_THREADS) eig_dgemm_kernel(const double* __r
   __syncthreads();
   for (int kk = k0; kk < k1; kk += EG_KT) {
     const bool more = kk + EG_KT < k1;
-    if (more) load_tiles(kk + EG_KT);  // global loads of the next tile are in flight during the products
+    if (more) load_tiles(kk + EG_KT);
 #pragma unroll
     for (int t = 0; t < EG_KT; ++t) {
-      double av[4], bv[NJ];
+      double av[RPT], bv[NJ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = sa[buf][ty * 4 + i][t];
+      for (int i = 0; i < RPT; ++i) av[i] = sa[buf][ty * RPT + i][t];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) bv[j] = sb[buf][t][tx + 16 * j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RPT; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
     }
@@ -196,9 +201,9 @@ __global__ void __launch_bounds__(EG_THREADS) eig_dgemm_kernel(const double* __r
   if (nsplit > 1) {
     double* mine = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(EG_TM * N);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RPT; ++i)
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) mine[(ty * 4 + i) * N + tx + 16 * j] = acc[i][j];
+      for (int j = 0; j < NJ; ++j) mine[(ty * RPT + i) * N + tx + 16 * j] = acc[i][j];
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = atomicAdd(counters + blockIdx.x, 1u) == (unsigned)(nsplit - 1) ? 1u : 0u;
@@ -206,21 +211,21 @@ __global__ void __launch_bounds__(EG_THREADS) eig_dgemm_kernel(const double* __r
     if (!s_last) return;
     __threadfence();
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RPT; ++i)
 #pragma unroll
       for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0;
     for (int s = 0; s < nsplit; ++s) {  // fixed order: the sum does not depend on which CTA came last
       const double* src = part + ((size_t)s * gridDim.x + blockIdx.x) * (size_t)(EG_TM * N);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RPT; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[i][j] += __ldcg(src + (ty * 4 + i) * N + tx + 16 * j);
+        for (int j = 0; j < NJ; ++j) acc[i][j] += __ldcg(src + (ty * RPT + i) * N + tx + 16 * j);
     }
     if (tid == 0) counters[blockIdx.x] = 0u;  // ready for the next launch
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gr = row0 + ty * 4 + i;
+  for (int i = 0; i < RPT; ++i) {
+    const int gr = row0 + ty * RPT + i;
     if (gr >= m) continue;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
@@ -322,12 +327,15 @@ __global__ void __launch_bounds__(EG_THREADS) eig_gram_kernel(const double* __re
 __global__ void __launch_bounds__(1024, 1) eig_chol_kernel(const double* __restrict__ s, int64_t lds, int b,
                                                            double* __restrict__ w, int64_t ldw, int* __restrict__ flags,
                                                            double* __restrict__ min_pivot) {
-  extern __shared__ __align__(16) double sm[];  // [b][b + 1]
-  __shared__ double sd[EG_MAXB];
-  __shared__ double s_invd[EG_MAXB];
+  extern __shared__ __align__(16) double sm[];  // [b][b + 1]: lower triangle L, upper triangle (L^-1)^T
+  __shared__ double sd[EG_MAXB];      // column scaling d_i = 1 / sqrt(s_ii)
+  __shared__ double s_invd[EG_MAXB];  // 1 / L_ii
+  __shared__ double s_tmp[EG_MAXB];
   __shared__ int s_bad;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int ld = b + 1;
+  const int grp = tid >> 3, sub = tid & 7, ngrp = nt >> 3;  // eight threads share one dot product
+  const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
   if (tid == 0) s_bad = 0;
   for (int i = tid; i < b; i += nt) {
     const double v = s[(int64_t)i * lds + i];
@@ -340,43 +348,43 @@ __global__ void __launch_bounds__(1024, 1) eig_chol_kernel(const double* __restr
   }
   __syncthreads();
   double minp = 1e300;
+  // left-looking: column j of L from the finished columns k < j; every row r >= j is one dot product of length j
   for (int j = 0; j < b; ++j) {
-    const double piv = sm[j * ld + j];
-    if (!(piv > 1e-14)) {  // the scaled matrix has a unit diagonal: a pivot this small means lost rank
-      if (tid == 0) s_bad = 1;
-    }
-    minp = fmin(minp, piv);
-    const double inv = piv > 1e-14 ? rsqrt(piv) : 0.0;
-    __syncthreads();
-    for (int r = j + tid; r < b; r += nt) sm[r * ld + j] = r == j ? (piv > 1e-14 ? sqrt(piv) : 1.0) : sm[r * ld + j] * inv;
-    __syncthreads();
-    // trailing update of the lower triangle: element (r, c), j < c <= r
-    const int n = b - j - 1;
-    for (int e = tid; e < n * n; e += nt) {
-      const int rr = e / n, cc = e - rr * n;
-      if (cc <= rr) {
-        const int r = j + 1 + rr, c = j + 1 + cc;
-        sm[r * ld + c] = fma(-sm[r * ld + j], sm[c * ld + j], sm[r * ld + c]);
-      }
-    }
-    __syncthreads();
-  }
-  // inverse of L, one warp per column c: x = L^-1 e_c by forward substitution, kept in the UPPER triangle of sm
-  // (entry (c, r) = x_r for r >= c), which the factorisation no longer needs
-  for (int i = tid; i < b; i += nt) s_invd[i] = 1.0 / sm[i * ld + i];
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  for (int c = warp; c < b; c += nw) {
-    const double xc = s_invd[c];  // x_c = 1 / L_cc; the diagonal of sm keeps L (other warps divide by it)
-    for (int r = c + 1; r < b; ++r) {
+    for (int r = j + grp; r < b; r += ngrp) {
       double acc = 0.0;
-      for (int k = c + lane; k < r; k += 32) acc = fma(sm[r * ld + k], k == c ? xc : sm[c * ld + k], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) sm[c * ld + r] = -acc * s_invd[r];
-      __syncwarp();
+      for (int k = sub; k < j; k += 8) acc = fma(sm[r * ld + k], sm[j * ld + k], acc);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+      if (sub == 0) s_tmp[r] = sm[r * ld + j] - acc;
     }
+    __syncthreads();
+    // The scaled matrix has a unit diagonal.  A filtered block may be ill conditioned up to ~1e7 (its Gram 1e14): tiny
+    // positive pivots are expected in the first pass and repaired by the second; only a non-positive (or NaN) pivot
+    // means the factorisation broke down.
+    const double piv = s_tmp[j];
+    const bool okp = piv > 0.0;
+    if (!okp && tid == 0) s_bad = 1;
+    minp = fmin(minp, piv);
+    const double inv = okp ? rsqrt(piv) : 0.0;
+    for (int r = j + tid; r < b; r += nt) sm[r * ld + j] = r == j ? (okp ? piv * inv : 1.0) : s_tmp[r] * inv;
+    __syncthreads();
   }
+  for (int i = tid; i < b; i += nt) s_invd[i] = __drcp_rn(sm[i * ld + i]);
   __syncthreads();
+  // X = L^-1 row by row (all columns c < r of row r at once): X[r][c] = -(sum_{k=c}^{r-1} L[r][k] X[k][c]) / L[r][r],
+  // X[k][c] kept at sm[c][k] (upper triangle), X[c][c] = s_invd[c]
+  for (int r = 1; r < b; ++r) {
+    for (int c = grp; c < r; c += ngrp) {
+      double acc = 0.0;
+      for (int k = c + sub; k < r; k += 8) acc = fma(sm[r * ld + k], k == c ? s_invd[c] : sm[c * ld + k], acc);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+      if (sub == 0) s_tmp[c] = -acc * s_invd[r];
+    }
+    __syncthreads();
+    for (int c = tid; c < r; c += nt) sm[c * ld + r] = s_tmp[c];
+    __syncthreads();
+  }
   // W[i][j] = d_i * (L^-1)[j][i] for i <= j  (upper triangular); (L^-1)[j][i] is stored at (i, j), its diagonal in s_invd
   for (int e = tid; e < b * (int)ldw; e += nt) {
     const int i = e / (int)ldw, j = e - i * (int)ldw;
@@ -511,6 +519,7 @@ struct Layout {
 bool make_layout(int h, int dims, Layout& L) {
   if (h < 1 || dims < 1 || dims > h) return false;
   int b = std::min(dims + EG_BUFFER, h);
+  if (b > 128 && dims + 24 <= 128) b = 128;  // 64 column pairs: the Jacobi kernel's fast configuration (16 threads a pair)
   if (b > EG_MAXB) b = std::min(EG_MAXB, h);
   if (b < dims + std::min(8, h - dims)) return false;  // dims too large for the shared-memory Cholesky
   L.b = b;
@@ -575,18 +584,20 @@ struct Ctx {
 
 typedef void (*GemmFn)(const double*, int64_t, const double*, int64_t, int, int, double, const double*, double,
                        const double*, double, double*, double*, unsigned int*, int);
+constexpr int EG_RPT_WIDE = 4;  // rows per thread for the widest blocks (register budget), 8 otherwise
+int gemm_threads(int nj) { return nj >= 9 ? 16 * (EG_TM / EG_RPT_WIDE) : 16 * (EG_TM / 8); }
 GemmFn gemm_for(int nj) {
   switch (nj) {
-    case 1: return eig_dgemm_kernel<1>;
-    case 2: return eig_dgemm_kernel<2>;
-    case 3: return eig_dgemm_kernel<3>;
-    case 4: return eig_dgemm_kernel<4>;
-    case 5: return eig_dgemm_kernel<5>;
-    case 6: return eig_dgemm_kernel<6>;
-    case 7: return eig_dgemm_kernel<7>;
-    case 8: return eig_dgemm_kernel<8>;
-    case 9: return eig_dgemm_kernel<9>;
-    default: return eig_dgemm_kernel<10>;
+    case 1: return eig_dgemm_kernel<1, 8>;
+    case 2: return eig_dgemm_kernel<2, 8>;
+    case 3: return eig_dgemm_kernel<3, 8>;
+    case 4: return eig_dgemm_kernel<4, 8>;
+    case 5: return eig_dgemm_kernel<5, 8>;
+    case 6: return eig_dgemm_kernel<6, 8>;
+    case 7: return eig_dgemm_kernel<7, 8>;
+    case 8: return eig_dgemm_kernel<8, 8>;
+    case 9: return eig_dgemm_kernel<9, EG_RPT_WIDE>;
+    default: return eig_dgemm_kernel<10, EG_RPT_WIDE>;
   }
 }
 
@@ -600,7 +611,7 @@ void gemm(const Ctx& c, const double* a, int64_t lda, int m, int k, const double
   if (k > 512) nsplit = L.nsplit, kps = L.k_per_split;  // the products with the covariance
   const int tiles = (m + EG_TM - 1) / EG_TM;
   ++c.launches;
-  gemm_for(L.nj)<<<dim3((unsigned)tiles, (unsigned)nsplit), EG_THREADS, gemm_smem(L.nj), c.st>>>(
+  gemm_for(L.nj)<<<dim3((unsigned)tiles, (unsigned)nsplit), gemm_threads(L.nj), gemm_smem(L.nj), c.st>>>(
       a, lda, bm, L.ldn, m, k, alpha, pm, gamma, qm, delta, out, c.p(L.off_part),
       reinterpret_cast<unsigned int*>(c.ws + L.off_counters), kps);
 }

@@ -17,18 +17,20 @@
 namespace {
 
 constexpr int JE_THREADS = 1024;
-constexpr int JE_TPP = 8;      // threads per column pair
+// threads per column pair: 16 while n / 2 pairs x 16 fit one CTA (n <= 128), else 8
 constexpr int JE_MAXN = 168;   // 168 * 168 * 8 B = 226 KB of shared memory
 constexpr int JE_MAX_SWEEPS = 40;
 
-// sum over the eight lanes of a pair; only the lanes of that group take part (a warp can hold idle groups)
-__device__ __forceinline__ double group_sum8(double v, unsigned mask) {
+// sum over the TPP lanes of a pair; only the lanes of that group take part (a warp can hold idle groups)
+template <int TPP>
+__device__ __forceinline__ double group_sum(double v, unsigned mask) {
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  for (int o = TPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
 
-__global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double* __restrict__ a, int n, int64_t lda,
+template <int JE_TPP>
+__global__ void __launch_bounds__(JE_TPP == 16 ? JE_THREADS : 704, 1) jacobi_eig_kernel(const double* __restrict__ a, int n, int64_t lda,
                                                                    double* __restrict__ evals,
                                                                    double* __restrict__ evecs, int64_t ldv,
                                                                    int* __restrict__ info, int descending) {
@@ -49,7 +51,8 @@ __global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double*
   const int pair = tid / JE_TPP, sub = tid % JE_TPP;
   const int npairs = ne / 2;
   const bool active = pair < npairs;
-  const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+  const unsigned gmask = (JE_TPP == 16 ? 0xFFFFu : 0xFFu) << ((tid & 31) & ~(JE_TPP - 1));
+  constexpr int RMAX = JE_TPP == 16 ? 8 : 21;  // rows of a column one thread holds (n <= 128 resp. 168)
   int sweeps = 0;
   for (; sweeps < JE_MAX_SWEEPS; ++sweeps) {
     for (int step = 0; step < ne - 1; ++step) {
@@ -64,27 +67,39 @@ __global__ void __launch_bounds__(JE_THREADS, 1) jacobi_eig_kernel(const double*
         }
         double* wi = w + (size_t)ci * n;
         double* wj = w + (size_t)cj * n;
+        // the thread's rows of both columns stay in registers between the dot products and the rotation
+        double xr[RMAX], yr[RMAX];
         double alpha = 0.0, beta = 0.0, gamma = 0.0;
-#pragma unroll 4
-        for (int r = sub; r < n; r += JE_TPP) {
-          const double x = wi[r], y = wj[r];
-          alpha = fma(x, x, alpha);
-          beta = fma(y, y, beta);
-          gamma = fma(x, y, gamma);
+#pragma unroll
+        for (int t = 0; t < RMAX; ++t) {
+          const int r = sub + t * JE_TPP;
+          xr[t] = r < n ? wi[r] : 0.0;
+          yr[t] = r < n ? wj[r] : 0.0;
+          alpha = fma(xr[t], xr[t], alpha);
+          beta = fma(yr[t], yr[t], beta);
+          gamma = fma(xr[t], yr[t], gamma);
         }
-        alpha = group_sum8(alpha, gmask), beta = group_sum8(beta, gmask), gamma = group_sum8(gamma, gmask);
-        const double lim = 1e-15 * sqrt(alpha * beta);
-        if (fabs(gamma) > lim && alpha > 0.0 && beta > 0.0) {  // uniform inside the group of eight
-          const double zeta = (beta - alpha) / (2.0 * gamma);
-          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = rsqrt(1.0 + t * t), s = c * t;
-#pragma unroll 4
-          for (int r = sub; r < n; r += JE_TPP) {  // the columns are re-read: a 1024-thread CTA has 64 registers a thread
-            const double x = wi[r], y = wj[r];
-            wi[r] = c * x - s * y;
-            wj[r] = s * x + c * y;
+        alpha = group_sum<JE_TPP>(alpha, gmask), beta = group_sum<JE_TPP>(beta, gmask);
+        gamma = group_sum<JE_TPP>(gamma, gmask);
+        // (thresholds compared in squared form: FP64 square roots and divisions are ~40-instruction sequences and sit
+        // on the critical path of every one of the n - 1 dependent steps of a sweep)
+        const double ab = alpha * beta, g2 = gamma * gamma;
+        if (g2 > 1e-30 * ab && alpha > 0.0 && beta > 0.0) {  // uniform inside the group
+          // tan of the rotation angle: t = 2 gamma / (d + sign(d) sqrt(d^2 + 4 gamma^2)), d = beta - alpha (the smaller
+          // root: |t| <= 1); sqrt(q) = q rsqrt(q), the division as a reciprocal
+          const double d = beta - alpha;
+          const double q = fma(d, d, 4.0 * g2);
+          const double t = 2.0 * gamma * __drcp_rn(d + copysign(q * rsqrt(q), d));
+          const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
+#pragma unroll
+          for (int u = 0; u < RMAX; ++u) {
+            const int r = sub + u * JE_TPP;
+            if (r < n) {
+              wi[r] = c * xr[u] - sn * yr[u];
+              wj[r] = sn * xr[u] + c * yr[u];
+            }
           }
-          if (sub == 0 && fabs(gamma) > 1e-13 * sqrt(alpha * beta)) s_rotated = 1;  // benign race: any writer wins
+          if (sub == 0 && g2 > 1e-26 * ab) s_rotated = 1;  // benign race: any writer wins
         }
       }
       __syncthreads();
@@ -141,15 +156,21 @@ int32_t jacobi_eig_launch(const double* a, int n, int64_t lda, double* evals, do
   SCF_ARG(a && evals && evecs, "null pointer");
   SCF_ARG(n >= 1 && n <= JE_MAXN && lda >= n && ldv >= n, "n must be within [1, 168]");
   const size_t smem = (size_t)n * (n + (n & 1)) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(jacobi_eig_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(jacobi_eig_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     scf_set_error("scf_sym_eig_jacobi: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
-  // one group of eight threads per column pair: a small matrix runs with few warps (cheaper barriers)
+  // one group of 16 (n <= 128) or 8 threads per column pair: a small matrix runs with few warps (cheaper barriers)
   const int npairs = (n + 1) / 2;
-  int threads = (npairs * JE_TPP + 31) / 32 * 32;
+  const int tpp = npairs * 16 <= JE_THREADS ? 16 : 8;
+  int threads = (npairs * tpp + 31) / 32 * 32;
   threads = threads < 64 ? 64 : (threads > JE_THREADS ? JE_THREADS : threads);
-  jacobi_eig_kernel<<<1, threads, smem, stream>>>(a, n, lda, evals, evecs, ldv, info, descending);
+  if (tpp == 16)
+    jacobi_eig_kernel<16><<<1, threads, smem, stream>>>(a, n, lda, evals, evecs, ldv, info, descending);
+  else
+    jacobi_eig_kernel<8><<<1, threads, smem, stream>>>(a, n, lda, evals, evecs, ldv, info, descending);
   return scf_check_launch("scf_sym_eig_jacobi");
 }

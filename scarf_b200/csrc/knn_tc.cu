@@ -47,6 +47,7 @@ constexpr int NEPI_WARPS = 16;
 constexpr int NTHREADS = 64 + 32 * NEPI_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-17: epilogue
 constexpr int NL = 32 * NEPI_WARPS;             // epilogue threads = candidate lists per CTA
 constexpr int HB = 8;          // buffered hits per epilogue thread
+constexpr int NDONE = 16;      // ring of "all MMAs of step t have completed" barriers (step t uses entry t % 16)
 
 // error model of the tensor-core score (see DESIGN.md "kNN guard band"), all in scaled units (a := s a, b := s b),
 // a~ = fp16(a), da = a - a~ (known exactly):
@@ -288,12 +289,14 @@ struct Epi {
   }
 };
 
-// The rare path of a 32-column pass: some lane of the warp has a score below its threshold among v[0..32).  Chunks of
-// 16 and groups of 4 columns are visited only when a lane has a candidate in them (the branches around the votes are
-// warp-uniform); before a group is appended the buffers are drained if one of them could overflow.
+// Some lane of the warp has a score below its threshold among v[0..32).  What bounds this kernel once the tensor pipe
+// is fed is the number of instructions a warp spends per reference tile (ncu: ~10 cycles between two instructions of
+// one warp), so the scan is organised to skip as much as it can with warp-uniform branches: chunks of 16 and groups of
+// 4 columns are visited only when some lane has a candidate in them (one vote each), a visited group costs four
+// predicated appends, and before a group is appended the buffers are drained if one of them could overflow.
 template <int KC, bool SHARED_THR>
 __device__ __forceinline__ void hits32(const uint32_t (&v)[32], float m_lo, float m_hi, int jb, Epi<KC>& ep, float* thr_pub,
-                                    const volatile float* thr_partner) {
+                                       const volatile float* thr_partner) {
   const bool count = (SCF_KNN_DEBUG & 16) && (threadIdx.x & 31) == 0;
   if (count) atomicAdd(&g_dbg[1], 1ull);
 #pragma unroll
@@ -355,10 +358,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(thr_x + NL);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + 1;
-  uint64_t* full = bars + 2;
-  uint64_t* empty = full + p.stages;
-  uint64_t* tmem_full = empty + p.stages;
-  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* full = bars + 2;               // [stages] TMA data of a stage has landed
+  uint64_t* done = full + p.stages;        // [NDONE]  every MMA of step t (entry t % NDONE) has completed: the epilogue
+                                           //          may read the accumulators, the producer may refill the stages
+  uint64_t* tmem_empty = done + NDONE;     // [2]      the epilogue has read accumulator buffer a
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   // the warp index through a shuffle: the compiler then knows that the role branches below are warp-uniform and may
@@ -394,14 +397,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   if (threadIdx.x == 0) {
     tc::mbar_init(a_full, 1);
     tc::mbar_init(a_empty, 1);
-    for (int s = 0; s < p.stages; ++s) {
-      tc::mbar_init(full + s, 1);
-      tc::mbar_init(empty + s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      tc::mbar_init(tmem_full + a, 1);
-      tc::mbar_init(tmem_empty + a, NEPI_WARPS);  // one arrive per epilogue warp
-    }
+    for (int s = 0; s < p.stages; ++s) tc::mbar_init(full + s, 1);
+    for (int d = 0; d < NDONE; ++d) tc::mbar_init(done + d, 1);
+    for (int a = 0; a < 2; ++a) tc::mbar_init(tmem_empty + a, NEPI_WARPS);  // one arrive per epilogue warp
     tc::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -419,6 +417,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     const bool leader = tc::elect_one();
     int seg = 0;
     uint32_t s = 0, ph = 0;  // pipeline stage and its phase, advanced without divisions (stay in uniform registers)
+    // A stage is refilled once the step that read its previous content has completed (`done` ring): one
+    // tcgen05.commit per step instead of one per stage -- a commit stalls the tensor pipe for ~150 cycles (measured).
+    // (rel_step, rel_c): the chunk loaded p.stages chunks ago, i.e. the previous user of the stage about to be filled.
+    uint32_t loaded = 0, rel_step = 0, rel_c = 0;
     for (long long cur = w0; cur < w1; ++seg) {
       const int q = (int)(cur / T), t0 = (int)(cur % T);
       const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
@@ -434,7 +436,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
       __syncwarp();
       for (int t = t0; t < t1; ++t)
         for (int c = 0; c < p.kchunks; ++c) {
-          tc::mbar_wait(empty + s, ph ^ 1u, backoff);
+          if (loaded >= (uint32_t)p.stages) {
+            tc::mbar_wait(done + (rel_step & (NDONE - 1)), (rel_step / NDONE) & 1u, backoff);
+            if (++rel_c == (uint32_t)p.kchunks) rel_c = 0, ++rel_step;
+          }
+          ++loaded;
           if (leader) {
             if (SCF_KNN_DEBUG & 128) {  // timing experiment: no reference traffic, the MMAs run on stale tiles
               tc::mbar_arrive(full + s);
@@ -487,11 +493,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
                 if (leader) tc::umma_f16_lo(d_tmem, a_lo + kk * 2u, b_lo + kk * 2u, idesc, (c | kk) != 0u);
               }
           }
-          if (leader) tc::umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
-          __syncwarp();
           if (++s == stages) s = 0, ph ^= 1u;
         }
-        if (leader) tc::umma_commit(tmem_full + acc);  // all accumulators of this reference tile complete
+        if (leader) tc::umma_commit(done + (lt & (NDONE - 1)));  // accumulators complete, stages of this step reusable
         __syncwarp();
       }
       if (leader) tc::umma_commit(a_empty);  // the query operand may be replaced once every MMA of the segment has run
@@ -522,7 +526,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
         for (int t = t0; t < t1; ++t, ++lt) {
           const int acc = lt & 1;
           const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
-          tc::mbar_wait(tmem_full + acc, acc_ph);
+          tc::mbar_wait(done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
           tc::tc_fence_after();
           const int j0 = t * BN + col0;
           const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + g * GCOLS);
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
         for (int t = t0; t < t1; ++t, ++lt) {
           const int acc = lt & 1;
           const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
-          tc::mbar_wait(tmem_full + acc, acc_ph);
+          tc::mbar_wait(done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
           tc::tc_fence_after();
           if (SCF_KNN_DEBUG & 32) {  // timing experiment: no accumulator read-out at all
             tc::tc_fence_before();
@@ -580,30 +584,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
           const int j0 = t * BN + col0;
           const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + g * GCOLS);
           if constexpr (HALVES == 2) ep.thr = fminf(ep.cl.thr, *thr_partner);
-          // Common case: no lane of the warp has a candidate among its 64 columns.  The two halves are reduced to
-          // their minima one after the other through ONE 32-register buffer (the list itself needs k' registers), then
-          // one vote decides.  A half with a candidate is simply read again: the accumulator stays in TMEM until this
-          // warp has arrived on tmem_empty.
+          // Two passes of 32 columns through one 32-register buffer (the list itself needs k' registers): minimum of
+          // the pass (FMNMX3 tree), one vote; only a pass in which some lane has a candidate is scanned.
           uint32_t v[32];
-          tc::tmem_ld32(t_row, v);
-          tc::tmem_ld_wait();
-          float m0 = 0.f, m1 = 0.f;
-          if (!(SCF_KNN_DEBUG & 8)) m0 = fminf(min16(v), min16(v + 16));
-          tc::tmem_ld32(t_row + 32u, v);
-          tc::tmem_ld_wait();
-          if (!(SCF_KNN_DEBUG & 8)) {
-            const float b0 = min16(v), b1 = min16(v + 16);
-            m1 = fminf(b0, b1);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            tc::tmem_ld32(t_row + (uint32_t)(32 * hh), v);
+            tc::tmem_ld_wait();
+            if (SCF_KNN_DEBUG & 8) continue;
+            const float m_lo = min16(v), m_hi = min16(v + 16);
             if ((SCF_KNN_DEBUG & 16) && lane == 0) atomicAdd(&g_dbg[0], 1ull);
-            if (__any_sync(SCF_FULL, fminf(m0, m1) < ep.thr)) {
-              if (__any_sync(SCF_FULL, m1 < ep.thr))
-                hits32<KC, HALVES == 2>(v, b0, b1, j0 + 32, ep, thr_pub, thr_partner);
-              if (__any_sync(SCF_FULL, m0 < ep.thr)) {
-                tc::tmem_ld32(t_row, v);
-                tc::tmem_ld_wait();
-                hits32<KC, HALVES == 2>(v, min16(v), min16(v + 16), j0, ep, thr_pub, thr_partner);
-              }
-            }
+            if (__any_sync(SCF_FULL, fminf(m_lo, m_hi) < ep.thr))
+              hits32<KC, HALVES == 2>(v, m_lo, m_hi, j0 + 32 * hh, ep, thr_pub, thr_partner);
           }
           tc::tc_fence_before();
           __syncwarp();
@@ -854,8 +846,8 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.kc = pick_kc(k);
   pl.kp = (dim + 3 + KCH - 1) / KCH * KCH;
   pl.kchunks = pl.kp / KCH;
-  if (pl.kc == 0 || pl.kchunks > 4) return false;  // k > 24 or dim > 253: method 0 handles those
-  pl.qt = pl.kchunks == 1 ? 4 : 2;  // see knn_tc_kernel
+  if (pl.kc == 0 || pl.kchunks > 3) return false;  // k > 24 or dim > 189: method 0 handles those
+  pl.qt = 2;  // see knn_tc_kernel (QT = 4 / BN = 64 halves the L2 traffic but an N = 64 MMA runs at 2/3 of the rate)
   pl.bn = ACC_COLS / pl.qt;
   pl.halves = pl.qt == 2 ? 2 : 1;
   const int rows = pl.qt * BM;
@@ -881,12 +873,13 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.tiles_per_split = pl.n_ref_tiles;
   auto smem_for = [&](int stages) {
     return (size_t)pl.qt * pl.kchunks * A_CHUNK_BYTES + (size_t)stages * pl.bn * 128 + (size_t)2 * HB * NL * 4 +
-           (size_t)NL * 4 + (size_t)(2 + 2 * stages + 4) * 8 + 64;
+           (size_t)NL * 4 + (size_t)(2 + stages + NDONE + 2 + 2) * 8 + 64;
   };
-  pl.stages = pl.qt == 4 ? 10 : 6;
+  pl.stages = 8;
   while (pl.stages > 2 && smem_for(pl.stages) + 1024 > 227 * 1024) --pl.stages;
   pl.smem = smem_for(pl.stages) + 1024;  // slack for the 1024-byte alignment of the swizzled tiles
-  if (pl.smem > 227 * 1024) return false;
+  // a stage is released when the whole step that read it has completed: more stages than chunks per step are needed
+  if (pl.smem > 227 * 1024 || pl.stages < pl.kchunks + 1) return false;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t o = 0;
   pl.off_qop = o, o = al(o + (size_t)std::max<int64_t>(pl.nq_pad, 512) * pl.kp * 2);
@@ -943,7 +936,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
                       int64_t self_offset, int64_t* out_idx, float* out_dist, void* workspace,
                       int64_t workspace_bytes, cudaStream_t stream) {
   Plan pl;
-  if (!make_plan(nq, nref, dim, k, pl))  // k > 24 or dim > 125: outside the tensor-core kernel's shapes
+  if (!make_plan(nq, nref, dim, k, pl))  // k > 24 or dim > 189: outside the tensor-core kernel's shapes
     return knn_exact_launch(q, nullptr, nullptr, nq, ref, nref, dim, ld, ld, k, self_offset, out_idx, out_dist,
                             stream);
   if (!workspace || workspace_bytes < (int64_t)pl.total) {

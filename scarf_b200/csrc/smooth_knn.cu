@@ -158,7 +158,52 @@ __global__ void fill_zero_kernel(float* __restrict__ w, int64_t n, float v) {
   if (e < n && w[e] == 0.f) w[e] = v;
 }
 
+// load_graph's symmetrisation g + g^T - g o g^T (scarf/datastore/graph_datastore.py:1052-1075) on the stored kNN graph:
+// one thread per directed edge (i -> j, weight w) of the first use_k neighbours of every row; the reverse edge's
+// weight w' is looked up in row j (0 when j does not list i).  s = (w + w') - w w' in float64, the two steps rounded
+// separately like the sparse-matrix expression.  Slot 2e holds (i, j, s); slot 2e + 1 holds the mirrored entry
+// (j, i, s) when the reverse edge is absent (otherwise that entry is produced by the reverse edge's own thread) and
+// row -1 when it is not needed.  upper_only: only the entries with row <= column survive (scipy.sparse.triu).
+__global__ void graph_symmetrize_kernel(const int64_t* __restrict__ idx, const double* __restrict__ w, int64_t n, int k,
+                                        int use_k, int upper_only, int64_t* __restrict__ out_row,
+                                        int64_t* __restrict__ out_col, double* __restrict__ out_val) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * use_k) return;
+  const int64_t i = e / use_k;
+  const int slot = (int)(e - i * use_k);
+  const int64_t j = idx[i * k + slot];
+  const double wij = w[i * k + slot];
+  double wji = 0.0;
+  bool reverse = false;
+  if (j >= 0 && j < n)
+    for (int t = 0; t < use_k; ++t)
+      if (idx[j * k + t] == i) {
+        wji = __dadd_rn(wji, w[j * k + t]);  // duplicates add up, as in the COO -> CSR conversion
+        reverse = true;
+      }
+  const double sv = __dsub_rn(__dadd_rn(wij, wji), __dmul_rn(wij, wji));
+  int64_t r0 = i, c0 = j, r1 = -1, c1 = -1;
+  if (!reverse) r1 = j, c1 = i;
+  if (upper_only) {
+    if (r0 > c0) r0 = -1;
+    if (r1 > c1) r1 = -1;
+  }
+  out_row[2 * e] = r0, out_col[2 * e] = c0, out_val[2 * e] = sv;
+  out_row[2 * e + 1] = r1, out_col[2 * e + 1] = c1, out_val[2 * e + 1] = sv;
+}
+
 }  // namespace
+
+extern "C" int32_t scf_graph_symmetrize(const int64_t* idx, const double* weights, int64_t n, int32_t k, int32_t use_k,
+                                        int32_t upper_only, int64_t* out_row, int64_t* out_col, double* out_val,
+                                        void* stream) {
+  SCF_ARG(idx && weights && out_row && out_col && out_val, "null pointer");
+  SCF_ARG(n >= 0 && k > 0 && use_k >= 1 && use_k <= k, "bad sizes");
+  if (n == 0) return 0;
+  graph_symmetrize_kernel<<<(unsigned)((n * use_k + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      idx, weights, n, k, use_k, upper_only, out_row, out_col, out_val);
+  return scf_check_launch("scf_graph_symmetrize");
+}
 
 extern "C" int32_t scf_chunk_sums(const float* dist, int64_t n, int32_t k, int64_t row_offset, int64_t chunk_size,
                                   double* chunk_sum, void* stream) {

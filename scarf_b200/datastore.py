@@ -822,7 +822,8 @@ class DataStore:
         knn_loc = graph_loc.rsplit("/", 1)[0]
         n_cells, k = self.zw[knn_loc]["indices"].shape
         store = self.zw[graph_loc]
-        return graph.graph_to_sparse(store["edges"][:], store["weights"][:], n_cells, k, use_k, symmetric, upper_only)
+        return graph.graph_to_sparse(store["edges"][:], store["weights"][:], n_cells, k, use_k, symmetric, upper_only,
+                                     device=getattr(self, "device", None))
 
     # ---------------------------------------------------------------------------------------------------------
     def run_mapping(self, target_assay: RNAassay, target_name: str, target_feat_key: str, target_cell_key: str = "I",

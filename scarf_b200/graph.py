@@ -382,13 +382,24 @@ def run_mapping_csr(target: CsrDevice, target_cell_idx, t_col_of_feature, ref_mu
 # =============================================================================================
 # small pieces of the AnnStream contract
 # =============================================================================================
-def graph_to_sparse(edges, weights, n_cells, k, use_k=None, symmetric=None, upper_only=None):
+def graph_to_sparse(edges, weights, n_cells, k, use_k=None, symmetric=None, upper_only=None, device=None):
     """The stored COO graph as a scipy CSR matrix: ``_store_to_sparse`` (scarf/datastore/graph_datastore.py:474-511:
     ``use_k`` clamped into [1, k], the first ``use_k`` of every row's k entries kept) and ``load_graph``'s
-    symmetrisation ``g + g.T - g * g.T`` with the optional upper triangle (graph_datastore.py:1052-1075)."""
+    symmetrisation ``g + g.T - g * g.T`` with the optional upper triangle (graph_datastore.py:1052-1075).  With a CUDA
+    ``device`` the symmetrisation arithmetic runs in ``scf_graph_symmetrize`` (the stored layout -- row i owns entries
+    [i k, (i + 1) k) -- is what the kernel needs); scipy then only assembles the container.  ``device=None`` (a store
+    read without a GPU, the CPU tests) evaluates the same expression with scipy."""
     from scipy.sparse import csr_matrix, triu
 
     use_k = k if use_k is None else min(max(int(use_k), 1), k)
+    if symmetric is True and device is not None and torch.device(device).type == "cuda":
+        dev = torch.device(device)
+        idx = torch.from_numpy(np.ascontiguousarray(edges[:, 1].astype(np.int64)).reshape(n_cells, k)).to(dev)
+        w = torch.from_numpy(np.ascontiguousarray(np.asarray(weights, dtype=np.float64)).reshape(n_cells, k)).to(dev)
+        rows, cols, vals = ops.graph_symmetrize(idx, w, use_k, upper_only is True)
+        rows, cols, vals = rows.cpu().numpy(), cols.cpu().numpy(), vals.cpu().numpy()
+        keep = rows >= 0
+        return csr_matrix((vals[keep], (rows[keep], cols[keep])), shape=(n_cells, n_cells))
     if use_k != k:
         keep = np.tile([True] * use_k + [False] * (k - use_k), n_cells)
         edges, weights = edges[keep], weights[keep]

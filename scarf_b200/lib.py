@@ -42,6 +42,7 @@ SIGNATURES = {
     "scf_smooth_knn": (_i32, [_p, _i64, _i32, _f32, _f32, _i64, _i64, _p, _p, _p, _p]),
     "scf_membership_coo": (_i32, [_p, _p, _p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p]),
     "scf_fill_zero_weights": (_i32, [_p, _i64, _f32, _p]),
+    "scf_graph_symmetrize": (_i32, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
     "scf_hvg_select_workspace_bytes": (_i64, [_i32]),
     "scf_hvg_select": (_i32, [_p, _p, _p, _p, _p, _i32, _f64, _f64, _i32, _f64, _i32, _f64, _f64, _f64, _f64, _p, _p, _p,
                        _p, _i64, _p]),

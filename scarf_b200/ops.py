@@ -421,3 +421,17 @@ def membership_coo(idx, dist, sigma, rho, row_offset, chunk_size, n_chunks_total
 def fill_zero_weights(weights, floor):
     lib.call("scf_fill_zero_weights", weights.data_ptr(), int(weights.numel()), float(floor), _stream())
     return weights
+
+
+def graph_symmetrize(idx, weights, use_k, upper_only):
+    """COO entries of g + g.T - g * g.T (optionally its upper triangle) of the kNN graph given as neighbour ids int64
+    [n, k] and weights float64 [n, k] on the device -> (rows int64, cols int64, vals float64), unused slots have row -1."""
+    n, k = idx.shape
+    assert idx.dtype == torch.int64 and weights.dtype == torch.float64 and idx.is_contiguous() and weights.is_contiguous()
+    m = 2 * n * int(use_k)
+    rows = torch.empty(m, dtype=torch.int64, device=idx.device)
+    cols = torch.empty(m, dtype=torch.int64, device=idx.device)
+    vals = torch.empty(m, dtype=torch.float64, device=idx.device)
+    lib.call("scf_graph_symmetrize", idx.data_ptr(), weights.data_ptr(), n, k, int(use_k), int(bool(upper_only)),
+             rows.data_ptr(), cols.data_ptr(), vals.data_ptr(), _stream())
+    return rows, cols, vals

@@ -135,6 +135,17 @@ def test_datastore_chain_layout_and_cache(tmp_path, pbmc):
     assert (pi.shape, pi.dtype.str, pi.chunks, pd_.dtype.str) == ((808, 3), "<u8", (1000, 3), "<f8")
     sc = P.mapping_score(pi[:], pd_[:], 808, per_k=False)
     assert (np.abs(sc - pbmc["mapping_scores"]) < 1e-2).mean() > 0.98
+    # run_mapping finds the finished graph in the store (mapping_datastore.py:143 -> the cached branches of make_graph,
+    # graph_datastore.py:797-881): loadings / mu / sigma / embedding are loaded, nothing is recomputed or rewritten
+    stamp = os.path.getmtime(os.path.join(z[knn]["indices"].path, "0.0"))
+    ds.run_mapping(target_assay=ds.RNA, target_name="selfmap2", target_feat_key="hvgs_self", save_k=3)
+    assert ds.last_make_graph_timing == {"cache_hit": True}
+    assert os.path.getmtime(os.path.join(z[knn]["indices"].path, "0.0")) == stamp
+    assert np.array_equal(z["RNA/projections/selfmap2"]["indices"][:], pi[:])
+    assert np.array_equal(z["RNA/projections/selfmap2"]["distances"][:], pd_[:])
+    # the subset hash is the reference's (an int, assay.py:317-329); a different cell subset makes the group stale
+    from scarf_b200.datastore import create_subset_hash
+    assert z[base].attrs["subset_hash"] == create_subset_hash(pbmc["cell_idx"], np.where(hv)[0])
     ann_obj = ds.make_graph(feat_key="hvgs", return_ann_object=True)
     assert ann_obj.k == 11 and ann_obj.loadings.shape == (100, 11) and ann_obj.kmeans.cluster_centers_.shape == (808, 11)
     one = ann_obj.reducer(np.zeros(100))

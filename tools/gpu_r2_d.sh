@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "knn or chain or mapping or eig or jacobi" > gpurun_out/r2_pytest_knn.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2_pytest_knn.log; tail -12 gpurun_out/r2_pytest_knn.log
+timeout 600 python tools/knn_probe.py 100000 50 11 100000 100 21 2>&1 | tee gpurun_out/r2_knn_probe.log
+KNN_PROBE_NQ=125000 timeout 600 python tools/knn_probe.py 1000000 100 21 2>&1 | tee -a gpurun_out/r2_knn_probe.log
+timeout 300 python tools/eig_probe.py 50 100 2>&1 | tail -4 | tee gpurun_out/r2_eig_probe.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_eig_launches.csv python tools/eig_probe.py 50 100 > /dev/null 2>&1
+python tools/ncu_times.py gpurun_out/r2_eig_launches.csv 2>&1 | grep -E "kernel|eig_|jacobi" | cut -c1-130 | tee gpurun_out/r2_eig_launches.txt
