@@ -647,7 +647,10 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     numa_cpus = pin_to_gpu_numa(local_rank)
     if world > 1:
-        td.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a rank that fails must not leave the others waiting for the default half hour
+        td.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=600))
     comm = Comm()
     name = args.workload or ("C2" if world == 1 else "C3")
     cfg = dict(WORKLOADS[name])

@@ -325,8 +325,8 @@ __global__ void __launch_bounds__(EG_THREADS) eig_gram_kernel(const double* __re
 // (the block is numerically rank deficient: the caller repeats with the eigenvalue-based factor); flags[1] (as double
 // bits in flagsd[0]) keeps the smallest pivot seen.
 __global__ void __launch_bounds__(1024, 1) eig_chol_kernel(const double* __restrict__ s, int64_t lds, int b,
-                                                           double* __restrict__ w, int64_t ldw, int* __restrict__ flags,
-                                                           double* __restrict__ min_pivot) {
+                                                           double shift, double* __restrict__ w, int64_t ldw,
+                                                           int* __restrict__ flags, double* __restrict__ min_pivot) {
   extern __shared__ __align__(16) double sm[];  // [b][b + 1]: lower triangle L, upper triangle (L^-1)^T
   __shared__ double sd[EG_MAXB];      // column scaling d_i = 1 / sqrt(s_ii)
   __shared__ double s_invd[EG_MAXB];  // 1 / L_ii
@@ -344,7 +344,11 @@ __global__ void __launch_bounds__(1024, 1) eig_chol_kernel(const double* __restr
   __syncthreads();
   for (int e = tid; e < b * b; e += nt) {
     const int r = e / b, c = e - r * b;
-    sm[r * ld + c] = 0.5 * (s[(int64_t)r * lds + c] + s[(int64_t)c * lds + r]) * sd[r] * sd[c];
+    // `shift` on the unit diagonal (first pass of an orthonormalisation): a block filtered from an orthonormal one is
+    // ill conditioned up to ~1e7-1e8, its Gram up to 1e16 -- rounding alone can push a pivot below zero.  With the shift
+    // the factor exists, X W comes out with a condition number of ~sqrt(1 + shift cond(X)^2) (<~ 1e3), and the second,
+    // unshifted pass restores orthonormality to ~1e-10 or better (shifted Cholesky-QR, Fukaya et al.).
+    sm[r * ld + c] = 0.5 * (s[(int64_t)r * lds + c] + s[(int64_t)c * lds + r]) * sd[r] * sd[c] + (r == c ? shift : 0.0);
   }
   __syncthreads();
   double minp = 1e300;
@@ -634,7 +638,7 @@ int32_t orthonormalise(const Ctx& c, double* y, double* tmp, double** result, bo
     c.launches += robust ? 3 : 1;
     if (!robust) {
       const size_t smem = (size_t)L.b * (L.b + 1) * 8;
-      eig_chol_kernel<<<1, 1024, smem, c.st>>>(c.p(L.off_s), L.ldn, L.b, c.p(L.off_w), L.ldn,
+      eig_chol_kernel<<<1, 1024, smem, c.st>>>(c.p(L.off_s), L.ldn, L.b, pass == 0 ? 1e-10 : 0.0, c.p(L.off_w), L.ldn,
                                                 reinterpret_cast<int*>(c.ws + L.off_flags), c.p(L.off_minp));
     } else {
       eig_svqb_scale_kernel<<<32, 256, 0, c.st>>>(c.p(L.off_s), L.ldn, L.b, c.p(L.off_t), L.ldn, c.p(L.off_d));

@@ -225,6 +225,12 @@ def make_graph_csr(csr: CsrDevice, cell_idx, feat_mask, dims=11, k=11, lc=1.0, b
 
     # ---- Z (K1) ----
     ldz = round_up(n_feat, 128)
+    if ldz * 24 > 227 * 1024:
+        # scf_hvg_dense_scale / scf_csr_norm_scale keep mu, sigma and one output row in shared memory (24 B per
+        # column): ~9,600 features.  The path is built for HVG-sized feature sets (the H x H Gram grows quadratically too)
+        raise NotImplementedError(f"make_graph: {n_feat} features selected; the GPU path handles up to "
+                                  f"{227 * 1024 // 24 // 128 * 128} (use a feature selection, e.g. mark_hvgs, instead of "
+                                  "feat_key='I' on a whole transcriptome)")
     z = torch.empty((max(n_local, 1), ldz), dtype=torch.float32, device=dev)
     z_lo = torch.empty_like(z) if (gram_mode == 3 and loadings is None) else None
     ops.hvg_dense_scale(*compact, n_feat, z, mu_d, sigma_d, z_lo=z_lo)
@@ -440,27 +446,53 @@ def fix_knn_query(indices: np.ndarray, distances: np.ndarray, ref_idx: np.ndarra
 def fit_kmeans(embedding_all, dims, n_clusters, rand_state=4466, n_iter=10):
     """The ``kmeans__<n>__<seed>`` arrays make_graph always writes (scarf/ann.py:328-346, read back by run_umap /
     run_tsne for initialisation, graph_datastore.py:427-457).  The reference fits sklearn MiniBatchKMeans; its result
-    is not pinned by any reference test, so this is a deterministic Lloyd iteration on the GPU: seeded choice of
-    start rows, assignment = exact 1-nearest-centre search with the kNN kernel, update = segment means.  Every rank
-    holds the full embedding and gets identical centres and labels.  -> (centres float32 [n_clusters, dims],
-    labels int64 [n_cells])."""
+    is not pinned by any reference test, so this is a deterministic k-means on the GPU: k-means++ seeding (D^2
+    sampling by inverse CDF with host-seeded uniforms, so every rank draws the same rows), then Lloyd iterations --
+    assignment = exact 1-nearest-centre search with the kNN kernel, update = segment means.  Every rank holds the
+    full embedding and gets identical centres and labels.  -> (centres float32 [n_clusters, dims], labels int64
+    [n_cells])."""
     n = int(embedding_all.shape[0])
     n_clusters = int(max(2, min(n_clusters, n)))
     dev = embedding_all.device
-    g = torch.Generator(device="cpu")
-    g.manual_seed(int(rand_state))
-    start = torch.sort(torch.randperm(n, generator=g)[:n_clusters]).values.to(dev)
     ld = int(embedding_all.stride(0))
-    centres = embedding_all[start].clone()  # [n_clusters, ld], pad columns zero
+    rng = np.random.default_rng(int(rand_state))
+    trials = 2 + int(math.log(n_clusters))  # greedy k-means++ (Arthur & Vassilvitskii; sklearn's n_local_trials)
+    u = torch.from_numpy(rng.random((n_clusters, trials))).to(dev)  # host-seeded uniforms: the same draws on every rank
+    y64 = embedding_all[:, :dims].to(torch.float64)
+    start = torch.empty(n_clusters, dtype=torch.int64, device=dev)
+    start[0] = int(u[0, 0].item() * n) % n
+    mind2 = ((y64 - y64[start[0]]) ** 2).sum(dim=1)
+    norm2 = (y64 * y64).sum(dim=1)
+    for c in range(1, n_clusters):
+        cdf = torch.cumsum(mind2, dim=0)
+        cand = torch.searchsorted(cdf, u[c] * cdf[-1]).clamp(max=n - 1)  # D^2 sampling by inverse CDF, `trials` draws
+        yc = y64[cand]  # [trials, dims]
+        d2 = (norm2[:, None] - 2.0 * (y64 @ yc.T) + norm2[cand][None, :]).clamp_(min=0.0)  # [n, trials]
+        d2[cand, torch.arange(trials, device=dev)] = 0.0  # a candidate is at distance zero from itself, exactly
+        d2 = torch.minimum(d2, mind2[:, None])
+        best = torch.argmin(d2.sum(dim=0))  # the draw that lowers the potential most (first on ties)
+        start[c] = cand[best]
+        mind2 = d2[:, best].contiguous()
+    if n_clusters == n:  # one centre per cell: the sampling above cannot draw a row twice only while mind2 > 0
+        start = torch.arange(n, dtype=torch.int64, device=dev)
+    centres = embedding_all[torch.sort(start).values].clone()  # [n_clusters, ld], pad columns zero
     labels = None
     for it in range(n_iter + 1):
         idx, _ = ops.knn_l2(embedding_all, centres, dims, 1, self_offset=-1, method=1)
         labels = idx[:, 0]
         if it == n_iter:
             break
-        sums = torch.zeros((n_clusters, ld), dtype=torch.float64, device=dev)
-        sums.index_add_(0, labels, embedding_all.to(torch.float64))
-        cnt = torch.bincount(labels, minlength=n_clusters).to(torch.float64)
-        new = (sums / cnt.clamp(min=1.0)[:, None]).to(torch.float32)
+        # segment means in a fixed order (no floating-point atomics: every rank must get the same bits): rows sorted
+        # by label (stable), float64 prefix sums, differences at the segment ends
+        order = torch.argsort(labels, stable=True)
+        cs = torch.cumsum(embedding_all.to(torch.float64)[order], dim=0)
+        cnt_i = torch.bincount(labels, minlength=n_clusters)
+        ends = torch.cumsum(cnt_i, dim=0)
+        lo_idx = ends - cnt_i - 1
+        hi = cs[(ends - 1).clamp(min=0)]
+        lo = torch.where((lo_idx >= 0)[:, None], cs[lo_idx.clamp(min=0)], torch.zeros_like(hi))
+        cnt = cnt_i.to(torch.float64)
+        new = ((hi - lo) / cnt.clamp(min=1.0)[:, None]).to(torch.float32)
         centres = torch.where((cnt > 0)[:, None], new, centres).contiguous()  # an empty cluster keeps its centre
+        del cs, hi, lo
     return centres[:, :dims].contiguous(), labels
