@@ -26,7 +26,9 @@
 #include "common.cuh"
 
 int32_t jacobi_eig_launch(const double* a, int n, int64_t lda, double* evals, double* evecs, int64_t ldv, int* info,
-                          int descending, cudaStream_t stream);
+                          int descending, const int* skip_if, cudaStream_t stream);
+int32_t tridiag_eig_launch(const double* a, int n, int64_t lda, double* evals, double* evecs, int64_t ldv, int descending,
+                           double* work, int* ok, cudaStream_t stream);
 
 namespace {
 
@@ -351,6 +353,32 @@ __global__ void __launch_bounds__(1024, 1) eig_chol_kernel(const double* __restr
     sm[r * ld + c] = 0.5 * (s[(int64_t)r * lds + c] + s[(int64_t)c * lds + r]) * sd[r] * sd[c] + (r == c ? shift : 0.0);
   }
   __syncthreads();
+  if (shift == 0.0) {
+    // Second pass of an orthonormalisation: when the block is orthonormal to 1e-5 already (the usual case once the
+    // first pass worked on a well-conditioned block), one Newton-Schulz step W = D (I - E / 2), E = S' - I, brings it
+    // to ~E^2 without a factorisation: (X W)^T (X W) = I - 3/4 E^2 + O(E^3).
+    double emax = 0.0;
+    for (int e = tid; e < b * b; e += nt) {
+      const int r = e / b, c = e - r * b;
+      if (r != c) emax = fmax(emax, fabs(sm[r * ld + c]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(SCF_FULL, emax, o));
+    if ((tid & 31) == 0) s_tmp[tid >> 5] = emax;
+    __syncthreads();
+    emax = 0.0;
+    for (int w2 = 0; w2 < (nt >> 5); ++w2) emax = fmax(emax, s_tmp[w2]);
+    __syncthreads();
+    if (emax <= 1e-5) {
+      for (int e = tid; e < b * (int)ldw; e += nt) {
+        const int i = e / (int)ldw, j = e - i * (int)ldw;
+        double v = 0.0;
+        if (j < b) v = sd[i] * (i == j ? 1.0 : -0.5 * sm[i * ld + j]);
+        w[(int64_t)i * ldw + j] = v;
+      }
+      return;
+    }
+  }
   double minp = 1e300;
   // left-looking: column j of L from the finished columns k < j; every row r >= j is one dot product of length j
   for (int j = 0; j < b; ++j) {
@@ -473,6 +501,7 @@ __global__ void __launch_bounds__(256) eig_resid_final_kernel(const double* __re
     report[1] = norms[0], report[2] = norms[1];
     report[3] = (double)flags[0];
     report[4] = *min_pivot;
+    report[169] = (double)flags[4];  // 1: the Ritz pairs of this round came from the tridiagonal kernel
   }
   for (int j = threadIdx.x; j < b; j += blockDim.x) report[8 + j] = theta[j];
 }
@@ -559,7 +588,7 @@ bool make_layout(int h, int dims, Layout& L) {
   L.off_norms = o, o = al(o + 64);
   L.off_rpart = o, o = al(o + (size_t)L.resid_chunks * EG_MAXB * 8);
   L.off_d = o, o = al(o + EG_MAXB * 8);
-  L.off_report = o, o = al(o + (size_t)(8 + EG_MAXB) * 8);
+  L.off_report = o, o = al(o + (size_t)(8 + EG_MAXB + 8) * 8);
   L.off_counters = o, o = al(o + (size_t)(L.row_tiles + L.gram_tiles + 8) * 4);
   L.off_flags = o, o = al(o + 64);
   L.off_minp = o, o = al(o + 64);
@@ -642,7 +671,8 @@ int32_t orthonormalise(const Ctx& c, double* y, double* tmp, double** result, bo
                                                 reinterpret_cast<int*>(c.ws + L.off_flags), c.p(L.off_minp));
     } else {
       eig_svqb_scale_kernel<<<32, 256, 0, c.st>>>(c.p(L.off_s), L.ldn, L.b, c.p(L.off_t), L.ldn, c.p(L.off_d));
-      int32_t rc = jacobi_eig_launch(c.p(L.off_t), L.b, L.ldn, c.p(L.off_lam), c.p(L.off_u), L.ldn, nullptr, 0, c.st);
+      int32_t rc = jacobi_eig_launch(c.p(L.off_t), L.b, L.ldn, c.p(L.off_lam), c.p(L.off_u), L.ldn, nullptr, 0, nullptr,
+                                     c.st);
       if (rc) return rc;
       eig_svqb_factor_kernel<<<32, 256, 0, c.st>>>(c.p(L.off_u), L.ldn, c.p(L.off_lam), c.p(L.off_d), L.b,
                                                     c.p(L.off_w), L.ldn);
@@ -780,7 +810,17 @@ extern "C" int32_t scf_eig_topk(const int64_t* gram_fx, int64_t ldg, int32_t h, 
       double* av = c.spare(q, aq, v);
       gemm(c, cov, L.ldc, h, h, q, 1.0, nullptr, 0.0, nullptr, 0.0, aq);
       gram(c, q, aq, c.p(L.off_t));
-      rc = jacobi_eig_launch(c.p(L.off_t), b, L.ldn, c.p(L.off_theta), c.p(L.off_u), L.ldn, nullptr, 1, c.st);
+      // Ritz pairs of T: tridiagonalisation + multisection + inverse iteration (tridiag_eig.cu); the Jacobi kernel is
+      // launched behind it and returns at once unless that result failed its orthogonality check
+      int* tri_ok = reinterpret_cast<int*>(c.ws + L.off_flags) + 4;
+      if (b >= 3) {
+        rc = tridiag_eig_launch(c.p(L.off_t), b, L.ldn, c.p(L.off_theta), c.p(L.off_u), L.ldn, 1, c.p(L.off_s), tri_ok,
+                                c.st);
+        if (rc) return rc;
+        ++c.launches;
+      }
+      rc = jacobi_eig_launch(c.p(L.off_t), b, L.ldn, c.p(L.off_theta), c.p(L.off_u), L.ldn, nullptr, 1,
+                             b >= 3 ? tri_ok : nullptr, c.st);
       if (rc) return rc;
       c.launches += 3;  // Jacobi + the two residual kernels below
       // V = Q S, AV = AQ S (S = Ritz vectors, descending Ritz values)
@@ -793,7 +833,7 @@ extern "C" int32_t scf_eig_topk(const int64_t* gram_fx, int64_t ldg, int32_t h, 
                                                   c.p(L.off_minp), c.p(L.off_report));
       rc = scf_check_launch("scf_eig_topk(rayleigh-ritz)");
       if (rc) return rc;
-      e = cudaMemcpyAsync(host_report, c.p(L.off_report), (size_t)(8 + b) * 8, cudaMemcpyDeviceToHost, c.st);
+      e = cudaMemcpyAsync(host_report, c.p(L.off_report), (size_t)(8 + EG_MAXB + 8) * 8, cudaMemcpyDeviceToHost, c.st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);  // the one synchronisation of the round
       if (e != cudaSuccess) {
         scf_set_error("scf_eig_topk: %s", cudaGetErrorString(e));

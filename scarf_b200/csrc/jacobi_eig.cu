@@ -33,7 +33,9 @@ template <int JE_TPP>
 __global__ void __launch_bounds__(JE_TPP == 16 ? JE_THREADS : 704, 1) jacobi_eig_kernel(const double* __restrict__ a, int n, int64_t lda,
                                                                    double* __restrict__ evals,
                                                                    double* __restrict__ evecs, int64_t ldv,
-                                                                   int* __restrict__ info, int descending) {
+                                                                   int* __restrict__ info, int descending,
+                                                                   const int* __restrict__ skip_if) {
+  if (skip_if && *skip_if == 1) return;  // the tridiagonal kernel (tridiag_eig.cu) has delivered: nothing to do
   extern __shared__ __align__(16) double w[];  // column major, n rows x ne columns (ne = n rounded up to even)
   __shared__ int s_rotated;
   __shared__ double s_norm[JE_MAXN + 1];
@@ -141,18 +143,18 @@ __global__ void __launch_bounds__(JE_TPP == 16 ? JE_THREADS : 704, 1) jacobi_eig
 }  // namespace
 
 int32_t jacobi_eig_launch(const double* a, int n, int64_t lda, double* evals, double* evecs, int64_t ldv, int* info,
-                          int descending, cudaStream_t stream);
+                          int descending, const int* skip_if, cudaStream_t stream);
 
 extern "C" int32_t scf_sym_eig_max_n(void) { return JE_MAXN; }
 
 extern "C" int32_t scf_sym_eig_jacobi(const double* a, int32_t n, int64_t lda, double* evals, double* evecs, int64_t ldv,
                                       int32_t* info, void* stream) {
-  return jacobi_eig_launch(a, n, lda, evals, evecs, ldv, info, 0, (cudaStream_t)stream);
+  return jacobi_eig_launch(a, n, lda, evals, evecs, ldv, info, 0, nullptr, (cudaStream_t)stream);
 }
 
 // descending != 0: eigenvalues (and the matching eigenvector columns) in descending order (eig_topk.cu)
 int32_t jacobi_eig_launch(const double* a, int n, int64_t lda, double* evals, double* evecs, int64_t ldv, int* info,
-                          int descending, cudaStream_t stream) {
+                          int descending, const int* skip_if, cudaStream_t stream) {
   SCF_ARG(a && evals && evecs, "null pointer");
   SCF_ARG(n >= 1 && n <= JE_MAXN && lda >= n && ldv >= n, "n must be within [1, 168]");
   const size_t smem = (size_t)n * (n + (n & 1)) * sizeof(double);
@@ -169,8 +171,8 @@ int32_t jacobi_eig_launch(const double* a, int n, int64_t lda, double* evals, do
   int threads = (npairs * tpp + 31) / 32 * 32;
   threads = threads < 64 ? 64 : (threads > JE_THREADS ? JE_THREADS : threads);
   if (tpp == 16)
-    jacobi_eig_kernel<16><<<1, threads, smem, stream>>>(a, n, lda, evals, evecs, ldv, info, descending);
+    jacobi_eig_kernel<16><<<1, threads, smem, stream>>>(a, n, lda, evals, evecs, ldv, info, descending, skip_if);
   else
-    jacobi_eig_kernel<8><<<1, threads, smem, stream>>>(a, n, lda, evals, evecs, ldv, info, descending);
+    jacobi_eig_kernel<8><<<1, threads, smem, stream>>>(a, n, lda, evals, evecs, ldv, info, descending, skip_if);
   return scf_check_launch("scf_sym_eig_jacobi");
 }

@@ -32,6 +32,7 @@ SIGNATURES = {
     "scf_project_tc": (_i32, [_p, _p, _i64, _i64, _i32, _p, _i64, _i32, _p, _i64, _p, _i64, _p]),
     "scf_sym_eig_max_n": (_i32, []),
     "scf_sym_eig_jacobi": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p]),
+    "scf_sym_eig_tridiag": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p, _p]),
     "scf_eig_topk_workspace_bytes": (_i64, [_i32, _i32]),
     "scf_eig_topk": (_i32, [_p, _i64, _i32, _f64, _p, _f64, _i32, _f64, _i32, _p, _p, _p, _i64, _p, _p, _i64, _p]),
     "scf_knn_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32]),

@@ -341,6 +341,7 @@ def eig_topk(g_fx, n_cols, dims, scale, col_mean=None, mean_weight=0.0, tol=1e-8
             stats["eig_rounds"], stats["eig_residual"] = int(report[5]), float(report[0])
             stats["eig_restarts"], stats["eig_robust"] = int(report[6]), bool(report[7])
             stats["eig_min_pivot"] = float(report[4])
+            stats["eig_ritz_solver"] = "tridiagonal" if report[169] == 1.0 else "jacobi"
     return (evals, evecs, v32) if ld32 else (evals, evecs)
 
 
@@ -357,6 +358,21 @@ def sym_eig_small(a, info=None):
     lib.call("scf_sym_eig_jacobi", _ptr(a), n, int(a.stride(0)), _ptr(w), _ptr(v), int(v.stride(0)),
              _ptr(info), _stream())
     return w, v
+
+
+def sym_eig_tridiag(a):
+    """Same result as :func:`sym_eig_small` from the tridiagonal kernel (scf_sym_eig_tridiag) -> (w, v, ok): ``ok`` is a
+    device int32 scalar, 1 when the eigenvectors are orthonormal to 1e-9 (else the Jacobi kernel has to be used)."""
+    n = int(a.shape[0])
+    _chk(a, torch.float64, "a")
+    a = a.contiguous()
+    w = torch.empty(n, dtype=torch.float64, device=a.device)
+    v = torch.empty((n, n), dtype=torch.float64, device=a.device)
+    work = torch.empty((n, n), dtype=torch.float64, device=a.device)
+    ok = torch.zeros(1, dtype=torch.int32, device=a.device)
+    lib.call("scf_sym_eig_tridiag", _ptr(a), n, int(a.stride(0)), _ptr(w), _ptr(v), int(v.stride(0)), _ptr(work),
+             _ptr(ok), _stream())
+    return w, v, ok
 
 
 # ------------------------------------------------------------------------------------------ K5

@@ -678,6 +678,34 @@ def test_sym_eig_jacobi_equals_eigh(gpu, n):
         assert float((a @ v - v * w).abs().max()) < 1e-11 * float(we[-1])
 
 
+@pytest.mark.parametrize("n", [3, 7, 82, 96, 128, 133, 160])
+def test_sym_eig_tridiag_equals_eigh(gpu, n):
+    """scf_sym_eig_tridiag (tridiagonalisation + multisection + inverse iteration, the fast Rayleigh-Ritz solver of
+    scf_eig_topk) against torch.linalg.eigh: a dense PSD matrix with a wide spectrum, a nearly diagonal one, and a matrix
+    with an exactly repeated eigenvalue -- for which the kernel must say ok = 0 (inverse iteration cannot separate the
+    pair) instead of returning a non-orthogonal basis."""
+    torch, ops = gpu["torch"], gpu["ops"]
+    g = torch.Generator(device="cuda").manual_seed(200 + n)
+    q = torch.linalg.qr(torch.randn((n, n), device="cuda", dtype=torch.float64, generator=g))[0]
+    lam = torch.sort(torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 60.0 + 0.2).values
+    for a in (q @ torch.diag(lam) @ q.T, torch.diag(lam) + 1e-6 * (q + q.T)):
+        a = 0.5 * (a + a.T)
+        w, v, ok = ops.sym_eig_tridiag(a)
+        we, _ = torch.linalg.eigh(a)
+        assert int(ok.item()) == 1
+        np.testing.assert_allclose(w.cpu().numpy(), we.cpu().numpy(), rtol=1e-12, atol=1e-12)
+        assert float((v.T @ v - torch.eye(n, device="cuda", dtype=torch.float64)).abs().max()) < 1e-9
+        assert float((a @ v - v * w).abs().max()) < 1e-11 * float(we[-1])
+    if n > 4:
+        lam2 = lam.clone()
+        lam2[3] = lam2[2]
+        a = q @ torch.diag(lam2) @ q.T
+        w, v, ok = ops.sym_eig_tridiag(0.5 * (a + a.T))
+        np.testing.assert_allclose(w.cpu().numpy(), torch.linalg.eigvalsh(0.5 * (a + a.T)).cpu().numpy(), rtol=1e-12, atol=1e-11)
+        defect = float((v.T @ v - torch.eye(n, device="cuda", dtype=torch.float64)).abs().max())
+        assert int(ok.item()) == (1 if defect <= 1e-9 else 0)
+
+
 def test_pca_on_a_cell_subset(gpu, chain, synth_small):
     """``pca_cell_key`` (scarf/ann.py:215-228): the PCA is fitted on a subset of the selected cells (z-scaled with the
     mu / sigma of all of them), every cell is projected and searched.  Against the oracle's exact route."""
