@@ -240,6 +240,140 @@ __global__ void __launch_bounds__(16 * (EG_TM / RPT)) eig_dgemm_kernel(const dou
   }
 }
 
+// The same product on the FP64 tensor path (mma.sync m8n8k4, SASS DMMA): a warp instruction does 256 FMAs where a DFMA
+// does 32, and the SM's vector FP64 pipe (32 lanes / clk: 18.6 TFLOP/s on the whole chip) is what bounded the SIMT
+// kernel above at 12.6 TFLOP/s.  Four warps per CTA, warp w owns rows 16 w .. 16 w + 15 of the 64-row tile (two 8-row
+// MMA tiles) x all N columns.  Fragments (PTX ISA): A 8 x 4 row major -- lane holds A[lane / 4][lane % 4]; B 4 x 8 column
+// major -- lane holds B[lane % 4][lane / 4]; C 8 x 8 -- lane holds C[lane / 4][2 (lane % 4) + {0, 1}].  Shared-memory row
+// strides are = 4 (mod 16) doubles so that the 16 lanes of a half warp hit 16 distinct 8-byte banks.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(128) eig_dgemm_mma_kernel(const double* __restrict__ a, int64_t lda,
+                                                            const double* __restrict__ bm, int64_t ldn, int m, int k,
+                                                            double alpha, const double* __restrict__ pm, double gamma,
+                                                            const double* __restrict__ qm, double delta,
+                                                            double* __restrict__ out, double* __restrict__ part,
+                                                            unsigned int* __restrict__ counters, int k_per_split) {
+  constexpr int N = NJ * 16, NT = N / 8, THREADS = 128;
+  constexpr int SA = EG_KT + 4, SB = N + 4;
+  constexpr int B_PER = EG_KT * N / THREADS;
+  extern __shared__ __align__(16) double eg_smem[];
+  double (*sa)[EG_TM][SA] = reinterpret_cast<double (*)[EG_TM][SA]>(eg_smem);
+  double (*sb)[EG_KT][SB] = reinterpret_cast<double (*)[EG_KT][SB]>(eg_smem + 2 * EG_TM * SA);
+  __shared__ unsigned int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int fr = lane >> 2, fc = lane & 3;  // fragment row / column
+  const int row0 = blockIdx.x * EG_TM;
+  const int k0 = blockIdx.y * k_per_split, k1 = min(k, k0 + k_per_split);
+  double acc[2][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  const int a_r = tid >> 1, a_c = (tid & 1) * 8;  // A tile 64 x 16: eight consecutive k of one row per thread
+  double ra[8];
+  double rb[B_PER];
+  auto load_tiles = [&](int kk) {
+    const int gr = row0 + a_r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gk = kk + a_c + i;
+      ra[i] = (gr < m && gk < k1) ? a[(int64_t)gr * lda + gk] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      const int e = tid + THREADS * i;
+      const int br = e / N, bc = e - br * N;
+      const int gk = kk + br;
+      rb[i] = gk < k1 ? bm[(int64_t)gk * ldn + bc] : 0.0;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sa[buf][a_r][a_c + i] = ra[i];
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      const int e = tid + THREADS * i;
+      const int br = e / N, bc = e - br * N;
+      sb[buf][br][bc] = rb[i];
+    }
+  };
+  int buf = 0;
+  if (k0 < k1) {
+    load_tiles(k0);
+    store_tiles(0);
+  }
+  __syncthreads();
+  for (int kk = k0; kk < k1; kk += EG_KT) {
+    const bool more = kk + EG_KT < k1;
+    if (more) load_tiles(kk + EG_KT);
+#pragma unroll
+    for (int k4 = 0; k4 < EG_KT / 4; ++k4) {
+      const double a0 = sa[buf][16 * w + fr][4 * k4 + fc], a1 = sa[buf][16 * w + 8 + fr][4 * k4 + fc];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const double b = sb[buf][4 * k4 + fc][8 * nt + fr];
+        dmma884(acc[0][nt], a0, b);
+        dmma884(acc[1][nt], a1, b);
+      }
+    }
+    if (more) store_tiles(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  const int nsplit = gridDim.y;
+  if (nsplit > 1) {
+    double* mine = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(EG_TM * N);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        *reinterpret_cast<double2*>(mine + ((size_t)((w * 2 + mt) * NT + nt) * 32 + lane) * 2) =
+            make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(counters + blockIdx.x, 1u) == (unsigned)(nsplit - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int s = 0; s < nsplit; ++s) {  // fixed order: the sum does not depend on which CTA came last
+      const double* src = part + ((size_t)s * gridDim.x + blockIdx.x) * (size_t)(EG_TM * N);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(src + ((size_t)((w * 2 + mt) * NT + nt) * 32 + lane) * 2));
+          acc[mt][nt][0] += v.x, acc[mt][nt][1] += v.y;
+        }
+    }
+    if (tid == 0) counters[blockIdx.x] = 0u;  // ready for the next launch
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int gr = row0 + 16 * w + 8 * mt + fr;
+    if (gr >= m) continue;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int64_t o = (int64_t)gr * ldn + 8 * nt + 2 * fc + h2;
+        double v = alpha * acc[mt][nt][h2];
+        if (pm) v = fma(gamma, pm[o], v);
+        if (qm) v = fma(delta, qm[o], v);
+        out[o] = v;
+      }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- Gram
 // s[b, b] (row stride lds) = X^T Y over the h rows; grid = (tiles of 64 x 64 outputs, row chunks); ordered reduction
 // by the last CTA of a tile, like the GEMM.
@@ -617,24 +751,23 @@ struct Ctx {
 
 typedef void (*GemmFn)(const double*, int64_t, const double*, int64_t, int, int, double, const double*, double,
                        const double*, double, double*, double*, unsigned int*, int);
-constexpr int EG_RPT_WIDE = 4;  // rows per thread for the widest blocks (register budget), 8 otherwise
-int gemm_threads(int nj) { return nj >= 9 ? 16 * (EG_TM / EG_RPT_WIDE) : 16 * (EG_TM / 8); }
+int gemm_threads(int) { return 128; }
 GemmFn gemm_for(int nj) {
   switch (nj) {
-    case 1: return eig_dgemm_kernel<1, 8>;
-    case 2: return eig_dgemm_kernel<2, 8>;
-    case 3: return eig_dgemm_kernel<3, 8>;
-    case 4: return eig_dgemm_kernel<4, 8>;
-    case 5: return eig_dgemm_kernel<5, 8>;
-    case 6: return eig_dgemm_kernel<6, 8>;
-    case 7: return eig_dgemm_kernel<7, 8>;
-    case 8: return eig_dgemm_kernel<8, 8>;
-    case 9: return eig_dgemm_kernel<9, EG_RPT_WIDE>;
-    default: return eig_dgemm_kernel<10, EG_RPT_WIDE>;
+    case 1: return eig_dgemm_mma_kernel<1>;
+    case 2: return eig_dgemm_mma_kernel<2>;
+    case 3: return eig_dgemm_mma_kernel<3>;
+    case 4: return eig_dgemm_mma_kernel<4>;
+    case 5: return eig_dgemm_mma_kernel<5>;
+    case 6: return eig_dgemm_mma_kernel<6>;
+    case 7: return eig_dgemm_mma_kernel<7>;
+    case 8: return eig_dgemm_mma_kernel<8>;
+    case 9: return eig_dgemm_mma_kernel<9>;
+    default: return eig_dgemm_mma_kernel<10>;
   }
 }
 
-size_t gemm_smem(int nj) { return (size_t)(2 * EG_TM * (EG_KT + 2) + 2 * EG_KT * nj * 16) * 8; }
+size_t gemm_smem(int nj) { return (size_t)(2 * EG_TM * (EG_KT + 4) + 2 * EG_KT * (nj * 16 + 4)) * 8; }
 
 // out = alpha * A B + gamma * P + delta * Q with A = [m, k]; k == 0: the element-wise epilogue alone
 void gemm(const Ctx& c, const double* a, int64_t lda, int m, int k, const double* bm, double alpha, const double* pm,

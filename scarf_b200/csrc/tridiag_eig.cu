@@ -23,28 +23,40 @@ __device__ __forceinline__ double group8_sum(double v, unsigned mask) {
   return v;
 }
 
-// number of eigenvalues of the tridiagonal (d, e2 = e^2) below x: sign changes of the characteristic polynomial
-// recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (no division: one FMA on the dependent chain per step;
-// rescaled every eight steps against overflow -- eight steps grow |p| by at most span^8)
-__device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, int n, double x) {
-  double p0 = 1.0, p1 = d[0] - x;
-  int cnt = p1 < 0.0;
+// numbers of eigenvalues of the tridiagonal (d, e2 = e^2) below x[0..3): sign changes of the characteristic polynomial
+// recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (no division: one FMA on the dependent chain per row;
+// rescaled every eight rows against overflow).  Three independent chains per thread: the instruction latency of one
+// chain (~10 cycles per instruction with four warps on the SM) hides behind the other two.
+__device__ __forceinline__ void sturm_count3(const double* __restrict__ d, const double* __restrict__ e2, int n,
+                                             const double (&x)[3], int (&cnt)[3]) {
+  double p0[3], p1[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    p0[c] = 1.0, p1[c] = d[0] - x[c];
+    cnt[c] = p1[c] < 0.0;
+  }
   int i = 1;
   while (i < n) {
     const int stop = min(n, i + 8);
     for (; i < stop; ++i) {
-      double p2 = fma(d[i] - x, p1, -e2[i - 1] * p0);
-      if (p2 == 0.0) p2 = p1 < 0.0 ? 1e-300 : -1e-300;  // a zero counts as a sign change (eigenvalue <= x)
-      cnt += (p2 < 0.0) != (p1 < 0.0);
-      p0 = p1, p1 = p2;
+      const double di = d[i], ei = e2[i - 1];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double p2 = fma(di - x[c], p1[c], -ei * p0[c]);
+        if (p2 == 0.0) p2 = p1[c] < 0.0 ? 1e-300 : -1e-300;  // a zero counts as a sign change (eigenvalue <= x)
+        cnt[c] += (p2 < 0.0) != (p1[c] < 0.0);
+        p0[c] = p1[c], p1[c] = p2;
+      }
     }
-    const double ap = fabs(p1);
-    if (ap > 1e100 || ap < 1e-100) {
-      const double sc = ap > 1.0 ? 1e-100 : 1e100;
-      p0 *= sc, p1 *= sc;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double ap = fabs(p1[c]);
+      if (ap > 1e100 || ap < 1e-100) {
+        const double sc = ap > 1.0 ? 1e-100 : 1e100;
+        p0[c] *= sc, p1[c] *= sc;
+      }
     }
   }
-  return cnt;
 }
 
 // reflectors k with max(0, (k - 6) / 8) == T, applied to the rows t >= T of the column held in xr
@@ -183,16 +195,22 @@ __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double
     }
     __syncthreads();
   }
-  // ---- eigenvalue j (ascending) by bisection on the Sturm count, one thread per eigenvalue: the count is one
-  //      dependent FMA per row, so 64 halvings cost ~64 n FMA latencies; more threads per eigenvalue (multisection)
-  //      were measured slower -- the SM's FP64 rate, not latency, then sets the time ----
+  // ---- eigenvalue j (ascending): one thread per eigenvalue, the bracket is cut in four per round (three interleaved
+  //      Sturm counts); 29 rounds = 58 bits below the Gershgorin span.  More threads per eigenvalue (multisection over
+  //      eight lanes) were measured slower: the SM's FP64 rate, not latency, then sets the time ----
   if (tid < n) {
     const int j = tid;
     double lo = s_scal[1], hi = s_scal[2];
-    for (int it = 0; it < 64; ++it) {
-      const double mid = 0.5 * (lo + hi);
-      if (sturm_count(s_d, s_e2, n, mid) <= j) lo = mid;
-      else hi = mid;
+    for (int it = 0; it < 29; ++it) {
+      const double w = 0.25 * (hi - lo);
+      const double x[3] = {lo + w, lo + 2.0 * w, lo + 3.0 * w};
+      int cnt[3];
+      sturm_count3(s_d, s_e2, n, x, cnt);
+      // count(x) <= j  <=>  x <= lambda_j: the bracket becomes the quarter that holds lambda_j
+      const int q = (cnt[0] <= j) + (cnt[1] <= j) + (cnt[2] <= j);
+      const double nlo = q == 0 ? lo : (q == 1 ? x[0] : (q == 2 ? x[1] : x[2]));
+      hi = q == 0 ? x[0] : (q == 1 ? x[1] : (q == 2 ? x[2] : hi));
+      lo = nlo;
     }
     s_lam[j] = 0.5 * (lo + hi);
   }
@@ -210,7 +228,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double
       x[i] = (double)(st >> 11) * (1.0 / 9007199254740992.0) - 0.5;
     }
     const double tiny = 1e-300;
-    for (int it = 0; it < 3; ++it) {
+    for (int it = 0; it < 2; ++it) {  // two solves reach the accuracy of three (measured; LAPACK's dstein stops on growth)
       // forward elimination with partial pivoting (row i against row i + 1), applied to the right-hand side as it goes
       double di = s_d[0] - lam, ui = n > 1 ? s_e[0] : 0.0, bi = x[0];
       for (int i = 0; i + 1 < n; ++i) {
