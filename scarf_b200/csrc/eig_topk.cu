@@ -13,7 +13,7 @@
 // Kernels (all deterministic: fixed-order reductions, no floating-point atomics -- every rank of a sharded run gets
 // bit-identical loadings from its bit-identical copy of the Gram matrix):
 //   eig_cov_kernel        covariance from the fixed-point Gram (optionally centred on a column mean)
-//   eig_dgemm_kernel      out = alpha A B + gamma P + delta Q, 64-row tiles x all columns, split K with an ordered
+//   eig_dgemm_mma_kernel  out = alpha A B + gamma P + delta Q (DMMA), 64-row tiles x all columns, split K with an ordered
 //                         reduction by the last CTA of a tile (serves the filter steps and the tall x small rotations)
 //   eig_gram_kernel       S = X^T Y over row chunks, ordered reduction by the last CTA of an output tile
 //   eig_chol_kernel       one CTA: column scaling, Cholesky of the b x b Gram in shared memory, triangular inverse
@@ -37,8 +37,6 @@ constexpr int EG_BUFFER = 32;      // columns carried beyond the wanted ones
 constexpr int EG_TM = 64;          // rows of a GEMM tile
 constexpr int EG_KT = 16;          // K step of the GEMM
 constexpr int EG_THREADS = 256;
-
-__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
 // ---------------------------------------------------------------------------------------------- covariance
 // cov = gram_fx * scale - mean_w * mean mean^T   (mean may be null), [h, ldc] row major, pad columns zero
@@ -115,134 +113,13 @@ __global__ void __launch_bounds__(256) eig_init_kernel(double* __restrict__ x, i
 // ---------------------------------------------------------------------------------------------- GEMM
 // out[M, N] = alpha * A[M, K] B[K, N] + gamma * P[M, N] + delta * Q[M, N]      (P, Q may be null)
 // All matrices row major; B, P, Q, out share the row stride ldn (a multiple of 16 >= 16 NJ, pad columns zero).
-// grid = (row tiles of 64, K splits).  A CTA accumulates its K range for the whole width (thread (ty, tx): rows
-// 4 ty .. 4 ty + 3, columns tx + 16 j, j < NJ), writes the partial tile to `part` and bumps the tile's counter; the CTA
-// that arrives last adds the partials in split order and applies the epilogue.
-template <int NJ, int RPT>
-__global__ void __launch_bounds__(16 * (EG_TM / RPT)) eig_dgemm_kernel(const double* __restrict__ a, int64_t lda,
-                                                                      const double* __restrict__ bm, int64_t ldn, int m,
-                                                                      int k, double alpha, const double* __restrict__ pm,
-                                                                      double gamma, const double* __restrict__ qm,
-                                                                      double delta, double* __restrict__ out,
-                                                                      double* __restrict__ part,
-                                                                      unsigned int* __restrict__ counters,
-                                                                      int k_per_split) {
-  constexpr int N = NJ * 16;
-  constexpr int THREADS = 16 * (EG_TM / RPT);
-  constexpr int A_PER = EG_TM * EG_KT / THREADS;  // doubles of the A tile per thread (consecutive k of one row)
-  constexpr int B_PER = EG_KT * N / THREADS;
-  static_assert(A_PER <= EG_KT && EG_KT % A_PER == 0, "A staging");
-  extern __shared__ __align__(16) double eg_smem[];
-  double (*sa)[EG_TM][EG_KT + 2] = reinterpret_cast<double (*)[EG_TM][EG_KT + 2]>(eg_smem);
-  double (*sb)[EG_KT][N] = reinterpret_cast<double (*)[EG_KT][N]>(eg_smem + 2 * EG_TM * (EG_KT + 2));
-  __shared__ unsigned int s_last;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int row0 = blockIdx.x * EG_TM;
-  const int k0 = blockIdx.y * k_per_split, k1 = min(k, k0 + k_per_split);
-  double acc[RPT][NJ];
-#pragma unroll
-  for (int i = 0; i < RPT; ++i)
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0;
-
-  // staging through registers: the global loads of the next tile are in flight during the products of this one
-  const int a_r = tid / (EG_KT / A_PER), a_c = (tid % (EG_KT / A_PER)) * A_PER;
-  double ra[A_PER];
-  double rb[B_PER];
-  auto load_tiles = [&](int kk) {
-    const int gr = row0 + a_r;
-#pragma unroll
-    for (int i = 0; i < A_PER; ++i) {
-      const int gk = kk + a_c + i;
-      ra[i] = (gr < m && gk < k1) ? a[(int64_t)gr * lda + gk] : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < B_PER; ++i) {
-      const int e = tid + THREADS * i;
-      const int br = e / N, bc = e - br * N;
-      const int gk = kk + br;
-      rb[i] = gk < k1 ? bm[(int64_t)gk * ldn + bc] : 0.0;
-    }
-  };
-  auto store_tiles = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < A_PER; ++i) sa[buf][a_r][a_c + i] = ra[i];
-#pragma unroll
-    for (int i = 0; i < B_PER; ++i) {
-      const int e = tid + THREADS * i;
-      const int br = e / N, bc = e - br * N;
-      sb[buf][br][bc] = rb[i];
-    }
-  };
-  int buf = 0;
-  if (k0 < k1) {
-    load_tiles(k0);
-    store_tiles(0);
-  }
-  __syncthreads();
-  for (int kk = k0; kk < k1; kk += EG_KT) {
-    const bool more = kk + EG_KT < k1;
-    if (more) load_tiles(kk + EG_KT);
-#pragma unroll
-    for (int t = 0; t < EG_KT; ++t) {
-      double av[RPT], bv[NJ];
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) av[i] = sa[buf][ty * RPT + i][t];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) bv[j] = sb[buf][t][tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < RPT; ++i)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-    }
-    if (more) store_tiles(buf ^ 1);
-    __syncthreads();
-    buf ^= 1;
-  }
-  const int nsplit = gridDim.y;
-  if (nsplit > 1) {
-    double* mine = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(EG_TM * N);
-#pragma unroll
-    for (int i = 0; i < RPT; ++i)
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) mine[(ty * RPT + i) * N + tx + 16 * j] = acc[i][j];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(counters + blockIdx.x, 1u) == (unsigned)(nsplit - 1) ? 1u : 0u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-#pragma unroll
-    for (int i = 0; i < RPT; ++i)
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) acc[i][j] = 0.0;
-    for (int s = 0; s < nsplit; ++s) {  // fixed order: the sum does not depend on which CTA came last
-      const double* src = part + ((size_t)s * gridDim.x + blockIdx.x) * (size_t)(EG_TM * N);
-#pragma unroll
-      for (int i = 0; i < RPT; ++i)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[i][j] += __ldcg(src + (ty * RPT + i) * N + tx + 16 * j);
-    }
-    if (tid == 0) counters[blockIdx.x] = 0u;  // ready for the next launch
-  }
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    const int gr = row0 + ty * RPT + i;
-    if (gr >= m) continue;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int64_t o = (int64_t)gr * ldn + tx + 16 * j;
-      double v = alpha * acc[i][j];
-      if (pm) v = fma(gamma, pm[o], v);
-      if (qm) v = fma(delta, qm[o], v);
-      out[o] = v;
-    }
-  }
-}
-
-// The same product on the FP64 tensor path (mma.sync m8n8k4, SASS DMMA): a warp instruction does 256 FMAs where a DFMA
-// does 32, and the SM's vector FP64 pipe (32 lanes / clk: 18.6 TFLOP/s on the whole chip) is what bounded the SIMT
-// kernel above at 12.6 TFLOP/s.  Four warps per CTA, warp w owns rows 16 w .. 16 w + 15 of the 64-row tile (two 8-row
+// grid = (row tiles of 64, K splits).  A CTA accumulates its K range for the whole width, writes the partial tile to
+// `part` and bumps the tile's counter; the CTA that arrives last adds the partials in split order and applies the
+// epilogue (deterministic).
+//
+// FP64 tensor path (mma.sync m8n8k4, SASS DMMA): a warp instruction does 256 FMAs where a DFMA does 32.  The SM's vector
+// FP64 pipe (~16-32 lanes / clk) bounded the SIMT version of this kernel (round 2, first half) at 12.6 TFLOP/s; this
+// one reaches 16.8.  Four warps per CTA, warp w owns rows 16 w .. 16 w + 15 of the 64-row tile (two 8-row
 // MMA tiles) x all N columns.  Fragments (PTX ISA): A 8 x 4 row major -- lane holds A[lane / 4][lane % 4]; B 4 x 8 column
 // major -- lane holds B[lane % 4][lane / 4]; C 8 x 8 -- lane holds C[lane / 4][2 (lane % 4) + {0, 1}].  Shared-memory row
 // strides are = 4 (mod 16) doubles so that the 16 lanes of a half warp hit 16 distinct 8-byte banks.
@@ -469,7 +346,7 @@ __global__ void __launch_bounds__(1024, 1) eig_chol_kernel(const double* __restr
   __shared__ double s_tmp[EG_MAXB];
   __shared__ int s_bad;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int ld = b + 1;
+  const int ld = (b + 1) | 1;  // odd row stride: rows and columns are both read without bank conflicts
   const int grp = tid >> 3, sub = tid & 7, ngrp = nt >> 3;  // eight threads share one dot product
   const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
   if (tid == 0) s_bad = 0;
@@ -513,44 +390,104 @@ __global__ void __launch_bounds__(1024, 1) eig_chol_kernel(const double* __restr
       return;
     }
   }
+  // Blocked (left-looking) Cholesky, eight columns at a time -- three CTA barriers per block instead of two per column:
+  //   (1) panel update   P = S'[jb.., jb..jb+8) - L[jb.., 0..jb) L[jb..jb+8, 0..jb)^T, one thread per entry
+  //   (2) the 8 x 8 diagonal block of P factored by warp 0 (row i in lane i, columns exchanged by shuffles)
+  //   (3) the rows below it solved against that block, one thread per row
   double minp = 1e300;
-  // left-looking: column j of L from the finished columns k < j; every row r >= j is one dot product of length j
-  for (int j = 0; j < b; ++j) {
-    for (int r = j + grp; r < b; r += ngrp) {
-      double acc = 0.0;
-      for (int k = sub; k < j; k += 8) acc = fma(sm[r * ld + k], sm[j * ld + k], acc);
+  for (int jb = 0; jb < b; jb += 8) {
+    const int nb = min(8, b - jb);
+    if (jb > 0) {
+      for (int idx = tid; idx < (b - jb) * 8; idx += nt) {
+        const int r = jb + (idx >> 3), cc = idx & 7;
+        if (cc < nb && jb + cc <= r) {
+          const double* lr = sm + (size_t)r * ld;
+          const double* lc = sm + (size_t)(jb + cc) * ld;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          for (int k = 0; k < jb; k += 4) {  // jb is a multiple of 8
+            a0 = fma(lr[k], lc[k], a0);
+            a1 = fma(lr[k + 1], lc[k + 1], a1);
+            a2 = fma(lr[k + 2], lc[k + 2], a2);
+            a3 = fma(lr[k + 3], lc[k + 3], a3);
+          }
+          sm[(size_t)r * ld + jb + cc] -= (a0 + a1) + (a2 + a3);
+        }
+      }
+      __syncthreads();
+    }
+    if (tid < 32) {
+      const int lane = tid, i = lane & 7;  // lanes >= 8 mirror lanes 0..7 (every lane takes part in the shuffles)
+      double d[8];
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
-      if (sub == 0) s_tmp[r] = sm[r * ld + j] - acc;
+      for (int c = 0; c < 8; ++c)
+        d[c] = (i < nb && c <= i) ? sm[(size_t)(jb + i) * ld + jb + c] : (c == i ? 1.0 : 0.0);
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // The scaled matrix has a unit diagonal.  A filtered block may be ill conditioned up to ~1e7 (its Gram 1e14):
+        // tiny positive pivots are expected in the first pass and repaired by the second; only a non-positive (or NaN)
+        // pivot means the factorisation broke down.
+        const double piv = __shfl_sync(SCF_FULL, d[j], j);
+        const bool okp = piv > 0.0;
+        if (j < nb) {
+          bad |= !okp;
+          minp = fmin(minp, piv);
+        }
+        const double inv = okp ? rsqrt(piv) : 0.0;
+        const double lij = i == j ? (okp ? piv * inv : 1.0) : d[j] * inv;  // rows i < j hold zeros in d[j]
+        d[j] = lij;
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) {
+          const double lcj = __shfl_sync(SCF_FULL, lij, c);
+          if (i >= c) d[c] = fma(-lij, lcj, d[c]);
+        }
+      }
+      if (lane < nb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c <= i) sm[(size_t)(jb + i) * ld + jb + c] = d[c];
+        double dii = 1.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c == i) dii = d[c];
+        s_invd[jb + i] = __drcp_rn(dii);
+      }
+      if (lane == 0 && bad) s_bad = 1;
     }
     __syncthreads();
-    // The scaled matrix has a unit diagonal.  A filtered block may be ill conditioned up to ~1e7 (its Gram 1e14): tiny
-    // positive pivots are expected in the first pass and repaired by the second; only a non-positive (or NaN) pivot
-    // means the factorisation broke down.
-    const double piv = s_tmp[j];
-    const bool okp = piv > 0.0;
-    if (!okp && tid == 0) s_bad = 1;
-    minp = fmin(minp, piv);
-    const double inv = okp ? rsqrt(piv) : 0.0;
-    for (int r = j + tid; r < b; r += nt) sm[r * ld + j] = r == j ? (okp ? piv * inv : 1.0) : s_tmp[r] * inv;
+    for (int r = jb + nb + tid; r < b; r += nt) {
+      double x[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) x[c] = c < nb ? sm[(size_t)r * ld + jb + c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < nb) {
+          double a = x[c];
+#pragma unroll
+          for (int k = 0; k < c; ++k) a = fma(-x[k], sm[(size_t)(jb + c) * ld + jb + k], a);
+          x[c] = a * s_invd[jb + c];
+        }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < nb) sm[(size_t)r * ld + jb + c] = x[c];
+    }
     __syncthreads();
   }
-  for (int i = tid; i < b; i += nt) s_invd[i] = __drcp_rn(sm[i * ld + i]);
+  // X = L^-1, one column per group of eight threads (no CTA barrier: the columns are independent, the groups run at
+  // their own pace): X[r][c] = -(sum_{k=c}^{r-1} L[r][k] X[k][c]) / L[r][r], X[k][c] kept at sm[c][k] (upper triangle,
+  // which the factor does not use), X[c][c] = s_invd[c]
+  for (int c = grp; c < b; c += ngrp) {
+    for (int r = c + 1; r < b; ++r) {
+      double acc = 0.0;
+      for (int k = c + sub; k < r; k += 8)
+        acc = fma(sm[(size_t)r * ld + k], k == c ? s_invd[c] : sm[(size_t)c * ld + k], acc);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+      if (sub == 0) sm[(size_t)c * ld + r] = -acc * s_invd[r];
+      __syncwarp(gmask);
+    }
+  }
   __syncthreads();
-  // X = L^-1 row by row (all columns c < r of row r at once): X[r][c] = -(sum_{k=c}^{r-1} L[r][k] X[k][c]) / L[r][r],
-  // X[k][c] kept at sm[c][k] (upper triangle), X[c][c] = s_invd[c]
-  for (int r = 1; r < b; ++r) {
-    for (int c = grp; c < r; c += ngrp) {
-      double acc = 0.0;
-      for (int k = c + sub; k < r; k += 8) acc = fma(sm[r * ld + k], k == c ? s_invd[c] : sm[c * ld + k], acc);
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
-      if (sub == 0) s_tmp[c] = -acc * s_invd[r];
-    }
-    __syncthreads();
-    for (int c = tid; c < r; c += nt) sm[c * ld + r] = s_tmp[c];
-    __syncthreads();
-  }
   // W[i][j] = d_i * (L^-1)[j][i] for i <= j  (upper triangular); (L^-1)[j][i] is stored at (i, j), its diagonal in s_invd
   for (int e = tid; e < b * (int)ldw; e += nt) {
     const int i = e / (int)ldw, j = e - i * (int)ldw;
@@ -679,7 +616,7 @@ struct Layout {
   int b, nj, ldn;
   int64_t ldc;
   int nsplit, k_per_split, row_tiles, gram_chunks, gram_rows, gram_tiles, resid_chunks, resid_rows;
-  size_t off_cov, off_tall[EG_NTALL], off_part, off_gpart, off_s, off_w, off_t, off_u, off_lam, off_theta, off_rowsum,
+  size_t off_cov, off_tall[EG_NTALL], off_part, off_gpart, off_s, off_w, off_t, off_u, off_x, off_lam, off_theta, off_rowsum,
       off_norms, off_rpart, off_d, off_report, off_counters, off_flags, off_minp, total;
 };
 
@@ -716,6 +653,7 @@ bool make_layout(int h, int dims, Layout& L) {
   L.off_w = o, o = al(o + small);
   L.off_t = o, o = al(o + small);
   L.off_u = o, o = al(o + small);
+  L.off_x = o, o = al(o + (size_t)(2 * EG_MAXB * EG_MAXB + EG_MAXB) * 8);  // scratch of the tridiagonal eigensolver
   L.off_lam = o, o = al(o + EG_MAXB * 8);
   L.off_theta = o, o = al(o + EG_MAXB * 8);
   L.off_rowsum = o, o = al(o + (size_t)h * 8);
@@ -799,7 +737,7 @@ int32_t orthonormalise(const Ctx& c, double* y, double* tmp, double** result, bo
     gram(c, src, src, c.p(L.off_s));
     c.launches += robust ? 3 : 1;
     if (!robust) {
-      const size_t smem = (size_t)L.b * (L.b + 1) * 8;
+      const size_t smem = (size_t)L.b * ((L.b + 1) | 1) * 8;
       eig_chol_kernel<<<1, 1024, smem, c.st>>>(c.p(L.off_s), L.ldn, L.b, pass == 0 ? 1e-10 : 0.0, c.p(L.off_w), L.ldn,
                                                 reinterpret_cast<int*>(c.ws + L.off_flags), c.p(L.off_minp));
     } else {
@@ -877,7 +815,7 @@ extern "C" int32_t scf_eig_topk(const int64_t* gram_fx, int64_t ldg, int32_t h, 
   c.h = h, c.dims = dims, c.ws = (unsigned char*)workspace, c.st = (cudaStream_t)stream;
   const int b = L.b;
   cudaError_t e = cudaFuncSetAttribute(eig_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)((size_t)EG_MAXB * (EG_MAXB + 1) * 8));
+                                       (int)((size_t)EG_MAXB * ((EG_MAXB + 1) | 1) * 8));
   if (e == cudaSuccess) e = cudaMemsetAsync(c.ws + L.off_counters, 0, (size_t)(L.row_tiles + L.gram_tiles + 8) * 4, c.st);
   if (e == cudaSuccess) e = cudaMemsetAsync(c.ws + L.off_flags, 0, 64, c.st);
   if (e != cudaSuccess) {
@@ -947,10 +885,10 @@ extern "C" int32_t scf_eig_topk(const int64_t* gram_fx, int64_t ldg, int32_t h, 
       // launched behind it and returns at once unless that result failed its orthogonality check
       int* tri_ok = reinterpret_cast<int*>(c.ws + L.off_flags) + 4;
       if (b >= 3) {
-        rc = tridiag_eig_launch(c.p(L.off_t), b, L.ldn, c.p(L.off_theta), c.p(L.off_u), L.ldn, 1, c.p(L.off_s), tri_ok,
+        rc = tridiag_eig_launch(c.p(L.off_t), b, L.ldn, c.p(L.off_theta), c.p(L.off_u), L.ldn, 1, c.p(L.off_x), tri_ok,
                                 c.st);
         if (rc) return rc;
-        ++c.launches;
+        c.launches += 3;  // tridiagonal solve, back-transformation, check
       }
       rc = jacobi_eig_launch(c.p(L.off_t), b, L.ldn, c.p(L.off_theta), c.p(L.off_u), L.ldn, nullptr, 1,
                              b >= 3 ? tri_ok : nullptr, c.st);

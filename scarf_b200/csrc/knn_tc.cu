@@ -224,9 +224,11 @@ struct KnnTcParams {
   float* cand_score;    // [nq_pad, nlists, KC]  (unsorted)
   int* cand_idx;
   float* cand_tau;      // [nq_pad, nlists]  largest kept score = lower bound of every rejected score
-  int balanced;         // 1: the (query tile, reference tile) space is cut into gridDim.x equal contiguous ranges;
-                        // 2: into gridDim.x contiguous ranges of WHOLE query tiles (no tile is cut: one list per row and half)
-  long long total_work; //    n_q_tiles * n_ref_tiles (balanced mode)
+  int balanced;         // 0: static grid (blockIdx.x = query tile, blockIdx.y = reference range: the collect pass);
+                        // 1: the schedule of SegWalk below
+  int rounds;           //    whole query tiles every unit (CTA / CTA pair) sweeps first, all units in step
+  int units_rem;        //    units that share the remaining query tiles (the others are done after their rounds)
+  long long rem_total;  //    tile steps of the remaining query tiles = (n_q_tiles - rounds * units) * n_ref_tiles
   int nq;               // live query rows (pad rows keep nothing)
   int nref;             // live reference rows (pad rows are rejected by index)
   int flags;            // developer switches (SCF_KNN_FLAGS): 2 = back off in waits
@@ -295,9 +297,18 @@ struct Epi {
 // one warp), so the scan is organised to skip as much as it can with warp-uniform branches: chunks of 16 and groups of
 // 4 columns are visited only when some lane has a candidate in them (one vote each), a visited group costs four
 // predicated appends, and before a group is appended the buffers are drained if one of them could overflow.
-template <int KC, bool SHARED_THR>
-__device__ __forceinline__ void hits32(const uint32_t (&v)[32], float m_lo, float m_hi, int jb, Epi<KC>& ep, float* thr_pub,
-                                       const volatile float* thr_partner) {
+// smallest published threshold of the NSHARE other lists of this thread's row (epilogue thread l ^ 128 j, j = 1..NSHARE)
+template <int NSHARE>
+__device__ __forceinline__ float partner_thr(const volatile float* thr_all, int l) {
+  float m = FLT_MAX;
+#pragma unroll
+  for (int j = 1; j <= NSHARE; ++j) m = fminf(m, thr_all[l ^ (128 * j)]);
+  return m;
+}
+
+template <int KC, int NSHARE>
+__device__ __forceinline__ void hits32(const uint32_t (&v)[32], float m_lo, float m_hi, int jb, Epi<KC>& ep,
+                                       volatile float* thr_all, int l) {
   const bool count = (SCF_KNN_DEBUG & 16) && (threadIdx.x & 31) == 0;
   if (count) atomicAdd(&g_dbg[1], 1ull);
 #pragma unroll
@@ -311,9 +322,9 @@ __device__ __forceinline__ void hits32(const uint32_t (&v)[32], float m_lo, floa
       if (__any_sync(SCF_FULL, ep.cnt > HB - 4)) {
         ep.drain();
         ep.thr = ep.cl.thr;
-        if constexpr (SHARED_THR) {
-          *thr_pub = ep.cl.thr;
-          ep.thr = fminf(ep.thr, *thr_partner);
+        if constexpr (NSHARE > 0) {
+          thr_all[l] = ep.cl.thr;
+          ep.thr = fminf(ep.thr, partner_thr<NSHARE>(thr_all, l));
         }
       }
 #pragma unroll
@@ -328,6 +339,59 @@ __device__ __forceinline__ void hits32(const uint32_t (&v)[32], float m_lo, floa
     }
   }
 }
+
+// The work of one unit (a CTA, or a pair of CTAs) as a sequence of segments (query tile q, reference tiles [t0, t1)).
+// Rounds first: in round r unit u sweeps ALL reference tiles for query tile r * units + u -- every unit is at (about)
+// the same reference tile at the same time, so a tile is fetched from HBM once and served to the other units from L2.
+// (Equal contiguous ranges of the whole (query tile, reference tile) space, the schedule of the first half of round 2,
+// put the units at `units` different places of a reference set that does not fit L2 -- 256 MB at 1M cells -- and every
+// tile load went to HBM: 94 GB of DRAM reads for the 125k x 1M shard, ncu; 1.1 GB with the rounds.)  Then the query
+// tiles that are left (fewer than units) are cut into equal contiguous ranges of tile steps over `units_rem` units, so
+// that all finish together; a tile cut by a range boundary keeps one candidate list per part (slot = this unit's index
+// minus the index of the unit that holds the tile's first step).  Static grid (the collect pass): one segment.
+struct SegWalk {
+  int T, units, u, rounds, r, units_rem, q_rem0;
+  long long cur, w1, rem_total;
+  __device__ __forceinline__ void init(const KnnTcParams& p, int unit, int n_units) {
+    T = p.n_ref_tiles, units = n_units, u = unit, r = 0;
+    if (!p.balanced) {
+      const int tile_begin = (int)blockIdx.y * p.tiles_per_split;
+      const int tile_end = min(tile_begin + p.tiles_per_split, T);
+      rounds = 0, units_rem = 1, q_rem0 = 0, rem_total = 0;
+      cur = (long long)blockIdx.x * T + tile_begin;
+      w1 = cur + max(tile_end - tile_begin, 0);
+      return;
+    }
+    rounds = p.rounds, units_rem = p.units_rem, rem_total = p.rem_total, q_rem0 = p.rounds * n_units;
+    if (u < units_rem) {
+      cur = (long long)u * rem_total / units_rem;
+      w1 = (long long)(u + 1) * rem_total / units_rem;
+    } else {
+      cur = w1 = 0;
+    }
+  }
+  __device__ __forceinline__ bool next(int& q, int& t0, int& t1) {
+    if (r < rounds) {
+      q = r * units + u, t0 = 0, t1 = T, ++r;
+      return true;
+    }
+    if (cur >= w1) return false;
+    q = q_rem0 + (int)(cur / T), t0 = (int)(cur % T);
+    t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
+    cur += t1 - t0;
+    return true;
+  }
+  // list slot of this unit's part of query tile q
+  __device__ __forceinline__ int slot_of(const KnnTcParams& p, int q) const {
+    if (!p.balanced) return (int)blockIdx.y;
+    if (q < q_rem0) return 0;
+    const long long target = (long long)(q - q_rem0) * T;  // first step of the tile: find c with b(c) <= target < b(c + 1)
+    long long c = target * units_rem / rem_total;
+    while (c + 1 < (long long)units_rem && (c + 1) * rem_total / units_rem <= target) ++c;
+    while (c > 0 && c * rem_total / units_rem > target) --c;
+    return u - (int)c;
+  }
+};
 
 // QT query tiles of 128 rows per CTA x reference tiles of BN = 256 / QT rows: QT = 4 (BN = 64) when the operand rows
 // fit one 128-byte swizzle row (Kp = 64: a reference tile is re-used by 512 queries, half the L2 -> shared-memory
@@ -370,35 +434,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   // considers divergent every operand of every MMA goes through an R2UR move: ~100 cycles per instruction, measured)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t backoff = (p.flags & 2) ? 32u : 0u;
-  // Work of this CTA: a contiguous range [w0, w1) of the linearised (query tile, reference tile) space, walked as
-  // segments that stay inside one query tile.  Static grid (blockIdx.x = query tile, blockIdx.y = reference split):
-  // exactly one segment.  Balanced grid: every CTA gets total_work / gridDim.x tile steps, so all SMs finish
-  // together whatever the number of query tiles; a query tile cut by a range boundary keeps one candidate list per
-  // part (slot = this CTA's index minus the index of the CTA that holds the tile's first step).
-  const int T = p.n_ref_tiles;
-  long long w0, w1;
-  if (p.balanced == 2) {
-    const long long qt_all = p.total_work / T;
-    w0 = ((long long)blockIdx.x * qt_all / gridDim.x) * T;
-    w1 = ((long long)(blockIdx.x + 1) * qt_all / gridDim.x) * T;
-  } else if (p.balanced) {
-    w0 = (long long)blockIdx.x * p.total_work / gridDim.x;
-    w1 = (long long)(blockIdx.x + 1) * p.total_work / gridDim.x;
-  } else {
-    const int tile_begin = (int)blockIdx.y * p.tiles_per_split;
-    const int tile_end = min(tile_begin + p.tiles_per_split, T);
-    w0 = (long long)blockIdx.x * T + tile_begin;
-    w1 = w0 + max(tile_end - tile_begin, 0);
-  }
-  auto split_of = [&](int q) -> int {
-    if (!p.balanced) return (int)blockIdx.y;
-    if (p.balanced == 2) return 0;
-    const long long target = (long long)q * T;  // first step of the tile; find c with b(c) <= target < b(c + 1)
-    long long c = target * gridDim.x / p.total_work;
-    while (c + 1 < (long long)gridDim.x && (c + 1) * p.total_work / gridDim.x <= target) ++c;
-    while (c > 0 && c * p.total_work / gridDim.x > target) --c;
-    return (int)blockIdx.x - (int)c;
-  };
+  SegWalk walk;
+  walk.init(p, (int)blockIdx.x, (int)gridDim.x);
 
   if (threadIdx.x == 0) {
     tc::mbar_init(a_full, 1);
@@ -427,10 +464,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     // tcgen05.commit per step instead of one per stage -- a commit stalls the tensor pipe for ~150 cycles (measured).
     // (rel_step, rel_c): the chunk loaded p.stages chunks ago, i.e. the previous user of the stage about to be filled.
     uint32_t loaded = 0, rel_step = 0, rel_c = 0;
-    for (long long cur = w0; cur < w1; ++seg) {
-      const int q = (int)(cur / T), t0 = (int)(cur % T);
-      const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
-      cur += t1 - t0;
+    for (int q, t0, t1; walk.next(q, t0, t1); ++seg) {
       if (seg > 0) tc::mbar_wait(a_empty, (uint32_t)(seg - 1) & 1u, backoff);  // MMAs of the last segment done with sA
       if (leader) {
         tc::mbar_expect_tx(a_full, (uint32_t)(QT * p.kchunks * A_CHUNK_BYTES));
@@ -474,10 +508,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     const uint32_t b_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sB));
     const uint32_t nk_last = (uint32_t)p.ksteps_last, kchunks = (uint32_t)p.kchunks, stages = (uint32_t)p.stages;
     uint32_t s = 0, ph = 0, lt = 0, seg = 0;
-    for (long long cur = w0; cur < w1; ++seg) {
-      const int t0 = (int)(cur % T);
-      const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
-      cur += t1 - t0;
+    for (int q, t0, t1; walk.next(q, t0, t1); ++seg) {
       tc::mbar_wait(a_full, seg & 1u);
       tc::tc_fence_after();
       for (int t = t0; t < t1; ++t, ++lt) {
@@ -517,21 +548,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     const int qt = QT == 4 ? g : (g >> 1);
     const int half = QT == 4 ? 0 : (g & 1);
     const int col0 = half * GCOLS;     // first reference of this thread inside a reference tile
-    float* thr_pub = thr_x + l;
-    const volatile float* thr_partner = thr_x + (l ^ 128);  // same row, other column half (QT = 2): warp w ^ 4
+    volatile float* thr_all = thr_x;  // the other list of this row (QT = 2): thread l ^ 128, warp w ^ 4
     const int pair_id = 1 + (w & 3) + 4 * (w >> 3);
     int lt = 0;
-    for (long long cur = w0; cur < w1;) {
-      const int q = (int)(cur / T), t0 = (int)(cur % T);
-      const int t1 = (int)min((long long)T, (long long)t0 + (w1 - cur));
-      cur += t1 - t0;
+    for (int q, t0, t1; walk.next(q, t0, t1);) {
       const int qrow = q * (QT * BM) + qt * BM + row;
       if constexpr (COLLECT) {
         // fixed per-row threshold, append-only: every reference whose score is below it goes on the row's list
         const float thr = qrow < n_fix ? p.fix_thr[qrow] : -FLT_MAX;
         for (int t = t0; t < t1; ++t, ++lt) {
           const int acc = lt & 1;
-          const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
           tc::mbar_wait(done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
           tc::tc_fence_after();
           const int j0 = t * BN + col0;
@@ -560,7 +586,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
           if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
         }
       } else {
-        const int split = split_of(q);
+        const int split = walk.slot_of(p, q);
         const size_t sub = (size_t)qrow * p.nlists + (size_t)(split * HALVES + half);
         Epi<KC> ep;
         ep.cl.init();
@@ -573,12 +599,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
         ep.nref = p.nref;
         if constexpr (HALVES == 2) {
           // both lists of a row publish the threshold of THIS segment before either reads the other's
-          *thr_pub = ep.cl.thr;
+          thr_all[l] = ep.cl.thr;
           pair_barrier(pair_id);
         }
         for (int t = t0; t < t1; ++t, ++lt) {
           const int acc = lt & 1;
-          const uint32_t acc_ph = (uint32_t)(lt >> 1) & 1u;
           tc::mbar_wait(done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
           tc::tc_fence_after();
           if (SCF_KNN_DEBUG & 32) {  // timing experiment: no accumulator read-out at all
@@ -589,7 +614,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
           }
           const int j0 = t * BN + col0;
           const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + g * GCOLS);
-          if constexpr (HALVES == 2) ep.thr = fminf(ep.cl.thr, *thr_partner);
+          if constexpr (HALVES == 2) ep.thr = fminf(ep.cl.thr, partner_thr<1>(thr_all, l));
           // Two passes of 32 columns through one 32-register buffer (the list itself needs k' registers): minimum of
           // the pass (FMNMX3 tree), one vote; only a pass in which some lane has a candidate is scanned.
           uint32_t v[32];
@@ -601,14 +626,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
             const float m_lo = min16(v), m_hi = min16(v + 16);
             if ((SCF_KNN_DEBUG & 16) && lane == 0) atomicAdd(&g_dbg[0], 1ull);
             if (__any_sync(SCF_FULL, fminf(m_lo, m_hi) < ep.thr))
-              hits32<KC, HALVES == 2>(v, m_lo, m_hi, j0 + 32 * hh, ep, thr_pub, thr_partner);
+              hits32<KC, HALVES == 2 ? 1 : 0>(v, m_lo, m_hi, j0 + 32 * hh, ep, thr_all, l);
           }
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
         }
         ep.drain();
-        if constexpr (HALVES == 2) *thr_pub = ep.cl.thr;
+        if constexpr (HALVES == 2) thr_all[l] = ep.cl.thr;
         // candidates out: [query, list, KC]; the ids are already in place
 #pragma unroll
         for (int e = 0; e < KC; ++e) p.cand_score[sub * KC + e] = ep.cl.r[e];
@@ -621,6 +646,212 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   if (warp == 1) {
     tc::tc_fence_after();
     tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- main, CTA pairs
+// The same search issued by PAIRS of CTAs (a 2-CTA cluster on the two SMs of a TPC, tcgen05 cta_group::2): one
+// M = 256, N = 256 MMA covers 256 queries (128 from each CTA's shared memory) x 256 references (128 from each CTA's
+// shared memory).  An N = 128 single-CTA MMA reads 128 B per clock from shared memory for its operands -- all there
+// is -- so the TMA fill of the reference stages takes bandwidth away from the tensor pipe (measured: 15.7 ms of MMA
+// become 25 ms with the fill at the C3 shape).  In a pair every CTA reads its 128 query rows and HALF of the reference
+// tile per MMA (64 B per clock) and fills half a reference tile per step (32 B per clock): the tensor pipe is the bound.
+// Per CTA: 1 query tile (128 rows) in shared memory, stages of 128 references, 2 accumulator buffers of 256 columns;
+// epilogue warp w reads lane quarter (warp id % 4), columns [64 g, 64 g + 64), g = w / 4: four lists per query row
+// (k' = 16 each: a row fails its guard only when 16 of its k <= 24 neighbours sit in one quarter of a tile), which
+// share their thresholds through shared memory.
+// Roles and barriers as in knn_tc_kernel, except that TMA completions of BOTH CTAs are counted on the leader's (even
+// CTA's) barriers, tcgen05.commit arrives on the barriers of both CTAs (multicast), and the epilogue warps of both
+// CTAs release an accumulator buffer on the leader's barrier.
+template <int KC>
+__global__ void __launch_bounds__(NTHREADS, 1) knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                                                                  const __grid_constant__ CUtensorMap tmap_r,
+                                                                  const KnnTcParams p) {
+  constexpr int BN2 = 256;                 // references per step (pair)
+  constexpr int B_STAGE_BYTES = BM * 128;  // this CTA's half of a reference tile chunk
+  constexpr int LISTS = 4;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;                                        // [kchunks][128 rows x 128 B]
+  unsigned char* sB = sA + (size_t)p.kchunks * A_CHUNK_BYTES;      // [stages][128 rows x 128 B]
+  float* hb_score = reinterpret_cast<float*>(sB + (size_t)p.stages * B_STAGE_BYTES);
+  int* hb_col = reinterpret_cast<int*>(hb_score + (size_t)HB * NL);
+  float* thr_x = reinterpret_cast<float*>(hb_col + (size_t)HB * NL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thr_x + NL);
+  uint64_t* a_full = bars;                 // leader's is used
+  uint64_t* a_empty = bars + 1;            // both (multicast commit)
+  uint64_t* full = bars + 2;               // [stages] leader's is used: bytes of both CTAs
+  uint64_t* done = full + p.stages;        // [NDONE]  both (multicast commit)
+  uint64_t* tmem_empty = done + NDONE;     // [2]      leader's is used: 2 x NEPI_WARPS arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t backoff = (p.flags & 2) ? 32u : 0u;
+  const uint32_t cta_rank = tc::cluster_ctarank();  // 0: leader
+  const int pid = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  SegWalk walk;  // tiles of 256 references
+  walk.init(p, pid, npairs);
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(a_full, 1);
+    tc::mbar_init(a_empty, 1);
+    for (int s = 0; s < p.stages; ++s) tc::mbar_init(full + s, 1);
+    for (int d = 0; d < NDONE; ++d) tc::mbar_init(done + d, 1);
+    for (int a = 0; a < 2; ++a) tc::mbar_init(tmem_empty + a, 2 * NEPI_WARPS);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmap_q);
+    tc::tma_prefetch_desc(&tmap_r);
+  }
+  __syncthreads();
+  tc::cluster_sync();  // the barriers of both CTAs exist before either touches the other's
+  if (warp == 1) tc::tmem_alloc_pair<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // the leader's copies of the barriers both CTAs signal
+  const uint32_t a_full_ld = tc::mapa_u32(tc::smem_u32(a_full), 0);
+  const uint32_t full_ld = tc::mapa_u32(tc::smem_u32(full), 0);
+  const uint32_t tmem_empty_ld = tc::mapa_u32(tc::smem_u32(tmem_empty), 0);
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own query rows, own half of every reference tile) =============
+    const bool leader = tc::elect_one();
+    int seg = 0;
+    uint32_t s = 0, ph = 0;
+    uint32_t loaded = 0, rel_step = 0, rel_c = 0;
+    for (int q, t0, t1; walk.next(q, t0, t1); ++seg) {
+      if (seg > 0) tc::mbar_wait(a_empty, (uint32_t)(seg - 1) & 1u, backoff);
+      if (leader) {
+        if (cta_rank == 0) tc::mbar_expect_tx(a_full, (uint32_t)(2 * p.kchunks * A_CHUNK_BYTES));
+        for (int c = 0; c < p.kchunks; ++c)
+          tc::tma_load_2d_pair(sA + (size_t)c * A_CHUNK_BYTES, &tmap_q, a_full_ld, c * KCH,
+                               q * (2 * BM) + (int)cta_rank * BM);
+      }
+      __syncwarp();
+      for (int t = t0; t < t1; ++t)
+        for (int c = 0; c < p.kchunks; ++c) {
+          if (loaded >= (uint32_t)p.stages) {
+            tc::mbar_wait(done + (rel_step & (NDONE - 1)), (rel_step / NDONE) & 1u, backoff);
+            if (++rel_c == (uint32_t)p.kchunks) rel_c = 0, ++rel_step;
+          }
+          ++loaded;
+          if (leader) {
+            if (SCF_KNN_DEBUG & 128) {  // timing experiment: no reference traffic, the MMAs run on stale tiles
+              if (cta_rank == 0) tc::mbar_arrive(full + s);
+            } else {
+              if (cta_rank == 0) tc::mbar_expect_tx(full + s, 2 * B_STAGE_BYTES);
+              tc::tma_load_2d_pair(sB + (size_t)s * B_STAGE_BYTES, &tmap_r, full_ld + s * 8u, c * KCH,
+                                   t * BN2 + (int)cta_rank * BM);
+            }
+          }
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) s = 0, ph ^= 1u;
+        }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_f16(2 * BM, BN2, false, false);
+      const bool leader = tc::elect_one();
+      const uint32_t a_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sA));
+      const uint32_t b_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sB));
+      const uint32_t nk_last = (uint32_t)p.ksteps_last, kchunks = (uint32_t)p.kchunks, stages = (uint32_t)p.stages;
+      uint32_t s = 0, ph = 0, lt = 0, seg = 0;
+      for (int q, t0, t1; walk.next(q, t0, t1); ++seg) {
+        tc::mbar_wait(a_full, seg & 1u);
+        tc::tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++lt) {
+          const uint32_t acc = lt & 1u;
+          tc::mbar_wait(tmem_empty + acc, ((lt >> 1) & 1u) ^ 1u, backoff);
+          tc::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * (uint32_t)ACC_COLS;
+          for (uint32_t c = 0; c < kchunks; ++c) {
+            tc::mbar_wait(full + s, ph, backoff);
+            tc::tc_fence_after();
+            const uint32_t a_lo = a_lo0 + c * (uint32_t)(A_CHUNK_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + s * (uint32_t)(B_STAGE_BYTES >> 4);
+            const uint32_t nk = c + 1 == kchunks ? nk_last : (uint32_t)(KCH / KSTEP);
+#pragma unroll
+            for (uint32_t kk = 0; kk < (uint32_t)(KCH / KSTEP); ++kk)
+              if (kk < nk && !(SCF_KNN_DEBUG & 64)) {
+                if (leader) tc::umma_f16_lo_pair(d_tmem, a_lo + kk * 2u, b_lo + kk * 2u, idesc, (c | kk) != 0u);
+              }
+            if (++s == stages) s = 0, ph ^= 1u;
+          }
+          if (leader) tc::umma_commit_pair(done + (lt & (NDONE - 1)), 3);
+          __syncwarp();
+        }
+        if (leader) tc::umma_commit_pair(a_empty, 3);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: 64 accumulator columns of one query row per thread =====================
+    const int w = warp - 2;
+    const int quarter = warp & 3;
+    const int g = w >> 2;              // column group: references [64 g, 64 g + 64) of the tile
+    const int l = w * 32 + lane;
+    const int row = quarter * 32 + lane;
+    volatile float* thr_all = thr_x;   // the other three lists of this row: threads l ^ 128, l ^ 256, l ^ 384
+    const int quad_id = 1 + (w & 3);
+    int lt = 0;
+    for (int q, t0, t1; walk.next(q, t0, t1);) {
+      const int qrow = q * (2 * BM) + (int)cta_rank * BM + row;
+      const int split = walk.slot_of(p, q);
+      const size_t sub = (size_t)qrow * p.nlists + (size_t)(split * LISTS + g);
+      Epi<KC> ep;
+      ep.cl.init();
+      if (qrow >= p.nq) ep.cl.thr = -FLT_MAX;
+      ep.thr = ep.cl.thr;
+      ep.cnt = 0;
+      ep.hs = hb_score + l;
+      ep.hc = hb_col + l;
+      ep.gid = p.cand_idx + sub * KC;
+      ep.nref = p.nref;
+      thr_all[l] = ep.cl.thr;
+      asm volatile("bar.sync %0, 128;" ::"r"(quad_id) : "memory");  // all four lists of a row have published
+      for (int t = t0; t < t1; ++t, ++lt) {
+        const int acc = lt & 1;
+        tc::mbar_wait(done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
+        tc::tc_fence_after();
+        if (SCF_KNN_DEBUG & 32) {  // timing experiment: no accumulator read-out at all
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive_cluster(tmem_empty_ld + (uint32_t)acc * 8u);
+          continue;
+        }
+        const int j0 = t * BN2 + g * GCOLS;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + g * GCOLS);
+        ep.thr = fminf(ep.cl.thr, partner_thr<3>(thr_all, l));
+        uint32_t v[32];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          tc::tmem_ld32(t_row + (uint32_t)(32 * hh), v);
+          tc::tmem_ld_wait();
+          if (SCF_KNN_DEBUG & 8) continue;
+          const float m_lo = min16(v), m_hi = min16(v + 16);
+          if (__any_sync(SCF_FULL, fminf(m_lo, m_hi) < ep.thr)) hits32<KC, 3>(v, m_lo, m_hi, j0 + 32 * hh, ep, thr_all, l);
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive_cluster(tmem_empty_ld + (uint32_t)acc * 8u);
+      }
+      ep.drain();
+      thr_all[l] = ep.cl.thr;
+#pragma unroll
+      for (int e = 0; e < KC; ++e) p.cand_score[sub * KC + e] = ep.cl.r[e];
+      p.cand_tau[sub] = ep.cl.thr;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();  // neither CTA leaves (or frees TMEM) while the other may still use its shared memory / barriers
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc_pair<512>(tmem_base);
   }
 }
 
@@ -839,14 +1070,22 @@ int pick_kc(int k) {
 }
 
 struct Plan {
-  int kp, kchunks, kc, qt, bn, halves, stages, nsplit, nlists, tiles_per_split, n_ref_tiles, grid, whole_tiles;
-  long long total_work;
+  int kp, kchunks, kc, qt, bn, halves, stages, nsplit, nlists, tiles_per_split, n_ref_tiles, grid, pair, rounds, units_rem;
+  long long total_work, rem_total;
   int64_t nq_pad, nr_pad;
-  size_t smem;
+  size_t smem, psmem;  // dynamic shared memory: single-CTA kernels / pair kernel
+  int pstages;
   // workspace offsets (bytes)
   size_t off_qop, off_rop, off_qn, off_qe, off_cs, off_ci, off_tau, off_fail, off_fkey, off_misc, off_fix, off_qfix,
       off_fthr, off_fcnt, off_flist, off_rest, off_rkey, total;
 };
+
+// CTA pairs (knn_tc_pair_kernel): measured slower than the single-CTA kernel on every shape of this round (see the
+// kernel's comment), so they are opt-in: SCF_KNN_PAIR = 1 selects them (the tests run both kernels on the same shapes).
+bool use_pair(int) {
+  const char* e = getenv("SCF_KNN_PAIR");  // read per call
+  return e && atoi(e) != 0;
+}
 
 bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.kc = pick_kc(k);
@@ -855,46 +1094,60 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   if (pl.kc == 0 || pl.kchunks > 3) return false;  // k > 24 or dim > 189: method 0 handles those
   pl.qt = 2;  // see knn_tc_kernel (QT = 4 / BN = 64 halves the L2 traffic but an N = 64 MMA runs at 2/3 of the rate)
   pl.bn = ACC_COLS / pl.qt;
-  pl.halves = pl.qt == 2 ? 2 : 1;
+  pl.pair = use_pair(pl.kchunks) ? 1 : 0;
+  pl.halves = pl.pair ? 4 : (pl.qt == 2 ? 2 : 1);
+  if (pl.pair) pl.kc = 16;  // four lists per row
   const int rows = pl.qt * BM;
+  const int ref_step = pl.pair ? 2 * pl.bn : pl.bn;  // references per tile step
   pl.nq_pad = (nq + rows - 1) / rows * rows;
-  pl.nr_pad = (nref + pl.bn - 1) / pl.bn * pl.bn;
-  pl.n_ref_tiles = (int)(pl.nr_pad / pl.bn);
+  pl.nr_pad = (nref + ref_step - 1) / ref_step * ref_step;
+  pl.n_ref_tiles = (int)(pl.nr_pad / ref_step);
   const int64_t q_tiles = pl.nq_pad / rows;
-  // Balanced schedule: the q_tiles x n_ref_tiles tile steps are cut into `grid` equal contiguous ranges (one CTA per
-  // SM, at least 8 steps of 128 references each).  A query tile spans at most nsplit = ceil(T / L) + 1 ranges (L = steps
-  // per range) and keeps one candidate list per range (and column half); with at least as many query tiles as SMs
-  // that is 2.  One list over (nearly) the whole reference range keeps the number of list updates at k' ln(N/k').
+  // Schedule (SegWalk): `rounds` whole query tiles per unit, all units in step, then the remaining query tiles cut into
+  // equal ranges of tile steps over units_rem units.  A remaining tile spans at most nsplit = ceil(T / L) + 1 ranges (L =
+  // steps per range) and keeps one candidate list per range (and column group); the re-rank kernel reads
+  // nsplit * halves * k' <= 32 * MAXU candidates per row, which bounds units_rem from above.
+  const int units_max = pl.pair ? SCF_NUM_SMS / 2 : SCF_NUM_SMS;  // CTAs (pairs of CTAs) that share the work
   const long long work = (long long)q_tiles * pl.n_ref_tiles;
-  long long grid = std::max<long long>(1, std::min<long long>(SCF_NUM_SMS, work / (8 * 128 / pl.bn)));
-  for (;;) {
-    const long long L = work / grid;
-    pl.nsplit = (int)((pl.n_ref_tiles + L - 1) / L) + 1;
-    if (pl.nsplit * pl.halves * pl.kc <= 32 * MAXU || grid == 1) break;
-    --grid;
-  }
-  // Whole-tile schedule: with several query tiles per CTA, ranges of whole tiles cost little balance (the busiest
-  // CTA has ceil(q_tiles / grid) tiles) and no tile is cut: one list per row and column half instead of two -- a cut
-  // tile builds its lists twice (k' ln(N / 2k') updates each): at C2 350 instead of ~250 list updates per query.
-  pl.whole_tiles = 0;
-  if (q_tiles >= 2 * SCF_NUM_SMS) {
-    const long long g2 = SCF_NUM_SMS;
-    const double busiest = (double)((q_tiles + g2 - 1) / g2), mean = (double)q_tiles / (double)g2;
-    if (busiest <= 1.05 * mean) pl.whole_tiles = 1, grid = g2, pl.nsplit = 1;  // (C2, 2.64 tiles per CTA: measured slower)
+  const int units = (int)std::max<long long>(1, std::min<long long>(units_max, work / (8 * 128 / pl.bn)));
+  // rounds (units in step) only when the reference operand is too large to stay in L2 anyway: with a set that fits
+  // (C2: 13 MB) every tile load hits L2 wherever the units are, and equal ranges over the whole space keep all lists
+  // long (measured at C2: 2.53 ms without rounds, 2.62 ms with)
+  const bool fits_l2 = (size_t)pl.nr_pad * pl.kp * 2 <= (size_t)48 << 20;
+  pl.rounds = fits_l2 ? 0 : (int)(q_tiles / units);
+  const long long rem_tiles = q_tiles - (long long)pl.rounds * units;
+  pl.rem_total = rem_tiles * pl.n_ref_tiles;
+  pl.units_rem = 1, pl.nsplit = 1;
+  if (rem_tiles > 0) {
+    long long ur = std::max<long long>(1, std::min<long long>(units, pl.rem_total / (8 * 128 / pl.bn)));
+    for (;;) {
+      const long long L = pl.rem_total / ur;
+      pl.nsplit = (int)((pl.n_ref_tiles + L - 1) / L) + 1;
+      if (pl.nsplit * pl.halves * pl.kc <= 32 * MAXU || ur == 1) break;
+      --ur;
+    }
+    if (ur == 1) pl.nsplit = 1;  // one unit takes whole tiles: never cut
+    pl.units_rem = (int)ur;
   }
   pl.nlists = pl.nsplit * pl.halves;
-  pl.grid = (int)grid;
+  pl.grid = units;
   pl.total_work = work;
   pl.tiles_per_split = pl.n_ref_tiles;
-  auto smem_for = [&](int stages) {
-    return (size_t)pl.qt * pl.kchunks * A_CHUNK_BYTES + (size_t)stages * pl.bn * 128 + (size_t)2 * HB * NL * 4 +
+  auto smem_for = [&](int q_tiles_in_smem, int stages) {
+    return (size_t)q_tiles_in_smem * pl.kchunks * A_CHUNK_BYTES + (size_t)stages * pl.bn * 128 + (size_t)2 * HB * NL * 4 +
            (size_t)NL * 4 + (size_t)(2 + stages + NDONE + 2 + 2) * 8 + 64;
   };
+  // single-CTA layout (main pass without pairs, and the collect pass): QT query tiles in shared memory
   pl.stages = 8;
-  while (pl.stages > 2 && smem_for(pl.stages) + 1024 > 227 * 1024) --pl.stages;
-  pl.smem = smem_for(pl.stages) + 1024;  // slack for the 1024-byte alignment of the swizzled tiles
+  while (pl.stages > 2 && smem_for(pl.qt, pl.stages) + 1024 > 227 * 1024) --pl.stages;
+  pl.smem = smem_for(pl.qt, pl.stages) + 1024;  // slack for the 1024-byte alignment of the swizzled tiles
   // a stage is released when the whole step that read it has completed: more stages than chunks per step are needed
   if (pl.smem > 227 * 1024 || pl.stages < pl.kchunks + 1) return false;
+  // pair layout: one query tile per CTA
+  pl.pstages = 8;
+  while (pl.pstages > 2 && smem_for(1, pl.pstages) + 1024 > 227 * 1024) --pl.pstages;
+  pl.psmem = smem_for(1, pl.pstages) + 1024;
+  if (pl.pair && (pl.psmem > 227 * 1024 || pl.pstages < pl.kchunks + 1)) return false;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t o = 0;
   pl.off_qop = o, o = al(o + (size_t)std::max<int64_t>(pl.nq_pad, 512) * pl.kp * 2);
@@ -1001,7 +1254,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   prm.nq = (int)nq, prm.nref = (int)nref;
   prm.ksteps_last = ((dim + 3 + KSTEP - 1) / KSTEP) - (pl.kchunks - 1) * (KCH / KSTEP);
   prm.tiles_per_split = pl.tiles_per_split, prm.nlists = pl.nlists, prm.cand_score = cs, prm.cand_idx = ci, prm.cand_tau = ctau;
-  prm.balanced = pl.whole_tiles ? 2 : 1, prm.total_work = pl.total_work;
+  prm.balanced = 1, prm.rounds = pl.rounds, prm.units_rem = pl.units_rem, prm.rem_total = pl.rem_total;
   // list slots that no range fills (a query tile that is not cut uses one of its nsplit slots): ids -1, tau "nothing rejected"
   e = cudaMemsetAsync(ci, 0xFF, (size_t)pl.nq_pad * pl.nlists * pl.kc * 4, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(ctau, 0x7F, (size_t)pl.nq_pad * pl.nlists * 4, stream);
@@ -1014,14 +1267,31 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     prm.flags = f ? atoi(f) : 2;
   }
   prm.fail_count = nullptr, prm.fix_thr = nullptr, prm.fix_cnt = nullptr, prm.fix_list = nullptr;
-  KnnKernel kern = pick_kernel(pl.kc, pl.qt, false);
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  KnnKernel kern = pl.pair ? (KnnKernel)knn_tc_pair_kernel<16> : pick_kernel(pl.kc, pl.qt, false);
+  const size_t main_smem = pl.pair ? pl.psmem : pl.smem;
+  if (pl.pair) prm.stages = pl.pstages;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem);
   if (e != cudaSuccess) {
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
   if (g_time_start) cudaEventRecord((cudaEvent_t)g_time_start, stream);
-  kern<<<dim3((unsigned)pl.grid), NTHREADS, pl.smem, stream>>>(tq, tr, prm);
+  if (pl.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * (unsigned)pl.grid), cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = main_smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, tq, tr, prm);
+    if (e != cudaSuccess) {
+      scf_set_error("scf_knn_l2(pair launch): %s", cudaGetErrorString(e));
+      return -(int32_t)e;
+    }
+  } else {
+    kern<<<dim3((unsigned)pl.grid), NTHREADS, pl.smem, stream>>>(tq, tr, prm);
+  }
   if (g_time_stop) cudaEventRecord((cudaEvent_t)g_time_stop, stream);
   g_time_start = g_time_stop = nullptr;  // one shot
   rc = scf_check_launch("scf_knn_l2(tcgen05)");
@@ -1052,10 +1322,12 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   if (rc) return rc;
   KnnTcParams fp = prm;
   fp.nq = FIXTC_ROWS;
-  fp.balanced = 0, fp.total_work = 0;  // collect pass: static (query tile, reference split) grid
-  int fsplit = std::max(1, std::min(FIXTC_NSPLIT, pl.n_ref_tiles));
-  fp.tiles_per_split = (pl.n_ref_tiles + fsplit - 1) / fsplit;
-  fsplit = (pl.n_ref_tiles + fp.tiles_per_split - 1) / fp.tiles_per_split;
+  fp.balanced = 0;  // collect pass: static (query tile, reference split) grid
+  fp.stages = pl.stages;
+  fp.n_ref_tiles = (int)(pl.nr_pad / pl.bn);  // tiles of 128 references (the pair kernel walks tiles of 256)
+  int fsplit = std::max(1, std::min(FIXTC_NSPLIT, fp.n_ref_tiles));
+  fp.tiles_per_split = (fp.n_ref_tiles + fsplit - 1) / fsplit;
+  fsplit = (fp.n_ref_tiles + fp.tiles_per_split - 1) / fp.tiles_per_split;
   fp.fail_count = fail_count, fp.fix_thr = fix_thr, fp.fix_cnt = fix_cnt, fp.fix_list = fix_list;
   KnnKernel fkern = pick_kernel(16, pl.qt, true);
   e = cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);

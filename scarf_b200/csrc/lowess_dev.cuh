@@ -16,7 +16,7 @@ __device__ __forceinline__ void lowess_block(const double* __restrict__ endog, c
                                              const uint8_t* __restrict__ valid, int n_in, double frac, int it,
                                              int cache_tri, double* __restrict__ out, double* dyn) {
   constexpr int kMaxN = kLowessMaxN, kThreads = kLowessThreads;
-  __shared__ double x[kMaxN], y[kMaxN], fit[kMaxN], rw[kMaxN], r[kMaxN];
+  __shared__ double x[kMaxN], y[kMaxN], fit[kMaxN], rw[kMaxN], r[kMaxN], prev[kMaxN];
   __shared__ int src[kMaxN], lefts[kMaxN], first[kMaxN];
   __shared__ int s_n;
   __shared__ double s_med[2];
@@ -62,6 +62,9 @@ __device__ __forceinline__ void lowess_block(const double* __restrict__ endog, c
     }
   }
   __syncthreads();
+  double still = 0.0;  // 2^-46 of the largest |y|: a fit that moves less than this has converged
+  for (int i = 0; i < n; ++i) still = fmax(still, fabs(y[i]));
+  still *= 0x1p-46;
   // tricube weights do not change between the robustness passes: kept in shared memory when n * k values fit
   // (always for the 200 x 20 problem of mark_hvgs), recomputed otherwise.  wn = this pass's normalised weights.
   const bool cached = cache_tri != 0;
@@ -139,7 +142,17 @@ __device__ __forceinline__ void lowess_block(const double* __restrict__ endog, c
     for (int i = tid; i < n; i += kThreads) {
       if (first[i] != i) fit[i] = fit[first[i]];
     }
-    __syncthreads();
+    // The robustness iteration contracts (the fit moves ~3x less from one pass to the next) until it reaches the
+    // rounding jitter of the window sums (~3e-15 of the data's scale, where it wanders for the rest of the `it` passes
+    // statsmodels always runs).  Once no point has moved by more than 2^-46 of the scale the remaining passes are
+    // skipped: what they would still change is below the 1e-13 agreement of this routine with the host / reference
+    // fit.  (The barrier also publishes the tied points' values.)
+    int moved = 0;
+    for (int i = tid; i < n; i += kThreads) {
+      moved |= !(fabs(__dsub_rn(fit[i], prev[i])) <= still);  // NaN counts as moved
+      prev[i] = fit[i];
+    }
+    if (!__syncthreads_or(moved) && pass > 0) break;
     if (pass == it) break;  // the weights of a further pass are never used
     for (int i = tid; i < n; i += kThreads) r[i] = fabs(__dsub_rn(y[i], fit[i]));
     __syncthreads();

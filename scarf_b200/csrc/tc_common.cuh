@@ -201,6 +201,67 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster on the SMs of one TPC issue ONE M = 256 MMA: each provides its 128 rows of A and half of the
+// columns of B from its own shared memory (same offsets in both), the accumulator rows land in each CTA's own TMEM.
+// Only the even CTA of the pair (the leader) issues the instruction; completion is multicast to barriers of both.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on the barrier at
+// `bar_cluster_addr` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {  // one full warp of EACH CTA (same warp index)
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_lo_pair(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_K_SW128)
+      : "memory");
+}
+// all MMAs issued so far by this thread: one arrival on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -1,11 +1,12 @@
-// All eigenpairs of a small symmetric matrix (n <= 160) in ONE CTA, the fast path of the Rayleigh-Ritz steps of
-// scf_eig_topk (eig_topk.cu): Householder tridiagonalisation in shared memory, eigenvalues by multisection on the Sturm
-// count, eigenvectors by inverse iteration (one thread per vector, Gaussian elimination with partial pivoting as in
-// LAPACK dstein / dlagtf), back-transformation with the stored reflectors.  ~0.15 ms at n = 128, where the one-sided
-// Jacobi kernel (jacobi_eig.cu) needs 2.3 ms: a Jacobi sweep is n - 1 dependent steps of ~2,500 cycles on one SM and
-// eight sweeps are needed.  Inverse iteration without re-orthogonalisation is accurate while the eigenvalues are
-// separated by more than ~1e-7 |T| (cross-contamination eps |T| / gap); the kernel measures the orthogonality of what it
-// produced and reports it in `ok`: the caller then runs the Jacobi kernel, which returns at once when *ok == 1.
+// All eigenpairs of a small symmetric matrix (n <= 160), the fast path of the Rayleigh-Ritz steps of scf_eig_topk
+// (eig_topk.cu).  One CTA: Householder tridiagonalisation in shared memory, eigenvalues by multisection on the Sturm
+// count, eigenvectors of the tridiagonal matrix by inverse iteration (one thread per vector, Gaussian elimination with
+// partial pivoting as in LAPACK dstein / dlagtf).  Then, over the whole GPU: back-transformation with the stored
+// reflectors (one warp per vector) and an orthogonality check.  The one-sided Jacobi kernel (jacobi_eig.cu) needs
+// 2.3 ms at n = 128: a Jacobi sweep is n - 1 dependent steps of ~2,500 cycles on one SM and eight sweeps are needed.
+// Inverse iteration without re-orthogonalisation is accurate while the eigenvalues are separated by more than
+// ~1e-7 |T| (cross-contamination eps |T| / gap); the check kernel measures the orthogonality of the result and reports
+// it in `ok`: the caller then runs the Jacobi kernel, which returns at once when *ok == 1.
 // Deterministic: fixed reduction orders, seeded start vectors.
 #include <math.h>
 #include <stdlib.h>
@@ -13,7 +14,7 @@
 
 namespace {
 
-__device__ long long g_te_clk[8];  // developer timing (SCF_EIG_DEBUG=1): cycles of the phases of the last launch
+__device__ long long g_te_clk[12];  // developer timing (SCF_EIG_DEBUG=1): cycles of the phases of the last launch
 constexpr int TE_MAXN = 160;
 constexpr int TE_THREADS = 1024;
 
@@ -24,76 +25,69 @@ __device__ __forceinline__ double group8_sum(double v, unsigned mask) {
 }
 
 // numbers of eigenvalues of the tridiagonal (d, e2 = e^2) below x[0..3): sign changes of the characteristic polynomial
-// recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (no division: one FMA on the dependent chain per row;
-// rescaled every eight rows against overflow).  Three independent chains per thread: the instruction latency of one
-// chain (~10 cycles per instruction with four warps on the SM) hides behind the other two.
+// recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (no division).  The SM's vector FP64 pipe issues a warp
+// instruction every ~8 cycles per scheduler (16 lanes per clock and SM on this part), so the phase costs three FP64
+// instructions per row and sequence plus whatever latency is not hidden: three sequences per thread are interleaved,
+// and the sign bookkeeping (an exact zero takes the sign opposite to its predecessor, i.e. counts as a change: the next
+// value, -e^2 p_{i-1}, then has that sign and adds none) runs on the high words in the integer pipe, off the FP64
+// chain.  e2 must be > 0 (the caller clamps it): with an exact zero a vanishing value would stay zero.  Rescaled every
+// eight rows against overflow.
 __device__ __forceinline__ void sturm_count3(const double* __restrict__ d, const double* __restrict__ e2, int n,
                                              const double (&x)[3], int (&cnt)[3]) {
   double p0[3], p1[3];
+  int h1[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     p0[c] = 1.0, p1[c] = d[0] - x[c];
-    cnt[c] = p1[c] < 0.0;
+    h1[c] = __double2hiint(p1[c]);
+    cnt[c] = (unsigned)h1[c] >> 31;
   }
+  auto step = [&](int i) {
+    const double di = d[i], ei = e2[i - 1];
+    double p2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p2[c] = fma(di - x[c], p1[c], -ei * p0[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int h2 = __double2hiint(p2[c]);
+      const bool zero = (((unsigned)h2 << 1) | (unsigned)__double2loint(p2[c])) == 0u;
+      h2 = zero ? (h1[c] ^ (int)0x80000000) : h2;
+      cnt[c] += (unsigned)(h2 ^ h1[c]) >> 31;
+      p0[c] = p1[c], p1[c] = p2[c], h1[c] = h2;
+    }
+  };
   int i = 1;
   while (i < n) {
-    const int stop = min(n, i + 8);
-    for (; i < stop; ++i) {
-      const double di = d[i], ei = e2[i - 1];
+    if (i + 8 <= n) {  // eight rows unrolled: their loads of d / e2 are issued together
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        double p2 = fma(di - x[c], p1[c], -ei * p0[c]);
-        if (p2 == 0.0) p2 = p1[c] < 0.0 ? 1e-300 : -1e-300;  // a zero counts as a sign change (eigenvalue <= x)
-        cnt[c] += (p2 < 0.0) != (p1[c] < 0.0);
-        p0[c] = p1[c], p1[c] = p2;
-      }
+      for (int u = 0; u < 8; ++u) step(i + u);
+      i += 8;
+    } else {
+      for (; i < n; ++i) step(i);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const double ap = fabs(p1[c]);
-      if (ap > 1e100 || ap < 1e-100) {
-        const double sc = ap > 1.0 ? 1e-100 : 1e100;
+      const unsigned ex = ((unsigned)h1[c] >> 20) & 0x7FFu;  // biased exponent: rescale outside 2^+-332 (~1e+-100)
+      if (ex > 1023u + 332u || (ex < 1023u - 332u && ex != 0u)) {
+        const double sc = ex > 1023u ? 1e-100 : 1e100;
         p0[c] *= sc, p1[c] *= sc;
       }
     }
   }
 }
 
-// reflectors k with max(0, (k - 6) / 8) == T, applied to the rows t >= T of the column held in xr
-template <int T, int RMAX>
-__device__ __forceinline__ void bt_range(double (&xr)[RMAX], const double* __restrict__ A, int ld, int n, int sub,
-                                         unsigned gmask) {
-  const int k_hi = min(n - 3, T == RMAX - 1 ? n - 3 : 8 * T + 13), k_lo = T == 0 ? 0 : 8 * T + 6;
-  for (int k = k_hi; k >= k_lo; --k) {
-    const double* vcol = A + (size_t)(k + 1) * ld + k;  // v_i = vcol[i * ld], row k + 1 + i
-    double dot = 0.0;
-#pragma unroll
-    for (int t = T; t < RMAX; ++t) {
-      const int r = sub + 8 * t;
-      if (r > k && r < n) dot = fma(vcol[(size_t)(r - k - 1) * ld], xr[t], dot);
-    }
-    dot = 2.0 * group8_sum(dot, gmask);
-#pragma unroll
-    for (int t = T; t < RMAX; ++t) {
-      const int r = sub + 8 * t;
-      if (r > k && r < n) xr[t] = fma(-dot, vcol[(size_t)(r - k - 1) * ld], xr[t]);
-    }
-  }
-}
-template <int T, int RMAX>
-__device__ __forceinline__ void bt_sweep(double (&xr)[RMAX], const double* __restrict__ A, int ld, int n, int sub,
-                                         unsigned gmask) {
-  bt_range<T, RMAX>(xr, A, ld, n, sub, gmask);
-  if constexpr (T > 0) bt_sweep<T - 1, RMAX>(xr, A, ld, n, sub, gmask);
-}
-
+// NT > 0: n <= 8 NT <= 128, the matrix lives in REGISTERS during the tridiagonalisation (eight threads per row, thread
+// (row i, sub) holds the columns sub + 8 t, t < NT); NT == 0: n <= 160, the matrix in shared memory ([n][n + 1] doubles
+// of dynamic shared memory).  Reflector k is stored as H_k = I - tau_k u u^T: u in vwork[k * n ..], tau_k in tauwork[k].
+template <int NT>
 __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double* __restrict__ a, int n, int64_t lda,
-                                                                   double* __restrict__ evals,
-                                                                   double* __restrict__ evecs, int64_t ldv,
-                                                                   int descending, double* __restrict__ work,
-                                                                   int* __restrict__ ok) {
-  extern __shared__ __align__(16) double A[];  // [n][n + 1]
+                                                                   double* __restrict__ evals, int descending,
+                                                                   double* __restrict__ xwork,
+                                                                   double* __restrict__ vwork,
+                                                                   double* __restrict__ tauwork, int* __restrict__ ok) {
+  extern __shared__ __align__(16) double A[];  // [n][n + 1] (NT == 0)
   __shared__ double s_d[TE_MAXN], s_e[TE_MAXN], s_e2[TE_MAXN], s_v[TE_MAXN], s_p[TE_MAXN], s_q[TE_MAXN];
+  __shared__ double s_x[2][128];  // NT > 0: the pivot column of the current / next step
   __shared__ double s_lam[TE_MAXN];
   __shared__ double s_red[32];
   __shared__ double s_scal[4];
@@ -101,11 +95,6 @@ __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double
   const int ld = n + 1;
   const int grp = tid >> 3, sub = tid & 7;
   const unsigned gmask = 0xFFu << (lane & ~7);
-  for (int e = tid; e < n * n; e += TE_THREADS) {
-    const int r = e / n, c = e - r * n;
-    A[r * ld + c] = 0.5 * (a[(int64_t)r * lda + c] + a[(int64_t)c * lda + r]);
-  }
-  __syncthreads();
   long long t_prev = clock64();
   auto stamp = [&](int slot) {
     if (tid == 0) {
@@ -114,56 +103,157 @@ __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double
       t_prev = t;
     }
   };
-
-  // ---- Householder tridiagonalisation: A <- H_k A H_k, H_k = I - 2 v v^T on rows / columns k+1 .. n-1 ----
-  for (int k = 0; k + 2 < n; ++k) {
-    const int m = n - k - 1;
-    double* col = A + (size_t)(k + 1) * ld + k;  // x_i = col[i * ld]
-    if (warp == 0) {
-      double s = 0.0;
-      for (int i = lane; i < m; i += 32) s = fma(col[i * ld], col[i * ld], s);
-      s = warp_sum(s);
-      const double x0 = col[0];
-      const double alpha = s > 0.0 ? -copysign(sqrt(s), x0) : 0.0;
-      const double v0 = x0 - alpha;
-      const double vn2 = s - x0 * x0 + v0 * v0;  // |v|^2
-      const double inv = vn2 > 0.0 ? rsqrt(vn2) : 0.0;
-      for (int i = lane; i < m; i += 32) s_v[i] = (i == 0 ? v0 : col[i * ld]) * inv;
-      if (lane == 0) s_scal[0] = alpha;
+  if constexpr (NT > 0) {
+    // ---- Householder tridiagonalisation, matrix in registers: step k applies H_k = I - tau u u^T (u = x - alpha e_1, x the
+    //      column k below the diagonal) from both sides to the trailing block S.  Four phases, a CTA barrier after each:
+    //        1  warp 0: |x|^2, alpha, tau, u -> shared memory          3  warp 0: K = tau / 2 u^T p, q = p - K u
+    //        2  p = tau S u (eight threads per row)                     4  S -= u q^T + q u^T; the owners of column k + 1
+    //                                                                      publish it as the next step's x
+    //      The vector FP64 rate of the SM (~16 lanes per clock on this part) bounds phases 2 and 4; scalars are therefore
+    //      computed ONCE (by warp 0) -- every warp computing them for itself to save the barriers costs more FP64 issue
+    //      slots than the matrix work.  Shared memory sees vectors only (eight distinct words per warp and load); the
+    //      shared-memory version below spends its time in bank conflicts on the matrix rows.
+    const int i = grp;  // this thread's row
+    double am[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int j = sub + 8 * t;
+      am[t] = (i < n && j < n) ? 0.5 * (a[(int64_t)i * lda + j] + a[(int64_t)j * lda + i]) : 0.0;
+    }
+    double* s_u = s_v;  // names of the shared-memory version's vectors reused
+    if (tid < 128) s_x[0][tid] = 0.0, s_x[1][tid] = 0.0;
+    for (int j = tid; j < TE_MAXN; j += TE_THREADS) s_p[j] = 0.0, s_q[j] = 0.0, s_u[j] = 0.0;
+    __syncthreads();
+    if (sub == 0 && i < n) s_x[0][i] = am[0];  // column 0
+    __syncthreads();
+    for (int k = 0; k + 2 < n; ++k) {
+      const double* x = s_x[k & 1];
+      const int k1 = k + 1;
+      const int t0 = k1 >> 3;                   // the columns of the register slots t < t0 are all <= k: dead
+      const bool live_warp = 4 * warp + 3 > k;  // some row of this warp is > k
+      // ---- 1 ----
+      if (warp == 0) {
+        double s = 0.0;
+        for (int r = k1 + lane; r < n; r += 32) s = fma(x[r], x[r], s);
+        s = warp_sum(s);
+        const double x0 = x[k1];
+        double alpha = 0.0, tau = 0.0;
+        if (s > 0.0) {
+          const double rs = rsqrt(s);
+          double sq = s * rs;
+          sq = fma(fma(-sq, sq, s), 0.5 * rs, sq);  // sqrt(s): one Newton step on s * rsqrt(s)
+          alpha = x0 >= 0.0 ? -sq : sq;
+          tau = 1.0 / fma(fabs(x0), sq, s);         // 2 / |u|^2, |u|^2 = 2 (s + |x0| sqrt(s))
+        }
+        for (int r = k + lane; r < n; r += 32) {
+          const double ur = r > k1 ? x[r] : (r == k1 ? x0 - alpha : 0.0);
+          s_u[r] = ur;
+          if (r > k) vwork[(size_t)k * n + (r - k1)] = ur;  // reflector k: rows k + 1 ...
+        }
+        if (lane == 0) s_scal[0] = tau, s_e[k] = alpha, tauwork[k] = tau;
+      }
+      __syncthreads();
+      // ---- 2 ----
+      const double tau = s_scal[0];
+      if (live_warp) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          if (t < t0) continue;
+          const double uj = s_u[sub + 8 * t];  // zero for the columns <= k
+          if (t & 1) a1 = fma(am[t], uj, a1);
+          else a0 = fma(am[t], uj, a0);
+        }
+        const double pi = tau * group8_sum(a0 + a1, gmask);
+        if (sub == 0) s_p[i] = i > k ? pi : 0.0;
+      }
+      __syncthreads();
+      // ---- 3 ----
+      if (warp == 0) {
+        double kk = 0.0;
+        for (int r = k1 + lane; r < n; r += 32) kk = fma(s_u[r], s_p[r], kk);
+        kk = 0.5 * tau * warp_sum(kk);
+        for (int r = k + lane; r < n; r += 32) s_q[r] = r > k ? fma(-kk, s_u[r], s_p[r]) : 0.0;
+      }
+      __syncthreads();
+      // ---- 4 ----
+      if (live_warp) {
+        const double ui = i > k ? s_u[i] : 0.0, qi = i > k ? s_q[i] : 0.0;
+        const int tsel = (sub == (k1 & 7)) ? t0 : -1;  // the register slot that holds column k + 1
+        double* xn = s_x[k1 & 1];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          if (t < t0) continue;
+          const int j = sub + 8 * t;
+          am[t] = fma(-ui, s_q[j], fma(-qi, s_u[j], am[t]));  // u, q are zero for the columns <= k
+          if (t == tsel && i > k1) xn[i] = am[t];             // column k + 1 of the rows below: the next step's x
+        }
+      }
+      __syncthreads();
+    }
+    stamp(0);
+    // the tridiagonal matrix: the diagonal entries are final once their row has left the trailing block
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int j = sub + 8 * t;
+      if (i < n && j == i) s_d[i] = am[t];
+      if (i == n - 1 && j == n - 2) s_e[n - 2] = am[t];
+    }
+  } else {
+    for (int e = tid; e < n * n; e += TE_THREADS) {
+      const int r = e / n, c = e - r * n;
+      A[r * ld + c] = 0.5 * (a[(int64_t)r * lda + c] + a[(int64_t)c * lda + r]);
     }
     __syncthreads();
-    // p = S v, S = A[k+1.., k+1..]; eight threads per row
-    for (int i = grp; i < m; i += TE_THREADS / 8) {
-      const double* row = A + (size_t)(k + 1 + i) * ld + (k + 1);
-      double acc = 0.0;
-      for (int j = sub; j < m; j += 8) acc = fma(row[j], s_v[j], acc);
-      acc = group8_sum(acc, gmask);
-      if (sub == 0) s_p[i] = acc;
-    }
     __syncthreads();
-    // K = v^T p (every warp computes it for itself), q = 2 (p - K v)
-    {
-      double kk = 0.0;
-      for (int i = lane; i < m; i += 32) kk = fma(s_v[i], s_p[i], kk);
-      kk = warp_sum(kk);
-      for (int i = tid; i < m; i += TE_THREADS) s_q[i] = 2.0 * (s_p[i] - kk * s_v[i]);
+    for (int k = 0; k + 2 < n; ++k) {
+      const int m = n - k - 1;
+      double* col = A + (size_t)(k + 1) * ld + k;  // x_i = col[i * ld]
+      if (warp == 0) {
+        double s = 0.0;
+        for (int i = lane; i < m; i += 32) s = fma(col[i * ld], col[i * ld], s);
+        s = warp_sum(s);
+        const double x0 = col[0];
+        const double alpha = s > 0.0 ? -copysign(sqrt(s), x0) : 0.0;
+        const double v0 = x0 - alpha;
+        const double vn2 = s - x0 * x0 + v0 * v0;  // |v|^2
+        const double inv = vn2 > 0.0 ? rsqrt(vn2) : 0.0;
+        for (int i = lane; i < m; i += 32) s_v[i] = (i == 0 ? v0 : col[i * ld]) * inv;
+        if (lane == 0) s_scal[0] = alpha;
+      }
+      __syncthreads();
+      // p = S v, S = A[k+1.., k+1..]; eight threads per row
+      for (int i = grp; i < m; i += TE_THREADS / 8) {
+        const double* row = A + (size_t)(k + 1 + i) * ld + (k + 1);
+        double acc = 0.0;
+        for (int j = sub; j < m; j += 8) acc = fma(row[j], s_v[j], acc);
+        acc = group8_sum(acc, gmask);
+        if (sub == 0) s_p[i] = acc;
+      }
+      __syncthreads();
+      // K = v^T p (every warp computes it for itself), q = 2 (p - K v)
+      {
+        double kk = 0.0;
+        for (int i = lane; i < m; i += 32) kk = fma(s_v[i], s_p[i], kk);
+        kk = warp_sum(kk);
+        for (int i = tid; i < m; i += TE_THREADS) s_q[i] = 2.0 * (s_p[i] - kk * s_v[i]);
+      }
+      __syncthreads();
+      // S -= v q^T + q v^T; the reflector replaces column k below the sub-diagonal, e_k = alpha
+      for (int i = grp; i < m; i += TE_THREADS / 8) {  // eight threads per row, no index arithmetic per element
+        double* row = A + (size_t)(k + 1 + i) * ld + (k + 1);
+        const double vi = s_v[i], qi = s_q[i];
+        for (int j = sub; j < m; j += 8) row[j] -= fma(vi, s_q[j], qi * s_v[j]);
+      }
+      for (int i = tid; i < m; i += TE_THREADS) vwork[(size_t)k * n + i] = s_v[i];  // reflector k: rows k + 1 + i
+      if (tid == 0) s_e[k] = s_scal[0], tauwork[k] = 2.0;  // unit vector: H = I - 2 v v^T
+      __syncthreads();
     }
-    __syncthreads();
-    // S -= v q^T + q v^T; the reflector replaces column k below the sub-diagonal, e_k = alpha
-    for (int i = grp; i < m; i += TE_THREADS / 8) {  // eight threads per row, no index arithmetic per element
-      double* row = A + (size_t)(k + 1 + i) * ld + (k + 1);
-      const double vi = s_v[i], qi = s_q[i];
-      for (int j = sub; j < m; j += 8) row[j] -= fma(vi, s_q[j], qi * s_v[j]);
-    }
-    for (int i = tid; i < m; i += TE_THREADS) col[i * ld] = s_v[i];
-    if (tid == 0) s_e[k] = s_scal[0];
-    __syncthreads();
+    stamp(0);
+    for (int i = tid; i < n; i += TE_THREADS) s_d[i] = A[i * ld + i];
+    if (tid == 0 && n >= 2) s_e[n - 2] = A[(size_t)(n - 1) * ld + (n - 2)];
   }
-  stamp(0);
-  for (int i = tid; i < n; i += TE_THREADS) s_d[i] = A[i * ld + i];
-  if (tid == 0 && n >= 2) s_e[n - 2] = A[(size_t)(n - 1) * ld + (n - 2)];
   __syncthreads();
-  for (int i = tid; i < n; i += TE_THREADS) s_e2[i] = i + 1 < n ? s_e[i] * s_e[i] : 0.0;
   // Gershgorin bounds of the spectrum
   {
     double lo = 1e300, hi = -1e300;
@@ -176,7 +266,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double
       lo = fmin(lo, __shfl_xor_sync(SCF_FULL, lo, o));
       hi = fmax(hi, __shfl_xor_sync(SCF_FULL, hi, o));
     }
-    __syncthreads();  // s_e2 complete, s_red free
+    __syncthreads();  // s_red free
     if (lane == 0) s_red[warp] = lo;
     __syncthreads();
     if (tid == 0) {
@@ -192,12 +282,20 @@ __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double
       for (int w = 0; w < TE_THREADS / 32; ++w) h2 = fmax(h2, s_red[w]);
       const double span = fmax(h2 - s_scal[1], 1e-300);
       s_scal[2] = h2 + 1e-12 * span, s_scal[1] -= 1e-12 * span;
+      s_scal[3] = span;
     }
+    __syncthreads();
+    // squared off-diagonals, kept above (1e-18 span)^2: moves no eigenvalue by more than 1e-18 span and keeps the
+    // recurrence of the Sturm count from sticking at zero when the matrix splits exactly
+    for (int i = tid; i < n; i += TE_THREADS)
+      s_e2[i] = i + 1 < n ? fmax(s_e[i] * s_e[i], 1e-36 * s_scal[3] * s_scal[3]) : 0.0;
     __syncthreads();
   }
   // ---- eigenvalue j (ascending): one thread per eigenvalue, the bracket is cut in four per round (three interleaved
-  //      Sturm counts); 29 rounds = 58 bits below the Gershgorin span.  More threads per eigenvalue (multisection over
-  //      eight lanes) were measured slower: the SM's FP64 rate, not latency, then sets the time ----
+  //      Sturm counts); 29 rounds = 58 bits below the Gershgorin span.  The SM issues FP64 at ~16 lanes per clock, so
+  //      this phase costs (number of Sturm counts) x 3 n FP64 operations whatever the number of threads: three counts
+  //      per round give 2 bits (87 counts per eigenvalue); two threads x three counts per round (cut in seven, 126
+  //      counts) and one count per thread on all 1024 threads were both measured slower ----
   if (tid < n) {
     const int j = tid;
     double lo = s_scal[1], hi = s_scal[2];
@@ -265,84 +363,136 @@ __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double
       const double inv = rsqrt(s2);
       for (int i = 0; i < n; ++i) x[i] *= inv;
     }
-    for (int i = 0; i < n; ++i) work[(size_t)i * n + j] = x[i];
+    for (int i = 0; i < n; ++i) xwork[(size_t)i * n + j] = x[i];
+    evals[descending ? n - 1 - j : j] = lam;
   }
+  if (tid == 0) *ok = 1;  // cleared by the check kernel
   __syncthreads();
   stamp(2);
+}
 
-  // ---- back-transformation S = H_0 ... H_{n-3} X: eight threads hold one column in registers ----
-  constexpr int RMAX = TE_MAXN / 8;
-  for (int c0 = 0; c0 < n; c0 += TE_THREADS / 8) {
-    const int c = c0 + grp;
-    double xr[RMAX];
-#pragma unroll
-    for (int t = 0; t < RMAX; ++t) {
-      const int r = sub + 8 * t;
-      xr[t] = (c < n && r < n) ? work[(size_t)r * n + c] : 0.0;
-    }
-    // reflector k touches the rows r > k only: for k in [8 T + 6, 8 T + 13] the register rows t < T (r = sub + 8 t <= k
-    // for every lane) are skipped at compile time (bt_range<T>), which halves the work of the triangular sweep
-    bt_sweep<RMAX - 1, RMAX>(xr, A, ld, n, sub, gmask);
-    if (c < n) {
-      const int cc = descending ? n - 1 - c : c;
-#pragma unroll
-      for (int t = 0; t < RMAX; ++t) {
-        const int r = sub + 8 * t;
-        if (r < n) evecs[(size_t)r * ldv + cc] = xr[t];
-      }
-      if (sub == 0) evals[cc] = s_lam[c];
-    }
+// Back-transformation S = H_0 ... H_{n-3} X over the whole GPU: one warp per column (lane l holds the rows l + 32 t),
+// four columns per CTA.  The reflectors are staged in shared memory first -- read from global memory inside the loop, every reflector cost an L2 round trip (~1,000 cycles each, 63 us
+// at n = 128, measured).  Each reflector then costs the warp one dot product and one update: 2 ROWS FMAs per lane and a
+// shuffle reduction, n - 2 of them in sequence.
+template <int ROWS>
+__global__ void __launch_bounds__(128) tridiag_back_kernel(int n, const double* __restrict__ xwork,
+                                                           const double* __restrict__ vwork,
+                                                           const double* __restrict__ tauwork,
+                                                           double* __restrict__ evecs, int64_t ldv, int descending) {
+  extern __shared__ __align__(16) double s_vt[];  // [n - 2][n]: reflector k in row k (n - k - 1 entries used)
+  double* s_tau = s_vt + (size_t)(n - 2) * n;
+  // all copies in flight at once (cp.async, 8 bytes each): the staging costs one L2 round trip, not one per element
+  for (int e = threadIdx.x; e < (n - 2) * n; e += blockDim.x) {
+    const int k = e / n, i = e - k * n;
+    if (i < n - k - 1)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(s_vt + e)),
+                   "l"(vwork + e)
+                   : "memory");
   }
-  __syncthreads();  // every thread is done with the reflectors in A; evecs written by this CTA are visible to it
-  __threadfence_block();
-  stamp(3);
-  // ---- orthogonality check: S^T S = I to 1e-9, else the caller's Jacobi kernel takes over ----
-  for (int e = tid; e < n * n; e += TE_THREADS) {
-    const int r = e / n, c = e - r * n;
-    A[r * ld + c] = evecs[(size_t)r * ldv + c];
-  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  for (int k = threadIdx.x; k < n - 2; k += blockDim.x) s_tau[k] = tauwork[k];
   __syncthreads();
-  double worst = 0.0;
-  for (int e = tid; e < n * n; e += TE_THREADS) {
-    const int i = e / n, j = e - i * n;
-    if (j < i) continue;
-    double s = 0.0;
-    for (int r = 0; r < n; ++r) s = fma(A[r * ld + i], A[r * ld + j], s);
-    worst = fmax(worst, fabs(s - (i == j ? 1.0 : 0.0)));
-  }
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= n) return;
+  double xr[ROWS];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(SCF_FULL, worst, o));
-  if (lane == 0) s_red[warp] = worst;
-  __syncthreads();
-  if (tid == 0) {
-    double w = 0.0;
-    for (int i = 0; i < TE_THREADS / 32; ++i) w = fmax(w, s_red[i]);
-    *ok = (w <= 1e-9) ? 1 : 0;  // NaN fails the comparison
+  for (int t = 0; t < ROWS; ++t) {
+    const int r = lane + 32 * t;
+    xr[t] = r < n ? xwork[(size_t)r * n + c] : 0.0;
   }
-  stamp(4);
+  for (int k = n - 3; k >= 0; --k) {
+    const double* v = s_vt + (size_t)k * n - (k + 1);  // v[r] = entry at row r (r > k)
+    double vr[ROWS];
+    double dot = 0.0;
+#pragma unroll
+    for (int t = 0; t < ROWS; ++t) {
+      const int r = lane + 32 * t;
+      vr[t] = (r > k && r < n) ? v[r] : 0.0;
+      dot = fma(vr[t], xr[t], dot);
+    }
+    dot = s_tau[k] * warp_sum(dot);
+#pragma unroll
+    for (int t = 0; t < ROWS; ++t) xr[t] = fma(-dot, vr[t], xr[t]);
+  }
+  const int cc = descending ? n - 1 - c : c;
+#pragma unroll
+  for (int t = 0; t < ROWS; ++t) {
+    const int r = lane + 32 * t;
+    if (r < n) evecs[(size_t)r * ldv + cc] = xr[t];
+  }
+}
+
+// Orthogonality check: S^T S = I to 1e-9, else *ok = 0 and the caller's Jacobi kernel takes over.  One thread per pair
+// (i <= j) of columns.
+__global__ void __launch_bounds__(256) tridiag_check_kernel(int n, const double* __restrict__ evecs, int64_t ldv,
+                                                            int* __restrict__ ok) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = e / n, j = e - i * n;
+  if (i >= n || j < i) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int r = 0;
+  for (; r + 16 <= n; r += 16) {  // sixteen rows (32 loads) in flight: the loop is bound by the L2 latency
+    double vi[16], vj[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      vi[u] = evecs[(size_t)(r + u) * ldv + i];
+      vj[u] = evecs[(size_t)(r + u) * ldv + j];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u += 4) {
+      s0 = fma(vi[u], vj[u], s0);
+      s1 = fma(vi[u + 1], vj[u + 1], s1);
+      s2 = fma(vi[u + 2], vj[u + 2], s2);
+      s3 = fma(vi[u + 3], vj[u + 3], s3);
+    }
+  }
+  for (; r < n; ++r) s0 = fma(evecs[(size_t)r * ldv + i], evecs[(size_t)r * ldv + j], s0);
+  const double dev = fabs((s0 + s1) + (s2 + s3) - (i == j ? 1.0 : 0.0));
+  if (!(dev <= 1e-9)) *ok = 0;  // NaN fails the comparison
 }
 
 }  // namespace
 
-// evals / evecs as scf_sym_eig_jacobi (descending != 0: descending order); work: n * n doubles of device scratch;
+// evals / evecs as scf_sym_eig_jacobi (descending != 0: descending order); work: 2 * n * n + n doubles of device scratch;
 // ok (device int): 1 when the eigenvectors are orthonormal to 1e-9, 0 when the caller has to fall back
 int32_t tridiag_eig_launch(const double* a, int n, int64_t lda, double* evals, double* evecs, int64_t ldv, int descending,
                            double* work, int* ok, cudaStream_t stream) {
   SCF_ARG(a && evals && evecs && work && ok, "null pointer");
   SCF_ARG(n >= 3 && n <= TE_MAXN && lda >= n && ldv >= n, "n must be within [3, 160]");
-  const size_t smem = (size_t)n * (n + 1) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(tridiag_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    scf_set_error("scf_eig_topk(tridiagonal): %s", cudaGetErrorString(e));
-    return -(int32_t)e;
+  double* xwork = work;
+  double* vwork = work + (size_t)n * n;
+  double* tauwork = vwork + (size_t)n * n;
+  if (n <= 128) {  // matrix in registers
+    auto fn = n <= 64 ? tridiag_eig_kernel<8> : (n <= 96 ? tridiag_eig_kernel<12> : tridiag_eig_kernel<16>);
+    fn<<<1, TE_THREADS, 0, stream>>>(a, n, lda, evals, descending, xwork, vwork, tauwork, ok);
+  } else {
+    const size_t smem = (size_t)n * (n + 1) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(tridiag_eig_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      scf_set_error("scf_eig_topk(tridiagonal): %s", cudaGetErrorString(e));
+      return -(int32_t)e;
+    }
+    tridiag_eig_kernel<0><<<1, TE_THREADS, smem, stream>>>(a, n, lda, evals, descending, xwork, vwork, tauwork, ok);
   }
-  tridiag_eig_kernel<<<1, TE_THREADS, smem, stream>>>(a, n, lda, evals, evecs, ldv, descending, work, ok);
+  {
+    const size_t bsmem = ((size_t)(n - 2) * n + n) * sizeof(double);
+    auto bk = n <= 128 ? tridiag_back_kernel<4> : tridiag_back_kernel<5>;
+    cudaError_t e = cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+    if (e != cudaSuccess) {
+      scf_set_error("scf_eig_topk(tridiagonal): %s", cudaGetErrorString(e));
+      return -(int32_t)e;
+    }
+    bk<<<(n + 3) / 4, 128, bsmem, stream>>>(n, xwork, vwork, tauwork, evecs, ldv, descending);
+  }
+  tridiag_check_kernel<<<(n * n + 255) / 256, 256, 0, stream>>>(n, evecs, ldv, ok);
   if (getenv("SCF_EIG_DEBUG")) {
-    long long h[8];
+    long long h[12];
     cudaStreamSynchronize(stream);
     cudaMemcpyFromSymbol(h, g_te_clk, sizeof(h));
-    fprintf(stderr, "[tridiag n=%d] cycles: tridiagonalise %lld, multisection %lld, inverse iteration %lld, "
-            "back-transform %lld, check %lld\n", n, h[0], h[1], h[2], h[3], h[4]);
+    fprintf(stderr, "[tridiag n=%d] cycles: tridiagonalise %lld, multisection %lld, inverse iteration %lld\n", n, h[0],
+            h[1], h[2]);
   }
   return scf_check_launch("scf_eig_topk(tridiagonal)");
 }

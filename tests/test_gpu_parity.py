@@ -678,7 +678,7 @@ def test_sym_eig_jacobi_equals_eigh(gpu, n):
         assert float((a @ v - v * w).abs().max()) < 1e-11 * float(we[-1])
 
 
-@pytest.mark.parametrize("n", [3, 7, 82, 96, 128, 133, 160])
+@pytest.mark.parametrize("n", [3, 7, 64, 65, 82, 96, 97, 128, 133, 160])
 def test_sym_eig_tridiag_equals_eigh(gpu, n):
     """scf_sym_eig_tridiag (tridiagonalisation + multisection + inverse iteration, the fast Rayleigh-Ritz solver of
     scf_eig_topk) against torch.linalg.eigh: a dense PSD matrix with a wide spectrum, a nearly diagonal one, and a matrix
@@ -757,6 +757,32 @@ def test_knn_fp16_scale_handling(gpu, scale, outlier, dim, k):
     idx_o, dist_o = P.exact_knn(y, y, k, self_offset=0)
     assert np.array_equal(idx.cpu().numpy().astype(np.uint64), idx_o)
     assert np.array_equal(dist.cpu().numpy(), dist_o)
+
+
+@pytest.mark.parametrize("nq,nref,dim,k", [(20_000, 20_000, 100, 21), (777, 40_001, 100, 11), (5000, 5000, 20, 11),
+                                           (40_000, 9_000, 130, 24)])
+def test_knn_cta_pair_kernel_equals_single_cta_and_fp64(gpu, monkeypatch, nq, nref, dim, k):
+    """The cta_group::2 kernel (pairs of CTAs issue M = 256 x N = 256 MMAs; the default for dim > 61) and the single-CTA
+    kernel, each forced through SCF_KNN_PAIR, against the FP64 brute force: identical ids and distances.  Covers ragged
+    tile counts, fewer query tiles than CTA pairs, one / two / three K chunks and a block of exact duplicates."""
+    torch, ops = gpu["torch"], gpu["ops"]
+    g = torch.Generator(device="cuda").manual_seed(nq + dim)
+    ld = ops.round_up(dim, 32)
+    scale = torch.sqrt(30.0 * 0.95 ** torch.arange(dim, device="cuda", dtype=torch.float32) + 1.0)
+    ref = torch.zeros((nref, ld), device="cuda")
+    ref[:, :dim] = torch.randn((nref, dim), generator=g, device="cuda") * scale
+    ref[300:330] = ref[200:230]
+    same = nq == nref
+    q = ref if same else torch.zeros((nq, ld), device="cuda")
+    if not same:
+        q[:, :dim] = torch.randn((nq, dim), generator=g, device="cuda") * scale
+    off = 0 if same else -1
+    idx0, dist0 = ops.knn_l2(q, ref, dim, k, self_offset=off, method=0)
+    for pair in ("1", "0"):
+        monkeypatch.setenv("SCF_KNN_PAIR", pair)
+        idx, dist = ops.knn_l2(q, ref, dim, k, self_offset=off, method=1)
+        assert torch.equal(idx, idx0), f"pair={pair}"
+        assert torch.equal(dist, dist0), f"pair={pair}"
 
 
 @pytest.mark.parametrize("top_n,bounds", [(500, {}), (50, {"max_cells": 2000.0, "min_mean": -3.0, "max_mean": 2.0}),

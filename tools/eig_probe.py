@@ -12,10 +12,10 @@ from scarf_b200 import lib, ops  # noqa: E402
 
 
 def main():
-    path = os.path.join("tools", "build", "c2_cov.npy")
+    path = os.environ.get("EIG_PROBE_COV", os.path.join("tools", "build", "c2_cov.npy"))
     cov = torch.from_numpy(np.load(path)).cuda()
     h = cov.shape[0]
-    n = 100000
+    n = int(os.environ.get("EIG_PROBE_N", "100000"))
     ld = (h + 31) // 32 * 32
     g = torch.zeros((ld, ld), dtype=torch.int64, device="cuda")
     g[:h, :h] = torch.round(cov * (n - 1) * 2.0 ** lib.GRAM_SHIFT).to(torch.int64)
