@@ -44,9 +44,14 @@ constexpr int A_CHUNK_BYTES = BM * 128;
 constexpr int ACC_COLS = 256;  // TMEM columns of one accumulator buffer: QT query tiles x BN references
 constexpr int GCOLS = 64;      // accumulator columns one epilogue thread examines per reference tile
 constexpr int NEPI_WARPS = 16;
-constexpr int NTHREADS = 64 + 32 * NEPI_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-17: epilogue
+constexpr int NTHREADS = 96 + 32 * NEPI_WARPS;  // warp 0: TMA, warp 1: MMA of query tile 0 + TMEM owner, warps 2-17: epilogue,
+                                                // warp 18: MMA of query tile 1
+constexpr int NTHREADS_PAIR = 64 + 32 * NEPI_WARPS;  // knn_tc_pair_kernel: warp 0 TMA, warp 1 MMA (leader CTA), warps 2-17 epilogue
 constexpr int NL = 32 * NEPI_WARPS;             // epilogue threads = candidate lists per CTA
-constexpr int HB = 8;          // buffered hits per epilogue thread
+#ifndef SCF_KNN_HB
+#define SCF_KNN_HB 8
+#endif
+constexpr int HB = SCF_KNN_HB;  // buffered hits per epilogue thread
 constexpr int NDONE = 16;      // ring of "all MMAs of step t have completed" barriers (step t uses entry t % 16)
 
 // error model of the tensor-core score (see DESIGN.md "kNN guard band"), all in scaled units (a := s a, b := s b),
@@ -290,6 +295,34 @@ struct Epi {
     }
     cnt = 0;
   }
+  // one buffered entry per lane (the last one appended): what a waiting warp does instead of spinning
+  __device__ __forceinline__ void drain_one() {
+    if (cnt > 0) {
+      --cnt;
+      const float sc = hs[cnt * NL];
+      const int j = hc[cnt * NL];
+      if (sc < cl.thr && j < nref) cl.replace_max(sc, j, gid);
+    }
+  }
+  // Wait for the accumulators of a step.  Every epilogue warp of the CTA has to release an accumulator buffer before
+  // the MMA warp may overwrite it, so the warps wait for each other once per step, and a step in which SOME warp updates
+  // its lists is as slow as that warp (ncu: a third of the warp stall samples sit on this wait).  The waiting time is
+  // therefore used for the list updates: hits are only appended to the buffers inside a step (cheap), and drained here,
+  // one entry per poll, while the barrier is not ready; a drain inside a step happens only when a buffer runs full.
+  // -> true when entries were drained (the caller refreshes / publishes its threshold)
+  __device__ __forceinline__ bool wait_draining(uint64_t* bar, uint32_t parity) {
+    bool drained = false;
+    uint32_t spins = 0;
+    while (!tc::mbar_try_wait(bar, parity)) {
+      if (__any_sync(SCF_FULL, cnt > 0)) {
+        drain_one();
+        drained = true;
+      } else if ((++spins & 0xFFFFu) == 0u) {
+        tc::spin_timeout(spins);
+      }
+    }
+    return drained;
+  }
 };
 
 // Some lane of the warp has a score below its threshold among v[0..32).  What bounds this kernel once the tensor pipe
@@ -400,12 +433,13 @@ struct SegWalk {
 // (warp id % 4) and the 64 accumulator columns [64 g, 64 g + 64), g = w / 4, of the 256-column buffer: with QT = 4
 // that is query tile g (one list per row), with QT = 2 query tile g / 2, column half g % 2 (two lists per row, which
 // share their thresholds through shared memory).
-template <int KC, int QT, bool COLLECT>
+template <int KC, int QT, bool COLLECT, int NI>
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                              const __grid_constant__ CUtensorMap tmap_r,
                                                              const KnnTcParams p) {
   constexpr int BN = ACC_COLS / QT;
-  constexpr int HALVES = QT == 2 ? 2 : 1;
+  static_assert(QT == 2, "two query tiles of 128 rows x reference tiles of 128 rows");
+  constexpr int HALVES = 2;
   constexpr int B_STAGE_BYTES = BN * 128;
   int n_fix = 0;
   if constexpr (COLLECT) {  // whole CTA leaves before any barrier / TMEM setup when its query tile is empty
@@ -424,10 +458,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + 1;
   uint64_t* full = bars + 2;               // [stages] TMA data of a stage has landed
-  uint64_t* done = full + p.stages;        // [NDONE]  every MMA of step t (entry t % NDONE) has completed: the epilogue
-                                           //          may read the accumulators, the producer may refill the stages
-  uint64_t* tmem_empty = done + NDONE;     // [2]      the epilogue has read accumulator buffer a
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // NI issuing warps = NI independent accumulator pipelines (NI == 2: one per query tile, NI == 1: both tiles together)
+  uint64_t* done = full + p.stages;        // [NI][NDONE] every MMA of pipeline i in step t (entry t % NDONE) has
+                                           //          completed: its epilogue warps may read the accumulators; the
+                                           //          producer refills a stage once ALL pipelines have done the step
+  uint64_t* tmem_empty = done + NI * NDONE;  // [NI][2]  the epilogue warps of pipeline i have read its buffer a
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NI * 2);
 
   // the warp index through a shuffle: the compiler then knows that the role branches below are warp-uniform and may
   // use the uniform datapath inside them (UTCHMMA takes its descriptors from uniform registers; in a branch it
@@ -439,10 +475,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
 
   if (threadIdx.x == 0) {
     tc::mbar_init(a_full, 1);
-    tc::mbar_init(a_empty, 1);
+    tc::mbar_init(a_empty, NI);  // one commit per issuing warp
     for (int s = 0; s < p.stages; ++s) tc::mbar_init(full + s, 1);
-    for (int d = 0; d < NDONE; ++d) tc::mbar_init(done + d, 1);
-    for (int a = 0; a < 2; ++a) tc::mbar_init(tmem_empty + a, NEPI_WARPS);  // one arrive per epilogue warp
+    for (int d = 0; d < NI * NDONE; ++d) tc::mbar_init(done + d, 1);
+    for (int a = 0; a < NI * 2; ++a) tc::mbar_init(tmem_empty + a, NEPI_WARPS / NI);  // one arrive per epilogue warp of the pipeline
     tc::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -460,8 +496,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     const bool leader = tc::elect_one();
     int seg = 0;
     uint32_t s = 0, ph = 0;  // pipeline stage and its phase, advanced without divisions (stay in uniform registers)
-    // A stage is refilled once the step that read its previous content has completed (`done` ring): one
-    // tcgen05.commit per step instead of one per stage -- a commit stalls the tensor pipe for ~150 cycles (measured).
+    // A stage is refilled once the step that read its previous content has completed (`done` rings of the MMA warps):
+    // one tcgen05.commit per step and query tile instead of one per stage.
     // (rel_step, rel_c): the chunk loaded p.stages chunks ago, i.e. the previous user of the stage about to be filled.
     uint32_t loaded = 0, rel_step = 0, rel_c = 0;
     for (int q, t0, t1; walk.next(q, t0, t1); ++seg) {
@@ -477,7 +513,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
       for (int t = t0; t < t1; ++t)
         for (int c = 0; c < p.kchunks; ++c) {
           if (loaded >= (uint32_t)p.stages) {
-            tc::mbar_wait(done + (rel_step & (NDONE - 1)), (rel_step / NDONE) & 1u, backoff);
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+              tc::mbar_wait(done + i * NDONE + (rel_step & (NDONE - 1)), (rel_step / NDONE) & 1u, backoff);
             if (++rel_c == (uint32_t)p.kchunks) rel_c = 0, ++rel_step;
           }
           ++loaded;
@@ -493,8 +531,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
           if (++s == (uint32_t)p.stages) s = 0, ph ^= 1u;
         }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 2 + NEPI_WARPS) {
+    // ===================== MMA issuers: one warp per query tile =====================
+    // Two issuing warps because ONE cannot keep the tensor pipe fed: between two MMAs the issuing thread spends ~70
+    // cycles on descriptor arithmetic and barrier polls (uniform datapath), as long as an N = 128 instruction runs, so
+    // every wait of the issuer (for an accumulator buffer, for a stage) is a bubble in the pipe (ncu: MMA warp 31 % of its
+    // time on the accumulator barrier, pipe 52 % active at the C3 shape; microbenchmark tools/ubench_tc.cu: two issuers
+    // reach 64.1 cycles per instruction whatever the commit frequency, one issuer 65 - 75).  Each warp owns one query
+    // tile: its half of both accumulator buffers, its own `done` ring and buffer barriers -- the two tiles hand their
+    // accumulators over to their own eight epilogue warps independently of each other.
     // The whole warp walks the loop with identical (warp-uniform) values and one elected lane issues the tensor
     // instructions: descriptors then live in uniform registers.  Issuing from inside an `if (lane == 0)` region makes
     // the compiler move every descriptor from vector to uniform registers through a waterfall loop per MMA (~110
@@ -504,39 +549,78 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     // Everything the instructions take is derived from warp-uniform counters with add / shift / select only, so that
     // the descriptors stay in uniform registers (a division, e.g. `it % stages`, sends them through vector registers
     // and every MMA then waits for a chain of R2UR moves: ~100 cycles per instruction instead of 32 - 64, measured).
-    const uint32_t a_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sA));
-    const uint32_t b_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sB));
+    // The tile loops are resolved at compile time (NI): with run-time tile bounds the extra uniform predicates per
+    // instruction cost 10 - 40 % of the kernel (measured).
     const uint32_t nk_last = (uint32_t)p.ksteps_last, kchunks = (uint32_t)p.kchunks, stages = (uint32_t)p.stages;
+    const uint32_t b_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sB));
     uint32_t s = 0, ph = 0, lt = 0, seg = 0;
-    for (int q, t0, t1; walk.next(q, t0, t1); ++seg) {
-      tc::mbar_wait(a_full, seg & 1u);
-      tc::tc_fence_after();
-      for (int t = t0; t < t1; ++t, ++lt) {
-        const uint32_t acc = lt & 1u;
-        tc::mbar_wait(tmem_empty + acc, ((lt >> 1) & 1u) ^ 1u, backoff);
+    if constexpr (NI == 2) {
+      // this warp issues for query tile tq
+      const uint32_t tq = warp == 1 ? 0u : 1u;
+      const uint32_t a_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sA)) + tq * kchunks * (uint32_t)(A_CHUNK_BYTES >> 4);
+      uint64_t* my_done = done + tq * NDONE;
+      uint64_t* my_empty = tmem_empty + tq * 2;
+      for (int q, t0, t1; walk.next(q, t0, t1); ++seg) {
+        tc::mbar_wait(a_full, seg & 1u);
         tc::tc_fence_after();
-        for (uint32_t c = 0; c < kchunks; ++c) {
-          tc::mbar_wait(full + s, ph, backoff);
+        for (int t = t0; t < t1; ++t, ++lt) {
+          const uint32_t acc = lt & 1u;
+          tc::mbar_wait(my_empty + acc, ((lt >> 1) & 1u) ^ 1u, backoff);
           tc::tc_fence_after();
-          const uint32_t b_lo = b_lo0 + s * (uint32_t)(B_STAGE_BYTES >> 4);
-          const uint32_t nk = c + 1 == kchunks ? nk_last : (uint32_t)(KCH / KSTEP);
-#pragma unroll
-          for (uint32_t tq = 0; tq < (uint32_t)QT; ++tq) {
-            const uint32_t a_lo = a_lo0 + (tq * kchunks + c) * (uint32_t)(A_CHUNK_BYTES >> 4);
-            const uint32_t d_tmem = tmem_base + acc * (uint32_t)ACC_COLS + tq * (uint32_t)BN;
+          const uint32_t d_tmem = tmem_base + acc * (uint32_t)ACC_COLS + tq * (uint32_t)BN;
+          for (uint32_t c = 0; c < kchunks; ++c) {
+            tc::mbar_wait(full + s, ph, backoff);
+            tc::tc_fence_after();
+            const uint32_t a_lo = a_lo0 + c * (uint32_t)(A_CHUNK_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + s * (uint32_t)(B_STAGE_BYTES >> 4);
+            const uint32_t nk = c + 1 == kchunks ? nk_last : (uint32_t)(KCH / KSTEP);
 #pragma unroll
             for (uint32_t kk = 0; kk < (uint32_t)(KCH / KSTEP); ++kk)  // K = 16 fp16 = 32 bytes: +2 in 16-byte units
               if (kk < nk && !(SCF_KNN_DEBUG & 64)) {
                 if (leader) tc::umma_f16_lo(d_tmem, a_lo + kk * 2u, b_lo + kk * 2u, idesc, (c | kk) != 0u);
               }
+            if (++s == stages) s = 0, ph ^= 1u;
           }
-          if (++s == stages) s = 0, ph ^= 1u;
+          if (leader) tc::umma_commit(my_done + (lt & (NDONE - 1)));  // the tile's accumulator complete, its stage reads done
+          __syncwarp();
         }
-        if (leader) tc::umma_commit(done + (lt & (NDONE - 1)));  // accumulators complete, stages of this step reusable
+        if (leader) tc::umma_commit(a_empty);  // the query operand may be replaced once every MMA of the segment has run
         __syncwarp();
       }
-      if (leader) tc::umma_commit(a_empty);  // the query operand may be replaced once every MMA of the segment has run
-      __syncwarp();
+    } else if (warp == 1) {
+      // one issuer for both query tiles (one K chunk per step, i.e. four instructions per tile: measured faster with
+      // one issuer, C2 2.43 ms against 2.60 ms); the second MMA warp has nothing to do
+      const uint32_t a_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(sA));
+      for (int q, t0, t1; walk.next(q, t0, t1); ++seg) {
+        tc::mbar_wait(a_full, seg & 1u);
+        tc::tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++lt) {
+          const uint32_t acc = lt & 1u;
+          tc::mbar_wait(tmem_empty + acc, ((lt >> 1) & 1u) ^ 1u, backoff);
+          tc::tc_fence_after();
+          for (uint32_t c = 0; c < kchunks; ++c) {
+            tc::mbar_wait(full + s, ph, backoff);
+            tc::tc_fence_after();
+            const uint32_t b_lo = b_lo0 + s * (uint32_t)(B_STAGE_BYTES >> 4);
+            const uint32_t nk = c + 1 == kchunks ? nk_last : (uint32_t)(KCH / KSTEP);
+#pragma unroll
+            for (uint32_t tq = 0; tq < (uint32_t)QT; ++tq) {
+              const uint32_t a_lo = a_lo0 + (tq * kchunks + c) * (uint32_t)(A_CHUNK_BYTES >> 4);
+              const uint32_t d_tmem = tmem_base + acc * (uint32_t)ACC_COLS + tq * (uint32_t)BN;
+#pragma unroll
+              for (uint32_t kk = 0; kk < (uint32_t)(KCH / KSTEP); ++kk)
+                if (kk < nk && !(SCF_KNN_DEBUG & 64)) {
+                  if (leader) tc::umma_f16_lo(d_tmem, a_lo + kk * 2u, b_lo + kk * 2u, idesc, (c | kk) != 0u);
+                }
+            }
+            if (++s == stages) s = 0, ph ^= 1u;
+          }
+          if (leader) tc::umma_commit(done + (lt & (NDONE - 1)));  // accumulators complete, stages of this step reusable
+          __syncwarp();
+        }
+        if (leader) tc::umma_commit(a_empty);
+        __syncwarp();
+      }
     }
   } else {
     // ===================== epilogue: 64 accumulator columns of one query row per thread =====================
@@ -545,8 +629,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
     const int g = w >> 2;              // column group
     const int l = w * 32 + lane;       // epilogue thread id
     const int row = quarter * 32 + lane;
-    const int qt = QT == 4 ? g : (g >> 1);
-    const int half = QT == 4 ? 0 : (g & 1);
+    const int qt = g >> 1;             // query tile
+    const int half = g & 1;            // column half of the tile's 128 accumulator columns
+    uint64_t* my_done = done + (NI == 2 ? qt : 0) * NDONE;
+    uint64_t* my_empty = tmem_empty + (NI == 2 ? qt : 0) * 2;
     const int col0 = half * GCOLS;     // first reference of this thread inside a reference tile
     volatile float* thr_all = thr_x;  // the other list of this row (QT = 2): thread l ^ 128, warp w ^ 4
     const int pair_id = 1 + (w & 3) + 4 * (w >> 3);
@@ -558,7 +644,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
         const float thr = qrow < n_fix ? p.fix_thr[qrow] : -FLT_MAX;
         for (int t = t0; t < t1; ++t, ++lt) {
           const int acc = lt & 1;
-          tc::mbar_wait(done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
+          tc::mbar_wait(my_done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
           tc::tc_fence_after();
           const int j0 = t * BN + col0;
           const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + g * GCOLS);
@@ -583,7 +669,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
           }
           tc::tc_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
+          if (lane == 0) tc::mbar_arrive(my_empty + acc);
         }
       } else {
         const int split = walk.slot_of(p, q);
@@ -604,12 +690,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
         }
         for (int t = t0; t < t1; ++t, ++lt) {
           const int acc = lt & 1;
-          tc::mbar_wait(done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
+          const bool drained = ep.wait_draining(my_done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
           tc::tc_fence_after();
+          if (drained) {
+            ep.thr = ep.cl.thr;
+            if constexpr (HALVES == 2) thr_all[l] = ep.cl.thr;
+          }
           if (SCF_KNN_DEBUG & 32) {  // timing experiment: no accumulator read-out at all
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
+            if (lane == 0) tc::mbar_arrive(my_empty + acc);
             continue;
           }
           const int j0 = t * BN + col0;
@@ -622,15 +712,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
           for (int hh = 0; hh < 2; ++hh) {
             tc::tmem_ld32(t_row + (uint32_t)(32 * hh), v);
             tc::tmem_ld_wait();
+            if (hh == 1) {
+              // The accumulator buffer is released as soon as its last columns are in registers, BEFORE they are
+              // examined: the hand-over (MMA done -> epilogue -> buffer free -> MMA of the step after next) is the
+              // loop that paces the kernel with only two buffers in TMEM, and a scan with list updates is its longest
+              // part.
+              tc::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(my_empty + acc);
+            }
             if (SCF_KNN_DEBUG & 8) continue;
             const float m_lo = min16(v), m_hi = min16(v + 16);
             if ((SCF_KNN_DEBUG & 16) && lane == 0) atomicAdd(&g_dbg[0], 1ull);
             if (__any_sync(SCF_FULL, fminf(m_lo, m_hi) < ep.thr))
               hits32<KC, HALVES == 2 ? 1 : 0>(v, m_lo, m_hi, j0 + 32 * hh, ep, thr_all, l);
           }
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(tmem_empty + acc);
         }
         ep.drain();
         if constexpr (HALVES == 2) thr_all[l] = ep.cl.thr;
@@ -664,7 +760,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_consta
 // CTA's) barriers, tcgen05.commit arrives on the barriers of both CTAs (multicast), and the epilogue warps of both
 // CTAs release an accumulator buffer on the leader's barrier.
 template <int KC>
-__global__ void __launch_bounds__(NTHREADS, 1) knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
+__global__ void __launch_bounds__(NTHREADS_PAIR, 1) knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                                   const __grid_constant__ CUtensorMap tmap_r,
                                                                   const KnnTcParams p) {
   constexpr int BN2 = 256;                 // references per step (pair)
@@ -815,7 +911,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_pair_kernel(const __grid_c
       asm volatile("bar.sync %0, 128;" ::"r"(quad_id) : "memory");  // all four lists of a row have published
       for (int t = t0; t < t1; ++t, ++lt) {
         const int acc = lt & 1;
-        tc::mbar_wait(done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u);
+        if (ep.wait_draining(done + (lt & (NDONE - 1)), (uint32_t)(lt / NDONE) & 1u)) thr_all[l] = ep.cl.thr;
         tc::tc_fence_after();
         if (SCF_KNN_DEBUG & 32) {  // timing experiment: no accumulator read-out at all
           tc::tc_fence_before();
@@ -1135,7 +1231,7 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   pl.tiles_per_split = pl.n_ref_tiles;
   auto smem_for = [&](int q_tiles_in_smem, int stages) {
     return (size_t)q_tiles_in_smem * pl.kchunks * A_CHUNK_BYTES + (size_t)stages * pl.bn * 128 + (size_t)2 * HB * NL * 4 +
-           (size_t)NL * 4 + (size_t)(2 + stages + NDONE + 2 + 2) * 8 + 64;
+           (size_t)NL * 4 + (size_t)(2 + stages + 2 * NDONE + 4 + 2) * 8 + 64;
   };
   // single-CTA layout (main pass without pairs, and the collect pass): QT query tiles in shared memory
   pl.stages = 8;
@@ -1172,10 +1268,11 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
 }
 
 typedef void (*KnnKernel)(const CUtensorMap, const CUtensorMap, const KnnTcParams);
-KnnKernel pick_kernel(int kc, int qt, bool collect) {
-  if (collect) return qt == 4 ? (KnnKernel)knn_tc_kernel<16, 4, true> : (KnnKernel)knn_tc_kernel<16, 2, true>;
-  if (qt == 4) return kc == 16 ? (KnnKernel)knn_tc_kernel<16, 4, false> : (KnnKernel)knn_tc_kernel<32, 4, false>;
-  return kc == 16 ? (KnnKernel)knn_tc_kernel<16, 2, false> : (KnnKernel)knn_tc_kernel<32, 2, false>;
+// NI = MMA-issuing warps: two (one per query tile) when a step has two or more K chunks, else one
+KnnKernel pick_kernel(int kc, int issuers, bool collect) {
+  if (collect) return issuers == 2 ? (KnnKernel)knn_tc_kernel<16, 2, true, 2> : (KnnKernel)knn_tc_kernel<16, 2, true, 1>;
+  if (issuers == 2) return kc == 16 ? (KnnKernel)knn_tc_kernel<16, 2, false, 2> : (KnnKernel)knn_tc_kernel<32, 2, false, 2>;
+  return kc == 16 ? (KnnKernel)knn_tc_kernel<16, 2, false, 1> : (KnnKernel)knn_tc_kernel<32, 2, false, 1>;
 }
 
 }  // namespace
@@ -1253,6 +1350,11 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   prm.kchunks = pl.kchunks, prm.stages = pl.stages, prm.n_ref_tiles = pl.n_ref_tiles;
   prm.nq = (int)nq, prm.nref = (int)nref;
   prm.ksteps_last = ((dim + 3 + KSTEP - 1) / KSTEP) - (pl.kchunks - 1) * (KCH / KSTEP);
+  int issuers = pl.kchunks >= 2 ? 2 : 1;
+  {
+    const char* e = getenv("SCF_KNN_ISSUERS");  // developer switch
+    if (e) issuers = atoi(e) == 1 ? 1 : 2;
+  }
   prm.tiles_per_split = pl.tiles_per_split, prm.nlists = pl.nlists, prm.cand_score = cs, prm.cand_idx = ci, prm.cand_tau = ctau;
   prm.balanced = 1, prm.rounds = pl.rounds, prm.units_rem = pl.units_rem, prm.rem_total = pl.rem_total;
   // list slots that no range fills (a query tile that is not cut uses one of its nsplit slots): ids -1, tau "nothing rejected"
@@ -1267,7 +1369,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     prm.flags = f ? atoi(f) : 2;
   }
   prm.fail_count = nullptr, prm.fix_thr = nullptr, prm.fix_cnt = nullptr, prm.fix_list = nullptr;
-  KnnKernel kern = pl.pair ? (KnnKernel)knn_tc_pair_kernel<16> : pick_kernel(pl.kc, pl.qt, false);
+  KnnKernel kern = pl.pair ? (KnnKernel)knn_tc_pair_kernel<16> : pick_kernel(pl.kc, issuers, false);
   const size_t main_smem = pl.pair ? pl.psmem : pl.smem;
   if (pl.pair) prm.stages = pl.pstages;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem);
@@ -1278,7 +1380,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   if (g_time_start) cudaEventRecord((cudaEvent_t)g_time_start, stream);
   if (pl.pair) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2u * (unsigned)pl.grid), cfg.blockDim = dim3(NTHREADS);
+    cfg.gridDim = dim3(2u * (unsigned)pl.grid), cfg.blockDim = dim3(NTHREADS_PAIR);
     cfg.dynamicSmemBytes = main_smem, cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1329,7 +1431,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
   fp.tiles_per_split = (fp.n_ref_tiles + fsplit - 1) / fsplit;
   fsplit = (fp.n_ref_tiles + fp.tiles_per_split - 1) / fp.tiles_per_split;
   fp.fail_count = fail_count, fp.fix_thr = fix_thr, fp.fix_cnt = fix_cnt, fp.fix_list = fix_list;
-  KnnKernel fkern = pick_kernel(16, pl.qt, true);
+  KnnKernel fkern = pick_kernel(16, issuers, true);
   e = cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) {
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));

@@ -32,14 +32,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Time limit of hand-written wait loops (called once per 65,536 polls): a protocol bug must trap, not hang the GPU.
+// Kept out of line so that the polling loops stay a handful of instructions.
+static __device__ __noinline__ void spin_timeout(uint32_t spins) {
+  if (spins >= (1u << 22)) __trap();  // 4M polls of a try_wait (20 cycles to ~1 us each): 40 ms to seconds
+}
 // Bounded wait: a protocol bug (wrong tx count, bad tensor map) must trap, not hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns = 0) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (backoff_ns) __nanosleep(backoff_ns);  // waiting roles should not steal issue slots from working warps
-    if ((++spins & 0x3FF) == 0 && clock64() - t0 > 8000000000LL) __trap();  // ~4 s
+    if ((++spins & 0xFFFFu) == 0u) spin_timeout(spins);
   }
 }
 

@@ -190,6 +190,79 @@ __global__ void __launch_bounds__(64, 1) ubench_issue(int variant, int reps, int
   }
 }
 
+// Two warps issue alternately-sized streams of their own (different accumulator columns), each with its own commits:
+// does a commit stall only the warp that issued it (then two issuers hide each other's stalls) or the tensor pipe?
+template <int N>
+__global__ void __launch_bounds__(96, 1) ubench_issue2(int reps, int per_commit, int issuers, long long* cyc_mma) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar[2], sink_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ long long t_end[2];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (16384 + 6 * N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bar[0], 1);
+    tc::mbar_init(&bar[1], 1);
+    tc::mbar_init(&sink_bar, 1 << 20);
+    tc::fence_barrier_init();
+  }
+  tc::fence_proxy_async();
+  if (warp == 2) tc::tmem_alloc<512>(&tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const long long t0 = clock64();
+  if (warp < issuers) {
+    constexpr uint32_t idesc = tc::umma_idesc_f16(128, N, false, false);
+    const bool leader = tc::elect_one();
+    const uint32_t a_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(smem));
+    const uint32_t b_lo0 = tc::umma_desc_lo_k_sw128(tc::smem_u32(smem + 16384));
+    const uint32_t d = tmem_base + (uint32_t)warp * 256u;
+    const int mine = reps / issuers;
+    for (int r = 0; r < mine; r += per_commit) {
+      for (int kk = 0; kk < per_commit; ++kk)
+        if (leader)
+          tc::umma_f16_lo(d + (uint32_t)(kk >> 2) * N % 256u, a_lo0 + (uint32_t)(kk & 3) * 2u, b_lo0 + (uint32_t)(kk & 3) * 2u,
+                          idesc, (kk & 3) != 0);
+      if (leader) tc::umma_commit(&sink_bar);
+      __syncwarp();
+    }
+    if (leader) tc::umma_commit(&bar[warp]);
+    __syncwarp();
+    tc::mbar_wait(&bar[warp], 0);
+    if (lane == 0) t_end[warp] = clock64();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) cyc_mma[blockIdx.x] = (issuers == 2 ? max(t_end[0], t_end[1]) : t_end[0]) - t0;
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int N>
+void run_issue2(int per_commit, int issuers) {
+  const int reps = 8192;
+  long long* c_mma;
+  CK(cudaMalloc(&c_mma, 148 * 8));
+  CK(cudaMemset(c_mma, 0, 148 * 8));
+  const int smem = 16384 + 6 * N * 128 + 1024;
+  CK(cudaFuncSetAttribute(ubench_issue2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int it = 0; it < 2; ++it) {
+    ubench_issue2<N><<<148, 96, smem>>>(reps, per_commit, issuers, c_mma);
+    CK(cudaDeviceSynchronize());
+  }
+  std::vector<long long> h(148);
+  CK(cudaMemcpy(h.data(), c_mma, 148 * 8, cudaMemcpyDeviceToHost));
+  std::sort(h.begin(), h.end());
+  printf("issue pattern: N=%3d, %d issuing warp(s), commit every %2d | %.1f cyc per MMA\n", N, issuers, per_commit,
+         (double)h[74] / reps);
+  CK(cudaFree(c_mma));
+}
+
 template <int N>
 void run_issue(int variant, int per_commit) {
   const int reps = 8192;
@@ -258,6 +331,11 @@ int main() {
   cudaDeviceProp p;
   CK(cudaGetDeviceProperties(&p, 0));
   printf("device %s, %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
+  if (getenv("UBENCH_ISSUE2")) {
+    for (int pc : {4, 8, 14, 32})
+      for (int is = 1; is <= 2; ++is) run_issue2<128>(pc, is);
+    return 0;
+  }
   for (int v = 0; v < 2; ++v) {
     run_issue<64>(v, 16);
     run_issue<128>(v, 8);
