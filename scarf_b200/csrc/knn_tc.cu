@@ -434,7 +434,7 @@ struct SegWalk {
 // that is query tile g (one list per row), with QT = 2 query tile g / 2, column half g % 2 (two lists per row, which
 // share their thresholds through shared memory).
 template <int KC, int QT, bool COLLECT, int NI>
-__global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
+__global__ void __launch_bounds__(NI == 2 ? NTHREADS : NTHREADS - 32, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                              const __grid_constant__ CUtensorMap tmap_r,
                                                              const KnnTcParams p) {
   constexpr int BN = ACC_COLS / QT;
@@ -1392,7 +1392,7 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
       return -(int32_t)e;
     }
   } else {
-    kern<<<dim3((unsigned)pl.grid), NTHREADS, pl.smem, stream>>>(tq, tr, prm);
+    kern<<<dim3((unsigned)pl.grid), issuers == 2 ? NTHREADS : NTHREADS - 32, pl.smem, stream>>>(tq, tr, prm);
   }
   if (g_time_stop) cudaEventRecord((cudaEvent_t)g_time_stop, stream);
   g_time_start = g_time_stop = nullptr;  // one shot
@@ -1437,7 +1437,8 @@ int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref
     scf_set_error("scf_knn_l2: %s", cudaGetErrorString(e));
     return -(int32_t)e;
   }
-  fkern<<<dim3(FIXTC_ROWS / (pl.qt * BM), (unsigned)fsplit), NTHREADS, pl.smem, stream>>>(tf, tr, fp);
+  fkern<<<dim3(FIXTC_ROWS / (pl.qt * BM), (unsigned)fsplit), issuers == 2 ? NTHREADS : NTHREADS - 32, pl.smem, stream>>>(tf, tr,
+                                                                                                                     fp);
   rc = scf_check_launch("scf_knn_l2(fix,collect)");
   if (rc) return rc;
   knn_fix_finish_kernel<<<SCF_NUM_SMS, 256, 0, stream>>>(q, ref, dim, ld, k, self_offset, fail_ids, fail_keys, fail_count,

@@ -8,7 +8,7 @@ import sys
 so = sys.argv[1] if len(sys.argv) > 1 else "scarf_b200/csrc/libscarf_b200.so"
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 pats = [("UTCxMMA", r"UTC[A-Z]*MMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("UTMALDG/STG", r"UTMA(LDG|STG)"),
-        ("UBLKCP/RED", r"UBLK(CP|RED)"), ("UTCBAR", r"UTCBAR"), ("HMMA", r"\bHMMA"), ("DFMA", r"\bDFMA"),
+        ("UBLKCP/RED", r"UBLK(CP|RED)"), ("UTCBAR", r"UTCBAR"), ("HMMA", r"\bHMMA"), ("DMMA", r"\bDMMA"), ("DFMA", r"\bDFMA"),
         ("FMNMX3", r"\bFMNMX3")]
 rows, name, cnt = [], None, None
 for line in sass.splitlines():
