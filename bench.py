@@ -10,7 +10,8 @@ store was created (scarf/datastore/base_datastore.py:324-401, scarf/assay.py:201
 
 Workloads (BASELINE.json `configs`):
   N = 1   headline C2 (100k cells x 30k genes, 2k HVGs, dims 50, k 11); extra leg `legs.C3`: the 1M-cell C3 workload on
-          this one GPU -- the N = 1 point of the strong-scaling series the N > 1 lines continue.
+          this one GPU -- the N = 1 point of the strong-scaling series the N > 1 lines continue; `legs.C5`: run_mapping of
+          500k query cells onto that 1M-cell reference; `legs.datastore_e2e`: the drop-in DataStore calls on a C2 store.
   N > 1   headline C3, STRONG scaling: 1M cells in total, rows sharded over the ranks (aligned to 1000), dims 100, k 21.
   N = 8   extra leg `legs.C4`: 4M cells x 30k genes, dims 100, k 11, one pass, seconds per phase against the 30 s target.
 
@@ -57,7 +58,7 @@ def parse():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="headline workload (default: C2 on one GPU, C3 strong scaling on several)")
     ap.add_argument("--cells", type=int, default=None, help="total cells (overrides the workload)")
-    ap.add_argument("--legs", default="auto", help="extra legs: auto | none | comma list of C3,C4,datastore")
+    ap.add_argument("--legs", default="auto", help="extra legs: auto | none | comma list of C3,C5,C4,datastore (C5 needs C3)")
     ap.add_argument("--gram-mode", type=int, default=int(os.environ.get("SCF_GRAM_MODE", "3")))
     ap.add_argument("--knn-method", type=int, default=int(os.environ.get("SCF_KNN_METHOD", "1")))
     ap.add_argument("--cpu-sample", type=int, default=4000, help="cells in the CPU-baseline sample")
@@ -600,6 +601,52 @@ def c4_leg(args, rank, world, dev, comm):
     return out
 
 
+def c5_leg(args, lr, dev):
+    """C5 (BASELINE.json configs[4]): run_mapping of 500k further cells of the same generative model onto the 1M-cell
+    reference of the C3 leg, on this GPU: row sums, normalisation with the reference's mu / sigma, tensor-core
+    projection, exact kNN against all 1M reference cells (graph.run_mapping_csr, the core of DataStore.run_mapping;
+    save_k = 3, the reference's default).  Timed with CUDA events, 64 query rows re-solved by the FP64 kernel."""
+    import numpy as np
+    import torch
+
+    from scarf_b200 import graph, ops, synth
+
+    cfg = lr.cfg
+    n_ref, n_q = lr.n_total, 500_000
+    res = lr.step(lr.csr)
+    torch.cuda.synchronize()
+    q_start = (n_ref + GEN_BLOCK - 1) // GEN_BLOCK * GEN_BLOCK
+    t0 = time.time()
+    qry = synth.make_counts_device(n_q, cfg["genes"], cfg["factors"], seed=SEED, device=dev, block=GEN_BLOCK,
+                                   row_start=q_start)
+    torch.cuda.synchronize()
+    gen_s = time.time() - t0
+    feat_idx = np.asarray(res.feat_idx)
+
+    def mapping():
+        return graph.run_mapping_csr(qry, None, feat_idx, res.mu, res.sigma, res.loadings, res.embedding_all, res.dims,
+                                     save_k=3)
+
+    m = mapping()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m = mapping()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    rows = torch.arange(0, n_q, n_q // 64, device=dev)[:64]
+    qi, qd = ops.knn_l2(m.embedding[rows].contiguous(), res.embedding_all, res.dims, 3, self_offset=-1, method=0)
+    ok = bool(torch.equal(qi, m.indices[rows])) and bool(torch.equal(qd, m.distances[rows]))
+    return {"workload": f"C5: run_mapping of {n_q} query cells onto the {n_ref}-cell reference of the C3 leg ({cfg['genes']} genes, "
+                        f"{len(feat_idx)} HVGs, dims={res.dims}, save_k=3), one GPU, queries resident in HBM",
+            "ms": ms, "queries_per_s": n_q / ms * 1e3, "generation_s": round(gen_s, 2), "query_nnz": int(qry.nnz),
+            "fp64_spot_rows": int(rows.numel()), "fp64_spot_equal": ok}
+
+
 def datastore_leg(args, dev):
     """The drop-in call itself, once: DataStore.mark_hvgs + DataStore.make_graph on a store holding the C2 counts --
     incl. the k-means arrays the reference always writes, the widening to u8 / f8 and the Zarr write."""
@@ -616,11 +663,22 @@ def datastore_leg(args, dev):
     m = synth.to_scipy(csr)
     del csr
     path = os.path.join(os.environ.get("SCF_BENCH_TMP", tempfile.gettempdir()), "scarf_b200_c2_store.zarr")
+    # warm-up pass on a 3,000-cell store (what the W warm-up steps are for the headline): kernel images, the FP64 GEMM
+    # handle of the k-means seeding, allocator pools -- the first k-means call of a process alone costs ~0.45 s
+    wpath = path + ".warmup"
+    wcsr = synth.make_counts_device(3000, cfg["genes"], cfg["factors"], seed=SEED + 1, device=dev, block=GEN_BLOCK)
+    wds = DataStore.from_csr(wpath, synth.to_scipy(wcsr), [f"g{i}" for i in range(cfg["genes"])], device=dev)
+    wds.mark_hvgs(top_n=cfg["hvgs"], show_plot=False)
+    wds.make_graph(feat_key="hvgs", dims=cfg["dims"], k=cfg["k"])
+    del wds, wcsr
+    shutil.rmtree(wpath, ignore_errors=True)
+    torch.cuda.synchronize()
     t0 = time.time()
     ds = DataStore.from_csr(path, m, [f"g{i}" for i in range(cfg["genes"])], device=dev)
     torch.cuda.synchronize()
     out = {"workload": f"DataStore.mark_hvgs + DataStore.make_graph, {n} cells x {cfg['genes']} genes, top_n={cfg['hvgs']}, "
-                       f"dims={cfg['dims']}, k={cfg['k']}, n_centroids=1000 (k-means and Zarr write included)",
+                       f"dims={cfg['dims']}, k={cfg['k']}, n_centroids=1000 (k-means and Zarr write included; one pass, after a "
+                       f"warm-up pass on a 3,000-cell store)",
            "store_create_s": round(time.time() - t0, 3)}
     t0 = time.time()
     ds.mark_hvgs(top_n=cfg["hvgs"], show_plot=False)
@@ -656,7 +714,7 @@ def run_ours(args, rank, world, local_rank):
     cfg = dict(WORKLOADS[name])
     n_total = args.cells or cfg["cells"]
     scaling = "weak" if world == 1 else "strong"
-    legs = (["C3", "datastore"] if world == 1 else (["C4"] if world == 8 else [])) if args.legs == "auto" else \
+    legs = (["C3", "C5", "datastore"] if world == 1 else (["C4"] if world == 8 else [])) if args.legs == "auto" else \
         [x for x in args.legs.split(",") if x and x != "none"]
     if name in legs:
         legs.remove(name)
@@ -677,9 +735,14 @@ def run_ours(args, rank, world, local_rank):
                 c3 = dict(WORKLOADS["C3"])
                 lr = Runner(args, "C3", c3, c3["cells"], rank, world, dev, comm, scaling)
                 lm = lr.run(max(2, min(args.steps, 3)), max(1, min(args.warmup, 2)), False, not args.no_parity)
-                lr.close()
                 lm["workload"] = describe("C3", c3, c3["cells"], world, scaling)
                 leg_out["C3"] = lm
+                if "C5" in legs and world == 1:  # the mapping leg re-uses the C3 leg's reference cells
+                    try:
+                        leg_out["C5"] = c5_leg(args, lr, dev)
+                    except Exception as e:
+                        leg_out["C5"] = {"error": f"{type(e).__name__}: {e}"}
+                lr.close()
             elif leg == "C4":
                 leg_out["C4"] = c4_leg(args, rank, world, dev, comm)
             elif leg == "datastore" and world == 1:

@@ -172,7 +172,8 @@ struct GsVariant {
                  const int64_t*, int, int, int64_t, unsigned long long*, double*, double*);
 };
 // measured on a 100k-cell shard (B200): 1.52 ms / 1.67 ms / 1.84 ms; wider batches, narrower windows and more entries
-// per lane were all slower (2.1 - 3.0 ms)
+// per lane were all slower (2.1 - 3.0 ms), and so were shared-memory atomics in place of the row barriers (FP64 and
+// 64-bit shared atomics are CAS loops, ATOMS.CAST.SPIN.64: 2.2 - 2.7 ms, round 2)
 const GsVariant kVariants[] = {
     {1024, 128, 8, 8, gene_stats_win_kernel<1024, 128, 1, 8, 8>},
     {2048, 128, 5, 8, gene_stats_win_kernel<2048, 128, 2, 8, 5>},

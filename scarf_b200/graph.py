@@ -490,22 +490,19 @@ def fit_kmeans(embedding_all, dims, n_clusters, rand_state=4466, n_iter=10):
         start = torch.arange(n, dtype=torch.int64, device=dev)
     centres = embedding_all[torch.sort(start).values].clone()  # [n_clusters, ld], pad columns zero
     labels = None
+    emb64 = embedding_all.to(torch.float64)
     for it in range(n_iter + 1):
         idx, _ = ops.knn_l2(embedding_all, centres, dims, 1, self_offset=-1, method=1)
         labels = idx[:, 0]
         if it == n_iter:
             break
-        # segment means in a fixed order (no floating-point atomics: every rank must get the same bits): rows sorted
-        # by label (stable), float64 prefix sums, differences at the segment ends
+        # segment means in a fixed order (no floating-point atomics: every rank must get the same bits): rows sorted by
+        # label (stable), then one sequential float64 sum per (cluster, column) -- torch.segment_reduce gives every
+        # output element to one thread.
         order = torch.argsort(labels, stable=True)
-        cs = torch.cumsum(embedding_all.to(torch.float64)[order], dim=0)
         cnt_i = torch.bincount(labels, minlength=n_clusters)
-        ends = torch.cumsum(cnt_i, dim=0)
-        lo_idx = ends - cnt_i - 1
-        hi = cs[(ends - 1).clamp(min=0)]
-        lo = torch.where((lo_idx >= 0)[:, None], cs[lo_idx.clamp(min=0)], torch.zeros_like(hi))
+        sums = torch.segment_reduce(emb64[order], "sum", lengths=cnt_i, axis=0, unsafe=True)
         cnt = cnt_i.to(torch.float64)
-        new = ((hi - lo) / cnt.clamp(min=1.0)[:, None]).to(torch.float32)
+        new = (sums / cnt.clamp(min=1.0)[:, None]).to(torch.float32)
         centres = torch.where((cnt > 0)[:, None], new, centres).contiguous()  # an empty cluster keeps its centre
-        del cs, hi, lo
     return centres[:, :dims].contiguous(), labels
