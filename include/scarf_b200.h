@@ -145,8 +145,8 @@ int32_t scf_sym_eig_jacobi(const double* a, int32_t n, int64_t lda, double* eval
                            int32_t* info, void* stream);
 
 /* The fast path of the same step: Householder tridiagonalisation, multisection on the Sturm count, inverse iteration
- * (one thread per eigenvector) in one CTA, then the back-transformation (one warp per eigenvector) and an orthogonality
- * check over the whole GPU -- three launches, n in [3, 160].  Same outputs as scf_sym_eig_jacobi; work: 2 * n * n + n doubles
+ * in a warp per eigenpair, back-transformation (one warp per eigenvector) and an orthogonality check -- four launches, the
+ * tridiagonalisation in one CTA and the rest over the whole GPU, n in [3, 160].  Same outputs as scf_sym_eig_jacobi; work: 2 * n * n + 3 * n doubles
  * of device scratch; ok (device int32): 1 when the eigenvectors it produced are orthonormal to 1e-9, 0 when the
  * eigenvalues are too tightly clustered for inverse iteration without re-orthogonalisation (then call
  * scf_sym_eig_jacobi). */

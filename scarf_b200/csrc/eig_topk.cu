@@ -631,8 +631,10 @@ bool make_layout(int h, int dims, Layout& L) {
   L.ldn = L.nj * 16;
   L.ldc = ((int64_t)h + 7) / 8 * 8;
   L.row_tiles = (h + EG_TM - 1) / EG_TM;
-  // K splits of the big products: about two CTAs per SM in flight
-  int want = std::max(1, (2 * SCF_NUM_SMS + L.row_tiles - 1) / L.row_tiles);
+  // K splits of the big products: AT MOST two CTAs per SM, so that no SM gets a third one while others hold two -- the
+  // kernel runs at the SM's FP64 rate, and with 32 row tiles x 10 splits = 320 CTAs on 148 SMs the SMs with three CTAs
+  // set the time (62 us; 32 x 9 = 288: see DESIGN.md for the measurement)
+  int want = std::max(1, (2 * SCF_NUM_SMS) / L.row_tiles);
   L.k_per_split = std::max(EG_KT * 4, ((h + want - 1) / want + EG_KT - 1) / EG_KT * EG_KT);
   L.nsplit = (h + L.k_per_split - 1) / L.k_per_split;
   L.gram_tiles = ((b + 63) / 64) * ((b + 63) / 64);
@@ -653,7 +655,7 @@ bool make_layout(int h, int dims, Layout& L) {
   L.off_w = o, o = al(o + small);
   L.off_t = o, o = al(o + small);
   L.off_u = o, o = al(o + small);
-  L.off_x = o, o = al(o + (size_t)(2 * EG_MAXB * EG_MAXB + EG_MAXB) * 8);  // scratch of the tridiagonal eigensolver
+  L.off_x = o, o = al(o + (size_t)(2 * EG_MAXB * EG_MAXB + 3 * EG_MAXB) * 8);  // scratch of the tridiagonal eigensolver
   L.off_lam = o, o = al(o + EG_MAXB * 8);
   L.off_theta = o, o = al(o + EG_MAXB * 8);
   L.off_rowsum = o, o = al(o + (size_t)h * 8);
@@ -888,7 +890,7 @@ extern "C" int32_t scf_eig_topk(const int64_t* gram_fx, int64_t ldg, int32_t h, 
         rc = tridiag_eig_launch(c.p(L.off_t), b, L.ldn, c.p(L.off_theta), c.p(L.off_u), L.ldn, 1, c.p(L.off_x), tri_ok,
                                 c.st);
         if (rc) return rc;
-        c.launches += 3;  // tridiagonal solve, back-transformation, check
+        c.launches += 4;  // tridiagonalisation, eigenpairs of the tridiagonal matrix, back-transformation, check
       }
       rc = jacobi_eig_launch(c.p(L.off_t), b, L.ldn, c.p(L.off_theta), c.p(L.off_u), L.ldn, nullptr, 1,
                              b >= 3 ? tri_ok : nullptr, c.st);

@@ -1,13 +1,16 @@
 // All eigenpairs of a small symmetric matrix (n <= 160), the fast path of the Rayleigh-Ritz steps of scf_eig_topk
-// (eig_topk.cu).  One CTA: Householder tridiagonalisation in shared memory, eigenvalues by multisection on the Sturm
-// count, eigenvectors of the tridiagonal matrix by inverse iteration (one thread per vector, Gaussian elimination with
-// partial pivoting as in LAPACK dstein / dlagtf).  Then, over the whole GPU: back-transformation with the stored
-// reflectors (one warp per vector) and an orthogonality check.  The one-sided Jacobi kernel (jacobi_eig.cu) needs
-// 2.3 ms at n = 128: a Jacobi sweep is n - 1 dependent steps of ~2,500 cycles on one SM and eight sweeps are needed.
-// Inverse iteration without re-orthogonalisation is accurate while the eigenvalues are separated by more than
-// ~1e-7 |T| (cross-contamination eps |T| / gap); the check kernel measures the orthogonality of the result and reports
-// it in `ok`: the caller then runs the Jacobi kernel, which returns at once when *ok == 1.
-// Deterministic: fixed reduction orders, seeded start vectors.
+// (eig_topk.cu), in four launches:
+//   tridiag_eig_kernel    one CTA: Householder tridiagonalisation (matrix in registers for n <= 128)
+//   tridiag_vec_kernel    a warp per eigenvalue over the whole GPU: multisection on the Sturm count (32 points per round),
+//                         eigenvector of the tridiagonal matrix by inverse iteration (Gaussian elimination with partial
+//                         pivoting as in LAPACK dstein / dlagtf)
+//   tridiag_back_kernel   a warp per eigenvector: back-transformation with the stored reflectors
+//   tridiag_check_kernel  orthogonality of the result
+// The one-sided Jacobi kernel (jacobi_eig.cu) needs 2.3 ms at n = 128: a Jacobi sweep is n - 1 dependent steps of ~2,500
+// cycles on one SM and eight sweeps are needed.  Inverse iteration without re-orthogonalisation is accurate while the
+// eigenvalues are separated by more than ~1e-7 |T| (cross-contamination eps |T| / gap); the check kernel measures the
+// orthogonality of the result and reports it in `ok`: the caller then runs the Jacobi kernel, which returns at once
+// when *ok == 1.  Deterministic: fixed reduction orders, seeded start vectors.
 #include <math.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -24,72 +27,17 @@ __device__ __forceinline__ double group8_sum(double v, unsigned mask) {
   return v;
 }
 
-// numbers of eigenvalues of the tridiagonal (d, e2 = e^2) below x[0..3): sign changes of the characteristic polynomial
-// recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (no division).  The SM's vector FP64 pipe issues a warp
-// instruction every ~8 cycles per scheduler (16 lanes per clock and SM on this part), so the phase costs three FP64
-// instructions per row and sequence plus whatever latency is not hidden: three sequences per thread are interleaved,
-// and the sign bookkeeping (an exact zero takes the sign opposite to its predecessor, i.e. counts as a change: the next
-// value, -e^2 p_{i-1}, then has that sign and adds none) runs on the high words in the integer pipe, off the FP64
-// chain.  e2 must be > 0 (the caller clamps it): with an exact zero a vanishing value would stay zero.  Rescaled every
-// eight rows against overflow.
-__device__ __forceinline__ void sturm_count3(const double* __restrict__ d, const double* __restrict__ e2, int n,
-                                             const double (&x)[3], int (&cnt)[3]) {
-  double p0[3], p1[3];
-  int h1[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    p0[c] = 1.0, p1[c] = d[0] - x[c];
-    h1[c] = __double2hiint(p1[c]);
-    cnt[c] = (unsigned)h1[c] >> 31;
-  }
-  auto step = [&](int i) {
-    const double di = d[i], ei = e2[i - 1];
-    double p2[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) p2[c] = fma(di - x[c], p1[c], -ei * p0[c]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      int h2 = __double2hiint(p2[c]);
-      const bool zero = (((unsigned)h2 << 1) | (unsigned)__double2loint(p2[c])) == 0u;
-      h2 = zero ? (h1[c] ^ (int)0x80000000) : h2;
-      cnt[c] += (unsigned)(h2 ^ h1[c]) >> 31;
-      p0[c] = p1[c], p1[c] = p2[c], h1[c] = h2;
-    }
-  };
-  int i = 1;
-  while (i < n) {
-    if (i + 8 <= n) {  // eight rows unrolled: their loads of d / e2 are issued together
-#pragma unroll
-      for (int u = 0; u < 8; ++u) step(i + u);
-      i += 8;
-    } else {
-      for (; i < n; ++i) step(i);
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const unsigned ex = ((unsigned)h1[c] >> 20) & 0x7FFu;  // biased exponent: rescale outside 2^+-332 (~1e+-100)
-      if (ex > 1023u + 332u || (ex < 1023u - 332u && ex != 0u)) {
-        const double sc = ex > 1023u ? 1e-100 : 1e100;
-        p0[c] *= sc, p1[c] *= sc;
-      }
-    }
-  }
-}
-
 // NT > 0: n <= 8 NT <= 128, the matrix lives in REGISTERS during the tridiagonalisation (eight threads per row, thread
 // (row i, sub) holds the columns sub + 8 t, t < NT); NT == 0: n <= 160, the matrix in shared memory ([n][n + 1] doubles
 // of dynamic shared memory).  Reflector k is stored as H_k = I - tau_k u u^T: u in vwork[k * n ..], tau_k in tauwork[k].
 template <int NT>
 __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double* __restrict__ a, int n, int64_t lda,
-                                                                   double* __restrict__ evals, int descending,
-                                                                   double* __restrict__ xwork,
+                                                                   double* __restrict__ dework,
                                                                    double* __restrict__ vwork,
                                                                    double* __restrict__ tauwork, int* __restrict__ ok) {
   extern __shared__ __align__(16) double A[];  // [n][n + 1] (NT == 0)
-  __shared__ double s_d[TE_MAXN], s_e[TE_MAXN], s_e2[TE_MAXN], s_v[TE_MAXN], s_p[TE_MAXN], s_q[TE_MAXN];
+  __shared__ double s_d[TE_MAXN], s_e[TE_MAXN], s_v[TE_MAXN], s_p[TE_MAXN], s_q[TE_MAXN];
   __shared__ double s_x[2][128];  // NT > 0: the pivot column of the current / next step
-  __shared__ double s_lam[TE_MAXN];
-  __shared__ double s_red[32];
   __shared__ double s_scal[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ld = n + 1;
@@ -254,72 +202,88 @@ __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double
     if (tid == 0 && n >= 2) s_e[n - 2] = A[(size_t)(n - 1) * ld + (n - 2)];
   }
   __syncthreads();
-  // Gershgorin bounds of the spectrum
-  {
-    double lo = 1e300, hi = -1e300;
-    for (int i = tid; i < n; i += TE_THREADS) {
-      const double r = (i > 0 ? fabs(s_e[i - 1]) : 0.0) + (i + 1 < n ? fabs(s_e[i]) : 0.0);
-      lo = fmin(lo, s_d[i] - r), hi = fmax(hi, s_d[i] + r);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = fmin(lo, __shfl_xor_sync(SCF_FULL, lo, o));
-      hi = fmax(hi, __shfl_xor_sync(SCF_FULL, hi, o));
-    }
-    __syncthreads();  // s_red free
-    if (lane == 0) s_red[warp] = lo;
-    __syncthreads();
-    if (tid == 0) {
-      double l = 1e300;
-      for (int w = 0; w < TE_THREADS / 32; ++w) l = fmin(l, s_red[w]);
-      s_scal[1] = l;
-    }
-    __syncthreads();
-    if (lane == 0) s_red[warp] = hi;
-    __syncthreads();
-    if (tid == 0) {
-      double h2 = -1e300;
-      for (int w = 0; w < TE_THREADS / 32; ++w) h2 = fmax(h2, s_red[w]);
-      const double span = fmax(h2 - s_scal[1], 1e-300);
-      s_scal[2] = h2 + 1e-12 * span, s_scal[1] -= 1e-12 * span;
-      s_scal[3] = span;
-    }
-    __syncthreads();
-    // squared off-diagonals, kept above (1e-18 span)^2: moves no eigenvalue by more than 1e-18 span and keeps the
-    // recurrence of the Sturm count from sticking at zero when the matrix splits exactly
-    for (int i = tid; i < n; i += TE_THREADS)
-      s_e2[i] = i + 1 < n ? fmax(s_e[i] * s_e[i], 1e-36 * s_scal[3] * s_scal[3]) : 0.0;
-    __syncthreads();
-  }
-  // ---- eigenvalue j (ascending): one thread per eigenvalue, the bracket is cut in four per round (three interleaved
-  //      Sturm counts); 29 rounds = 58 bits below the Gershgorin span.  The SM issues FP64 at ~16 lanes per clock, so
-  //      this phase costs (number of Sturm counts) x 3 n FP64 operations whatever the number of threads: three counts
-  //      per round give 2 bits (87 counts per eigenvalue); two threads x three counts per round (cut in seven, 126
-  //      counts) and one count per thread on all 1024 threads were both measured slower ----
-  if (tid < n) {
-    const int j = tid;
-    double lo = s_scal[1], hi = s_scal[2];
-    for (int it = 0; it < 29; ++it) {
-      const double w = 0.25 * (hi - lo);
-      const double x[3] = {lo + w, lo + 2.0 * w, lo + 3.0 * w};
-      int cnt[3];
-      sturm_count3(s_d, s_e2, n, x, cnt);
-      // count(x) <= j  <=>  x <= lambda_j: the bracket becomes the quarter that holds lambda_j
-      const int q = (cnt[0] <= j) + (cnt[1] <= j) + (cnt[2] <= j);
-      const double nlo = q == 0 ? lo : (q == 1 ? x[0] : (q == 2 ? x[1] : x[2]));
-      hi = q == 0 ? x[0] : (q == 1 ? x[1] : (q == 2 ? x[2] : hi));
-      lo = nlo;
-    }
-    s_lam[j] = 0.5 * (lo + hi);
-  }
-  __syncthreads();
-  stamp(1);
+  for (int i = tid; i < n; i += TE_THREADS) dework[i] = s_d[i], dework[n + i] = i + 1 < n ? s_e[i] : 0.0;
+  if (tid == 0) *ok = 1;  // cleared by the check kernel
+}
 
-  // ---- eigenvectors of the tridiagonal matrix by inverse iteration: thread j solves (T - lam_j) x = b three times ----
-  if (tid < n) {
-    const int j = tid;
-    const double lam = s_lam[j];
-    double dd[TE_MAXN], du[TE_MAXN], du2[TE_MAXN], x[TE_MAXN];
+// Eigenpairs of the tridiagonal matrix (d, e) over the whole GPU: one WARP per eigenvalue j (ascending).
+//   eigenvalue   multisection on the Sturm count: the 32 lanes evaluate the count at 32 interior points of the bracket,
+//                which shrinks 33-fold per round; 12 rounds = 60 bits below the Gershgorin span.  One sequence per lane,
+//                so the phase runs at the latency of the dependent FMA chain (n steps per round) instead of the FP64
+//                issue rate of one SM: inside the single CTA (one thread per eigenvalue, 29 rounds of three counts)
+//                it took 0.24 ms at n = 128.
+//   eigenvector  inverse iteration by lane 0 (Gaussian elimination with partial pivoting as in LAPACK dstein / dlagtf,
+//                two solves from a seeded start vector), work arrays in shared memory.
+// number of eigenvalues of the tridiagonal (d, e2 = e^2) below x: sign changes of the characteristic polynomial
+// recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (no division: one FMA on the dependent chain per row).  The sign
+// bookkeeping -- an exact zero takes the sign opposite to its predecessor, i.e. counts as a change: the next value,
+// -e^2 p_{i-1}, then has that sign and adds none -- runs on the high words in the integer pipe.  e2 must be > 0 (clamped
+// by the caller): with an exact zero a vanishing value would stay zero.  Rescaled every eight rows against overflow.
+__device__ __forceinline__ int sturm_count1(const double* __restrict__ d, const double* __restrict__ e2, int n, double x) {
+  double p0 = 1.0, p1 = d[0] - x;
+  int h1 = __double2hiint(p1);
+  int cnt = (unsigned)h1 >> 31;
+  for (int i = 1; i < n; ++i) {
+    const double p2 = fma(d[i] - x, p1, -e2[i - 1] * p0);
+    int h2 = __double2hiint(p2);
+    const bool zero = (((unsigned)h2 << 1) | (unsigned)__double2loint(p2)) == 0u;
+    h2 = zero ? (h1 ^ (int)0x80000000) : h2;
+    cnt += (unsigned)(h2 ^ h1) >> 31;
+    p0 = p1, p1 = p2, h1 = h2;
+    if ((i & 7) == 0) {
+      const unsigned ex = ((unsigned)h1 >> 20) & 0x7FFu;  // biased exponent: rescale outside 2^+-332 (~1e+-100)
+      if (ex > 1023u + 332u || (ex < 1023u - 332u && ex != 0u)) {
+        const double sc = ex > 1023u ? 1e-100 : 1e100;
+        p0 *= sc, p1 *= sc;
+      }
+    }
+  }
+  return cnt;
+}
+
+constexpr int TV_WARPS = 4;
+__global__ void __launch_bounds__(32 * TV_WARPS) tridiag_vec_kernel(int n, const double* __restrict__ dework,
+                                                                   double* __restrict__ evals, int descending,
+                                                                   double* __restrict__ xwork) {
+  __shared__ double s_d[TE_MAXN], s_e[TE_MAXN], s_e2[TE_MAXN];
+  __shared__ double s_w[TV_WARPS][4][TE_MAXN];  // per warp: dd, du, du2, x of the elimination
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n; i += blockDim.x) s_d[i] = dework[i], s_e[i] = dework[n + i];
+  __syncthreads();
+  // Gershgorin bounds of the spectrum (every warp for itself: the same values in every warp of every CTA)
+  double lo = 1e300, hi = -1e300;
+  for (int i = lane; i < n; i += 32) {
+    const double r = (i > 0 ? fabs(s_e[i - 1]) : 0.0) + (i + 1 < n ? fabs(s_e[i]) : 0.0);
+    lo = fmin(lo, s_d[i] - r), hi = fmax(hi, s_d[i] + r);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(SCF_FULL, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(SCF_FULL, hi, o));
+  }
+  const double span = fmax(hi - lo, 1e-300);
+  hi += 1e-12 * span, lo -= 1e-12 * span;
+  // squared off-diagonals, kept above (1e-18 span)^2: moves no eigenvalue by more than 1e-18 span and keeps the
+  // recurrence of the Sturm count from sticking at zero when the matrix splits exactly
+  for (int i = tid; i < n; i += blockDim.x) s_e2[i] = i + 1 < n ? fmax(s_e[i] * s_e[i], 1e-36 * span * span) : 0.0;
+  __syncthreads();
+  const int j = blockIdx.x * TV_WARPS + warp;
+  if (j >= n) return;
+  for (int it = 0; it < 12; ++it) {
+    const double w = (hi - lo) * (1.0 / 33.0);
+    const int cnt = sturm_count1(s_d, s_e2, n, fma((double)(lane + 1), w, lo));
+    // count(x) <= j  <=>  x <= lambda_j; the counts are monotone in x: the lanes that satisfy it are a prefix
+    const int q = __popc(__ballot_sync(SCF_FULL, cnt <= j));
+    const double nlo = q == 0 ? lo : fma((double)q, w, lo);
+    hi = q == 32 ? hi : fma((double)(q + 1), w, lo);
+    lo = nlo;
+  }
+  const double lam = 0.5 * (lo + hi);
+  if (lane == 0) {
+    double* dd = s_w[warp][0];
+    double* du = s_w[warp][1];
+    double* du2 = s_w[warp][2];
+    double* x = s_w[warp][3];
     unsigned long long st = 0x9E3779B97F4A7C15ull * (unsigned long long)(j + 1);
     for (int i = 0; i < n; ++i) {
       st = st * 6364136223846793005ull + 1442695040888963407ull;
@@ -366,9 +330,6 @@ __global__ void __launch_bounds__(TE_THREADS, 1) tridiag_eig_kernel(const double
     for (int i = 0; i < n; ++i) xwork[(size_t)i * n + j] = x[i];
     evals[descending ? n - 1 - j : j] = lam;
   }
-  if (tid == 0) *ok = 1;  // cleared by the check kernel
-  __syncthreads();
-  stamp(2);
 }
 
 // Back-transformation S = H_0 ... H_{n-3} X over the whole GPU: one warp per column (lane l holds the rows l + 32 t),
@@ -455,7 +416,7 @@ __global__ void __launch_bounds__(256) tridiag_check_kernel(int n, const double*
 
 }  // namespace
 
-// evals / evecs as scf_sym_eig_jacobi (descending != 0: descending order); work: 2 * n * n + n doubles of device scratch;
+// evals / evecs as scf_sym_eig_jacobi (descending != 0: descending order); work: 2 * n * n + 3 * n doubles of device scratch;
 // ok (device int): 1 when the eigenvectors are orthonormal to 1e-9, 0 when the caller has to fall back
 int32_t tridiag_eig_launch(const double* a, int n, int64_t lda, double* evals, double* evecs, int64_t ldv, int descending,
                            double* work, int* ok, cudaStream_t stream) {
@@ -464,9 +425,10 @@ int32_t tridiag_eig_launch(const double* a, int n, int64_t lda, double* evals, d
   double* xwork = work;
   double* vwork = work + (size_t)n * n;
   double* tauwork = vwork + (size_t)n * n;
+  double* dework = tauwork + n;  // diagonal and off-diagonal of the tridiagonal matrix
   if (n <= 128) {  // matrix in registers
     auto fn = n <= 64 ? tridiag_eig_kernel<8> : (n <= 96 ? tridiag_eig_kernel<12> : tridiag_eig_kernel<16>);
-    fn<<<1, TE_THREADS, 0, stream>>>(a, n, lda, evals, descending, xwork, vwork, tauwork, ok);
+    fn<<<1, TE_THREADS, 0, stream>>>(a, n, lda, dework, vwork, tauwork, ok);
   } else {
     const size_t smem = (size_t)n * (n + 1) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(tridiag_eig_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -474,8 +436,9 @@ int32_t tridiag_eig_launch(const double* a, int n, int64_t lda, double* evals, d
       scf_set_error("scf_eig_topk(tridiagonal): %s", cudaGetErrorString(e));
       return -(int32_t)e;
     }
-    tridiag_eig_kernel<0><<<1, TE_THREADS, smem, stream>>>(a, n, lda, evals, descending, xwork, vwork, tauwork, ok);
+    tridiag_eig_kernel<0><<<1, TE_THREADS, smem, stream>>>(a, n, lda, dework, vwork, tauwork, ok);
   }
+  tridiag_vec_kernel<<<(n + TV_WARPS - 1) / TV_WARPS, 32 * TV_WARPS, 0, stream>>>(n, dework, evals, descending, xwork);
   {
     const size_t bsmem = ((size_t)(n - 2) * n + n) * sizeof(double);
     auto bk = n <= 128 ? tridiag_back_kernel<4> : tridiag_back_kernel<5>;
@@ -491,8 +454,7 @@ int32_t tridiag_eig_launch(const double* a, int n, int64_t lda, double* evals, d
     long long h[12];
     cudaStreamSynchronize(stream);
     cudaMemcpyFromSymbol(h, g_te_clk, sizeof(h));
-    fprintf(stderr, "[tridiag n=%d] cycles: tridiagonalise %lld, multisection %lld, inverse iteration %lld\n", n, h[0],
-            h[1], h[2]);
+    fprintf(stderr, "[tridiag n=%d] cycles: tridiagonalise %lld\n", n, h[0]);
   }
   return scf_check_launch("scf_eig_topk(tridiagonal)");
 }

@@ -368,7 +368,7 @@ def sym_eig_tridiag(a):
     a = a.contiguous()
     w = torch.empty(n, dtype=torch.float64, device=a.device)
     v = torch.empty((n, n), dtype=torch.float64, device=a.device)
-    work = torch.empty(2 * n * n + n, dtype=torch.float64, device=a.device)
+    work = torch.empty(2 * n * n + 3 * n, dtype=torch.float64, device=a.device)
     ok = torch.zeros(1, dtype=torch.int32, device=a.device)
     lib.call("scf_sym_eig_tridiag", _ptr(a), n, int(a.stride(0)), _ptr(w), _ptr(v), int(v.stride(0)), _ptr(work),
              _ptr(ok), _stream())
