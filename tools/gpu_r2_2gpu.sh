@@ -7,7 +7,7 @@ timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mas
 tail -4 gpurun_out/r2_bench_n2.err | cut -c1-300
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/r2_bench_n2.json'))
+s=open('gpurun_out/r2_bench_n2.json').read(); d=json.loads(s[s.index('{\"metric'):].splitlines()[0])
 print('value', d['value'], 'ms', d['ms_per_step'], d['scaling'], d['stage_ms'])
 print('e2e', d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e']['latency_ms'])
 print('parity', d['parity']); print('eig', d['eig']); print('roofline', d['roofline']['frac'], d['roofline']['ms_per_launch'])
