@@ -378,7 +378,7 @@ def sym_eig_tridiag(a):
 # ------------------------------------------------------------------------------------------ K5
 def knn_l2(q, ref, dim, k, self_offset=-1, method=0, stats=None, kernel_events=None):
     """Exact kNN (squared L2).  q, ref: float32 [n, ld] sharing the row stride.  -> (int64 idx, float32 dist).
-    ``stats`` (optional dict) receives ``guard_fail_rows`` as a device scalar tensor (method 1).
+    ``stats`` (optional dict) receives ``guard_fail_rows`` / ``guard_rest_rows`` as device scalar tensors (method 1).
     ``kernel_events``: optional pair of recorded ``torch.cuda.Event(enable_timing=True)``; the library re-records them
     around the tensor-core kernel of this call alone (measurement hook of bench.py)."""
     assert q.dtype == torch.float32 and ref.dtype == torch.float32
@@ -395,6 +395,8 @@ def knn_l2(q, ref, dim, k, self_offset=-1, method=0, stats=None, kernel_events=N
     if stats is not None:
         off = int(lib.raw("scf_knn_fail_count_offset")(nq, nref, int(dim), int(k), int(method)))
         stats["guard_fail_rows"] = ws[off:off + 4].view(torch.int32).clone() if off >= 0 else None
+        # rows the tensor-core collect pass could not settle either (FP64 scan over all references)
+        stats["guard_rest_rows"] = ws[off + 128:off + 132].view(torch.int32).clone() if off >= 0 else None
     return idx, dist
 
 
