@@ -785,6 +785,24 @@ def test_knn_cta_pair_kernel_equals_single_cta_and_fp64(gpu, monkeypatch, nq, nr
         assert torch.equal(dist, dist0), f"pair={pair}"
 
 
+@pytest.mark.parametrize("nq,nref,dim,k", [(40_000, 400_000, 100, 21), (300, 500_000, 40, 11)])
+def test_knn_rounds_schedule_on_a_reference_set_larger_than_l2(gpu, nq, nref, dim, k):
+    """Reference operands that do not fit L2 (> 48 MB of FP16 rows) take the `rounds` schedule of knn_tc_kernel: whole
+    query tiles per CTA with all CTAs in step, then the remaining query tiles cut into equal ranges (first case: 157 query
+    tiles on 148 CTAs = one round + nine tiles cut four ways; second case: two query tiles, no round, 74 ranges each).
+    Ids and float32 distances against the FP64 brute-force kernel, every row."""
+    torch, ops = gpu["torch"], gpu["ops"]
+    g = torch.Generator(device="cuda").manual_seed(nq)
+    ld = ops.round_up(dim, 32)
+    scale = torch.sqrt(40.0 * 0.96 ** torch.arange(dim, device="cuda", dtype=torch.float32) + 1.0)
+    ref = torch.zeros((nref, ld), device="cuda")
+    ref[:, :dim] = torch.randn((nref, dim), generator=g, device="cuda") * scale
+    q = ref[:nq]
+    idx, dist = ops.knn_l2(q, ref, dim, k, self_offset=0, method=1)
+    idx0, dist0 = ops.knn_l2(q, ref, dim, k, self_offset=0, method=0)
+    assert torch.equal(idx, idx0) and torch.equal(dist, dist0)
+
+
 @pytest.mark.parametrize("top_n,bounds", [(500, {}), (50, {"max_cells": 2000.0, "min_mean": -3.0, "max_mean": 2.0}),
                                            (100000, {})])
 def test_fused_hvg_selection_equals_tensor_ops(gpu, synth_small, top_n, bounds):
