@@ -1037,17 +1037,68 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   const int64_t self = self_offset >= 0 ? qi + self_offset : -1;
   const float* a = q + qi * ld;
   const bool vec = (ld & 3) == 0 && ((((uintptr_t)q) | ((uintptr_t)ref)) & 15) == 0;
+  // scaled units: the operands were multiplied by s, so scores / norms / eps are s^2 times the distance scale
+  const double an2 = qnorm2[qi], an = sqrt(an2), bm = (double)bmax[0], dbm = (double)bmax[1], s2 = (double)bmax[2];
+  const double eps = 2.0 * ((double)qerr[qi] * bm + an * dbm) * (1.0 + 1e-6) +
+                     eps_acc(kp) * (2.0 * an * bm + bm * bm) + EPS_SPLIT_ABS;
+  // Which candidates need the exact distance at all?  A tensor-core score is within eps of (exact scaled distance -
+  // |a|^2).  Let t be the (k + 1)-th smallest score of the row's candidates (k of those k + 1 are not the query itself):
+  // a candidate that scores above t + 2 eps is strictly farther than k others and cannot be among the k nearest.  The
+  // FP64 distance (500 FP64 instructions per candidate at D = 100, on a part that issues 16 FP64 lanes per clock and
+  // SM) is evaluated for the others only -- normally k + a few of the 64 - 128 candidates.
+  int cj[MAXU];
+  float cs[MAXU];
+#pragma unroll
+  for (int u = 0; u < MAXU; ++u) {
+    const int c = lane + 32 * u;
+    cj[u] = -1, cs[u] = FLT_MAX;
+    if (c < ncand) {
+      const int j = cand_idx[(size_t)qi * ncand + c];
+      if (j >= 0 && j < nref) cj[u] = j, cs[u] = cand_score[(size_t)qi * ncand + c];
+    }
+  }
+  float cut = FLT_MAX;  // evaluate candidates with score <= cut
+  {
+    float rest[MAXU];
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) rest[u] = cs[u];
+    float t = -FLT_MAX;
+    bool full = true;
+    for (int r = 0; r <= k; ++r) {  // the k + 1 smallest scores, one per round
+      float m = rest[0];
+#pragma unroll
+      for (int u = 1; u < MAXU; ++u) m = fminf(m, rest[u]);
+      float wm = m;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wm = fminf(wm, __shfl_xor_sync(SCF_FULL, wm, o));
+      if (!(wm < FLT_MAX)) {  // fewer than k + 1 candidates: nothing to prune
+        full = false;
+        break;
+      }
+      t = wm;
+      const unsigned holders = __ballot_sync(SCF_FULL, m == wm);
+      if (lane == __ffs(holders) - 1) {  // remove ONE instance (the first slot of the first lane that holds it)
+        bool gone = false;
+#pragma unroll
+        for (int u = 0; u < MAXU; ++u)
+          if (!gone && rest[u] == wm) rest[u] = FLT_MAX, gone = true;
+      }
+    }
+    // margins: the kept scores carry their list slot in the low mantissa bits (<= 31 ulp: 1e-5 relative covers it), and a
+    // pruned candidate must stay farther after the distances are rounded to float32 (the order is (float32 distance,
+    // index): a tie would be decided by the index), hence 1e-6 of the scaled distance |t| + |a|^2
+    if (full)
+      cut = __double2float_ru((double)t + 2.0 * eps + 1e-5 * (fabs((double)t) + 2.0 * eps) + 1e-6 * (fabs((double)t) + an2) +
+                              1e-30);
+  }
   unsigned long long key[MAXU];
 #pragma unroll
   for (int u = 0; u < MAXU; ++u) {
     key[u] = ~0ull;
-    const int c = lane + 32 * u;
-    if (c < ncand) {
-      const int j = cand_idx[(size_t)qi * ncand + c];
-      if (j >= 0 && j < nref && j != self) {
-        const double acc = oracle_dist(a, ref + (int64_t)j * ld, dim, vec);
-        key[u] = ((unsigned long long)__float_as_uint((float)acc) << 32) | (unsigned)j;
-      }
+    const int j = cj[u];
+    if (j >= 0 && j != self && cs[u] <= cut) {
+      const double acc = oracle_dist(a, ref + (int64_t)j * ld, dim, vec);
+      key[u] = ((unsigned long long)__float_as_uint((float)acc) << 32) | (unsigned)j;
     }
   }
   // smallest kept-list threshold over the splits: every rejected reference scored >= tau
@@ -1082,10 +1133,6 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   }
   if (lane == 0) {
     bool ok = enough;
-    // scaled units: the operands were multiplied by s, so scores / norms / eps are s^2 times the distance scale
-    const double an2 = qnorm2[qi], an = sqrt(an2), bm = (double)bmax[0], dbm = (double)bmax[1], s2 = (double)bmax[2];
-    const double eps = 2.0 * ((double)qerr[qi] * bm + an * dbm) * (1.0 + 1e-6) +
-                       eps_acc(kp) * (2.0 * an * bm + bm * bm) + EPS_SPLIT_ABS;
     const float dk = __uint_as_float((unsigned)(last >> 32));
     if (ok && tau < 1e29f) {  // lists were full: something was rejected, prove it is farther than the k-th kept
       const double lower = ((double)tau - eps + an2) * (1.0 - 1e-12) / s2;  // bound on any rejected exact distance
@@ -1238,7 +1285,8 @@ bool make_plan(int64_t nq, int64_t nref, int dim, int k, Plan& pl) {
   // rounds (units in step) only when the reference operand is too large to stay in L2 anyway: with a set that fits
   // (C2: 13 MB) every tile load hits L2 wherever the units are, and equal ranges over the whole space keep all lists
   // long (measured at C2: 2.53 ms without rounds, 2.62 ms with)
-  const bool fits_l2 = (size_t)pl.nr_pad * pl.kp * 2 <= (size_t)48 << 20;
+  bool fits_l2 = (size_t)pl.nr_pad * pl.kp * 2 <= (size_t)48 << 20;
+  if (const char* e = getenv("SCF_KNN_ROUNDS")) fits_l2 = atoi(e) == 0;  // developer switch: 1 forces the rounds, 0 forbids them
   pl.rounds = fits_l2 ? 0 : (int)(q_tiles / units);
   const long long rem_tiles = q_tiles - (long long)pl.rounds * units;
   pl.rem_total = rem_tiles * pl.n_ref_tiles;
