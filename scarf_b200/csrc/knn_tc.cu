@@ -7,21 +7,26 @@
 //
 //   Operands are FP16 (kind::f16, FP32 accumulate), not TF32: both formats keep an 11-bit significand, so the
 //   guard band is the same, but an FP16 instruction covers K = 16 instead of 8 for the same 32 bytes per operand
-//   row.  On B200 one M128 x N128 tcgen05.mma costs ~175 cycles whatever the kind (measured, profiles/), so half
-//   the instructions is half the tensor time, and the reference stream through L2 / shared memory halves too.
+//   row: half the instructions, and the reference stream through L2 / shared memory halves too.
 //   FP16's 5-bit exponent is handled by an exact power-of-two scale s (both operands are multiplied by s before
 //   rounding, s^2 max|b|^2 <= 2^15): distances scale by s^2, the guard works in scaled units.
 //
 //   kernel 0 (knn_range)   max |b|^2 over the references, max |a_t| over the queries -> s.
 //   kernel 1 (knn_prep)    builds A', B' (s * value rounded to FP16, round-to-nearest), |a|^2, max|b|, rounding norms.
-//   kernel 2 (knn_tc)      one CTA per SM walks an equal share of the (256-query tile, 128-reference tile) space:
-//                          TMA -> smem (128B swizzle) -> tcgen05.mma kind::f16 (M=128, N=128, K=16) -> TMEM
-//                          (2 x 2 x 128 columns, double buffered) -> 8 epilogue warps, one query row per thread,
-//                          keep the k' smallest.
-//   kernel 3 (knn_rerank)  one warp per query: the oracle's FP64 distance for every candidate, order by
-//                          (float32 distance, index), and the guard: everything the tensor cores rejected is
-//                          provably farther than the k-th kept neighbour, else the row goes on the fail list.
-//   kernel 4 (knn_exact)   FP64 brute force for the fail list (device-side count, no host round trip).
+//   kernel 2 (knn_tc)      one CTA per SM walks its share of the (256-query tile, 128-reference tile) space (SegWalk:
+//                          rounds with all CTAs in step, then a balanced remainder): TMA -> smem (128B swizzle) ->
+//                          tcgen05.mma kind::f16 (M=128, N=128, K=16), one issuing warp per query tile -> TMEM
+//                          (2 x 2 x 128 columns, double buffered) -> 16 epilogue warps, one query row x 64 columns per
+//                          thread, keep the k' smallest.  knn_tc_pair_kernel: the same over CTA pairs (cta_group::2),
+//                          opt-in.
+//   kernel 3 (knn_rerank)  one warp per query: the oracle's FP64 distance for every candidate that can still reach the k
+//                          nearest, order by (float32 distance, index), and the guard: everything the tensor cores
+//                          rejected is provably farther than the k-th kept neighbour, else the row goes on the fail list.
+//   repair                 collect pass (kernel 2 with a fixed per-row threshold, append-only) + FP64 selection for the
+//                          fail list; the FP64 brute force (knn_exact) for what is left (device-side counts, no host
+//                          round trip).
+// Developer switches (environment): SCF_KNN_PAIR=1 (CTA-pair kernel), SCF_KNN_ISSUERS=1|2, SCF_KNN_ROUNDS=0|1,
+// SCF_KNN_FLAGS; compile-time: SCF_KNN_DEBUG (timing skeletons, counters), SCF_KNN_HB (hit-buffer depth).
 #include <cuda_fp16.h>
 #include <float.h>
 #include <stdlib.h>
@@ -455,13 +460,12 @@ struct SegWalk {
   }
 };
 
-// QT query tiles of 128 rows per CTA x reference tiles of BN = 256 / QT rows: QT = 4 (BN = 64) when the operand rows
-// fit one 128-byte swizzle row (Kp = 64: a reference tile is re-used by 512 queries, half the L2 -> shared-memory
-// traffic of QT = 2), QT = 2 (BN = 128) for longer rows (the query operand of 512 rows would not fit).
-// 18 warps: warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-17 epilogue.  Epilogue warp w reads TMEM lane quarter
-// (warp id % 4) and the 64 accumulator columns [64 g, 64 g + 64), g = w / 4, of the 256-column buffer: with QT = 4
-// that is query tile g (one list per row), with QT = 2 query tile g / 2, column half g % 2 (two lists per row, which
-// share their thresholds through shared memory).
+// Two query tiles of 128 rows per CTA (QT = 2) x reference tiles of BN = 128 rows.  (QT = 4 / BN = 64 halves the L2 ->
+// shared-memory traffic but an N = 64 MMA is bound by operand bandwidth at 2/3 of the rate: tried and dropped.)
+// Warps: 0 TMA; 1 MMA + TMEM owner; 2-17 epilogue; with NI = 2 warp 18 is the second MMA issuer (warp 1 issues for query
+// tile 0, warp 18 for tile 1; NI = 1: warp 1 for both, no warp 18).  Epilogue warp w reads TMEM lane quarter (warp id %
+// 4) and the 64 accumulator columns [64 g, 64 g + 64), g = w / 4, of the 256-column buffer: query tile g / 2, column
+// half g % 2 -- two lists per row, which share their thresholds through shared memory.
 template <int KC, int QT, bool COLLECT, int NI>
 __global__ void __launch_bounds__(NI == 2 ? NTHREADS : NTHREADS - 32, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                                              const __grid_constant__ CUtensorMap tmap_r,
