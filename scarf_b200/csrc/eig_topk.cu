@@ -3,7 +3,8 @@
 //
 // Chebyshev-filtered subspace iteration (Zhou & Saad) on a block of b = dims + 32 columns, all arithmetic FP64:
 //   start     X = seeded random block; a few filter steps of degree 3, each followed by a Cholesky-QR2
-//   round     Rayleigh-Ritz:  AQ = C Q,  T = Q^T AQ,  T = S diag(theta) S^T (one-CTA Jacobi),  V = Q S,  AV = AQ S
+//   round     Rayleigh-Ritz:  AQ = C Q,  T = Q^T AQ,  T = S diag(theta) S^T (tridiag_eig.cu; Jacobi as the checked
+//             fallback),  V = Q S,  AV = AQ S
 //             residual max_j |AV_j - theta_j V_j| / theta_1 over the wanted pairs;  converged -> sign rule -> done
 //             else filter of degree m (largest m with rho^m <= 1e20, rho from the Ritz values) applied to V, whose
 //             first step needs no product with C (C V = AV is there already), then Cholesky-QR2
@@ -16,9 +17,9 @@
 //   eig_dgemm_mma_kernel  out = alpha A B + gamma P + delta Q (DMMA), 64-row tiles x all columns, split K with an ordered
 //                         reduction by the last CTA of a tile (serves the filter steps and the tall x small rotations)
 //   eig_gram_kernel       S = X^T Y over row chunks, ordered reduction by the last CTA of an output tile
-//   eig_chol_kernel       one CTA: column scaling, Cholesky of the b x b Gram in shared memory, triangular inverse
-//                         -> the factor W with (X W)^T (X W) = I
-//   jacobi_eig_kernel     (jacobi_eig.cu) one CTA: all eigenpairs of the b x b Rayleigh-Ritz matrix
+//   eig_chol_kernel       one CTA: column scaling, blocked Cholesky of the b x b Gram in shared memory, triangular inverse
+//                         (one column per group of eight threads) -> the factor W with (X W)^T (X W) = I
+//   tridiag_* / jacobi_eig_kernel   (tridiag_eig.cu, jacobi_eig.cu) all eigenpairs of the b x b Rayleigh-Ritz matrix
 //   eig_resid_* / eig_sign_kernel   residual norms and sklearn's sign rule
 #include <math.h>
 #include <string.h>
