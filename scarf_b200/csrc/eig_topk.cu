@@ -16,7 +16,7 @@
 //   eig_cov_kernel        covariance from the fixed-point Gram (optionally centred on a column mean)
 //   eig_dgemm_mma_kernel  out = alpha A B + gamma P + delta Q (DMMA), 64-row tiles x all columns, split K with an ordered
 //                         reduction by the last CTA of a tile (serves the filter steps and the tall x small rotations)
-//   eig_gram_kernel       S = X^T Y over row chunks, ordered reduction by the last CTA of an output tile
+//   eig_gram_kernel       S = X^T Y over row chunks; eig_gram_reduce_kernel adds the partial tiles in chunk order
 //   eig_chol_kernel       one CTA: column scaling, blocked Cholesky of the b x b Gram in shared memory, triangular inverse
 //                         (one column per group of eight threads) -> the factor W with (X W)^T (X W) = I
 //   tridiag_* / jacobi_eig_kernel   (tridiag_eig.cu, jacobi_eig.cu) all eigenpairs of the b x b Rayleigh-Ritz matrix
@@ -253,15 +253,13 @@ __global__ void __launch_bounds__(128) eig_dgemm_mma_kernel(const double* __rest
 }
 
 // ---------------------------------------------------------------------------------------------- Gram
-// s[b, b] (row stride lds) = X^T Y over the h rows; grid = (tiles of 64 x 64 outputs, row chunks); ordered reduction
-// by the last CTA of a tile, like the GEMM.
+// s[b, b] (row stride lds) = X^T Y over the h rows; grid = (tiles of 64 x 64 outputs, row chunks); with more than one
+// chunk the partial tiles go to `part` and eig_gram_reduce_kernel adds them in chunk order.
 __global__ void __launch_bounds__(EG_THREADS) eig_gram_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                                               int64_t ldn, int h, int b, double* __restrict__ s,
-                                                              int64_t lds, double* __restrict__ part,
-                                                              unsigned int* __restrict__ counters, int rows_per_chunk) {
+                                                              int64_t lds, double* __restrict__ part, int rows_per_chunk) {
   __shared__ __align__(16) double sx[EG_KT][64];
   __shared__ __align__(16) double sy[EG_KT][64];
-  __shared__ unsigned int s_last;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int tiles = (b + 63) / 64;
   const int ti = blockIdx.x / tiles, tj = blockIdx.x - ti * tiles;
@@ -303,24 +301,7 @@ __global__ void __launch_bounds__(EG_THREADS) eig_gram_kernel(const double* __re
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) mine[(ty * 4 + i) * 64 + tx + 16 * j] = acc[i][j];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(counters + blockIdx.x, 1u) == (unsigned)(nchunk - 1) ? 1u : 0u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    for (int c = 0; c < nchunk; ++c) {
-      const double* src = part + ((size_t)c * gridDim.x + blockIdx.x) * 4096;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += __ldcg(src + (ty * 4 + i) * 64 + tx + 16 * j);
-    }
-    if (tid == 0) counters[blockIdx.x] = 0u;
+    return;  // eig_gram_reduce_kernel adds the partial tiles in chunk order
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -331,6 +312,23 @@ __global__ void __launch_bounds__(EG_THREADS) eig_gram_kernel(const double* __re
       if (gi < b && gj < b) s[(int64_t)gi * lds + gj] = acc[i][j];
     }
   }
+}
+
+// The partial tiles of eig_gram_kernel summed in chunk order (deterministic), one thread per output element: its
+// loads are independent, so they are in flight together.  (The last CTA of a tile used to walk the ~37 chunks one L2 round
+// trip after the other: 25 of the kernel's 34 us.)
+__global__ void __launch_bounds__(256) eig_gram_reduce_kernel(const double* __restrict__ part, int n_tiles, int nchunk, int b,
+                                                             double* __restrict__ s, int64_t lds) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // tile * 4096 + element
+  if (e >= n_tiles * 4096) return;
+  const int tile = e >> 12, el = e & 4095;
+  const int tiles = (b + 63) / 64;
+  const int ti = tile / tiles, tj = tile - ti * tiles;
+  const int gi = ti * 64 + (el >> 6), gj = tj * 64 + (el & 63);
+  double acc = 0.0;
+#pragma unroll 8
+  for (int c = 0; c < nchunk; ++c) acc += __ldcg(part + ((size_t)c * n_tiles + tile) * 4096 + el);
+  if (gi < b && gj < b) s[(int64_t)gi * lds + gj] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------- Cholesky factor
@@ -727,8 +725,12 @@ void gram(const Ctx& c, const double* x, const double* y, double* s) {
   const Layout& L = c.L;
   ++c.launches;
   eig_gram_kernel<<<dim3((unsigned)L.gram_tiles, (unsigned)L.gram_chunks), EG_THREADS, 0, c.st>>>(
-      x, y, L.ldn, c.h, L.b, s, L.ldn, c.p(L.off_gpart),
-      reinterpret_cast<unsigned int*>(c.ws + L.off_counters) + L.row_tiles, L.gram_rows);
+      x, y, L.ldn, c.h, L.b, s, L.ldn, c.p(L.off_gpart), L.gram_rows);
+  if (L.gram_chunks > 1) {
+    ++c.launches;
+    eig_gram_reduce_kernel<<<(L.gram_tiles * 4096 + 255) / 256, 256, 0, c.st>>>(c.p(L.off_gpart), L.gram_tiles, L.gram_chunks,
+                                                                                 L.b, s, L.ldn);
+  }
 }
 
 // q <- orthonormal basis of range(y) (two passes); `robust`: eigenvalue-based factor instead of Cholesky
