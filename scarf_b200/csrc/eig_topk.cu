@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(1024, 1) eig_chol_kernel(const double* __restr
           if (i >= c) d[c] = fma(-lij, lcj, d[c]);
         }
       }
+      __syncwarp();  // the mirror lanes have read the block before it is overwritten
       if (lane < nb) {
 #pragma unroll
         for (int c = 0; c < 8; ++c)
