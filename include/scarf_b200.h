@@ -189,6 +189,13 @@ int64_t scf_knn_workspace_bytes(int64_t nq, int64_t nref, int32_t dim, int32_t k
 /* diagnostics: byte offset inside the workspace of an int32 that, after scf_knn_l2(method 1), holds the
  * number of query rows whose guard band could not be proven (recomputed by method 0); -1 if n/a. */
 int64_t scf_knn_fail_count_offset(int64_t nq, int64_t nref, int32_t dim, int32_t k, int32_t method);
+/* diagnostics (host only, no GPU work): how method 1 would run a shape.  out16 (host memory, 16 x int32): [0] k' per
+ * candidate list, [1] 64-wide K chunks, [2] 1 = CTA-pair kernel, [3] units (CTAs, or CTA pairs) launched, [4] rounds of
+ * whole query tiles per unit, [5] units that share the remaining query tiles, [6] lists a cut query tile keeps per column
+ * group, [7] candidate lists per query row, [8] column groups per row, [9] reference tiles, [10] query tiles, [11] TMA
+ * stages, [12] MMA-issuing warps, [13] dynamic shared memory in KiB, [14] candidates per row the re-rank can take,
+ * [15] 0.  Returns 1 when the shape takes method 0 (k > 24 or dim > 189). */
+int32_t scf_knn_plan(int64_t nq, int64_t nref, int32_t dim, int32_t k, int32_t* out16);
 /* measurement hook: the next scf_knn_l2(method 1) issued by the calling thread records the two cudaEvent_t (created
  * by the caller with timing enabled) on its stream around the tcgen05 distance / top-k' kernel alone, so that the
  * dominant kernel can be timed live without a profiler (bench.py `roofline`).  One shot; NULL, NULL cancels. */

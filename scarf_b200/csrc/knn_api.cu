@@ -11,6 +11,12 @@ extern "C" int64_t scf_knn_fail_count_offset(int64_t nq, int64_t nref, int32_t d
   return method == 1 ? knn_tc_fail_count_offset(nq, nref, dim, k) : -1;
 }
 
+extern "C" int32_t scf_knn_plan(int64_t nq, int64_t nref, int32_t dim, int32_t k, int32_t* out16) {
+  SCF_ARG(out16, "null pointer");
+  SCF_ARG(nq > 0 && nref > 0 && dim > 0 && k > 0, "bad sizes");
+  return knn_tc_plan_describe(nq, nref, dim, k, out16) ? 0 : 1;
+}
+
 extern "C" int32_t scf_knn_l2(const float* q, int64_t nq, const float* ref, int64_t nref, int32_t dim, int64_t ld,
                               int32_t k, int64_t self_offset, int64_t* out_idx, float* out_dist, int32_t method,
                               void* workspace, int64_t workspace_bytes, void* stream) {

@@ -21,6 +21,7 @@ int32_t knn_exact_fix_launch(const float* q, const int64_t* q_ids, const unsigne
 // method 1 (knn_tc.cu)
 int64_t knn_tc_workspace_bytes(int64_t nq, int64_t nref, int dim, int k);
 int64_t knn_tc_fail_count_offset(int64_t nq, int64_t nref, int dim, int k);
+bool knn_tc_plan_describe(int64_t nq, int64_t nref, int dim, int k, int32_t* out);
 int32_t knn_tc_launch(const float* q, int64_t nq, const float* ref, int64_t nref, int dim, int64_t ld, int k,
                       int64_t self_offset, int64_t* out_idx, float* out_dist, void* workspace,
                       int64_t workspace_bytes, cudaStream_t stream);

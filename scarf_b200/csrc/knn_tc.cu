@@ -1372,6 +1372,17 @@ int64_t knn_tc_fail_count_offset(int64_t nq, int64_t nref, int dim, int k) {
   return (int64_t)pl.off_misc;
 }
 
+// diagnostics (scf_knn_plan): how the tensor-core path would run a shape; false when it takes method 0 instead
+bool knn_tc_plan_describe(int64_t nq, int64_t nref, int dim, int k, int32_t* out) {
+  Plan pl;
+  if (!make_plan(nq, nref, dim, k, pl)) return false;
+  const int v[16] = {pl.kc, pl.kchunks, pl.pair, pl.grid, pl.rounds, pl.units_rem, pl.nsplit, pl.nlists, pl.halves,
+                     pl.n_ref_tiles, (int)(pl.nq_pad / (pl.qt * BM)), pl.pair ? pl.pstages : pl.stages,
+                     pl.kchunks >= 2 ? 2 : 1, (int)((pl.pair ? pl.psmem : pl.smem) >> 10), 32 * MAXU, 0};
+  for (int i = 0; i < 16; ++i) out[i] = v[i];
+  return true;
+}
+
 int64_t knn_tc_workspace_bytes(int64_t nq, int64_t nref, int dim, int k) {
   Plan pl;
   if (!make_plan(nq, nref, dim, k, pl)) return 0;

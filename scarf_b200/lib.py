@@ -37,6 +37,7 @@ SIGNATURES = {
     "scf_eig_topk": (_i32, [_p, _i64, _i32, _f64, _p, _f64, _i32, _f64, _i32, _p, _p, _p, _i64, _p, _p, _i64, _p]),
     "scf_knn_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32]),
     "scf_knn_fail_count_offset": (_i64, [_i64, _i64, _i32, _i32, _i32]),
+    "scf_knn_plan": (_i32, [_i64, _i64, _i32, _i32, _p]),
     "scf_knn_time_next_call": (_i32, [_p, _p]),
     "scf_knn_l2": (_i32, [_p, _i64, _p, _i64, _i32, _i64, _i32, _i64, _p, _p, _i32, _p, _i64, _p]),
     "scf_chunk_sums": (_i32, [_p, _i64, _i32, _i64, _i64, _p, _p]),

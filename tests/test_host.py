@@ -35,6 +35,47 @@ def test_abi_argument_errors_do_not_need_a_gpu():
     assert b"method" in lib.raw("scf_last_error")()
 
 
+def _knn_plan(nq, nref, dim, k):
+    from scarf_b200 import lib
+
+    out = (ctypes.c_int32 * 16)()
+    rc = lib.raw("scf_knn_plan")(nq, nref, dim, k, ctypes.cast(out, ctypes.c_void_p))
+    names = ("kc", "kchunks", "pair", "units", "rounds", "units_rem", "nsplit", "nlists", "groups", "ref_tiles", "q_tiles",
+             "stages", "issuers", "smem_kib", "max_cands")
+    return rc, dict(zip(names, list(out)))
+
+
+@pytest.mark.parametrize("shape", [(100_000, 100_000, 50, 11), (125_000, 1_000_000, 100, 21), (1_000_000, 1_000_000, 100, 21),
+                                   (500_000, 4_000_000, 100, 11), (300, 500_000, 40, 11), (1, 10, 5, 3), (7, 40_001, 130, 24),
+                                   (40_000, 400_000, 100, 21), (5000, 5000, 189, 24)])
+def test_knn_plan_invariants(shape, monkeypatch):
+    """scf_knn_plan (host only): the schedule the tensor-core kNN would run.  Rounds cover whole query tiles and only
+    when the reference operand exceeds L2; the lists a row can end up with fit the re-rank kernel; the pipeline is deeper
+    than a step; the CTA-pair kernel (opt-in) keeps four lists of 16 per row."""
+    nq, nref, dim, k = shape
+    for pair in ("0", "1"):
+        monkeypatch.setenv("SCF_KNN_PAIR", pair)
+        rc, p = _knn_plan(nq, nref, dim, k)
+        assert rc == 0, shape
+        assert p["pair"] == int(pair)
+        units_max = 74 if p["pair"] else 148
+        assert 1 <= p["units"] <= units_max and 1 <= p["units_rem"] <= p["units"]
+        assert p["rounds"] * p["units"] <= p["q_tiles"] and (p["q_tiles"] - p["rounds"] * p["units"]) < max(p["units"], p["q_tiles"] + 1)
+        assert p["nlists"] == p["nsplit"] * p["groups"] and p["nlists"] * p["kc"] <= p["max_cands"]
+        assert p["groups"] == (4 if p["pair"] else 2) and p["kc"] in (16, 32) and (not p["pair"] or p["kc"] == 16)
+        assert p["kchunks"] == (dim + 3 + 63) // 64 and p["stages"] >= p["kchunks"] + 1 and p["smem_kib"] <= 227
+        assert p["issuers"] == (2 if p["kchunks"] >= 2 else 1)
+        ref_step = 256 if p["pair"] else 128
+        assert p["ref_tiles"] == -(-nref // ref_step) and p["q_tiles"] == -(-nq // 256)
+        fits_l2 = p["ref_tiles"] * ref_step * p["kchunks"] * 64 * 2 <= 48 << 20
+        assert (p["rounds"] == 0) if fits_l2 else (p["rounds"] == p["q_tiles"] // p["units"])
+
+
+def test_knn_plan_rejects_shapes_of_the_fp64_kernel():
+    assert _knn_plan(1000, 1000, 190, 11)[0] == 1   # dim + 3 > 192
+    assert _knn_plan(1000, 1000, 20, 25)[0] == 1    # k > 24
+
+
 def test_missing_library_fails_loudly(tmp_path):
     """No CPU fallback: importing the binding without the built library is an ImportError."""
     code = ("import importlib.util, sys; spec = importlib.util.spec_from_file_location('lib', sys.argv[1]);"
